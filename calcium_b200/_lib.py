@@ -1,0 +1,89 @@
+"""ctypes binding of ``libcalcium_b200.so`` (the C ABI in ``include/cab200.h``).
+
+There is no CPU fallback: if the library is missing the import of any compute module fails with
+instructions to build it, and every compute entry point needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcalcium_b200.so")
+
+FP64_STRICT = 64
+FP32 = 32
+NPARAM = 16
+PARAM_SLOTS = ["k_1", "k_a", "k_p", "k_2", "V_SERCA", "K_SERCA", "K_PLC", "K_5", "c_tot", "beta",
+               "k_tau", "tau_max", "k_i", "D_c", "D_p", "dt"]
+ST_NONFINITE = 1
+ST_BADGEOM = 2
+
+#: every symbol include/cab200.h declares (tests check the library exports all of them)
+EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
+           "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_set_plan",
+           "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask",
+           "cab200_peak_fp64", "cab200_peak_hbm_write"]
+
+
+class Cab200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m calcium_b200.build` "
+            f"(needs nvcc, targets sm_100a). calcium_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    i32p, i64p, f64p = POINTER(c_int32), POINTER(c_int64), POINTER(c_double)
+    lib.cab200_version.restype = c_int
+    lib.cab200_last_error.restype = c_char_p
+    lib.cab200_device_info.argtypes = [c_int, i64p]
+    lib.cab200_sim_scratch_bytes.restype = c_size_t
+    lib.cab200_sim_scratch_bytes.argtypes = [c_int, c_int]
+    lib.cab200_sim_batch.restype = c_int
+    lib.cab200_sim_batch.argtypes = [
+        c_int, i32p, c_int, i32p, i32p, i32p, i64p, i64p,      # pouch/geometry tables (host)
+        c_void_p, c_void_p, c_void_p,                          # rowptr, colidx, vals (device)
+        i64p,                                                  # cell_off (host)
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,      # params, c0, p0, r0, vplc (device)
+        c_int, c_int, i32p,                                    # T, n_frames, frame_steps (host)
+        c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
+    lib.cab200_sim_set_plan.restype = c_int
+    lib.cab200_sim_set_plan.argtypes = [c_int, c_int, c_int]
+    lib.cab200_raster_scratch_bytes.restype = c_size_t
+    lib.cab200_raster_scratch_bytes.argtypes = [c_int]
+    lib.cab200_raster_batch.restype = c_int
+    lib.cab200_raster_batch.argtypes = [
+        c_int, i32p, i32p, i64p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+        c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.cab200_cells_mask.restype = c_int
+    lib.cab200_cells_mask.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.cab200_peak_fp64.restype = c_int
+    lib.cab200_peak_fp64.argtypes = [c_int, f64p, c_void_p]
+    lib.cab200_peak_hbm_write.restype = c_int
+    lib.cab200_peak_hbm_write.argtypes = [c_void_p, c_size_t, c_int, f64p, c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cab200_last_error().decode("utf-8", "replace")
+        raise Cab200Error(f"{what} failed ({rc}): {msg}")
+
+
+def as_i32p(a):
+    return a.ctypes.data_as(POINTER(c_int32))
+
+
+def as_i64p(a):
+    return a.ctypes.data_as(POINTER(c_int64))

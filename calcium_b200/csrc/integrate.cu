@@ -1,0 +1,218 @@
+// integrate.cu -- host launcher of K1 (see integrate.cuh) behind cab200_sim_batch.
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "integrate.cuh"
+
+namespace cab200 {
+
+struct Shape { int n_max, threads, cpt, minb; };
+
+// Default planner: CTA shape by cell count.  One CTA per pouch; small pouches get several CTAs per
+// SM (MINB) because one step is latency bound (~6 dependent FP64 divides + barrier).
+static const Shape kShapes[] = {
+    {128, 128, 1, 8},
+    {256, 256, 1, 4},
+    {512, 256, 2, 2},
+    {1024, 512, 2, 1},
+    {1536, 512, 3, 1},
+    {2048, 1024, 2, 1},
+    {3072, 1024, 3, 1},
+    {4096, 1024, 4, 1},
+};
+
+static std::mutex g_plan_mu;
+static int g_force_nmax = 0, g_force_threads = 0, g_force_cpt = 0;
+
+typedef void (*KernelFn)(const SimArgs);
+
+template <typename R, int THREADS, int CPT, int MINB>
+static KernelFn pick_variant(int ep, bool unit)
+{
+    if (unit) {
+        if (ep <= 5) return integrate_kernel<R, THREADS, CPT, 5, true, MINB>;
+        return integrate_kernel<R, THREADS, CPT, 8, true, MINB>;
+    }
+    return integrate_kernel<R, THREADS, CPT, 8, false, MINB>;
+}
+
+template <typename R>
+static KernelFn pick_kernel(int threads, int cpt, int ep, bool unit)
+{
+#define CAB_SHAPE(T_, C_, M_) \
+    if (threads == T_ && cpt == C_) return pick_variant<R, T_, C_, M_>(ep, unit);
+    CAB_SHAPE(128, 1, 8)
+    CAB_SHAPE(256, 1, 4)
+    CAB_SHAPE(256, 2, 2)
+    CAB_SHAPE(512, 1, 2)
+    CAB_SHAPE(512, 2, 1)
+    CAB_SHAPE(512, 3, 1)
+    CAB_SHAPE(768, 2, 1)
+    CAB_SHAPE(1024, 2, 1)
+    CAB_SHAPE(1024, 3, 1)
+    CAB_SHAPE(1024, 4, 1)
+#undef CAB_SHAPE
+    return nullptr;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace cab200
+
+using namespace cab200;
+
+extern "C" int cab200_sim_set_plan(int n_max, int threads, int cells_per_thread)
+{
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (threads == 0) { g_force_nmax = g_force_threads = g_force_cpt = 0; return CAB200_OK; }
+    if (!pick_kernel<double>(threads, cells_per_thread, 5, true)) {
+        set_error("cab200_sim_set_plan: unsupported shape threads=%d cells_per_thread=%d", threads,
+                  cells_per_thread);
+        return CAB200_EINVAL;
+    }
+    g_force_nmax = n_max; g_force_threads = threads; g_force_cpt = cells_per_thread;
+    return CAB200_OK;
+}
+
+extern "C" size_t cab200_sim_scratch_bytes(int n_pouch, int n_frames)
+{
+    // pouch_list [P] i32 + cell_off [P+1] i64 + frame_steps [F] i32, each 16-byte aligned
+    return align_up(sizeof(int32_t) * (size_t)std::max(n_pouch, 1), 16) +
+           align_up(sizeof(int64_t) * ((size_t)n_pouch + 1), 16) +
+           align_up(sizeof(int32_t) * (size_t)std::max(n_frames, 1), 16);
+}
+
+extern "C" int cab200_sim_batch(
+    int n_pouch, const int32_t *geom_id, int n_geom, const int32_t *g_ncell,
+    const int32_t *g_max_row, const int32_t *g_unit, const int64_t *g_rowptr_off,
+    const int64_t *g_nnz_off, const int32_t *rowptr, const int32_t *colidx, const double *vals,
+    const int64_t *cell_off, const double *params, const double *c0, const double *p0,
+    const double *r0, const double *vplc, int T, int n_frames, const int32_t *frame_steps,
+    void *frames_out, int32_t *status_out, int precision, void *scratch, size_t scratch_bytes,
+    void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pouch < 0 || n_geom <= 0 || T < 1 || n_frames < 0) {
+        set_error("cab200_sim_batch: bad sizes (n_pouch=%d n_geom=%d T=%d n_frames=%d)", n_pouch,
+                  n_geom, T, n_frames);
+        return CAB200_EINVAL;
+    }
+    if (precision != CAB200_FP64_STRICT && precision != CAB200_FP32) {
+        set_error("cab200_sim_batch: precision must be 64 or 32, got %d", precision);
+        return CAB200_EINVAL;
+    }
+    if (n_pouch == 0) return CAB200_OK;
+    if (!geom_id || !g_ncell || !g_max_row || !g_unit || !g_rowptr_off || !g_nnz_off || !rowptr ||
+        !colidx || !vals || !cell_off || !params || !c0 || !p0 || !r0 || !vplc || !status_out ||
+        (n_frames > 0 && (!frame_steps || !frames_out)) || !scratch) {
+        set_error("cab200_sim_batch: null pointer argument");
+        return CAB200_EINVAL;
+    }
+    if (scratch_bytes < cab200_sim_scratch_bytes(n_pouch, n_frames)) {
+        set_error("cab200_sim_batch: scratch too small (%zu < %zu)", scratch_bytes,
+                  cab200_sim_scratch_bytes(n_pouch, n_frames));
+        return CAB200_ESIZE;
+    }
+    for (int f = 0; f < n_frames; ++f) {
+        if (frame_steps[f] < 0 || frame_steps[f] > T - 1 || (f > 0 && frame_steps[f] <= frame_steps[f - 1])) {
+            set_error("cab200_sim_batch: frame_steps must be strictly ascending within [0, T-1]");
+            return CAB200_EINVAL;
+        }
+    }
+    for (int p = 0; p < n_pouch; ++p) {
+        const int g = geom_id[p];
+        if (g < 0 || g >= n_geom || cell_off[p + 1] - cell_off[p] != g_ncell[g]) {
+            set_error("cab200_sim_batch: pouch %d: geom_id/cell_off inconsistent", p);
+            return CAB200_EINVAL;
+        }
+    }
+
+    // ---- device copies of the small metadata (scratch layout as in cab200_sim_scratch_bytes) ----
+    unsigned char *sp = (unsigned char *)scratch;
+    int32_t *d_list = (int32_t *)sp;
+    sp += align_up(sizeof(int32_t) * (size_t)n_pouch, 16);
+    int64_t *d_cell_off = (int64_t *)sp;
+    sp += align_up(sizeof(int64_t) * ((size_t)n_pouch + 1), 16);
+    int32_t *d_frame_steps = (int32_t *)sp;
+
+    // pouch ids grouped by geometry
+    std::vector<int32_t> list;
+    list.reserve(n_pouch);
+    std::vector<int> g_begin(n_geom + 1, 0);
+    for (int g = 0; g < n_geom; ++g) {
+        g_begin[g] = (int)list.size();
+        for (int p = 0; p < n_pouch; ++p)
+            if (geom_id[p] == g) list.push_back(p);
+    }
+    g_begin[n_geom] = (int)list.size();
+    CAB_CUDA(cudaMemcpyAsync(d_list, list.data(), sizeof(int32_t) * list.size(),
+                             cudaMemcpyHostToDevice, stream));
+    CAB_CUDA(cudaMemcpyAsync(d_cell_off, cell_off, sizeof(int64_t) * ((size_t)n_pouch + 1),
+                             cudaMemcpyHostToDevice, stream));
+    if (n_frames > 0)
+        CAB_CUDA(cudaMemcpyAsync(d_frame_steps, frame_steps, sizeof(int32_t) * (size_t)n_frames,
+                                 cudaMemcpyHostToDevice, stream));
+    CAB_CUDA(cudaMemsetAsync(status_out, 0, sizeof(int32_t) * (size_t)n_pouch, stream));
+    // the host vectors above are pageable: the copies are staged before cudaMemcpyAsync returns.
+
+    int force_nmax, force_threads, force_cpt;
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        force_nmax = g_force_nmax; force_threads = g_force_threads; force_cpt = g_force_cpt;
+    }
+
+    for (int g = 0; g < n_geom; ++g) {
+        const int count = g_begin[g + 1] - g_begin[g];
+        if (count == 0) continue;
+        const int n = g_ncell[g];
+        if (n <= 0) { set_error("cab200_sim_batch: geometry %d has no cells", g); return CAB200_EINVAL; }
+        int threads = 0, cpt = 0;
+        if (force_threads && n <= force_nmax && force_threads * force_cpt >= n) {
+            threads = force_threads; cpt = force_cpt;
+        } else {
+            for (const Shape &s : kShapes)
+                if (n <= s.n_max) { threads = s.threads; cpt = s.cpt; break; }
+        }
+        if (!threads) {
+            set_error("cab200_sim_batch: geometry %d has %d cells; one CTA holds at most 4096", g, n);
+            return CAB200_ESIZE;
+        }
+        const int max_row = g_max_row[g];
+        if (max_row > 16 || max_row < 1) {
+            set_error("cab200_sim_batch: geometry %d: longest CSR row %d outside [1,16]", g, max_row);
+            return CAB200_ESIZE;
+        }
+        const int ep = (max_row + 1) / 2;
+        const bool unit = g_unit[g] != 0;
+        KernelFn fn = (precision == CAB200_FP64_STRICT) ? pick_kernel<double>(threads, cpt, ep, unit)
+                                                        : pick_kernel<float>(threads, cpt, ep, unit);
+        if (!fn) { set_error("cab200_sim_batch: no kernel for shape %dx%d", threads, cpt); return CAB200_EINVAL; }
+        const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
+        const int np = (n + 31) & ~31;
+        const size_t smem = integrate_smem_bytes(np, threads * cpt, elem2);
+        if (smem > 227 * 1024) {
+            set_error("cab200_sim_batch: geometry %d needs %zu bytes of shared memory (> 227 KB)", g, smem);
+            return CAB200_ESIZE;
+        }
+        CAB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+        SimArgs a;
+        a.pouch_list = d_list + g_begin[g];
+        a.cell_off = d_cell_off;
+        a.rowptr = rowptr + g_rowptr_off[g];
+        a.colidx = colidx + g_nnz_off[g];
+        a.vals = vals + g_nnz_off[g];
+        a.n = n;
+        a.np = np;
+        a.params = params;
+        a.c0 = c0; a.p0 = p0; a.r0 = r0; a.vplc = vplc;
+        a.T = T; a.n_frames = n_frames;
+        a.frame_steps = d_frame_steps;
+        a.frames_out = frames_out;
+        a.status_out = status_out;
+        fn<<<count, threads, smem, stream>>>(a);
+        CAB_CUDA(cudaGetLastError());
+    }
+    return CAB200_OK;
+}

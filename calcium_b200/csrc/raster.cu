@@ -1,0 +1,345 @@
+// raster.cu -- K2 (per-frame image / active mask / instance mask) and K0 (static cells_mask).
+//
+// K2 replaces, per (pouch, frame): Pouch.generate_image default branch (core/pouch.py:412-453),
+// get_active_cells (:563-565), get_cell_masks(active_only=True) (:540-546) and
+// create_instance_mask_from_cells (utils/sam2_data_generator.py:31-35).  The reference repaints n
+// polygons per frame; here a frame is a pure gather through two static label maps: per frame the
+// CTA builds three small look-up tables in shared memory (gray level, active flag, instance id per
+// label value) and then streams the pixels with 16-byte loads and stores.  HBM-write bound:
+// 4 bytes written per pixel (image 2 + instance 2), +4 when the int32 active mask is requested;
+// the label maps (4 bytes read per pixel) stay L2 resident per geometry.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cab200 {
+
+struct PouchEntry {
+    int64_t cell_off;
+    int32_t n;
+    int32_t geom;
+};
+
+struct RasterArgs {
+    const PouchEntry *pouches;   // [P]
+    const uint16_t *label_img;   // [G][H][W]
+    const uint16_t *label_mask;  // [G][H][W]
+    const double *ca_frames;
+    int n_frames, npix, tiles;
+    double threshold;
+    int quirk;
+    uint8_t *image_out;
+    int32_t *active_out;
+    uint16_t *instance_out;
+    int32_t *n_active_out;
+};
+
+constexpr int RT = 256;   // threads per CTA
+
+__global__ void __launch_bounds__(RT, 4) raster_kernel(const RasterArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[RT / 32];
+    __shared__ int wsum[RT / 32];
+    __shared__ double s_vmax;
+    __shared__ int s_total;
+
+    const int tile = blockIdx.x % a.tiles;
+    const int pf = blockIdx.x / a.tiles;
+    const int f = pf % a.n_frames;
+    const int pi = pf / a.n_frames;
+    const PouchEntry pe = a.pouches[pi];
+    const int n = pe.n;
+    const double *ca = a.ca_frames + (size_t)pe.cell_off * 4 * a.n_frames + (size_t)f * 4 * n;
+
+    // LUTs indexed by label value v in [0, n]
+    uint16_t *inst_lut = reinterpret_cast<uint16_t *>(smem_raw);                 // [n+1]
+    uint16_t *rank1 = inst_lut + ((n + 2 + 7) & ~7);                            // [n+1] scratch
+    uint8_t *gray_lut = reinterpret_cast<uint8_t *>(rank1 + ((n + 2 + 7) & ~7)); // [n+1]
+    uint8_t *act8 = gray_lut + ((n + 2 + 15) & ~15);                            // [n+1] act8[v]=active(cell v-1)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- vmax = max(np.max(ca), 0.5)  (core/pouch.py:421-422) --------------------------------
+    double mx = -INFINITY;
+    for (int i = tid; i < n; i += RT) mx = fmax(mx, ca[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        double m = red[0];
+        for (int w = 1; w < RT / 32; ++w) m = fmax(m, red[w]);
+        s_vmax = (0.5 > m) ? 0.5 : m;
+    }
+    __syncthreads();
+    const double vmax = s_vmax;
+
+    // ---- per-cell gray level, active flag, 1-based rank among active cells ---------------------
+    // contiguous chunk per thread so the scan keeps ascending cell order (np.where, :564)
+    const int chunk = (n + RT - 1) / RT;
+    const int beg = min(tid * chunk, n), end = min(beg + chunk, n);
+    int cnt = 0;
+    for (int i = beg; i < end; ++i) {
+        const double v = ca[i];
+        double nv = __ddiv_rn(__dsub_rn(v, 0.0), __dsub_rn(vmax, 0.0));        // :426
+        nv = (nv < 0.0) ? 0.0 : ((nv > 1.0) ? 1.0 : nv);                       // np.clip
+        gray_lut[i + 1] = (uint8_t)(int)__dmul_rn(255.0, nv);                  // int(255*x), :427
+        const int act = v > a.threshold;                                        // strict >, :564
+        act8[i + 1] = (uint8_t)act;
+        cnt += act;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < RT / 32; ++w) { const int t = wsum[w]; wsum[w] = run; run += t; }
+        s_total = run;
+        gray_lut[0] = 0; act8[0] = 0;
+    }
+    __syncthreads();
+    int run = wsum[warp] + incl - cnt;
+    for (int i = beg; i < end; ++i) {
+        const int act = act8[i + 1];
+        run += act;
+        rank1[i] = (uint16_t)(act ? run : 0);      // rank1[cell], 1-based
+    }
+    if (tid == 0) rank1[n] = 0;
+    __syncthreads();
+    // instance id per label value
+    for (int v = tid; v <= n; v += RT) {
+        uint16_t id;
+        if (a.quirk) {
+            // reference semantics: masked value m = v if cell v-1 active else 0; then the loop
+            // `instance[mask == cell_id] = new_id` over 0-based active ids (D5)
+            const int m = (v > 0 && act8[v]) ? v : 0;
+            id = (m < n && act8[m + 1]) ? rank1[m] : 0;
+        } else {
+            id = (v > 0 && act8[v]) ? rank1[v - 1] : 0;
+        }
+        inst_lut[v] = id;
+    }
+    if (tid == 0 && tile == 0 && a.n_active_out) a.n_active_out[pf] = s_total;
+    __syncthreads();
+
+    // ---- stream the pixels ---------------------------------------------------------------------
+    const size_t gbase = (size_t)pe.geom * a.npix;
+    const uint16_t *limg = a.label_img + gbase;
+    const uint16_t *lmsk = a.label_mask + gbase;
+    const size_t obase = (size_t)pf * a.npix;
+    const int groups = a.npix >> 3;                       // 8-pixel groups
+    const int gper = (groups + a.tiles - 1) / a.tiles;
+    const int g0 = tile * gper, g1 = min(g0 + gper, groups);
+    const bool vec_ok = ((a.npix & 7) == 0);
+    if (vec_ok) {
+        for (int g = g0 + tid; g < g1; g += RT) {
+            const size_t px = (size_t)g * 8;
+            if (a.image_out) {
+                const uint4 li = __ldg(reinterpret_cast<const uint4 *>(limg + px));
+                const uint32_t w[4] = {li.x, li.y, li.z, li.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t l0 = w[q] & 0xffffu, l1 = w[q] >> 16;
+                    const uint32_t p0 = l0 ? ((uint32_t)gray_lut[l0] | 0xff00u) : 0u;
+                    const uint32_t p1 = l1 ? ((uint32_t)gray_lut[l1] | 0xff00u) : 0u;
+                    o[q] = p0 | (p1 << 16);
+                }
+                __stcs(reinterpret_cast<uint4 *>(a.image_out + (obase + px) * 2),
+                       make_uint4(o[0], o[1], o[2], o[3]));
+            }
+            if (a.instance_out || a.active_out) {
+                const uint4 lm = __ldg(reinterpret_cast<const uint4 *>(lmsk + px));
+                const uint32_t w[4] = {lm.x, lm.y, lm.z, lm.w};
+                if (a.instance_out) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        o[q] = (uint32_t)inst_lut[w[q] & 0xffffu] | ((uint32_t)inst_lut[w[q] >> 16] << 16);
+                    __stcs(reinterpret_cast<uint4 *>(a.instance_out + obase + px),
+                           make_uint4(o[0], o[1], o[2], o[3]));
+                }
+                if (a.active_out) {
+                    int32_t o[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t l0 = w[q] & 0xffffu, l1 = w[q] >> 16;
+                        o[2 * q] = act8[l0] ? (int32_t)l0 : 0;
+                        o[2 * q + 1] = act8[l1] ? (int32_t)l1 : 0;
+                    }
+                    int4 *dst = reinterpret_cast<int4 *>(a.active_out + obase + px);
+                    __stcs(dst, make_int4(o[0], o[1], o[2], o[3]));
+                    __stcs(dst + 1, make_int4(o[4], o[5], o[6], o[7]));
+                }
+            }
+        }
+    } else {
+        const int per = (a.npix + a.tiles - 1) / a.tiles;
+        const int p0 = tile * per, p1 = min(p0 + per, a.npix);
+        for (int px = p0 + tid; px < p1; px += RT) {
+            if (a.image_out) {
+                const uint32_t l = limg[px];
+                a.image_out[(obase + px) * 2] = l ? gray_lut[l] : 0;
+                a.image_out[(obase + px) * 2 + 1] = l ? 255 : 0;
+            }
+            const uint32_t m = lmsk[px];
+            if (a.instance_out) a.instance_out[obase + px] = inst_lut[m];
+            if (a.active_out) a.active_out[obase + px] = act8[m] ? (int32_t)m : 0;
+        }
+    }
+}
+
+// ---- K0: cells_mask with scikit-image's point_in_polygon rule -----------------------------------
+// One CTA per polygon; integer pixel vertices make the O'Rourke crossing test exact in int64:
+// the reference's quotient (x0*y1 - x1*y0)/(y1 - y0) is only compared with 0, and its eps=1e-12
+// vertex test degenerates to equality on integers.
+__global__ void __launch_bounds__(128) cells_mask_kernel(int n_cells, const int32_t *poly_off,
+                                                         const int32_t *pts, int H, int W,
+                                                         uint32_t *label32)
+{
+    constexpr int MAXV = 64;
+    __shared__ int vx[MAXV], vy[MAXV];
+    __shared__ int box[4];
+    const int cell = blockIdx.x;
+    const int b = poly_off[cell], nv = min(poly_off[cell + 1] - b, MAXV);
+    if (nv <= 0) return;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) { vx[i] = pts[2 * (b + i)]; vy[i] = pts[2 * (b + i) + 1]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];
+        for (int i = 1; i < nv; ++i) {
+            minx = min(minx, vx[i]); maxx = max(maxx, vx[i]);
+            miny = min(miny, vy[i]); maxy = max(maxy, vy[i]);
+        }
+        box[0] = max(0, minx); box[1] = min(W - 1, maxx);     // minc..maxc
+        box[2] = max(0, miny); box[3] = min(H - 1, maxy);     // minr..maxr
+    }
+    __syncthreads();
+    const int minc = box[0], maxc = box[1], minr = box[2], maxr = box[3];
+    if (maxc < minc || maxr < minr) return;
+    const int bw = maxc - minc + 1, bh = maxr - minr + 1;
+    const uint32_t id = (uint32_t)cell + 1u;
+    for (int q = threadIdx.x; q < bw * bh; q += blockDim.x) {
+        const int y = minr + q / bw, x = minc + q % bw;
+        long long x1 = vx[nv - 1] - x, y1 = vy[nv - 1] - y;
+        unsigned rc = 0, lc = 0;
+        bool vertex = false;
+        for (int i = 0; i < nv; ++i) {
+            const long long x0 = vx[i] - x, y0 = vy[i] - y;
+            if (x0 == 0 && y0 == 0) { vertex = true; break; }
+            if ((y0 > 0) != (y1 > 0) || (y0 < 0) != (y1 < 0)) {
+                const long long num = x0 * y1 - x1 * y0, den = y1 - y0;
+                const int sg = (num > 0 ? 1 : (num < 0 ? -1 : 0)) * (den > 0 ? 1 : -1);
+                if ((y0 > 0) != (y1 > 0) && sg > 0) ++rc;
+                if ((y0 < 0) != (y1 < 0) && sg < 0) ++lc;
+            }
+            x1 = x0; y1 = y0;
+        }
+        const bool inside = vertex || ((rc & 1) != (lc & 1)) || (rc & 1);
+        if (inside) {
+            // highest id wins (later cells overwrite, core/pouch.py:285): max on the u16 half
+            const size_t px = (size_t)y * W + x;
+            uint32_t *word = label32 + (px >> 1);
+            const uint32_t sh = (px & 1) * 16;
+            uint32_t old = *word;
+            while (((old >> sh) & 0xffffu) < id) {
+                const uint32_t want = (old & ~(0xffffu << sh)) | (id << sh);
+                const uint32_t prev = atomicCAS(word, old, want);
+                if (prev == old) break;
+                old = prev;
+            }
+        }
+    }
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace cab200
+
+using namespace cab200;
+
+extern "C" size_t cab200_raster_scratch_bytes(int n_pouch)
+{
+    return align_up(sizeof(PouchEntry) * (size_t)std::max(n_pouch, 1), 16);
+}
+
+extern "C" int cab200_raster_batch(
+    int n_pouch, const int32_t *geom_id, const int32_t *g_ncell, const int64_t *cell_off,
+    const uint16_t *label_img, const uint16_t *label_mask, int H, int W, int n_frames,
+    const double *ca_frames, double threshold, int quirk_mode, uint8_t *image_out,
+    int32_t *active_mask_out, uint16_t *instance_out, int32_t *n_active_out, void *scratch,
+    size_t scratch_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pouch < 0 || H <= 0 || W <= 0 || n_frames < 0) {
+        set_error("cab200_raster_batch: bad sizes");
+        return CAB200_EINVAL;
+    }
+    if (n_pouch == 0 || n_frames == 0) return CAB200_OK;
+    if (!geom_id || !g_ncell || !cell_off || !label_img || !label_mask || !ca_frames || !scratch) {
+        set_error("cab200_raster_batch: null pointer argument");
+        return CAB200_EINVAL;
+    }
+    if (scratch_bytes < cab200_raster_scratch_bytes(n_pouch)) {
+        set_error("cab200_raster_batch: scratch too small");
+        return CAB200_ESIZE;
+    }
+    if ((size_t)H * W >= (1u << 30)) { set_error("cab200_raster_batch: image too large"); return CAB200_ESIZE; }
+    std::vector<PouchEntry> tab(n_pouch);
+    int n_max = 0;
+    for (int p = 0; p < n_pouch; ++p) {
+        tab[p].cell_off = cell_off[p];
+        tab[p].geom = geom_id[p];
+        tab[p].n = g_ncell[geom_id[p]];
+        if (tab[p].n > 65534 || tab[p].n <= 0 || cell_off[p + 1] - cell_off[p] != tab[p].n) {
+            set_error("cab200_raster_batch: pouch %d: bad cell count", p);
+            return CAB200_EINVAL;
+        }
+        n_max = std::max(n_max, tab[p].n);
+    }
+    CAB_CUDA(cudaMemcpyAsync(scratch, tab.data(), sizeof(PouchEntry) * (size_t)n_pouch,
+                             cudaMemcpyHostToDevice, stream));
+    RasterArgs a;
+    a.pouches = (const PouchEntry *)scratch;
+    a.label_img = label_img; a.label_mask = label_mask; a.ca_frames = ca_frames;
+    a.n_frames = n_frames; a.npix = H * W;
+    a.threshold = threshold; a.quirk = quirk_mode;
+    a.image_out = image_out; a.active_out = active_mask_out; a.instance_out = instance_out;
+    a.n_active_out = n_active_out;
+    // whole frame per CTA when there are plenty of frames; split frames when few so all SMs stream
+    const long long pf = (long long)n_pouch * n_frames;
+    int tiles = 1;
+    while ((long long)tiles * pf < 148 * 8 && tiles < 32) tiles *= 2;
+    a.tiles = tiles;
+    const size_t smem = 2 * (size_t)((n_max + 2 + 7) & ~7) * 2 + 2 * (size_t)((n_max + 2 + 15) & ~15);
+    if (smem > 48 * 1024)
+        CAB_CUDA(cudaFuncSetAttribute((const void *)raster_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (pf * tiles > 0x7fffffffLL) { set_error("cab200_raster_batch: too many frames"); return CAB200_ESIZE; }
+    raster_kernel<<<(unsigned)(pf * tiles), RT, smem, stream>>>(a);
+    CAB_CUDA(cudaGetLastError());
+    return CAB200_OK;
+}
+
+extern "C" int cab200_cells_mask(int n_cells, const int32_t *poly_off, const int32_t *pts, int H,
+                                 int W, uint16_t *label_out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_cells <= 0 || n_cells > 65534 || H <= 0 || W <= 0 || !poly_off || !pts || !label_out) {
+        set_error("cab200_cells_mask: bad argument");
+        return CAB200_EINVAL;
+    }
+    if (((size_t)H * W) & 1) { set_error("cab200_cells_mask: H*W must be even"); return CAB200_EINVAL; }
+    CAB_CUDA(cudaMemsetAsync(label_out, 0, sizeof(uint16_t) * (size_t)H * W, stream));
+    cells_mask_kernel<<<n_cells, 128, 0, stream>>>(n_cells, poly_off, pts, H, W,
+                                                   reinterpret_cast<uint32_t *>(label_out));
+    CAB_CUDA(cudaGetLastError());
+    return CAB200_OK;
+}

@@ -1,0 +1,396 @@
+"""Ensemble driver: many independent pouches through the CUDA kernels in one go.
+
+This is the batched form of what the reference does one pouch at a time in
+``generate_simulation_batch``'s loop (reference ``main.py:202-390``): ``Pouch(...)`` ->
+``simulate()`` -> per sampled time step ``generate_image`` / ``get_active_cells`` /
+``get_cell_masks(active_only=True)`` / ``create_instance_mask_from_cells``.
+
+Host side (numpy): parameter packing and the reference's random draws (same legacy ``np.random``
+call sequence, so V_PLC / r0 / initiator cells are bit-identical).  Device side: K1
+(``cab200_sim_batch``) and K2 (``cab200_raster_batch``) through the C ABI; torch only provides
+device memory, pinned host memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .geometry import Geometry, get_geometry
+
+DT = 0.2                                  # reference core/pouch.py:127
+DURATION = 3600                           # reference core/pouch.py:128
+T_DEFAULT = int(DURATION / DT)            # 18000, reference core/pouch.py:188
+DEFAULT_FRAME_STEPS = list(range(0, 18000, 200))   # reference main.py:167
+REQUIRED_PARAMS = ["D_c_ratio", "D_p", "K_5", "K_PLC", "K_SERCA", "V_SERCA", "beta", "c_tot",
+                   "frac", "k_1", "k_2", "k_a", "k_i", "k_p", "k_tau", "lower", "tau_max", "upper"]
+
+
+def pack_params(p: Dict[str, float], dt: float = DT) -> np.ndarray:
+    """18-key dict -> the 16 doubles K1 consumes; ``D_c = D_c_ratio * D_p`` (core/pouch.py:194)."""
+    q = dict(p)
+    q["D_c"] = p["D_c_ratio"] * p["D_p"]
+    q["dt"] = dt
+    return np.array([q[k] for k in _lib.PARAM_SLOTS], dtype=np.float64)
+
+
+def draw_vplc(p: Dict[str, float], n_cells: int, sim_number: int) -> np.ndarray:
+    """``Pouch.__init__``'s per-cell V_PLC draw (reference ``core/pouch.py:199-200``), ``(n,1)``."""
+    np.random.seed(sim_number)
+    return np.random.uniform(p["lower"], p["upper"], (n_cells, 1))
+
+
+def draw_initial_state(p: Dict[str, float], n_cells: int, sim_number: int, vplc: np.ndarray
+                       ) -> Tuple[np.ndarray, np.ndarray]:
+    """``Pouch.simulate``'s preamble (reference ``core/pouch.py:317-331``): reseed, r0 ~ U(.5,.7),
+    initiator cells get V_PLC ~ U(1.3,1.5).  Mutates ``vplc`` in place like the reference mutates
+    ``self.V_PLC``; returns (r0 (n,), initiator ids)."""
+    np.random.seed(sim_number)
+    r0 = np.random.uniform(0.5, 0.7, size=(n_cells, 1))
+    n_init = max(1, int(p["frac"] * n_cells))
+    init = np.random.choice(n_cells, n_init, replace=False)
+    vplc[init, 0] = np.random.uniform(1.3, 1.5, len(init))
+    return r0.flatten(), init
+
+
+def validate_for_simulation(p: Dict[str, float]) -> None:
+    """The two ``ValueError`` checks at the top of ``Pouch.simulate`` (core/pouch.py:309-313)."""
+    if p["c_tot"] <= 0 or p["beta"] <= 0 or p["D_p"] <= 0:
+        raise ValueError("Invalid simulation parameters: c_tot, beta, and D_p must be positive")
+    if not 0 <= p["frac"] <= 1:
+        raise ValueError(f"Invalid fraction of initiator cells: {p['frac']}. Must be between 0 and 1")
+
+
+@dataclass
+class PouchSpec:
+    """One pouch of an ensemble, fully drawn on the host."""
+    params: Dict[str, float]
+    geometry: Geometry
+    sim_number: int = 0
+    vplc: Optional[np.ndarray] = None     # (n,) final per-cell V_PLC (initiators applied)
+    r0: Optional[np.ndarray] = None       # (n,)
+    c0: Optional[np.ndarray] = None       # (n,), default zeros (core/pouch.py:320)
+    p0: Optional[np.ndarray] = None
+
+    @classmethod
+    def draw(cls, params: Dict[str, float], size: str = "medium", sim_number: int = 0,
+             geometry_dir: Optional[str] = None) -> "PouchSpec":
+        validate_for_simulation(params)
+        geo = get_geometry(size, geometry_dir)
+        v = draw_vplc(params, geo.n_cells, sim_number)
+        r0, _ = draw_initial_state(params, geo.n_cells, sim_number, v)
+        return cls(params=params, geometry=geo, sim_number=sim_number, vplc=v.flatten(), r0=r0)
+
+
+# ---- per-device geometry cache ---------------------------------------------------------------
+
+class _DeviceGeometry:
+    def __init__(self, geo: Geometry, device: torch.device):
+        rowptr, col, val = geo.csr
+        self.geo = geo
+        self.n = geo.n_cells
+        self.max_row = int(np.diff(rowptr).max())
+        offdiag = np.ones(len(col), dtype=bool)
+        rows = np.repeat(np.arange(self.n), np.diff(rowptr))
+        offdiag &= rows != col
+        self.unit = bool(np.all(val[offdiag] == 1.0))
+        self.rowptr = torch.from_numpy(rowptr).to(device)
+        self.col = torch.from_numpy(col).to(device)
+        self.val = torch.from_numpy(val).to(device)
+        self.label_maps: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+_DEV_GEO: Dict[Tuple[int, int], _DeviceGeometry] = {}
+_DEV_GEO_LOCK = threading.Lock()
+
+
+def device_geometry(geo: Geometry, device: torch.device) -> _DeviceGeometry:
+    key = (id(geo), device.index or 0)
+    with _DEV_GEO_LOCK:
+        dg = _DEV_GEO.get(key)
+        if dg is None:
+            dg = _DeviceGeometry(geo, device)
+            _DEV_GEO[key] = dg
+        return dg
+
+
+def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def build_label_maps(geo: Geometry, output_size: Tuple[int, int], device: torch.device
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The two static uint16 label maps of one (geometry, output size), on ``device``.
+
+    ``label_mask`` = ``Pouch.cells_mask`` (reference ``core/pouch.py:260-287``), computed on the GPU
+    by K0 (``cab200_cells_mask``, scikit-image's polygon rule).
+    ``label_img`` = which cell's ``cv2.fillPoly`` painted each pixel last in ``generate_image``'s
+    loop (reference ``core/pouch.py:441-453``); obtained once with the same OpenCV call the
+    reference makes per cell and frame, on an int32 canvas with the cell id as colour.
+    """
+    import cv2
+    dg = device_geometry(geo, device)
+    key = (int(output_size[0]), int(output_size[1]))
+    if key in dg.label_maps:
+        return dg.label_maps[key]
+    width, height = key
+    if geo.n_cells > 65534:
+        raise ValueError("label maps are uint16: at most 65534 cells")
+    offs, pts = geo.scaled_polygons(key)
+    canvas = np.zeros((height, width), dtype=np.int32)
+    for cell in range(geo.n_cells):
+        poly = pts[offs[cell]:offs[cell + 1]].reshape((-1, 1, 2))
+        cv2.fillPoly(canvas, [poly], color=int(cell + 1))
+    label_img = torch.from_numpy(canvas.astype(np.uint16).view(np.int16)).to(device)
+
+    lib = _lib.load()
+    d_offs = torch.from_numpy(offs).to(device)
+    d_pts = torch.from_numpy(pts).to(device)
+    if (height * width) % 2:
+        raise ValueError("output_size with an odd pixel count is not supported")
+    label_mask = torch.empty((height, width), dtype=torch.int16, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.cab200_cells_mask(geo.n_cells, d_offs.data_ptr(), d_pts.data_ptr(), height,
+                                         width, label_mask.data_ptr(), _stream_ptr(device)),
+                   "cab200_cells_mask")
+        torch.cuda.current_stream(device).synchronize()
+    dg.label_maps[key] = (label_img, label_mask)
+    return dg.label_maps[key]
+
+
+def _u16_numpy(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint16)
+
+
+# ---- the ensemble ------------------------------------------------------------------------------
+
+class Ensemble:
+    """P independent pouches on one GPU.
+
+    ``simulate()`` integrates all of them with one ``cab200_sim_batch`` call; ``rasterize()`` turns
+    the captured frames into images / instance masks with ``cab200_raster_batch``.  All results
+    stay on the device until asked for.
+    """
+
+    def __init__(self, specs: Sequence[PouchSpec], *, output_size: Tuple[int, int] = (512, 512),
+                 T: int = T_DEFAULT, frame_steps: Optional[Sequence[int]] = None,
+                 device: Optional[torch.device] = None, precision: int = _lib.FP64_STRICT,
+                 dt: float = DT):
+        if not torch.cuda.is_available():
+            raise RuntimeError("calcium_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+        self.specs = list(specs)
+        self.P = len(self.specs)
+        self.T = int(T)
+        self.dt = dt
+        self.precision = precision
+        self.output_size = (int(output_size[0]), int(output_size[1]))
+        fs = DEFAULT_FRAME_STEPS if frame_steps is None else list(frame_steps)
+        self.frame_steps = np.array(sorted(int(t) for t in fs if 0 <= int(t) < self.T), dtype=np.int32)
+        self.F = len(self.frame_steps)
+        self._frame_index = {int(t): i for i, t in enumerate(self.frame_steps)}
+
+        # geometry table
+        geos: List[Geometry] = []
+        gid = np.zeros(self.P, dtype=np.int32)
+        for i, s in enumerate(self.specs):
+            for j, g in enumerate(geos):
+                if g is s.geometry:
+                    gid[i] = j
+                    break
+            else:
+                geos.append(s.geometry)
+                gid[i] = len(geos) - 1
+        self.geometries = geos
+        self.geom_id = gid
+        self.dgeo = [device_geometry(g, self.device) for g in geos]
+        self.g_ncell = np.array([d.n for d in self.dgeo], dtype=np.int32)
+        self.g_max_row = np.array([d.max_row for d in self.dgeo], dtype=np.int32)
+        self.g_unit = np.array([1 if d.unit else 0 for d in self.dgeo], dtype=np.int32)
+        rp_sizes = [d.n + 1 for d in self.dgeo]
+        nnz_sizes = [int(d.col.numel()) for d in self.dgeo]
+        self.g_rowptr_off = np.concatenate([[0], np.cumsum(rp_sizes)[:-1]]).astype(np.int64)
+        self.g_nnz_off = np.concatenate([[0], np.cumsum(nnz_sizes)[:-1]]).astype(np.int64)
+        if len(self.dgeo) == 1:
+            self.d_rowptr, self.d_col, self.d_val = self.dgeo[0].rowptr, self.dgeo[0].col, self.dgeo[0].val
+        else:
+            self.d_rowptr = torch.cat([d.rowptr for d in self.dgeo])
+            self.d_col = torch.cat([d.col for d in self.dgeo])
+            self.d_val = torch.cat([d.val for d in self.dgeo])
+        ncell = self.g_ncell[gid].astype(np.int64)
+        self.cell_off = np.concatenate([[0], np.cumsum(ncell)]).astype(np.int64)
+        self.total_cells = int(self.cell_off[-1])
+
+        # host staging (pinned) for the per-pouch inputs: params | c0 | p0 | r0 | vplc
+        self._h_in = torch.empty(self.P * _lib.NPARAM + 4 * self.total_cells, dtype=torch.float64,
+                                 pin_memory=True)
+        h = self._h_in.numpy()
+        hp = h[: self.P * _lib.NPARAM].reshape(self.P, _lib.NPARAM)
+        hc = h[self.P * _lib.NPARAM:].reshape(4, self.total_cells)
+        for i, s in enumerate(self.specs):
+            a, b = self.cell_off[i], self.cell_off[i + 1]
+            n = b - a
+            hp[i] = pack_params(s.params, dt)
+            hc[0, a:b] = 0.0 if s.c0 is None else np.asarray(s.c0, dtype=np.float64).reshape(n)
+            hc[1, a:b] = 0.0 if s.p0 is None else np.asarray(s.p0, dtype=np.float64).reshape(n)
+            hc[2, a:b] = np.asarray(s.r0, dtype=np.float64).reshape(n)
+            hc[3, a:b] = np.asarray(s.vplc, dtype=np.float64).reshape(n)
+        self.h2d_bytes = self._h_in.numel() * 8
+        self._d_in: Optional[torch.Tensor] = None
+        self.frames: Optional[torch.Tensor] = None
+        self.status: Optional[torch.Tensor] = None
+        self._scratch = torch.empty(
+            int(self.lib.cab200_sim_scratch_bytes(self.P, self.F)
+                + self.lib.cab200_raster_scratch_bytes(self.P)) + 64,
+            dtype=torch.uint8, device=self.device)
+        self._label_img: Optional[torch.Tensor] = None
+        self._label_mask: Optional[torch.Tensor] = None
+
+    # -- sizes ---------------------------------------------------------------------------------
+    @property
+    def cell_timesteps(self) -> int:
+        """Work of one ``simulate()``: sum over pouches of n * (T - 1)."""
+        return self.total_cells * (self.T - 1)
+
+    @property
+    def frame_elems(self) -> int:
+        return self.total_cells * 4 * self.F
+
+    # -- K1 ------------------------------------------------------------------------------------
+    def upload(self) -> None:
+        """Host -> device copy of params / initial state (from pinned memory, async)."""
+        with torch.cuda.device(self.device):
+            if self._d_in is None:
+                self._d_in = torch.empty(self._h_in.numel(), dtype=torch.float64, device=self.device)
+            self._d_in.copy_(self._h_in, non_blocking=True)
+
+    def simulate(self, upload: bool = True) -> torch.Tensor:
+        """Integrate every pouch for T-1 steps; returns the flat frames tensor (device)."""
+        if upload or self._d_in is None:
+            self.upload()
+        real = torch.float64 if self.precision == _lib.FP64_STRICT else torch.float32
+        with torch.cuda.device(self.device):
+            if self.frames is None or self.frames.dtype != real:
+                self.frames = torch.empty(max(self.frame_elems, 1), dtype=real, device=self.device)
+                self.status = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+            d = self._d_in
+            np_ = self.P * _lib.NPARAM
+            tc = self.total_cells
+            base = d.data_ptr()
+            rc = self.lib.cab200_sim_batch(
+                self.P, _lib.as_i32p(self.geom_id), len(self.dgeo), _lib.as_i32p(self.g_ncell),
+                _lib.as_i32p(self.g_max_row), _lib.as_i32p(self.g_unit),
+                _lib.as_i64p(self.g_rowptr_off), _lib.as_i64p(self.g_nnz_off),
+                self.d_rowptr.data_ptr(), self.d_col.data_ptr(), self.d_val.data_ptr(),
+                _lib.as_i64p(self.cell_off),
+                base, base + 8 * np_, base + 8 * (np_ + tc), base + 8 * (np_ + 2 * tc),
+                base + 8 * (np_ + 3 * tc),
+                self.T, self.F, _lib.as_i32p(self.frame_steps),
+                self.frames.data_ptr(), self.status.data_ptr(), self.precision,
+                self._scratch.data_ptr(), self.lib.cab200_sim_scratch_bytes(self.P, self.F),
+                _stream_ptr(self.device))
+            _lib.check(rc, "cab200_sim_batch")
+        return self.frames
+
+    def frames_of(self, i: int) -> torch.Tensor:
+        """Device view ``[F, 4, n_i]`` of pouch i's captured frames."""
+        a, b = int(self.cell_off[i]), int(self.cell_off[i + 1])
+        n = b - a
+        return self.frames[a * 4 * self.F: b * 4 * self.F].view(self.F, 4, n)
+
+    def frame_index(self, time_step: int) -> int:
+        try:
+            return self._frame_index[int(time_step)]
+        except KeyError:
+            raise KeyError(f"time step {time_step} was not captured; captured steps: "
+                           f"{self.frame_steps[:8].tolist()}... ({self.F} frames)") from None
+
+    def check_status(self) -> np.ndarray:
+        st = self.status.cpu().numpy()
+        if np.any(st & _lib.ST_BADGEOM):
+            raise _lib.Cab200Error("integrator rejected the geometry (CSR row too long, column out "
+                                   "of range, or off-diagonal weights declared unit but are not)")
+        return st
+
+    # -- K2 ------------------------------------------------------------------------------------
+    def label_maps(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self._label_img is None:
+            maps = [build_label_maps(g, self.output_size, self.device) for g in self.geometries]
+            self._label_img = torch.stack([m[0] for m in maps]).contiguous()
+            self._label_mask = torch.stack([m[1] for m in maps]).contiguous()
+        return self._label_img, self._label_mask
+
+    def raster_out_bytes(self, image=True, instance=True, active=False, count: Optional[int] = None) -> int:
+        w, h = self.output_size
+        c = self.P if count is None else count
+        return c * self.F * h * w * (2 * bool(image) + 2 * bool(instance) + 4 * bool(active))
+
+    def rasterize(self, image: bool = True, instance: bool = True, active: bool = False,
+                  pouches: Optional[Tuple[int, int]] = None, threshold: float = 0.1,
+                  quirk: bool = True, out: Optional[Dict[str, torch.Tensor]] = None
+                  ) -> Dict[str, torch.Tensor]:
+        """K2 over pouches ``[a, b)`` (default all).  Returns device tensors
+        ``image [p,F,H,W,2] u8``, ``instance [p,F,H,W] i16 (bit pattern of uint16)``,
+        ``active [p,F,H,W] i32``, ``n_active [p,F] i32``.  ``out`` may hold preallocated tensors."""
+        if self.frames is None:
+            raise RuntimeError("simulate() first")
+        if self.precision != _lib.FP64_STRICT:
+            raise RuntimeError("rasterize() reads float64 frames; run the FP64 mode")
+        a, b = (0, self.P) if pouches is None else pouches
+        cnt = b - a
+        w, h = self.output_size
+        limg, lmsk = self.label_maps()
+        res: Dict[str, torch.Tensor] = {} if out is None else out
+        with torch.cuda.device(self.device):
+            def need(name, shape, dtype):
+                t = res.get(name)
+                if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                    t = torch.empty(shape, dtype=dtype, device=self.device)
+                    res[name] = t
+                return t
+            img = need("image", (cnt, self.F, h, w, 2), torch.uint8) if image else None
+            ins = need("instance", (cnt, self.F, h, w), torch.int16) if instance else None
+            act = need("active", (cnt, self.F, h, w), torch.int32) if active else None
+            nact = need("n_active", (cnt, self.F), torch.int32)
+            gid = np.ascontiguousarray(self.geom_id[a:b])
+            coff = np.ascontiguousarray(self.cell_off[a:b + 1])
+            sim_scr = int(self.lib.cab200_sim_scratch_bytes(self.P, self.F))
+            sim_scr = (sim_scr + 15) // 16 * 16
+            rc = self.lib.cab200_raster_batch(
+                cnt, _lib.as_i32p(gid), _lib.as_i32p(self.g_ncell), _lib.as_i64p(coff),
+                limg.data_ptr(), lmsk.data_ptr(), h, w, self.F, self.frames.data_ptr(),
+                float(threshold), 1 if quirk else 0,
+                img.data_ptr() if img is not None else None,
+                act.data_ptr() if act is not None else None,
+                ins.data_ptr() if ins is not None else None,
+                nact.data_ptr(), self._scratch.data_ptr() + sim_scr,
+                self.lib.cab200_raster_scratch_bytes(cnt), _stream_ptr(self.device))
+            _lib.check(rc, "cab200_raster_batch")
+        return res
+
+    def synchronize(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()
+
+
+def make_specs(n: int, size: str = "medium", sim_types: Optional[Sequence[str]] = None,
+               first_seed: int = 0, geometry_dir: Optional[str] = None,
+               randomize: bool = True) -> List[PouchSpec]:
+    """The deterministic ensemble of SURVEY.md section 8(d): pouch i uses seed = sim_number =
+    first_seed + i, sim type round-robin over ``sim_types`` (default: all four, in the order of
+    reference ``core/parameters.py:69-90``), parameters from ``generate_random_params(seed)``."""
+    from .parameters import SimulationParameters
+    types = list(sim_types) if sim_types else SimulationParameters.get_available_sim_types()
+    specs = []
+    for i in range(n):
+        seed = first_seed + i
+        sp = SimulationParameters(types[i % len(types)])
+        prm = sp.generate_random_params(seed=seed) if randomize else sp.get_params_dict()
+        specs.append(PouchSpec.draw(prm, size=size, sim_number=seed, geometry_dir=geometry_dir))
+    return specs
