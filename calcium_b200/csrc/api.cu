@@ -36,9 +36,62 @@ __global__ void __launch_bounds__(256) fill_kernel(uint4 *dst, size_t n16, uint3
         __stcs(dst + i, make_uint4(v, v + 1, v + 2, v + 3));
 }
 
+// ---- self-test of the branch-free division used by K1 -------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t &x)
+{
+    uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D2049BB133111Bull;
+    return z ^ (z >> 31);
+}
+
+// Operands: random mantissas, exponents uniform in [-exp_range, exp_range]; every 16th numerator 0.
+__global__ void __launch_bounds__(256) divtest_kernel(uint64_t seed, int per_thread, int exp_range,
+                                                      unsigned long long *mismatch)
+{
+    uint64_t st = seed + 0x1234567ull * (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x);
+    unsigned long long bad = 0;
+    for (int i = 0; i < per_thread; ++i) {
+        const uint64_t ra = splitmix64(st), rb = splitmix64(st), re = splitmix64(st);
+        const int ea = (int)(re % (2 * exp_range + 1)) - exp_range;
+        const int eb = (int)((re >> 32) % (2 * exp_range + 1)) - exp_range;
+        double a = __longlong_as_double((ra & 0x800FFFFFFFFFFFFFull) | ((uint64_t)(1023 + ea) << 52));
+        const double b = __longlong_as_double((rb & 0x800FFFFFFFFFFFFFull) | ((uint64_t)(1023 + eb) << 52));
+        if ((i & 15) == 0) a = 0.0;
+        const double ref = __ddiv_rn(a, b);
+        const double got = Strict<double>::fdiv(a, b);
+        const Strict<double>::Recip rc = Strict<double>::recip(b);
+        const double got2 = Strict<double>::div(a, rc);
+        bad += (__double_as_longlong(ref) != __double_as_longlong(got)) ||
+               (__double_as_longlong(ref) != __double_as_longlong(got2));
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
 }  // namespace cab200
 
 using namespace cab200;
+
+extern "C" int cab200_selftest_division(long long n_pairs, int exp_range, unsigned long long seed,
+                                        unsigned long long *mismatches_out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pairs <= 0 || exp_range < 0 || exp_range > 900 || !mismatches_out) {
+        set_error("cab200_selftest_division: bad argument");
+        return CAB200_EINVAL;
+    }
+    unsigned long long *d = nullptr;
+    CAB_CUDA(cudaMalloc(&d, sizeof(*d)));
+    CAB_CUDA(cudaMemsetAsync(d, 0, sizeof(*d), stream));
+    const int blocks = 148 * 8, threads = 256;
+    const int per_thread = (int)((n_pairs + (long long)blocks * threads - 1) / ((long long)blocks * threads));
+    divtest_kernel<<<blocks, threads, 0, stream>>>(seed, per_thread, exp_range, d);
+    CAB_CUDA(cudaGetLastError());
+    CAB_CUDA(cudaMemcpyAsync(mismatches_out, d, sizeof(*d), cudaMemcpyDeviceToHost, stream));
+    CAB_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d);
+    return CAB200_OK;
+}
 
 extern "C" int cab200_version(void) { return CAB200_VERSION; }
 extern "C" const char *cab200_last_error(void) { return g_err; }

@@ -22,26 +22,45 @@ static const Shape kShapes[] = {
     {4096, 1024, 4, 1},
 };
 
+void default_shape(int n, int *threads, int *cpt)
+{
+    *threads = 0; *cpt = 0;
+    for (const Shape &s : kShapes)
+        if (n <= s.n_max) { *threads = s.threads; *cpt = s.cpt; return; }
+}
+
+// Two value copies (conflict dodging, see integrate.cuh) whenever they fit in shared memory.
+int sim_copies(int n, bool unit, size_t elem2, int nslot)
+{
+    if (!unit) return 1;
+    const int np = (n + 31) & ~31;
+    return integrate_smem_bytes(np, nslot, elem2, 2) <= 200 * 1024 ? 2 : 1;
+}
+
 static std::mutex g_plan_mu;
 static int g_force_nmax = 0, g_force_threads = 0, g_force_cpt = 0;
 
 typedef void (*KernelFn)(const SimArgs);
 
 template <typename R, int THREADS, int CPT, int MINB>
-static KernelFn pick_variant(int ep, bool unit)
+static KernelFn pick_variant(int ep, bool unit, int copies)
 {
     if (unit) {
-        if (ep <= 5) return integrate_kernel<R, THREADS, CPT, 5, true, MINB>;
-        return integrate_kernel<R, THREADS, CPT, 8, true, MINB>;
+        if (copies == 2) {
+            if (ep <= 5) return integrate_kernel<R, THREADS, CPT, 5, true, 2, MINB>;
+            return integrate_kernel<R, THREADS, CPT, 8, true, 2, MINB>;
+        }
+        if (ep <= 5) return integrate_kernel<R, THREADS, CPT, 5, true, 1, MINB>;
+        return integrate_kernel<R, THREADS, CPT, 8, true, 1, MINB>;
     }
-    return integrate_kernel<R, THREADS, CPT, 8, false, MINB>;
+    return integrate_kernel<R, THREADS, CPT, 8, false, 1, MINB>;
 }
 
 template <typename R>
-static KernelFn pick_kernel(int threads, int cpt, int ep, bool unit)
+static KernelFn pick_kernel(int threads, int cpt, int ep, bool unit, int copies)
 {
 #define CAB_SHAPE(T_, C_, M_) \
-    if (threads == T_ && cpt == C_) return pick_variant<R, T_, C_, M_>(ep, unit);
+    if (threads == T_ && cpt == C_) return pick_variant<R, T_, C_, M_>(ep, unit, copies);
     CAB_SHAPE(128, 1, 8)
     CAB_SHAPE(256, 1, 4)
     CAB_SHAPE(256, 2, 2)
@@ -66,12 +85,34 @@ extern "C" int cab200_sim_set_plan(int n_max, int threads, int cells_per_thread)
 {
     std::lock_guard<std::mutex> lk(g_plan_mu);
     if (threads == 0) { g_force_nmax = g_force_threads = g_force_cpt = 0; return CAB200_OK; }
-    if (!pick_kernel<double>(threads, cells_per_thread, 5, true)) {
+    if (!pick_kernel<double>(threads, cells_per_thread, 5, true, 1)) {
         set_error("cab200_sim_set_plan: unsupported shape threads=%d cells_per_thread=%d", threads,
                   cells_per_thread);
         return CAB200_EINVAL;
     }
     g_force_nmax = n_max; g_force_threads = threads; g_force_cpt = cells_per_thread;
+    return CAB200_OK;
+}
+
+extern "C" int cab200_sim_layout(int n, int unit, int precision, int64_t out[4])
+{
+    if (!out || n <= 0 || (precision != CAB200_FP64_STRICT && precision != CAB200_FP32)) {
+        set_error("cab200_sim_layout: bad argument");
+        return CAB200_EINVAL;
+    }
+    int threads = 0, cpt = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        if (g_force_threads && n <= g_force_nmax && g_force_threads * g_force_cpt >= n) {
+            threads = g_force_threads; cpt = g_force_cpt;
+        }
+    }
+    if (!threads) default_shape(n, &threads, &cpt);
+    if (!threads) { set_error("cab200_sim_layout: %d cells exceed one CTA (4096)", n); return CAB200_ESIZE; }
+    const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
+    const int copies = sim_copies(n, unit != 0, elem2, threads * cpt);
+    out[0] = threads; out[1] = cpt; out[2] = copies;
+    out[3] = (int64_t)integrate_smem_bytes((n + 31) & ~31, threads * cpt, elem2, copies);
     return CAB200_OK;
 }
 
@@ -87,7 +128,7 @@ extern "C" int cab200_sim_batch(
     int n_pouch, const int32_t *geom_id, int n_geom, const int32_t *g_ncell,
     const int32_t *g_max_row, const int32_t *g_unit, const int64_t *g_rowptr_off,
     const int64_t *g_nnz_off, const int32_t *rowptr, const int32_t *colidx, const double *vals,
-    const int64_t *cell_off, const double *params, const double *c0, const double *p0,
+    const uint16_t *slot_plan, const int64_t *cell_off, const double *params, const double *c0, const double *p0,
     const double *r0, const double *vplc, int T, int n_frames, const int32_t *frame_steps,
     void *frames_out, int32_t *status_out, int precision, void *scratch, size_t scratch_bytes,
     void *stream_)
@@ -162,7 +203,8 @@ extern "C" int cab200_sim_batch(
         force_nmax = g_force_nmax; force_threads = g_force_threads; force_cpt = g_force_cpt;
     }
 
-    for (int g = 0; g < n_geom; ++g) {
+    int64_t plan_off = 0;
+    for (int g = 0; g < n_geom; plan_off += 2 * (int64_t)g_ncell[g], ++g) {
         const int count = g_begin[g + 1] - g_begin[g];
         if (count == 0) continue;
         const int n = g_ncell[g];
@@ -171,8 +213,7 @@ extern "C" int cab200_sim_batch(
         if (force_threads && n <= force_nmax && force_threads * force_cpt >= n) {
             threads = force_threads; cpt = force_cpt;
         } else {
-            for (const Shape &s : kShapes)
-                if (n <= s.n_max) { threads = s.threads; cpt = s.cpt; break; }
+            default_shape(n, &threads, &cpt);
         }
         if (!threads) {
             set_error("cab200_sim_batch: geometry %d has %d cells; one CTA holds at most 4096", g, n);
@@ -185,12 +226,13 @@ extern "C" int cab200_sim_batch(
         }
         const int ep = (max_row + 1) / 2;
         const bool unit = g_unit[g] != 0;
-        KernelFn fn = (precision == CAB200_FP64_STRICT) ? pick_kernel<double>(threads, cpt, ep, unit)
-                                                        : pick_kernel<float>(threads, cpt, ep, unit);
-        if (!fn) { set_error("cab200_sim_batch: no kernel for shape %dx%d", threads, cpt); return CAB200_EINVAL; }
         const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
         const int np = (n + 31) & ~31;
-        const size_t smem = integrate_smem_bytes(np, threads * cpt, elem2);
+        const int copies = sim_copies(n, unit, elem2, threads * cpt);
+        KernelFn fn = (precision == CAB200_FP64_STRICT) ? pick_kernel<double>(threads, cpt, ep, unit, copies)
+                                                        : pick_kernel<float>(threads, cpt, ep, unit, copies);
+        if (!fn) { set_error("cab200_sim_batch: no kernel for shape %dx%d", threads, cpt); return CAB200_EINVAL; }
+        const size_t smem = integrate_smem_bytes(np, threads * cpt, elem2, copies);
         if (smem > 227 * 1024) {
             set_error("cab200_sim_batch: geometry %d needs %zu bytes of shared memory (> 227 KB)", g, smem);
             return CAB200_ESIZE;
@@ -204,6 +246,7 @@ extern "C" int cab200_sim_batch(
         a.colidx = colidx + g_nnz_off[g];
         a.vals = vals + g_nnz_off[g];
         a.n = n;
+        a.slot_plan = slot_plan ? slot_plan + plan_off : nullptr;
         a.np = np;
         a.params = params;
         a.c0 = c0; a.p0 = p0; a.r0 = r0; a.vplc = vplc;

@@ -4,10 +4,13 @@
 // scipy CSR products per step (:346-347) for a whole ensemble in one launch.
 //
 // Data placement for one pouch (n cells), fixed for all T steps:
-//   shared   two buffers (step parity) of ENT = 2*NP+1 entries, one entry = the pair (c, p):
-//              [0, NP)       value entries   (c_i, p_i)            written by cell i's owner
-//              [NP, 2NP)     diagonal entries (L_ii*c_i, L_ii*p_i)  written by cell i's owner
-//              [2NP]         the zero entry (+0, +0), never written after the prologue
+//   shared   two buffers (step parity) of ENT = (COPIES+1)*NP+1 entries, one entry = the pair (c, p):
+//              [0, NP)            value entries   (c_i, p_i) at index slot_i
+//              [NP, 2NP)          (COPIES == 2) a second copy of the values at NP + (slot_i ^ 4),
+//                                 i.e. in the bank group 4 away: every gather may read either copy,
+//                                 which the host planner uses to dodge bank conflicts
+//              [COPIES*NP, +NP)   diagonal entries (L_ii*c_i, L_ii*p_i)
+//              [(COPIES+1)*NP]    the zero entry (+0, +0), never written after the prologue
 //            Step t reads buffer t&1 and writes buffer (t+1)&1: ONE __syncthreads() per step.
 //   regs     per owned cell: c, p, s, r, V_PLC, L_ii and the row's entry indices (16-bit, packed in
 //            pairs; time-invariant), plus the pouch's parameters (uniform registers).
@@ -34,6 +37,7 @@ struct SimArgs {
     const int32_t *rowptr;      // this geometry's CSR
     const int32_t *colidx;
     const double *vals;
+    const uint16_t *slot_plan;  // optional plan (cab200_plan_slots): slot_of[n] then copy_sel[n]
     int n;
     int np;                     // n rounded up to 32: entries per region
     const double *params;
@@ -45,9 +49,9 @@ struct SimArgs {
 };
 
 // Shared-memory bytes K1 needs for a pouch padded to `np` slots.
-static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2)
+static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2, int copies)
 {
-    const size_t ent = 2 * (size_t)np + 1;
+    const size_t ent = ((size_t)copies + 1) * (size_t)np + 1;
     size_t bytes = 2 * ent * elem2;          // the two step-parity buffers
     bytes = (bytes + 15) & ~(size_t)15;
     bytes += 2 * (size_t)nslot;              // orig_of[NSLOT] u16
@@ -58,7 +62,8 @@ static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2)
 // individually rounded.  lap_c / lap_p are the already D-scaled Laplacian terms (:346-347).
 template <typename R>
 struct StepConsts {
-    R k_1, k_a, k_p, k_2, V_S, KS2, KP2, K_5, c_tot, beta, k_tau_4, rec_den, k_i, D_c, D_p, dt;
+    R k_1, k_a, k_p, k_2, V_S, KS2, KP2, K_5, c_tot, k_tau_4, k_i, D_c, D_p, dt;
+    typename Strict<R>::Recip beta, rec_den, k_i_r;   // divisors that never change: reciprocal hoisted
 };
 
 template <typename R>
@@ -68,25 +73,25 @@ __device__ __forceinline__ void euler_step(const StepConsts<R> &q, R ca, R ipt, 
     typedef Strict<R> S;
     const R num = S::mul(S::mul(rv, ca), ipt);                              // :77
     const R den = S::mul(S::add(q.k_a, ca), S::add(q.k_p, ipt));            // :78-80
-    const R x = S::div(num, den);                                           // :80
+    const R x = S::fdiv(num, den);                                          // :80
     const R x3 = S::mul(S::mul(x, x), x);                                   // x**3 as numba expands it
     const R J_ch = S::mul(S::add(S::mul(q.k_1, x3), q.k_2), S::sub(sv, ca));            // :81
     const R ca_sq = S::mul(ca, ca);                                         // :84
-    const R J_S = S::div(S::mul(q.V_S, ca_sq), S::add(ca_sq, q.KS2));       // :85
+    const R J_S = S::fdiv(S::mul(q.V_S, ca_sq), S::add(ca_sq, q.KS2));      // :85
     c_new = S::add(ca, S::mul(q.dt, S::sub(S::add(lap_c, J_ch), J_S)));     // :87
-    const R J_PLC = S::div(S::mul(vplc, ca_sq), S::add(ca_sq, q.KP2));      // :91
+    const R J_PLC = S::fdiv(S::mul(vplc, ca_sq), S::add(ca_sq, q.KP2));     // :91
     p_new = S::add(ipt, S::mul(q.dt, S::sub(S::add(lap_p, J_PLC), S::mul(q.K_5, ipt))));  // :92
     s_new = S::div(S::sub(q.c_tot, c_new), q.beta);                         // :95
     const R ca_4 = S::mul(ca_sq, ca_sq);                                    // :98
     const R rec = S::div(S::add(q.k_tau_4, ca_4), q.rec_den);               // :100
-    const R inact = S::sub((R)1, S::div(S::mul(rv, S::add(q.k_i, ca)), q.k_i));         // :101
+    const R inact = S::sub((R)1, S::div(S::mul(rv, S::add(q.k_i, ca)), q.k_i_r));         // :101
     r_new = S::add(rv, S::mul(S::mul(q.dt, rec), inact));                   // :102
 }
 
 // EP = number of packed entry-index pairs kept in registers per cell (row length <= 2*EP).
 // UNIT: every off-diagonal value is exactly 1.0 (verified in the prologue).  !UNIT: general weights,
 // read from global/L1 each step and multiplied per entry.
-template <typename R, int THREADS, int CPT, int EP, bool UNIT, int MINB>
+template <typename R, int THREADS, int CPT, int EP, bool UNIT, int COPIES, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs a)
 {
     typedef Strict<R> S;
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, np = a.np;
-    const int ent = 2 * np + 1;
+    const int ent = (COPIES + 1) * np + 1;
     R2 *buf0 = reinterpret_cast<R2 *>(smem_raw);
     R2 *buf1 = buf0 + ent;
     uint16_t *orig_of = reinterpret_cast<uint16_t *>(
@@ -105,6 +110,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     unsigned char *scr = reinterpret_cast<unsigned char *>(buf1);
     uint8_t *rlen = scr;                                                           // [n]
     uint16_t *slot_of = reinterpret_cast<uint16_t *>(scr + np);                    // [n]
+    uint16_t *copy_sel = slot_of + np;                                             // [n]
 
     const int tid = threadIdx.x;
     const int pouch = a.pouch_list[blockIdx.x];
@@ -119,16 +125,30 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     }
     for (int s = tid; s < NSLOT; s += THREADS) orig_of[s] = 0xffff;
     __syncthreads();
-    // ---- prologue 2: stable rank by (length desc, id asc) -> slot ------------------------------
-    for (int i = tid; i < n; i += THREADS) {
-        const int li = rlen[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const int lj = rlen[j];
-            rank += (lj > li) || (lj == li && j < i);
+    // ---- prologue 2: cell -> slot.  Host plan if given, else stable rank by (length desc, id asc) --
+    if (a.slot_plan) {
+        for (int i = tid; i < n; i += THREADS) {
+            int sl = a.slot_plan[i];
+            if (sl >= n) { bad = 1; sl = i; }
+            slot_of[i] = (uint16_t)sl;
+            orig_of[sl] = (uint16_t)i;
+            copy_sel[i] = (COPIES == 2) ? a.slot_plan[n + i] : (uint16_t)0;
         }
-        slot_of[i] = (uint16_t)rank;
-        orig_of[rank] = (uint16_t)i;
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS)       // a permutation hits every slot exactly once
+            if (orig_of[slot_of[i]] != i) bad = 1;
+    } else {
+        for (int i = tid; i < n; i += THREADS) {
+            const int li = rlen[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const int lj = rlen[j];
+                rank += (lj > li) || (lj == li && j < i);
+            }
+            slot_of[i] = (uint16_t)rank;
+            orig_of[rank] = (uint16_t)i;
+            copy_sel[i] = 0;
+        }
     }
     __syncthreads();
 
@@ -140,15 +160,16 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         const R k_tau = (R)prm[CAB200_KTAU], tau_max = (R)prm[CAB200_TAUMAX];
         q.k_1 = (R)prm[CAB200_K1]; q.k_a = (R)prm[CAB200_KA]; q.k_p = (R)prm[CAB200_KP];
         q.k_2 = (R)prm[CAB200_K2]; q.V_S = (R)prm[CAB200_VSERCA]; q.K_5 = (R)prm[CAB200_K5];
-        q.c_tot = (R)prm[CAB200_CTOT]; q.beta = (R)prm[CAB200_BETA]; q.k_i = (R)prm[CAB200_KI];
+        q.c_tot = (R)prm[CAB200_CTOT]; q.k_i = (R)prm[CAB200_KI];
+        q.beta = S::recip((R)prm[CAB200_BETA]); q.k_i_r = S::recip(q.k_i);
         q.D_c = (R)prm[CAB200_DC]; q.D_p = (R)prm[CAB200_DP]; q.dt = (R)prm[CAB200_DT];
         q.KS2 = S::mul(K_S, K_S);                                              // :85
         q.KP2 = S::mul(K_PLC, K_PLC);                                          // :91
         q.k_tau_4 = S::mul(S::mul(S::mul(k_tau, k_tau), k_tau), k_tau);        // :99
-        q.rec_den = S::mul(tau_max, q.k_tau_4);                                // :100
+        q.rec_den = S::recip(S::mul(tau_max, q.k_tau_4));                      // :100
     }
 
-    const uint32_t ZERO_ENT = (uint32_t)(2 * np);
+    const uint32_t ZERO_ENT = (uint32_t)((COPIES + 1) * np);
     R c[CPT], p[CPT], s[CPT], r[CPT], vplc[CPT], dcoef[CPT];
     uint32_t nb[CPT][EP];
     int wlen[CPT], rowbeg[CPT];
@@ -165,6 +186,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         for (int e = 0; e < EP; ++e) nb[k][e] = ZERO_ENT | (ZERO_ENT << 16);
         if (live[k]) {
             len = rlen[cell];
+            const uint32_t sel = copy_sel[cell];
             const int rb = a.rowptr[cell];
             rowbeg[k] = rb;
 #pragma unroll
@@ -173,10 +195,13 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
                     const int col = a.colidx[rb + e];
                     uint32_t j = ZERO_ENT;
                     if (col < 0 || col >= n) bad = 1;
-                    else j = slot_of[col];
+                    else {
+                        j = slot_of[col];
+                        if (COPIES == 2 && ((sel >> e) & 1u)) j = (uint32_t)np + (j ^ 4u);
+                    }
                     if (UNIT) {
                         const double w = a.vals[rb + e];
-                        if (col == cell) { dcoef[k] = (R)w; j = (uint32_t)(np + slot); }
+                        if (col == cell) { dcoef[k] = (R)w; j = (uint32_t)(COPIES * np + slot); }
                         else if (w != 1.0) bad = 1;
                     }
                     const uint32_t sh = (e & 1) * 16;
@@ -201,7 +226,8 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         if (live[k]) {
             const int slot = k * THREADS + tid;
             buf0[slot] = S::make2(c[k], p[k]);
-            if (UNIT) buf0[np + slot] = S::make2(S::mul(dcoef[k], c[k]), S::mul(dcoef[k], p[k]));
+            if (COPIES == 2) buf0[np + (slot ^ 4)] = S::make2(c[k], p[k]);
+            if (UNIT) buf0[COPIES * np + slot] = S::make2(S::mul(dcoef[k], c[k]), S::mul(dcoef[k], p[k]));
         }
     }
     __syncthreads();
@@ -263,7 +289,8 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
                 c[k] = cn; p[k] = pn; s[k] = sn; r[k] = rn;
                 const int slot = k * THREADS + tid;
                 nxt[slot] = S::make2(cn, pn);
-                if (UNIT) nxt[np + slot] = S::make2(S::mul(dcoef[k], cn), S::mul(dcoef[k], pn));
+                if (COPIES == 2) nxt[np + (slot ^ 4)] = S::make2(cn, pn);
+                if (UNIT) nxt[COPIES * np + slot] = S::make2(S::mul(dcoef[k], cn), S::mul(dcoef[k], pn));
             }
         }
         __syncthreads();

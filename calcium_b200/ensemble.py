@@ -13,6 +13,8 @@ device memory, pinned host memory and streams.
 from __future__ import annotations
 
 import ctypes
+import hashlib
+import os
 import threading
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -103,6 +105,56 @@ class _DeviceGeometry:
         self.col = torch.from_numpy(col).to(device)
         self.val = torch.from_numpy(val).to(device)
         self.label_maps: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.plans: Dict[int, torch.Tensor] = {}
+
+    def plan(self, precision: int) -> torch.Tensor:
+        """Device copy of the K1 slot plan (``cab200_plan_slots``) for this geometry; the plan is
+        pure layout (bank-conflict avoidance), computed once on the host and cached on disk."""
+        t = self.plans.get(precision)
+        if t is None:
+            t = torch.from_numpy(slot_plan(self.geo, self.unit, precision).view(np.int16)).to(
+                self.rowptr.device)
+            self.plans[precision] = t
+        return t
+
+
+PLAN_ITERS = int(os.environ.get("CALCIUM_B200_PLAN_ITERS", "300000"))
+
+
+def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = None) -> np.ndarray:
+    """uint16[2n] plan for ``geo`` (see ``cab200_plan_slots`` in include/cab200.h)."""
+    lib = _lib.load()
+    rowptr, col, _ = geo.csr
+    n = geo.n_cells
+    iters = PLAN_ITERS if iters is None else iters
+    lay = np.zeros(4, dtype=np.int64)
+    _lib.check(lib.cab200_sim_layout(n, 1 if unit else 0, precision, _lib.as_i64p(lay)),
+               "cab200_sim_layout")
+    copies = int(lay[2])
+    h = hashlib.sha1()
+    h.update(rowptr.tobytes()); h.update(col.tobytes())
+    h.update(f"{copies}:{iters}:v1".encode())
+    from .geometry import _synthetic_cache_path
+    path = os.path.join(os.path.dirname(_synthetic_cache_path("x")), f"plan_{h.hexdigest()[:16]}.npy")
+    if os.path.exists(path):
+        try:
+            plan = np.load(path)
+            if plan.shape == (2 * n,) and plan.dtype == np.uint16:
+                return plan
+        except Exception:  # noqa: BLE001 - a corrupt cache entry is just recomputed
+            pass
+    plan = np.zeros(2 * n, dtype=np.uint16)
+    _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, iters, 1, 0,
+                                     plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None),
+               "cab200_plan_slots")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + f".{os.getpid()}.tmp.npy"
+        np.save(tmp, plan)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return plan
 
 
 _DEV_GEO: Dict[Tuple[int, int], _DeviceGeometry] = {}
@@ -180,7 +232,7 @@ class Ensemble:
     def __init__(self, specs: Sequence[PouchSpec], *, output_size: Tuple[int, int] = (512, 512),
                  T: int = T_DEFAULT, frame_steps: Optional[Sequence[int]] = None,
                  device: Optional[torch.device] = None, precision: int = _lib.FP64_STRICT,
-                 dt: float = DT):
+                 dt: float = DT, use_plan: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("calcium_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -227,6 +279,11 @@ class Ensemble:
         ncell = self.g_ncell[gid].astype(np.int64)
         self.cell_off = np.concatenate([[0], np.cumsum(ncell)]).astype(np.int64)
         self.total_cells = int(self.cell_off[-1])
+        self.use_plan = use_plan
+        self.d_plan: Optional[torch.Tensor] = None
+        if use_plan:
+            plans = [d.plan(precision) for d in self.dgeo]
+            self.d_plan = plans[0] if len(plans) == 1 else torch.cat(plans)
 
         # host staging (pinned) for the per-pouch inputs: params | c0 | p0 | r0 | vplc
         self._h_in = torch.empty(self.P * _lib.NPARAM + 4 * self.total_cells, dtype=torch.float64,
@@ -289,6 +346,7 @@ class Ensemble:
                 _lib.as_i32p(self.g_max_row), _lib.as_i32p(self.g_unit),
                 _lib.as_i64p(self.g_rowptr_off), _lib.as_i64p(self.g_nnz_off),
                 self.d_rowptr.data_ptr(), self.d_col.data_ptr(), self.d_val.data_ptr(),
+                self.d_plan.data_ptr() if self.d_plan is not None else None,
                 _lib.as_i64p(self.cell_off),
                 base, base + 8 * np_, base + 8 * (np_ + tc), base + 8 * (np_ + 2 * tc),
                 base + 8 * (np_ + 3 * tc),
