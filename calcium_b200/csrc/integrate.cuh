@@ -66,26 +66,56 @@ struct StepConsts {
     typename Strict<R>::Recip beta, rec_den, k_i_r;   // divisors that never change: reciprocal hoisted
 };
 
+// The part of a step that needs only the cell's own state (core/pouch.py:77-85, 91, 98-102): the
+// three non-constant fluxes and the complete r update.  FP64 heavy, no shared memory.
 template <typename R>
-__device__ __forceinline__ void euler_step(const StepConsts<R> &q, R ca, R ipt, R sv, R rv, R vplc,
-                                           R lap_c, R lap_p, R &c_new, R &p_new, R &s_new, R &r_new)
+__device__ __forceinline__ void step_local(const StepConsts<R> &q, R ca, R ipt, R sv, R rv, R vplc,
+                                           R &J_ch, R &J_S, R &J_PLC, R &r_new)
 {
     typedef Strict<R> S;
     const R num = S::mul(S::mul(rv, ca), ipt);                              // :77
     const R den = S::mul(S::add(q.k_a, ca), S::add(q.k_p, ipt));            // :78-80
     const R x = S::fdiv(num, den);                                          // :80
     const R x3 = S::mul(S::mul(x, x), x);                                   // x**3 as numba expands it
-    const R J_ch = S::mul(S::add(S::mul(q.k_1, x3), q.k_2), S::sub(sv, ca));            // :81
+    J_ch = S::mul(S::add(S::mul(q.k_1, x3), q.k_2), S::sub(sv, ca));        // :81
     const R ca_sq = S::mul(ca, ca);                                         // :84
-    const R J_S = S::fdiv(S::mul(q.V_S, ca_sq), S::add(ca_sq, q.KS2));      // :85
-    c_new = S::add(ca, S::mul(q.dt, S::sub(S::add(lap_c, J_ch), J_S)));     // :87
-    const R J_PLC = S::fdiv(S::mul(vplc, ca_sq), S::add(ca_sq, q.KP2));     // :91
-    p_new = S::add(ipt, S::mul(q.dt, S::sub(S::add(lap_p, J_PLC), S::mul(q.K_5, ipt))));  // :92
-    s_new = S::div(S::sub(q.c_tot, c_new), q.beta);                         // :95
+    J_S = S::fdiv(S::mul(q.V_S, ca_sq), S::add(ca_sq, q.KS2));              // :85
+    J_PLC = S::fdiv(S::mul(vplc, ca_sq), S::add(ca_sq, q.KP2));             // :91
     const R ca_4 = S::mul(ca_sq, ca_sq);                                    // :98
     const R rec = S::div(S::add(q.k_tau_4, ca_4), q.rec_den);               // :100
     const R inact = S::sub((R)1, S::div(S::mul(rv, S::add(q.k_i, ca)), q.k_i_r));         // :101
     r_new = S::add(rv, S::mul(S::mul(q.dt, rec), inact));                   // :102
+}
+
+// The part that needs the neighbours (core/pouch.py:87, 92): lap_c / lap_p are the D-scaled rows.
+template <typename R>
+__device__ __forceinline__ void step_finish(const StepConsts<R> &q, R ca, R ipt, R lap_c, R lap_p,
+                                            R J_ch, R J_S, R J_PLC, R &c_new, R &p_new)
+{
+    typedef Strict<R> S;
+    c_new = S::add(ca, S::mul(q.dt, S::sub(S::add(lap_c, J_ch), J_S)));     // :87
+    p_new = S::add(ipt, S::mul(q.dt, S::sub(S::add(lap_p, J_PLC), S::mul(q.K_5, ipt))));  // :92
+}
+
+// ---- split-phase CTA barrier (mbarrier): arrive after publishing, wait before gathering -----------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
 }
 
 // EP = number of packed entry-index pairs kept in registers per cell (row length <= 2*EP).
@@ -239,24 +269,52 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     const R2 *cur = buf0;
     R2 *nxt = buf1;
 
-    for (int t = 0;; ++t) {
-        if (t == cap_t) {   // uniform across the CTA
-            int nonfinite = 0;
+    // Writes the state at the current time (c, p, s, r of every owned cell) as frame fi.
+    auto capture = [&]() {
+        int nonfinite = 0;
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                if (live[k]) {
-                    const int cell = orig_of[k * THREADS + tid];
-                    R *f = frames + (size_t)fi * 4 * n + cell;
-                    f[0] = c[k]; f[n] = p[k]; f[2 * (size_t)n] = s[k]; f[3 * (size_t)n] = r[k];
-                    nonfinite |= !(isfinite(c[k]) && isfinite(p[k]) && isfinite(s[k]) && isfinite(r[k]));
-                }
+        for (int k = 0; k < CPT; ++k) {
+            if (live[k]) {
+                const int cell = orig_of[k * THREADS + tid];
+                R *f = frames + (size_t)fi * 4 * n + cell;
+                f[0] = c[k]; f[n] = p[k]; f[2 * (size_t)n] = s[k]; f[3 * (size_t)n] = r[k];
+                nonfinite |= !(isfinite(c[k]) && isfinite(p[k]) && isfinite(s[k]) && isfinite(r[k]));
             }
-            if (nonfinite) atomicOr(a.status_out + pouch, CAB200_ST_NONFINITE);
-            ++fi;
-            cap_t = (fi < a.n_frames) ? a.frame_steps[fi] : -1;
         }
-        if (t >= T - 1) break;
+        if (nonfinite) atomicOr(a.status_out + pouch, CAB200_ST_NONFINITE);
+        ++fi;
+        cap_t = (fi < a.n_frames) ? a.frame_steps[fi] : -1;
+    };
 
+    // Step organisation.  Everything that needs only the cell's own state (step_local: the five
+    // divisions, ~75 % of the FP64 work) is computed one step ahead, *between* publishing the new
+    // (c, p) and waiting for everybody else's: publish -> arrive -> local work -> wait -> gather ->
+    // finish -> publish ...  The barrier is split (mbarrier arrive / try_wait), so a warp rarely
+    // blocks, warps drift apart, and the shared-memory-bound gathers of some warps overlap the
+    // FP64-bound local work of others instead of all warps hammering one pipe at a time.
+    // Buffer safety: a thread overwrites buffer (t+1)&1 only after passing wait(t), i.e. after every
+    // thread has arrived for step t, which each does after its own gather of step t-1 -- the last
+    // reader of that buffer.
+    __shared__ uint64_t step_bar;
+    if (tid == 0) mbar_init(&step_bar, THREADS);
+    __syncthreads();
+    if (cap_t == 0) capture();
+    R J_ch[CPT], J_S[CPT], J_PLC[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        J_ch[k] = J_S[k] = J_PLC[k] = (R)0;
+        if (live[k]) {
+            R rn;
+            step_local<R>(q, c[k], p[k], s[k], r[k], vplc[k], J_ch[k], J_S[k], J_PLC[k], rn);
+            r[k] = rn;      // r now holds r(t+1); r(t) was captured above if requested
+        }
+    }
+    mbar_arrive(&step_bar);     // state(0) was published before the __syncthreads above
+    unsigned parity = 0;
+
+    for (int t = 0; t < T - 1; ++t) {
+        mbar_wait(&step_bar, parity);
+        parity ^= 1u;
         // ---- Laplacian rows (csr_matvec order), all owned cells interleaved ---------------------
         R sc[CPT], sp[CPT];
 #pragma unroll
@@ -284,16 +342,29 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             if (live[k]) {
                 const R lap_c = S::mul(q.D_c, sc[k]);                          // :346
                 const R lap_p = S::mul(q.D_p, sp[k]);                          // :347
-                R cn, pn, sn, rn;
-                euler_step<R>(q, c[k], p[k], s[k], r[k], vplc[k], lap_c, lap_p, cn, pn, sn, rn);
-                c[k] = cn; p[k] = pn; s[k] = sn; r[k] = rn;
+                R cn, pn;
+                step_finish<R>(q, c[k], p[k], lap_c, lap_p, J_ch[k], J_S[k], J_PLC[k], cn, pn);
+                c[k] = cn; p[k] = pn;
                 const int slot = k * THREADS + tid;
                 nxt[slot] = S::make2(cn, pn);
                 if (COPIES == 2) nxt[np + (slot ^ 4)] = S::make2(cn, pn);
                 if (UNIT) nxt[COPIES * np + slot] = S::make2(S::mul(dcoef[k], cn), S::mul(dcoef[k], pn));
             }
         }
-        __syncthreads();
+        mbar_arrive(&step_bar);
+        // ---- own-state work for the next step, overlapping the other warps' gathers --------------
+#pragma unroll
+        for (int k = 0; k < CPT; ++k)
+            if (live[k]) s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);         // :95
+        if (t + 1 == cap_t) capture();   // uniform across the CTA; r[] holds r(t+1) here
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            if (live[k]) {
+                R rn;
+                step_local<R>(q, c[k], p[k], s[k], r[k], vplc[k], J_ch[k], J_S[k], J_PLC[k], rn);
+                r[k] = rn;
+            }
+        }
         const R2 *tmp = cur; cur = nxt; nxt = const_cast<R2 *>(tmp);
     }
 }
