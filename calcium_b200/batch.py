@@ -1,0 +1,308 @@
+"""Batch entry points: ``generate_simulation_batch`` and ``BatchGenerationController``.
+
+Signatures, defaults, result dictionaries and callback protocol follow the reference's
+``main.py:115-424`` and ``utils/batch_controller.py:20-403``.  The body is re-plumbed: instead of
+constructing, integrating and rasterising one pouch at a time (reference ``main.py:202-390``, plus
+~3.3 s of deliberate ``time.sleep`` per pouch), all pouches are drawn on the host first -- with the
+same ``random.choice`` / ``np.random`` call sequence -- and then pushed through the GPU in chunks:
+K1 integrates a whole chunk in one launch, K2 rasterises every sampled frame, results stream back
+through pinned buffers to a pool of writer threads.
+
+Out of scope here: the stochastic defect pipeline (``defect_configs`` is
+accepted and ignored, images are the clean frames), prompt generation and label JSON.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import datetime
+import gc
+import json
+import os
+import random
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import io as cio
+from .ensemble import DEFAULT_FRAME_STEPS, Ensemble, PouchSpec
+from .parameters import SimulationParameters
+
+DEFAULT_SIZES = ["xsmall", "small", "medium", "large"]
+DEFAULT_TYPES = ["Single cell spikes", "Intercellular transients", "Intercellular waves", "Fluttering"]
+
+
+class _NumpyEncoder(json.JSONEncoder):
+    def default(self, obj):
+        if isinstance(obj, np.integer):
+            return int(obj)
+        if isinstance(obj, np.floating):
+            return float(obj)
+        if isinstance(obj, np.ndarray):
+            return obj.tolist()
+        return None          # e.g. a saved Pouch object: not serialisable, recorded as null
+
+
+def _parse_image_size(image_size) -> tuple:
+    if isinstance(image_size, str):
+        try:
+            w, h = map(int, image_size.split("x"))
+            return (w, h)
+        except (ValueError, AttributeError):
+            print(f"Failed to parse image size '{image_size}', using default 512x512")
+            return (512, 512)
+    return tuple(image_size)
+
+
+def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim_types=None,
+                              time_steps=None, defect_configs=None, progress_callback=None,
+                              memory_threshold=70, create_stats=True, edge_blur=False,
+                              blur_kernel_size=3, blur_type="mean", generate_masks=True,
+                              generate_labels=False, image_size="512x512", jpeg_quality=90,
+                              save_pouch=False, dataset_split="train", *, geometry_dir=None,
+                              device=None, write_files=True, keep_arrays=False,
+                              max_chunk_bytes=4 << 30, writer_threads=8):
+    """Generate a batch of simulations with images and instance masks (see module docstring).
+
+    Extra keyword-only arguments: ``geometry_dir``, ``device``, ``write_files`` (False: compute only),
+    ``keep_arrays`` (return the images / masks in ``results['arrays']``), ``max_chunk_bytes`` (device
+    memory budget for one chunk's raster outputs), ``writer_threads``.
+    """
+    os.makedirs(output_dir, exist_ok=True)
+    if pouch_sizes is None:
+        pouch_sizes = list(DEFAULT_SIZES)
+    if sim_types is None:
+        sim_types = list(DEFAULT_TYPES)
+    if time_steps is None:
+        time_steps = list(DEFAULT_FRAME_STEPS)
+    batch_dir = output_dir
+    batch_run_id = datetime.datetime.now().strftime("%Y%m%d%H%M%S")
+    img_dir = os.path.join(batch_dir, "images", dataset_split)
+    mask_dir = os.path.join(batch_dir, "masks", dataset_split)
+    prompt_dir = os.path.join(batch_dir, "prompts", dataset_split)
+    for d in (img_dir, mask_dir, prompt_dir):
+        os.makedirs(d, exist_ok=True)
+    results: Dict[str, Any] = {"simulations": [], "output_dir": batch_dir,
+                               "num_simulations": num_simulations, "batch_index": 0}
+    output_size = _parse_image_size(image_size)
+
+    # ---- host: draw every pouch (same RNG call order as the reference loop, main.py:202-249) ----
+    drawn: List[Dict[str, Any]] = []
+    for sim_idx in range(num_simulations):
+        if progress_callback:
+            progress_callback(sim_idx + 1, num_simulations)
+        pouch_size = random.choice(pouch_sizes)
+        sim_type = random.choice(sim_types)
+        try:
+            sim_params = SimulationParameters(sim_type=sim_type).generate_random_params(seed=sim_idx)
+            spec = PouchSpec.draw(sim_params, size=pouch_size, sim_number=sim_idx,
+                                  geometry_dir=geometry_dir)
+            drawn.append({"sim_idx": sim_idx, "spec": spec, "type": sim_type, "size": pouch_size,
+                          "name": f"{sim_type.replace(' ', '_')}_{sim_idx}", "params": sim_params})
+            print(f"Running simulation {sim_idx+1}/{num_simulations}: {sim_type} on {pouch_size} pouch")
+        except Exception as e:  # noqa: BLE001 - the reference skips a failing simulation (main.py:388-390)
+            print(f"Error in simulation {sim_idx}: {str(e)}")
+            continue
+
+    arrays: Dict[int, Dict[str, Any]] = {}
+    mappings: List[tuple] = []
+    pool = cf.ThreadPoolExecutor(max_workers=max(1, writer_threads)) if write_files else None
+    pending: List[cf.Future] = []
+    T = int(3600 / 0.2)
+    steps = sorted({int(t) for t in time_steps if 0 <= int(t) < T})
+    w, h = output_size
+    per_pouch_bytes = max(1, len(steps)) * h * w * (2 + (2 if generate_masks else 0))
+    chunk = max(1, int(max_chunk_bytes // per_pouch_bytes))
+
+    try:
+        for c0 in range(0, len(drawn), chunk):
+            part = drawn[c0:c0 + chunk]
+            ens = Ensemble([d["spec"] for d in part], output_size=output_size, T=T,
+                           frame_steps=steps, device=device)
+            ens.simulate()
+            status = ens.check_status()
+            out = ens.rasterize(image=True, instance=bool(generate_masks)) if steps else {}
+            ens.synchronize()
+            img = out["image"].cpu().numpy() if steps else None
+            ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and generate_masks) else None
+            nact = out["n_active"].cpu().numpy() if steps else None
+            for li, d in enumerate(part):
+                image_files, mask_files = [], []
+                for fi, t in enumerate(steps):
+                    base = f"{d['name']}_t{t:05d}_{batch_run_id}"
+                    ipath = os.path.join(img_dir, base + ".png")
+                    image_files.append(ipath)
+                    if pool is not None:
+                        pending.append(pool.submit(cio.save_gray_alpha_png, img[li, fi], ipath, 10))
+                    if generate_masks and nact[li, fi] > 0:      # no active cell -> no mask (sam2_data_generator.py:318-319)
+                        mpath = os.path.join(mask_dir, base + ".npz")
+                        mask_files.append(mpath)
+                        mappings.append((os.path.basename(ipath), os.path.basename(mpath)))
+                        if pool is not None:
+                            pending.append(pool.submit(cio.save_instance_mask, ins[li, fi], mpath))
+                if keep_arrays:
+                    arrays[d["sim_idx"]] = {
+                        "time_steps": list(steps), "image": img[li].copy() if img is not None else None,
+                        "instance": ins[li].copy() if ins is not None else None,
+                        "n_active": nact[li].copy() if nact is not None else None,
+                        "frames": ens.frames_of(li).cpu().numpy(), "status": int(status[li])}
+                pouch_obj = None
+                if save_pouch:
+                    from .pouch import Pouch
+                    pouch_obj = Pouch(params=d["params"], size=d["size"], sim_number=d["sim_idx"],
+                                      save=True, save_name=d["name"], geometry_dir=geometry_dir,
+                                      output_size=output_size, jpeg_quality=jpeg_quality, device=device)
+                    pouch_obj.simulate()
+                results["simulations"].append({
+                    "simulation_id": d["sim_idx"], "simulation_name": d["name"],
+                    "simulation_type": d["type"], "pouch_size": d["size"], "parameters": d["params"],
+                    "image_count": len(image_files), "image_dir": img_dir, "mask_dir": mask_dir,
+                    "mask_count": len(mask_files), "pouch": pouch_obj})
+            del ens, out
+    finally:
+        if pool is not None:
+            for f in pending:
+                f.result()
+            pool.shutdown()
+
+    try:
+        if mappings and write_files:
+            results["image_mask_csv"] = cio.save_csv_mapping(mappings, batch_dir, "train.csv")
+            print(f"Created CSV mapping: {results['image_mask_csv']}")
+        else:
+            results["csv_error"] = "Failed to create CSV mapping"
+    except Exception as e:  # noqa: BLE001
+        results["csv_error"] = str(e)
+    if create_stats:
+        results["stats"] = {"total_simulations": len(results["simulations"]),
+                            "total_images": sum(s["image_count"] for s in results["simulations"]),
+                            "total_masks": sum(s["mask_count"] for s in results["simulations"])}
+    try:
+        with open(os.path.join(batch_dir, "simulation_results.json"), "w") as fh:
+            json.dump(results, fh, indent=4, cls=_NumpyEncoder)
+    except Exception as e:  # noqa: BLE001
+        print(f"Error saving results: {str(e)}")
+    if keep_arrays:
+        results["arrays"] = arrays
+    gc.collect()
+    return results
+
+
+class BatchGenerationController:
+    """Controls batch generation independent of any GUI (reference ``utils/batch_controller.py``)."""
+
+    def __init__(self):
+        self.cancel_requested = False
+
+    def cancel(self):
+        self.cancel_requested = True
+
+    def run_batch_generation(self, batch_params: Dict[str, Any], output_dir: str,
+                             progress_callback: Optional[Callable] = None,
+                             status_callback: Optional[Callable[[str], None]] = None) -> Dict[str, Any]:
+        self.cancel_requested = False
+        try:
+            if status_callback:
+                status_callback("Initializing batch generation...")
+            config = self._parse_batch_config(batch_params)
+            if config["enable_multi_batch"]:
+                results = self._run_multi_batch_generation(config, output_dir, progress_callback, status_callback)
+            else:
+                results = self._run_single_batch_generation(config, output_dir, progress_callback, status_callback)
+            if self.cancel_requested:
+                if status_callback:
+                    status_callback("Batch generation cancelled")
+                results["success"] = False
+                results["cancelled"] = True
+                return results
+            if config["create_csv"] and results.get("simulations"):
+                results["csv_path"] = results.get("image_mask_csv")
+                if status_callback and results["csv_path"]:
+                    status_callback(f"CSV mapping created: {os.path.basename(results['csv_path'])}")
+            if config["enable_video"] and results.get("simulations") and status_callback:
+                # the reference calls Pouch.make_animation, which does not exist
+                status_callback("Video generation error: 'Pouch' object has no attribute 'make_animation'")
+            if status_callback:
+                sims = results.get("simulations", [])
+                status_callback(f"Batch complete: {len(sims)} simulations, "
+                                f"{sum(s.get('image_count', 0) for s in sims)} images")
+            results["success"] = True
+            return results
+        except Exception as e:  # noqa: BLE001 - same conversion as the reference (:134-144)
+            msg = f"Batch generation error: {str(e)}"
+            if status_callback:
+                status_callback(msg)
+            return {"success": False, "error": msg, "simulations": [], "output_dir": output_dir}
+
+    def _parse_batch_config(self, bp: Dict[str, Any]) -> Dict[str, Any]:
+        cfg: Dict[str, Any] = {"enable_multi_batch": bp.get("enable_multi_batch", False)}
+        if cfg["enable_multi_batch"]:
+            cfg["num_batches"] = int(bp.get("num_batches", 1))
+            cfg["sims_per_batch"] = int(bp.get("sims_per_batch", 10))
+            cfg["total_simulations"] = cfg["num_batches"] * cfg["sims_per_batch"]
+        else:
+            cfg["num_simulations"] = int(bp.get("num_simulations", 5))
+            cfg["total_simulations"] = cfg["num_simulations"]
+        try:
+            w, h = map(int, bp.get("image_size", "512x512").split("x"))
+            cfg["output_size"] = (w, h)
+        except (ValueError, AttributeError):
+            cfg["output_size"] = (512, 512)
+        cfg["pouch_sizes"] = bp.get("pouch_sizes", ["small"])
+        cfg["sim_types"] = bp.get("sim_types", None)
+        cfg["time_steps"] = bp.get("time_steps", None)
+        cfg["jpeg_quality"] = bp.get("jpeg_quality", 90)
+        cfg["edge_blur"] = bp.get("edge_blur", False)
+        cfg["blur_kernel_size"] = int(bp.get("blur_kernel_size", 3))
+        cfg["blur_type"] = bp.get("blur_type", "mean")
+        cfg["generate_masks"] = bp.get("generate_masks", True)
+        cfg["create_csv"] = bp.get("create_csv", False)
+        cfg["enable_video"] = bp.get("enable_video", False)
+        cfg["defect_config"] = bp.get("defect_config", None)
+        cfg["dataset_split"] = bp.get("dataset_split", "train")
+        cfg["memory_threshold"] = 60 if ("large" in cfg["pouch_sizes"] or "xlarge" in cfg["pouch_sizes"]) else 70
+        for k in ("geometry_dir", "device", "write_files", "keep_arrays"):
+            if k in bp:
+                cfg[k] = bp[k]
+        return cfg
+
+    def _call(self, config, output_dir, n, progress_callback, save_pouch):
+        dc = config.get("defect_config")
+        extra = {k: config[k] for k in ("geometry_dir", "device", "write_files", "keep_arrays") if k in config}
+        return generate_simulation_batch(
+            num_simulations=n, output_dir=output_dir, pouch_sizes=config["pouch_sizes"],
+            sim_types=config["sim_types"], time_steps=config["time_steps"],
+            defect_configs=[dc] * n if dc else None, progress_callback=progress_callback,
+            create_stats=True, edge_blur=config["edge_blur"], blur_kernel_size=config["blur_kernel_size"],
+            blur_type=config["blur_type"], generate_masks=config["generate_masks"],
+            image_size=config["output_size"], jpeg_quality=config["jpeg_quality"],
+            memory_threshold=config["memory_threshold"], save_pouch=save_pouch,
+            dataset_split=config.get("dataset_split", "train"), **extra)
+
+    def _run_single_batch_generation(self, config, output_dir, progress_callback, status_callback):
+        if status_callback:
+            status_callback(f"Generating {config['num_simulations']} simulations...")
+        return self._call(config, output_dir, config["num_simulations"], progress_callback,
+                          config["enable_video"])
+
+    def _run_multi_batch_generation(self, config, output_dir, progress_callback, status_callback):
+        all_results: Dict[str, Any] = {"simulations": [], "output_dir": output_dir}
+        for b in range(config["num_batches"]):
+            if self.cancel_requested:
+                break
+            if status_callback:
+                status_callback(f"Batch {b + 1}/{config['num_batches']}: "
+                                f"Generating {config['sims_per_batch']} simulations...")
+
+            def batch_progress(current, total, _b=b):
+                if progress_callback:
+                    info = {"batch_idx": _b, "batch_total": config["num_batches"]}
+                    return progress_callback(current + _b * config["sims_per_batch"],
+                                             config["total_simulations"], info)
+                return False
+
+            r = self._call(config, output_dir, config["sims_per_batch"], batch_progress, False)
+            all_results["simulations"].extend(r.get("simulations", []))
+            if "image_mask_csv" in r:
+                all_results["image_mask_csv"] = r["image_mask_csv"]
+        return all_results

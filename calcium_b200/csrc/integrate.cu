@@ -220,11 +220,11 @@ extern "C" int cab200_sim_batch(
             return CAB200_ESIZE;
         }
         const int max_row = g_max_row[g];
-        if (max_row > 16 || max_row < 1) {
-            set_error("cab200_sim_batch: geometry %d: longest CSR row %d outside [1,16]", g, max_row);
+        if (max_row > 16 || max_row < 0) {
+            set_error("cab200_sim_batch: geometry %d: longest CSR row %d outside [0,16]", g, max_row);
             return CAB200_ESIZE;
         }
-        const int ep = (max_row + 1) / 2;
+        const int ep = (max_row + 1) / 2;   // 0 and 1..10 use the 5-pair variant
         const bool unit = g_unit[g] != 0;
         const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
         const int np = (n + 31) & ~31;

@@ -17,7 +17,7 @@ import hashlib
 import os
 import threading
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -96,11 +96,14 @@ class _DeviceGeometry:
         rowptr, col, val = geo.csr
         self.geo = geo
         self.n = geo.n_cells
-        self.max_row = int(np.diff(rowptr).max())
+        self.max_row = int(np.diff(rowptr).max()) if self.n else 0
         offdiag = np.ones(len(col), dtype=bool)
         rows = np.repeat(np.arange(self.n), np.diff(rowptr))
         offdiag &= rows != col
         self.unit = bool(np.all(val[offdiag] == 1.0))
+        self.nnz = len(col)
+        if self.nnz == 0:        # a graph without any entry still needs non-null device pointers
+            col, val = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.float64)
         self.rowptr = torch.from_numpy(rowptr).to(device)
         self.col = torch.from_numpy(col).to(device)
         self.val = torch.from_numpy(val).to(device)
@@ -435,6 +438,76 @@ class Ensemble:
 
     def synchronize(self) -> None:
         torch.cuda.current_stream(self.device).synchronize()
+
+    # -- end to end: host in, host out -----------------------------------------------------------
+    def run_to_host(self, chunk_pouches: int = 16, image: bool = True, instance: bool = True,
+                    consumer=None, threshold: float = 0.1, quirk: bool = True) -> Dict[str, int]:
+        """The whole hot path with HOST buffers on both sides, as a user of the reference gets it:
+        pinned host inputs -> device, K1, then K2 chunk by chunk with every result (frames, images,
+        instance masks, active counts) copied back into pinned host memory.  Device->host copies
+        run on a second stream and overlap the rasterisation of the next chunk (two device and two
+        host buffers).  ``consumer(lo, hi, arrays)`` is called with numpy views of the pinned
+        buffers once a chunk has landed (e.g. to hand them to file writers); without a consumer
+        the data is simply left in the pinned buffers.  Returns the byte counts moved."""
+        dev = self.device
+        w, h = self.output_size
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._h_frames = torch.empty(max(self.frame_elems, 1), dtype=torch.float64, pin_memory=True)
+            self._ring: List[Dict[str, Any]] = []
+        cs = self._copy_stream
+        cp = max(1, min(chunk_pouches, self.P))
+        if not self._ring or self._ring[0]["cp"] != cp or self._ring[0]["key"] != (image, instance):
+            self._ring = []
+            for _ in range(2):
+                slot: Dict[str, Any] = {"cp": cp, "key": (image, instance), "dev": {}, "host": {},
+                                        "done": torch.cuda.Event()}
+                if image:
+                    slot["host"]["image"] = torch.empty((cp, self.F, h, w, 2), dtype=torch.uint8, pin_memory=True)
+                if instance:
+                    slot["host"]["instance"] = torch.empty((cp, self.F, h, w), dtype=torch.int16, pin_memory=True)
+                slot["host"]["n_active"] = torch.empty((cp, self.F), dtype=torch.int32, pin_memory=True)
+                self._ring.append(slot)
+        d2h = 0
+        with torch.cuda.device(dev):
+            self.simulate(upload=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                self._h_frames.copy_(self.frames, non_blocking=True)
+            d2h += self.frames.numel() * self.frames.element_size()
+            k = 0
+            landed = []
+            for lo in range(0, self.P, cp):
+                hi = min(lo + cp, self.P)
+                slot = self._ring[k % 2]
+                cur.wait_event(slot["done"])            # its previous copy-out has finished
+                if consumer is not None and len(landed) >= 2:
+                    plo, phi, pslot = landed.pop(0)
+                    pslot["done"].synchronize()
+                    consumer(plo, phi, {n_: t[: phi - plo].numpy() for n_, t in pslot["host"].items()})
+                if hi - lo != cp:
+                    slot["dev"] = {}                    # ragged tail: fresh, smaller device tensors
+                out = self.rasterize(image=image, instance=instance, pouches=(lo, hi),
+                                     threshold=threshold, quirk=quirk, out=slot["dev"])
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                cs.wait_event(ev)
+                with torch.cuda.stream(cs):
+                    for name, t in out.items():
+                        slot["host"][name][: hi - lo].copy_(t, non_blocking=True)
+                        d2h += t.numel() * t.element_size()
+                    slot["done"].record(cs)
+                landed.append((lo, hi, slot))
+                k += 1
+            cur.wait_stream(cs)
+            if consumer is not None:
+                for plo, phi, pslot in landed:
+                    pslot["done"].synchronize()
+                    consumer(plo, phi, {n_: t[: phi - plo].numpy() for n_, t in pslot["host"].items()})
+        return {"h2d_bytes": self.h2d_bytes, "d2h_bytes": d2h}
 
 
 def make_specs(n: int, size: str = "medium", sim_types: Optional[Sequence[str]] = None,

@@ -115,6 +115,13 @@ def main() -> None:
             am = pr.get_cell_masks(active_only=True, time_step=t)
             rz[f"activemask_{tag}_{t}"] = am.astype(np.uint16)
             rz[f"instance_{tag}_{t}"] = ns.create_instance_mask_from_cells(am, act)
+    pr = ns.Pouch(params=p, size="xsmall", sim_number=0, geometry_dir=gdir, output_size=(160, 120))
+    pr.disc_dynamics = pouch.disc_dynamics
+    rz["edge_mean3_160x120_10000"] = pr.generate_image(10000, edge_blur=True, blur_kernel_size=3, blur_type="mean")
+    rz["edge_motion5_160x120_10000"] = pr.generate_image(10000, edge_blur=True, blur_kernel_size=5, blur_type="motion")
+    # with_border=True alone raises in the reference under OpenCV 4.13 (cv2.polylines on the
+    # non-contiguous view img_data[:, :, 0], core/pouch.py:481) -> no fixture for that branch.
+    rz["border_blur_160x120_10000"] = pr.generate_image(10000, with_border=True, edge_blur=True)
     rz["ca"] = np.ascontiguousarray(pouch.disc_dynamics[:, 0, [0, 1000, 4000, 10000, 17999]].T)
     np.savez_compressed(os.path.join(OUT, "raster_xsmall.npz"), **rz)
 

@@ -1,0 +1,463 @@
+"""Parity tests proper: the CUDA path (through the C ABI, via calcium_b200.ensemble / Pouch) against
+the oracle and against fixtures recorded from the reference.  Run with `-m gpu` on a B200.
+
+Bars (north_star): trajectories within rtol 1e-9 of the reference's numba build (stated in RTOL
+below); against the oracle -- the reference's arithmetic in source order, every operation rounded
+once -- the FP64 mode is required to be BIT-IDENTICAL, which is the stronger statement the kernel is
+designed for.  Images and masks: bit-exact.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TYPES = ["Single cell spikes", "Intercellular transients", "Intercellular waves", "Fluttering"]
+RTOL = 1e-9          # tolerance of BASELINE.json's north_star for FP64 trajectories vs the reference
+
+
+@pytest.fixture(scope="module")
+def env(cuda_device, oracle):
+    import torch
+    from calcium_b200 import _lib, build
+    build.build()
+    from calcium_b200 import ensemble
+    return dict(dev=cuda_device, O=oracle, lib=_lib.load(), L=_lib, E=ensemble, torch=torch)
+
+
+def _oracle_frames(O, spec, T, steps, f32=False):
+    g = spec.geometry
+    c0 = np.zeros(g.n_cells) if spec.c0 is None else spec.c0
+    p0 = np.zeros(g.n_cells) if spec.p0 is None else spec.p0
+    return O.simulate_c(g.csr, O.pack_params(spec.params), c0, p0, spec.r0, spec.vplc, T, steps, f32=f32)
+
+
+def _max_rel(a, b):
+    return float((np.abs(a - b) / np.maximum(np.abs(b), 1e-300)).max())
+
+
+# ---- the division K1 relies on --------------------------------------------------------------------
+
+def test_branch_free_division_is_ieee(env):
+    mm = ctypes.c_ulonglong(1)
+    for er in (4, 40, 300):
+        env["L"].check(env["lib"].cab200_selftest_division(1 << 28, er, 1234 + er, ctypes.byref(mm), None), "selftest")
+        assert mm.value == 0, f"{mm.value} mismatches vs __ddiv_rn at exponent range +-{er}"
+
+
+# ---- K1 against the oracle: bit-exact -------------------------------------------------------------
+
+@pytest.mark.parametrize("size,count,T", [("xsmall", 8, 18000), ("small", 4, 18000), ("medium", 2, 18000),
+                                          ("large", 1, 3000)])
+def test_k1_bit_exact_vs_oracle(env, size, count, T):
+    E, O = env["E"], env["O"]
+    specs = E.make_specs(count, size=size, first_seed=17)       # types round-robin, randomised params
+    steps = sorted(set(list(range(0, T, 200)) + [1, T - 1]))
+    ens = E.Ensemble(specs, T=T, frame_steps=steps, device=env["dev"])
+    ens.simulate(); ens.synchronize()
+    assert not ens.check_status().any()
+    for i, s in enumerate(specs):
+        want = _oracle_frames(O, s, T, ens.frame_steps)
+        got = ens.frames_of(i).cpu().numpy()
+        assert np.array_equal(want, got), f"{size}[{i}] max abs diff {np.abs(want - got).max():.3e}"
+
+
+def test_k1_against_reference_fixtures(env, golden_dir):
+    """GPU vs what the reference itself produced (numba fastmath build) -- rtol 1e-9."""
+    E = env["E"]
+    from calcium_b200.parameters import SimulationParameters as SP
+    from calcium_b200.geometry import get_geometry
+    z = np.load(os.path.join(golden_dir, "traj_xsmall_waves.npz"))
+    spec = E.PouchSpec.draw(SP("Intercellular waves").get_params_dict(), "xsmall", 0)
+    ens = E.Ensemble([spec], frame_steps=z["steps"].tolist(), device=env["dev"])
+    ens.simulate()
+    got = ens.frames_of(0).cpu().numpy()
+    assert _max_rel(got, z["frames_jit"]) < RTOL and _max_rel(got, z["frames_pyfunc"]) < RTOL
+    z = np.load(os.path.join(golden_dir, "traj_small_types.npz"))
+    specs = [E.PouchSpec.draw(SP(st).generate_random_params(seed=i), "small", i) for i, st in enumerate(TYPES)]
+    ens = E.Ensemble(specs, frame_steps=z["steps"].tolist(), device=env["dev"])
+    ens.simulate()
+    for i in range(4):
+        assert _max_rel(ens.frames_of(i).cpu().numpy(), z[f"frames_{i}"]) < RTOL, TYPES[i]
+    z = np.load(os.path.join(golden_dir, "traj_medium_flutter.npz"))
+    spec = E.PouchSpec.draw(SP("Fluttering").generate_random_params(seed=3), "medium", 3)
+    ens = E.Ensemble([spec], frame_steps=z["steps"].tolist(), device=env["dev"])
+    ens.simulate()
+    assert _max_rel(ens.frames_of(0).cpu().numpy(), z["frames"]) < RTOL
+
+
+def test_layout_choices_never_change_results(env):
+    """Slot plan on/off and every CTA shape give the same bits (layout is not arithmetic)."""
+    E, lib, L = env["E"], env["lib"], env["L"]
+    specs = E.make_specs(3, size="medium", first_seed=40)
+    T, steps = 3000, [0, 1500, 2999]
+    ref = None
+    try:
+        for shape in [(0, 0), (512, 3), (768, 2), (1024, 2)]:
+            L.check(lib.cab200_sim_set_plan(100000, *shape), "set_plan")
+            for use_plan in (False, True):
+                ens = E.Ensemble(specs, T=T, frame_steps=steps, device=env["dev"], use_plan=use_plan)
+                f = ens.simulate().cpu().numpy().copy()
+                assert not ens.check_status().any()
+                if ref is None:
+                    ref = f
+                assert np.array_equal(ref, f), (shape, use_plan)
+    finally:
+        lib.cab200_sim_set_plan(0, 0, 0)
+    want = _oracle_frames(env["O"], specs[1], T, steps)
+    assert np.array_equal(want, ref.reshape(-1)[1500 * 4 * 3: 2 * 1500 * 4 * 3].reshape(3, 4, 1500))
+
+
+def _weighted_geometry(n=300, seed=5):
+    from calcium_b200.geometry import Geometry, make_synthetic_geometry
+    g = make_synthetic_geometry("w", n_cells=n, seed=seed)
+    rng = np.random.RandomState(seed)
+    w = np.zeros((n, n))
+    vals = rng.uniform(0.2, 1.7, len(g.edges))
+    w[g.edges[:, 0], g.edges[:, 1]] = vals
+    w[g.edges[:, 1], g.edges[:, 0]] = vals
+    lap = w - np.diag(w.sum(axis=1))
+    return Geometry(size="w", vertices=g.vertices, edges=g.edges, weights=lap)
+
+
+def test_weighted_laplacian_path(env):
+    """General CSR weights (not adjacency - degree) take the multiply-per-entry kernel; still bit-exact."""
+    E, O = env["E"], env["O"]
+    from calcium_b200.parameters import SimulationParameters as SP
+    g = _weighted_geometry()
+    specs = []
+    for i in range(3):
+        prm = SP(TYPES[i + 1]).generate_random_params(seed=i)
+        v = E.draw_vplc(prm, g.n_cells, i)
+        r0, _ = E.draw_initial_state(prm, g.n_cells, i, v)
+        specs.append(E.PouchSpec(params=prm, geometry=g, sim_number=i, vplc=v.flatten(), r0=r0))
+    ens = E.Ensemble(specs, T=2500, frame_steps=[0, 1200, 2499], device=env["dev"])
+    assert ens.g_unit[0] == 0
+    ens.simulate()
+    assert not ens.check_status().any()
+    for i, s in enumerate(specs):
+        assert np.array_equal(_oracle_frames(O, s, 2500, [0, 1200, 2499]), ens.frames_of(i).cpu().numpy())
+
+
+def test_false_unit_declaration_is_flagged(env):
+    E = env["E"]
+    g = _weighted_geometry(n=64, seed=9)
+    from calcium_b200.parameters import SimulationParameters as SP
+    prm = SP("Fluttering").get_params_dict()
+    v = E.draw_vplc(prm, g.n_cells, 0)
+    r0, _ = E.draw_initial_state(prm, g.n_cells, 0, v)
+    ens = E.Ensemble([E.PouchSpec(params=prm, geometry=g, vplc=v.flatten(), r0=r0)], T=10, frame_steps=[9],
+                     device=env["dev"], use_plan=False)
+    ens.g_unit[:] = 1                      # lie: declare unit off-diagonals
+    ens.simulate()
+    with pytest.raises(env["L"].Cab200Error, match="rejected the geometry"):
+        ens.check_status()
+
+
+def test_tiny_and_degenerate_graphs(env):
+    """n = 1 (no entries at all), a 2-cell path, an isolated cell, n not a multiple of 32."""
+    E, O = env["E"], env["O"]
+    from calcium_b200.geometry import Geometry
+    from calcium_b200.parameters import SimulationParameters as SP
+    prm = SP("Fluttering").get_params_dict()
+
+    def geo(n, edges):
+        verts = np.empty(n, dtype=object)
+        for i in range(n):
+            verts[i] = np.array([[i, 0.0], [i + 1, 0.0], [i + 1, 1.0], [i, 1.0]])
+        return Geometry(size=f"g{n}", vertices=verts, edges=np.array(edges, dtype=np.int32).reshape(-1, 2))
+
+    for g in (geo(1, []), geo(2, [(0, 1)]), geo(3, [(0, 1)]), geo(37, [(i, i + 1) for i in range(36)])):
+        n = g.n_cells
+        rng = np.random.RandomState(n)
+        spec = E.PouchSpec(params=prm, geometry=g, vplc=rng.uniform(1.3, 1.5, n), r0=rng.uniform(.5, .7, n),
+                           c0=rng.uniform(0, .2, n), p0=rng.uniform(0, .3, n))
+        ens = E.Ensemble([spec], T=800, frame_steps=[0, 799], device=env["dev"])
+        ens.simulate()
+        assert not ens.check_status().any()
+        assert np.array_equal(_oracle_frames(O, spec, 800, [0, 799]), ens.frames_of(0).cpu().numpy()), n
+
+
+def test_horizon_and_capture_edge_cases(env):
+    E, O = env["E"], env["O"]
+    specs = E.make_specs(2, size="xsmall", first_seed=3)
+    # T = 1: only the initial state exists
+    ens = E.Ensemble(specs, T=1, frame_steps=[0], device=env["dev"])
+    ens.simulate()
+    f = ens.frames_of(1).cpu().numpy()
+    assert np.all(f[0, 0] == 0) and np.array_equal(f[0, 3], specs[1].r0)
+    assert np.all(f[0, 2] == specs[1].params["c_tot"] / specs[1].params["beta"])
+    # no frames at all: runs, writes nothing
+    ens = E.Ensemble(specs, T=50, frame_steps=[], device=env["dev"])
+    ens.simulate(); ens.synchronize()
+    assert ens.F == 0 and not ens.check_status().any()
+    # every step captured (config 4's mode, short horizon)
+    T = 300
+    ens = E.Ensemble(specs, T=T, frame_steps=range(T), device=env["dev"])
+    ens.simulate()
+    assert np.array_equal(_oracle_frames(O, specs[0], T, list(range(T))), ens.frames_of(0).cpu().numpy())
+    # out-of-range steps are dropped like the reference's `if time_step >= pouch.T: continue` (main.py:270)
+    ens = E.Ensemble(specs, T=100, frame_steps=[0, 50, 100, 18000], device=env["dev"])
+    assert ens.frame_steps.tolist() == [0, 50]
+
+
+def test_non_finite_status(env):
+    E = env["E"]
+    spec = E.make_specs(1, size="xsmall")[0]
+    spec.params = dict(spec.params, D_p=1e6)       # explicit Euler blows up
+    ens = E.Ensemble([spec], T=400, frame_steps=[0, 399], device=env["dev"])
+    ens.simulate()
+    st = ens.check_status()
+    assert st[0] & env["L"].ST_NONFINITE
+
+
+def test_ragged_ensemble_more_pouches_than_sms(env):
+    """Mixed sizes in one call, more CTAs than SMs; every 23rd pouch checked against the oracle."""
+    E, O = env["E"], env["O"]
+    sizes = ["xsmall", "small", "xsmall", "medium", "xsmall", "small"]
+    specs = []
+    for i in range(330):
+        specs.append(E.make_specs(1, size=sizes[i % len(sizes)], first_seed=i, sim_types=[TYPES[i % 4]])[0])
+    T, steps = 1200, [0, 600, 1199]
+    ens = E.Ensemble(specs, T=T, frame_steps=steps, device=env["dev"])
+    ens.simulate()
+    assert not ens.check_status().any()
+    for i in range(0, 330, 23):
+        assert np.array_equal(_oracle_frames(O, specs[i], T, steps), ens.frames_of(i).cpu().numpy()), i
+
+
+def test_fp32_mode_matches_float_oracle_and_reports_error(env):
+    E, O, L = env["E"], env["O"], env["L"]
+    specs = E.make_specs(4, size="small", first_seed=0)
+    steps = [0, 6000, 17999]
+    e32 = E.Ensemble(specs, frame_steps=steps, device=env["dev"], precision=L.FP32)
+    e32.simulate()
+    e64 = E.Ensemble(specs, frame_steps=steps, device=env["dev"])
+    e64.simulate()
+    for i, s in enumerate(specs):
+        got = e32.frames_of(i).cpu().numpy()
+        assert got.dtype == np.float32
+        want = _oracle_frames(O, s, 18000, steps, f32=True)
+        assert np.array_equal(want, got), f"fp32 pouch {i}: {np.abs(want - got).max():.3e}"
+        err = np.abs(got.astype(np.float64) - e64.frames_of(i).cpu().numpy())
+        assert np.isfinite(err).all()          # the magnitude is reported by bench.py --fp32-report
+
+
+# ---- K0 / K2 ----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("size,out", [("xsmall", (512, 512)), ("xsmall", (160, 120)), ("small", (640, 480)),
+                                      ("medium", (512, 512)), ("large", (512, 512)), ("medium", (1024, 1024))])
+def test_label_maps_bit_exact(env, size, out):
+    E, O = env["E"], env["O"]
+    from calcium_b200.geometry import get_geometry
+    g = get_geometry(size)
+    limg, lmsk = E.build_label_maps(g, out, env["dev"])
+    assert np.array_equal(E._u16_numpy(lmsk), O.cells_mask_oracle(g.vertices, out).astype(np.uint16))
+    assert np.array_equal(E._u16_numpy(limg), O.paint_label_map_cv2(g.vertices, out).astype(np.uint16))
+
+
+@pytest.mark.parametrize("size,out,quirk,thr", [("xsmall", (512, 512), True, 0.1), ("medium", (512, 512), True, 0.1),
+                                                ("small", (160, 120), False, 0.1), ("medium", (640, 480), True, 0.35),
+                                                ("xsmall", (250, 130), True, 0.1)])
+def test_k2_bit_exact_vs_oracle(env, size, out, quirk, thr):
+    E, O = env["E"], env["O"]
+    specs = E.make_specs(4, size=size, first_seed=100)      # includes a Fluttering pouch: many active cells
+    steps = list(range(0, 18000, 1500)) + [17999]
+    ens = E.Ensemble(specs, frame_steps=steps, device=env["dev"], output_size=out)
+    ens.simulate()
+    res = ens.rasterize(image=True, instance=True, active=True, threshold=thr, quirk=quirk)
+    ens.synchronize()
+    limg, lmsk = [E._u16_numpy(t)[0] for t in ens.label_maps()]
+    img = res["image"].cpu().numpy(); ins = res["instance"].cpu().numpy().view(np.uint16)
+    act = res["active"].cpu().numpy(); nact = res["n_active"].cpu().numpy()
+    seen_active = 0
+    for i in range(len(specs)):
+        fr = ens.frames_of(i).cpu().numpy()
+        for f in range(ens.F):
+            oi, oa, oin, on = O.raster_frame_c(fr[f, 0], limg, lmsk, thr, quirk)
+            assert np.array_equal(oi, img[i, f]) and np.array_equal(oa, act[i, f])
+            assert np.array_equal(oin, ins[i, f]) and on == nact[i, f]
+            seen_active = max(seen_active, on)
+    assert seen_active > 20, "the fixture ensemble should exercise frames with many active cells"
+    # sub-range rasterisation writes the same bytes
+    part = ens.rasterize(image=True, instance=True, pouches=(1, 3), threshold=thr, quirk=quirk)
+    assert np.array_equal(part["image"].cpu().numpy(), img[1:3])
+    assert np.array_equal(part["instance"].cpu().numpy().view(np.uint16), ins[1:3])
+
+
+def test_k2_literal_reference_loops(env):
+    """One frame against the reference's literal algorithm: a fillPoly per cell, a full-image pass
+    per active cell, a relabel pass per active cell."""
+    E, O = env["E"], env["O"]
+    spec = E.make_specs(4, size="small", first_seed=0)[3]       # Fluttering
+    ens = E.Ensemble([spec], frame_steps=[9000], device=env["dev"])
+    ens.simulate()
+    res = ens.rasterize(image=True, instance=True, active=True)
+    ca = ens.frames_of(0).cpu().numpy()[0, 0]
+    g = spec.geometry
+    assert np.array_equal(O.generate_image_oracle(g.vertices, ca, (512, 512)), res["image"].cpu().numpy()[0, 0])
+    active = O.active_cells_oracle(ca)
+    cm = O.cells_mask_oracle(g.vertices, (512, 512))
+    am = O.active_mask_oracle(cm, active)
+    assert np.array_equal(am, res["active"].cpu().numpy()[0, 0])
+    assert np.array_equal(O.instance_mask_oracle(am, active), res["instance"].cpu().numpy().view(np.uint16)[0, 0])
+    assert len(active) == int(res["n_active"].cpu().numpy()[0, 0]) > 0
+
+
+# ---- the Pouch drop-in against fixtures recorded from the reference's own methods ------------------
+
+def test_pouch_api_against_reference_fixtures(env, golden_dir):
+    from calcium_b200 import Pouch, SimulationParameters, create_instance_mask_from_cells
+    z = np.load(os.path.join(golden_dir, "raster_xsmall.npz"))
+    traj = np.load(os.path.join(golden_dir, "traj_xsmall_waves.npz"))
+    p = SimulationParameters("Intercellular waves").get_params_dict()
+    for tag in ("160x120", "512x512"):
+        w, h = map(int, tag.split("x"))
+        pouch = Pouch(params=p, size="xsmall", sim_number=0, output_size=(w, h))
+        assert pouch.simulate() is True
+        assert np.array_equal(pouch.V_PLC.flatten(), traj["vplc"])           # initiators applied in place
+        assert pouch.cells_mask.dtype == np.int32
+        assert np.array_equal(pouch.cells_mask.astype(np.uint16), z[f"cells_mask_{tag}"])
+        for t in z[f"t_{tag}"].tolist():
+            img = pouch.generate_image(t)
+            assert img.shape == (h, w, 2) and img.dtype == np.uint8
+            assert np.array_equal(img, z[f"image_{tag}_{t}"]), (tag, t)
+            act = pouch.get_active_cells(t)
+            assert act == z[f"active_{tag}_{t}"].tolist()
+            am = pouch.get_cell_masks(active_only=True, time_step=t)
+            assert am.dtype == np.int32 and np.array_equal(am.astype(np.uint16), z[f"activemask_{tag}_{t}"])
+            inst = create_instance_mask_from_cells(am, act)
+            assert np.array_equal(inst, z[f"instance_{tag}_{t}"])
+            assert np.array_equal(pouch.get_instance_mask(t), z[f"instance_{tag}_{t}"])
+        if tag == "160x120":
+            assert np.array_equal(pouch.generate_image(10000, edge_blur=True), z["edge_mean3_160x120_10000"])
+            assert np.array_equal(pouch.generate_image(10000, edge_blur=True, blur_kernel_size=5, blur_type="motion"),
+                                  z["edge_motion5_160x120_10000"])
+            assert np.array_equal(pouch.generate_image(10000, with_border=True, edge_blur=True),
+                                  z["border_blur_160x120_10000"])
+            assert pouch.generate_image(10000, with_border=True).shape == (h, w, 2)
+    # disc_dynamics indexing like the reference's callers (labeling.py:166, pouch.py:418,563,584)
+    steps = traj["steps"].tolist()
+    dd = pouch.disc_dynamics
+    assert dd.shape == (200, 4, 18000)
+    got = np.transpose(dd[:, :, steps], (2, 1, 0))
+    assert _max_rel(got, traj["frames_jit"]) < RTOL
+    assert float(dd[7, 0, 10000]) == got[steps.index(10000), 0, 7]
+    assert np.array_equal(dd[:, 0, 10000], got[steps.index(10000), 0])
+    # a step outside the default sampling is produced on demand (deterministic re-integration)
+    assert 4321 not in pouch._steps
+    ca = dd[:, 0, 4321]
+    O = env["O"]
+    spec = env["E"].PouchSpec.draw(p, "xsmall", 0)
+    assert np.array_equal(ca, _oracle_frames(O, spec, 18000, [4321])[0, 0])
+    assert np.array_equal(dd[:, 0, 10000], got[steps.index(10000), 0])       # earlier frames unchanged
+    lbl = pouch.generate_label_data(10000)
+    assert lbl["n_active"] == len(lbl["active_cells"]) == len(lbl["calcium_values"])
+    assert lbl["simulation_info"] == {"sim_number": 0, "size": "xsmall", "time_step": 10000, "total_cells": 200}
+    with pytest.raises(RuntimeError, match="Error generating image"):
+        Pouch(params=p, size="xsmall", output_size=(3, 3)).generate_image(0)   # odd pixel count unsupported
+
+
+# ---- BASELINE-size properties (config 3's per-GPU shard) --------------------------------------------
+
+def test_full_size_medium_wave_properties(env):
+    """148 medium pouches (one wave on 148 SMs), full T, all 90 frames + masks: properties that
+    hold at any size, plus bit-exact spot checks of three pouches against the oracle."""
+    E, O, torch = env["E"], env["O"], env["torch"]
+    specs = E.make_specs(148, size="medium", first_seed=0)
+    ens = E.Ensemble(specs, device=env["dev"])
+    ens.simulate(); ens.synchronize()
+    assert not ens.check_status().any()
+    frames = ens.frames.view(148, ens.F, 4, 1500)
+    first = frames.clone()
+    # conservation: s == (c_tot - c)/beta at every stored step, exactly (core/pouch.py:95)
+    prm = torch.from_numpy(np.stack([E.pack_params(s.params) for s in specs])).to(env["dev"])
+    c_tot, beta = prm[:, 8].view(-1, 1, 1), prm[:, 9].view(-1, 1, 1)
+    assert torch.equal(frames[:, :, 2], (c_tot - frames[:, :, 0]) / beta)
+    assert torch.isfinite(frames).all()
+    # t = 0 frame is the initial state
+    assert torch.count_nonzero(frames[:, 0, 0]) == 0 and torch.count_nonzero(frames[:, 0, 1]) == 0
+    # determinism: a second run gives the same bits
+    ens.simulate(); ens.synchronize()
+    assert torch.equal(first, ens.frames.view(148, ens.F, 4, 1500))
+    # sharding: two half-ensembles (what two ranks would run) equal the single run
+    for lo, hi in ((0, 74), (74, 148)):
+        half = E.Ensemble(specs[lo:hi], device=env["dev"])
+        half.simulate()
+        assert torch.equal(half.frames.view(hi - lo, ens.F, 4, 1500), first[lo:hi])
+    for i in (5, 78, 147):
+        assert np.array_equal(_oracle_frames(O, specs[i], 18000, ens.frame_steps), first[i].cpu().numpy()), i
+    # rasterise in two chunks; image alpha is the static footprint, gray is 0 on background,
+    # instance ids never exceed the active count, and a frame without active cells is all zero
+    limg, lmsk = ens.label_maps()
+    foot = (limg[0] != 0)
+    for lo, hi in ((0, 74), (74, 148)):
+        res = ens.rasterize(pouches=(lo, hi))
+        img, ins, nact = res["image"], res["instance"], res["n_active"]
+        assert torch.equal(img[..., 1] == 255, foot.expand_as(img[..., 1]))
+        assert torch.count_nonzero(img[..., 0][~foot.expand_as(img[..., 0])]) == 0
+        mx = ins.view(hi - lo, ens.F, -1).to(torch.int32).amax(dim=2)
+        assert torch.all(mx <= nact)
+        assert torch.count_nonzero(mx[nact == 0]) == 0
+        active = (frames[lo:hi, :, 0] > 0.1).sum(dim=2).to(torch.int32)
+        assert torch.equal(active, nact)
+        del res
+    # one full frame against the oracle raster
+    fr = first[147, 60].cpu().numpy()
+    res = ens.rasterize(pouches=(147, 148), active=True)
+    oi, oa, oin, on = O.raster_frame_c(fr[0], E._u16_numpy(limg)[0], E._u16_numpy(lmsk)[0], 0.1, True)
+    assert np.array_equal(oi, res["image"][0, 60].cpu().numpy())
+    assert np.array_equal(oin, res["instance"][0, 60].cpu().numpy().view(np.uint16))
+    assert np.array_equal(oa, res["active"][0, 60].cpu().numpy())
+
+
+# ---- batch entry points ------------------------------------------------------------------------------
+
+def test_generate_simulation_batch_and_controller(env, tmp_path):
+    import random
+    from calcium_b200 import BatchGenerationController, generate_simulation_batch
+    O = env["O"]
+    random.seed(5)
+    seen = []
+    res = generate_simulation_batch(5, str(tmp_path / "b"), pouch_sizes=["xsmall", "small"],
+                                    time_steps=[0, 5000, 9000, 17800, 99999],
+                                    progress_callback=lambda a, b: seen.append((a, b)), keep_arrays=True)
+    assert seen == [(i + 1, 5) for i in range(5)]
+    assert res["num_simulations"] == 5 and len(res["simulations"]) == 5 and res["batch_index"] == 0
+    sim = res["simulations"][2]
+    assert set(sim) >= {"simulation_id", "simulation_name", "simulation_type", "pouch_size", "parameters",
+                        "image_count", "image_dir", "mask_dir", "pouch"}
+    assert sim["image_count"] == 4 and sim["pouch"] is None
+    assert sim["simulation_name"] == f"{sim['simulation_type'].replace(' ', '_')}_2"
+    imgs = os.listdir(tmp_path / "b" / "images" / "train")
+    assert len(imgs) == 20 and os.path.exists(tmp_path / "b" / "simulation_results.json")
+    # arrays equal the oracle for one simulation (parameters drawn with seed = sim index)
+    from calcium_b200.parameters import SimulationParameters as SP
+    from calcium_b200.ensemble import PouchSpec
+    a = res["arrays"][2]
+    spec = PouchSpec.draw(SP(sim["simulation_type"]).generate_random_params(seed=2), sim["pouch_size"], 2)
+    assert sim["parameters"] == spec.params
+    assert np.array_equal(_oracle_frames(O, spec, 18000, a["time_steps"]), a["frames"])
+    masks = os.listdir(tmp_path / "b" / "masks" / "train")
+    assert len(masks) == sum(int((s_["n_active"] > 0).sum()) for s_ in res["arrays"].values())
+    if masks:
+        m = np.load(tmp_path / "b" / "masks" / "train" / masks[0])["mask"]
+        assert m.dtype == np.uint16 and m.shape == (512, 512)
+        assert "image_mask_csv" in res
+
+    msgs = []
+    ctl = BatchGenerationController()
+    out = ctl.run_batch_generation({"num_simulations": 3, "pouch_sizes": ["xsmall"], "time_steps": [0, 9000],
+                                    "image_size": "160x120", "create_csv": True, "write_files": True},
+                                   str(tmp_path / "c"), progress_callback=lambda *a: False,
+                                   status_callback=msgs.append)
+    assert out["success"] is True and len(out["simulations"]) == 3
+    assert msgs[0] == "Initializing batch generation..." and msgs[-1].startswith("Batch complete: 3 simulations, 6 images")
+    out = ctl.run_batch_generation({"enable_multi_batch": True, "num_batches": 2, "sims_per_batch": 2,
+                                    "pouch_sizes": ["xsmall"], "time_steps": [100], "write_files": False},
+                                   str(tmp_path / "d"))
+    assert out["success"] and len(out["simulations"]) == 4
+    bad = ctl.run_batch_generation({"num_simulations": "x"}, str(tmp_path / "e"))
+    assert bad["success"] is False and bad["error"].startswith("Batch generation error:")

@@ -1,0 +1,216 @@
+"""Host logic and the C-ABI library without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from calcium_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "cab200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(cab200_[a-z0-9_]+)\s*\(", header)))
+    from calcium_b200 import _lib
+    assert declared == sorted(_lib.EXPORTS), "keep _lib.EXPORTS in sync with include/cab200.h"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libcalcium_b200.so"
+    assert lib.cab200_version() == 100
+
+
+def test_library_targets_sm100a_only():
+    so = os.path.join(ROOT, "calcium_b200", "libcalcium_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_compute_fails_loudly_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from calcium_b200.ensemble import Ensemble, make_specs
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Ensemble(make_specs(1, size="xsmall"))
+    info = np.zeros(4, dtype=np.int64)
+    assert lib.cab200_device_info(0, info.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))) == -2
+    assert b"cuda" in lib.cab200_last_error().lower()
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    from calcium_b200 import _lib
+    z32 = np.zeros(4, dtype=np.int32); z64 = np.zeros(4, dtype=np.int64)
+    rc = lib.cab200_sim_batch(1, _lib.as_i32p(z32), 0, _lib.as_i32p(z32), _lib.as_i32p(z32),
+                              _lib.as_i32p(z32), _lib.as_i64p(z64), _lib.as_i64p(z64), None, None, None,
+                              None, _lib.as_i64p(z64), None, None, None, None, None, 10, 0,
+                              _lib.as_i32p(z32), None, None, 64, None, 0, None)
+    assert rc == -1 and b"bad sizes" in lib.cab200_last_error()
+    assert lib.cab200_sim_set_plan(2000, 333, 2) == -1
+    assert lib.cab200_sim_set_plan(0, 0, 0) == 0
+
+
+def test_layout_and_planner(lib):
+    from calcium_b200 import _lib
+    from calcium_b200.geometry import get_geometry
+    lay = np.zeros(4, dtype=np.int64)
+    assert lib.cab200_sim_layout(1500, 1, 64, _lib.as_i64p(lay)) == 0
+    threads, cpt, copies, smem = lay.tolist()
+    assert threads * cpt >= 1500 and copies == 2 and smem <= 227 * 1024
+    assert lib.cab200_sim_layout(3255, 1, 64, _lib.as_i64p(lay)) == 0 and lay[2] == 1
+    assert lib.cab200_sim_layout(5000, 1, 64, _lib.as_i64p(lay)) == -3
+    g = get_geometry("small")
+    rowptr, col, _ = g.csr
+    n = g.n_cells
+    for copies in (1, 2):
+        plan = np.zeros(2 * n, dtype=np.uint16)
+        cost = np.zeros(4, dtype=np.int64)
+        rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 20000, 7, 0,
+                                   plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(cost))
+        assert rc == 0
+        assert sorted(plan[:n].tolist()) == list(range(n)), "slot_of must be a permutation"
+        assert cost[1] == cost[2] <= cost[0]
+        lens = np.diff(rowptr)
+        order = np.argsort(plan[:n])
+        assert np.all(np.diff(lens[order]) <= 0), "cells stay sorted by row length"
+        assert np.all(plan[n:] < (1 << lens.max())) and (copies == 2 or not plan[n:].any())
+
+
+def test_parameters_api():
+    from calcium_b200.parameters import SimulationParameters
+    sp = SimulationParameters("Fluttering", custom_params={"D_p": 0.01})
+    assert sp.params["lower"] == 1.4 and sp.params["D_p"] == 0.01 and len(sp.params) == 18
+    assert SimulationParameters("nope").sim_type == "Intercellular waves"
+    assert sp.validate()
+    with pytest.raises(ValueError):
+        SimulationParameters(custom_params={"beta": -1.0}).validate()
+    with pytest.raises(ValueError):
+        SimulationParameters(custom_params={"lower": 0.9, "upper": 0.5}).validate()
+    assert SimulationParameters.get_available_sim_types()[0] == "Single cell spikes"
+
+
+def test_parameters_roundtrip(tmp_path):
+    from calcium_b200.parameters import SimulationParameters
+    sp = SimulationParameters("Single cell spikes")
+    f = tmp_path / "a" / "p.json"
+    sp.save_to_file(str(f))
+    sp2 = SimulationParameters.load_from_file(str(f))
+    assert sp2.params == sp.params and sp2.sim_type == sp.sim_type
+
+
+def test_geometry_loader_reference_format(tmp_path):
+    from calcium_b200 import geometry as G
+    G.write_reference_format(str(tmp_path), sizes=("xsmall",))
+    ld = G.GeometryLoader(str(tmp_path))
+    assert ld.get_available_sizes() == ["xsmall"]
+    v, adj, lap = ld.load_geometry("xsmall")
+    g = G.get_geometry("xsmall")
+    assert len(v) == 200 and adj.shape == (200, 200) and np.array_equal(lap, g.laplacian)
+    with pytest.raises(ValueError, match="not available"):
+        ld.load_geometry("large")
+    # file-backed geometry yields the same CSR as the synthetic object it was written from
+    gf = ld.geometry("xsmall")
+    for a, b in zip(gf.csr, g.csr):
+        assert np.array_equal(a, b)
+    assert ld.get_geometry_info("xsmall")["n_cells"] == 200
+
+
+def test_host_draws_match_reference_sequence(golden_dir):
+    from calcium_b200.ensemble import draw_initial_state, draw_vplc, pack_params
+    from calcium_b200.parameters import SimulationParameters
+    z = np.load(os.path.join(golden_dir, "traj_xsmall_waves.npz"))
+    p = SimulationParameters("Intercellular waves").get_params_dict()
+    v = draw_vplc(p, 200, 0)
+    assert v.shape == (200, 1)
+    r0, init = draw_initial_state(p, 200, 0, v)
+    assert np.array_equal(v.flatten(), z["vplc"]) and np.array_equal(r0, z["r0"])
+    assert len(init) == max(1, int(p["frac"] * 200))
+    prm = pack_params(p)
+    assert prm.shape == (16,) and prm[13] == p["D_c_ratio"] * p["D_p"] and prm[15] == 0.2
+
+
+def test_pouch_validation_without_gpu():
+    from calcium_b200.pouch import Pouch
+    with pytest.raises(ValueError, match="Missing: D_p"):
+        Pouch(params={k: 1.0 for k in Pouch.REQUIRED_PARAMS if k != "D_p"}, size="xsmall")
+    with pytest.raises(ValueError, match="Unexpected: bogus"):
+        Pouch(params={**{k: 1.0 for k in Pouch.REQUIRED_PARAMS}, "bogus": 1}, size="xsmall")
+    p = Pouch(size="xsmall", sim_number=3)
+    assert p.n_cells == 200 and p.T == 18000 and p.dt == 0.2 and p.V_PLC.shape == (200, 1)
+    assert p.disc_dynamics.shape == (200, 4, 18000)
+    assert p.D_c == p.D_c_ratio * p.D_p                      # reference defect D1 fixed
+    assert p.get_active_cells(100) == []                     # all-zero state before simulate()
+    assert p.adj_matrix.shape == (200, 200) and p.laplacian_sparse.nnz == len(p._geometry.csr[1])
+    with pytest.raises(ValueError, match="time_step must be provided"):
+        p.get_cell_masks(active_only=True)
+    with pytest.raises(ValueError, match="Time step must be between"):
+        p.generate_image(18000)
+    bad = Pouch(params={**p.param_dict, "beta": 0.0}, size="xsmall")
+    with pytest.raises(ValueError, match="must be positive"):
+        bad.simulate()
+    bad = Pouch(params={**p.param_dict, "frac": 1.5}, size="xsmall")
+    with pytest.raises(ValueError, match="fraction of initiator"):
+        bad.simulate()
+
+
+def test_lpt_partition():
+    from calcium_b200.parallel import lpt_partition, shard_indices
+    parts = shard_indices([1500] * 1184, 18000, 8)
+    assert [len(p) for p in parts] == [148] * 8
+    assert sorted(i for p in parts for i in p) == list(range(1184))
+    sizes = [200, 500, 1500, 3255] * 64
+    parts = shard_indices(sizes, 18000, 8)
+    loads = [sum(sizes[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= 3255 and sorted(i for p in parts for i in p) == list(range(256))
+    assert lpt_partition([], 4) == [[], [], [], []]
+    assert lpt_partition([5.0], 1) == [[0]]
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "calcium_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "/root/reference" not in src, f
+    code = "import sys; import calcium_b200, calcium_b200.ensemble, calcium_b200.pouch, calcium_b200.batch; " \
+           "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_io_writers(tmp_path):
+    import cv2
+    from calcium_b200 import io
+    rng = np.random.RandomState(1)
+    img = rng.randint(0, 256, (40, 56, 2)).astype(np.uint8)
+    path = io.save_gray_alpha_png(img, str(tmp_path / "x" / "a.png"))
+    back = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert back.dtype == np.uint16 and back.shape == (40, 56, 4)
+    assert np.array_equal(back[:, :, 0], img[:, :, 0].astype(np.uint16) * 4)      # 8 -> 10 bit
+    assert np.array_equal(back[:, :, 3], img[:, :, 1].astype(np.uint16) * 257)
+    m = rng.randint(0, 900, (40, 56)).astype(np.uint16)
+    mp = io.save_instance_mask(m, str(tmp_path / "m.npz"))
+    assert np.array_equal(np.load(mp)["mask"], m)
+    cp = io.save_csv_mapping([("a.png", "a.npz")], str(tmp_path), "train")
+    assert open(cp).read().splitlines() == ["ImageId,MaskId", "a.png,a.npz"]
+
+
+def test_create_instance_mask_helper(oracle):
+    from calcium_b200.masks import create_instance_mask_from_cells
+    rng = np.random.RandomState(0)
+    for _ in range(25):
+        m = rng.randint(0, 40, (30, 30)).astype(np.int32)
+        act = sorted(rng.choice(40, rng.randint(0, 15), replace=False).tolist())
+        assert np.array_equal(create_instance_mask_from_cells(m, act), oracle.instance_mask_oracle(m, act))
+    assert np.array_equal(create_instance_mask_from_cells(m), m.astype(np.uint16))
