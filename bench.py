@@ -49,7 +49,7 @@ def workload_config(n_gpus: int, pouches_per_gpu: int) -> dict:
 # CPU arm / cpu_baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------------
 
-def cpu_port_throughput(n_pouches: int, threads: int, first_seed: int = 0) -> dict:
+def cpu_port_throughput(n_pouches: int, threads: int, first_seed: int = 0, min_seconds: float = 10.0) -> dict:
     """The oracle's C restatement of the reference path (integrate + rasterise every sampled frame),
     one pouch per host thread.  Returns cell-timesteps/s over the sample."""
     from concurrent.futures import ThreadPoolExecutor
@@ -70,9 +70,15 @@ def cpu_port_throughput(n_pouches: int, threads: int, first_seed: int = 0) -> di
 
     job(specs[0])                                     # warm (page-in, lib load)
     t0 = time.perf_counter()
+    rounds = 0
     with ThreadPoolExecutor(max_workers=threads) as ex:
-        list(ex.map(job, specs))
+        while True:                                   # bounded sample: whole rounds until >= min_seconds
+            list(ex.map(job, specs))
+            rounds += 1
+            if time.perf_counter() - t0 >= min_seconds or rounds >= 64:
+                break
     dt = time.perf_counter() - t0
+    n_pouches *= rounds
     work = n_pouches * g.n_cells * (T_STEPS - 1)
     return {"value": work / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_pouches} medium pouches (full T, 90 frames rasterised) on {threads} host threads, "

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     // thread has arrived for step t, which each does after its own gather of step t-1 -- the last
     // reader of that buffer.
     __shared__ uint64_t step_bar;
-    if (tid == 0) mbar_init(&step_bar, THREADS);
+    if (tid == 0) mbar_init(&step_bar, THREADS / 32);   // one arrival per warp
     __syncthreads();
     if (cap_t == 0) capture();
     R J_ch[CPT], J_S[CPT], J_PLC[CPT];
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             r[k] = rn;      // r now holds r(t+1); r(t) was captured above if requested
         }
     }
-    mbar_arrive(&step_bar);     // state(0) was published before the __syncthreads above
+    if ((tid & 31) == 0) mbar_arrive(&step_bar);   // state(0) was published before the __syncthreads above
     unsigned parity = 0;
 
     for (int t = 0; t < T - 1; ++t) {
@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
                 if (UNIT) nxt[COPIES * np + slot] = S::make2(S::mul(dcoef[k], cn), S::mul(dcoef[k], pn));
             }
         }
-        mbar_arrive(&step_bar);
+        // one arrival per warp: __syncwarp orders the other lanes' stores before lane 0's release
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&step_bar);
         // ---- own-state work for the next step, overlapping the other warps' gathers --------------
 #pragma unroll
         for (int k = 0; k < CPT; ++k)

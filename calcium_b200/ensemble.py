@@ -122,6 +122,29 @@ class _DeviceGeometry:
 
 
 PLAN_ITERS = int(os.environ.get("CALCIUM_B200_PLAN_ITERS", "300000"))
+_PLANS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "plans")
+
+
+def plan_copies(n: int, unit: bool, precision: int) -> int:
+    lay = np.zeros(4, dtype=np.int64)
+    _lib.check(_lib.load().cab200_sim_layout(n, 1 if unit else 0, precision, _lib.as_i64p(lay)),
+               "cab200_sim_layout")
+    return int(lay[2])
+
+
+def plan_path(geo: Geometry, copies: int, tracked: bool) -> str:
+    """Plans are keyed by the CSR structure and the layout they were made for.  ``tracked`` plans
+    (long offline annealing, scripts/make_plans.py) ship with the package under ``plans/``; others
+    are computed on first use and cached next to the synthetic geometry cache."""
+    rowptr, col, _ = geo.csr
+    h = hashlib.sha1()
+    h.update(rowptr.tobytes()); h.update(col.tobytes())
+    h.update(f"copies={copies}:v2".encode())
+    name = f"plan_{h.hexdigest()[:16]}.npy"
+    if tracked:
+        return os.path.join(_PLANS_DIR, name)
+    from .geometry import _synthetic_cache_path
+    return os.path.join(os.path.dirname(_synthetic_cache_path("x")), name)
 
 
 def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = None) -> np.ndarray:
@@ -129,34 +152,30 @@ def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = 
     lib = _lib.load()
     rowptr, col, _ = geo.csr
     n = geo.n_cells
-    iters = PLAN_ITERS if iters is None else iters
-    lay = np.zeros(4, dtype=np.int64)
-    _lib.check(lib.cab200_sim_layout(n, 1 if unit else 0, precision, _lib.as_i64p(lay)),
-               "cab200_sim_layout")
-    copies = int(lay[2])
-    h = hashlib.sha1()
-    h.update(rowptr.tobytes()); h.update(col.tobytes())
-    h.update(f"{copies}:{iters}:v1".encode())
-    from .geometry import _synthetic_cache_path
-    path = os.path.join(os.path.dirname(_synthetic_cache_path("x")), f"plan_{h.hexdigest()[:16]}.npy")
-    if os.path.exists(path):
-        try:
-            plan = np.load(path)
-            if plan.shape == (2 * n,) and plan.dtype == np.uint16:
-                return plan
-        except Exception:  # noqa: BLE001 - a corrupt cache entry is just recomputed
-            pass
+    copies = plan_copies(n, unit, precision)
+    paths = [plan_path(geo, copies, True), plan_path(geo, copies, False)]
+    if iters is None:
+        for path in paths:
+            if os.path.exists(path):
+                try:
+                    plan = np.load(path)
+                    if plan.shape == (2 * n,) and plan.dtype == np.uint16:
+                        return plan
+                except Exception:  # noqa: BLE001 - a corrupt cache entry is just recomputed
+                    pass
     plan = np.zeros(2 * n, dtype=np.uint16)
-    _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, iters, 1, 0,
+    _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies,
+                                     PLAN_ITERS if iters is None else iters, 1, 0,
                                      plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None),
                "cab200_plan_slots")
-    try:
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        tmp = path + f".{os.getpid()}.tmp.npy"
-        np.save(tmp, plan)
-        os.replace(tmp, path)
-    except OSError:
-        pass
+    if iters is None:
+        try:
+            os.makedirs(os.path.dirname(paths[1]), exist_ok=True)
+            tmp = paths[1] + f".{os.getpid()}.tmp.npy"
+            np.save(tmp, plan)
+            os.replace(tmp, paths[1])
+        except OSError:
+            pass
     return plan
 
 
