@@ -86,6 +86,22 @@ def cpu_port_throughput(n_pouches: int, threads: int, first_seed: int = 0, min_s
             "seconds": dt}
 
 
+def cpu_reference_style_throughput() -> dict:
+    """One medium pouch, full T, on ONE core, executed the way the reference executes it (dense
+    (n,4,T) history with time as the fastest axis, two scipy CSR products per step, numba fastmath
+    step function): oracle/reference_style.py.  Context for the C port's number."""
+    from oracle import reference_style as RS
+    from calcium_b200.ensemble import make_specs
+    s = make_specs(1, size=SIZE, first_seed=2)[0]          # an "Intercellular waves" pouch
+    RS.simulate_reference_style(s.geometry.csr, s.params, s.r0, s.vplc, 300)      # JIT warm-up
+    t0 = time.perf_counter()
+    RS.simulate_reference_style(s.geometry.csr, s.params, s.r0, s.vplc, T_STEPS)
+    dt = time.perf_counter() - t0
+    return {"value": s.geometry.n_cells * (T_STEPS - 1) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"1 medium pouch, full T, simulate() only, reference execution style "
+                      f"(numba={'yes' if RS.HAVE_NUMBA else 'no'}, scipy CSR, strided (n,4,T) history), {dt:.1f} s"}
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -103,6 +119,7 @@ def run_reference_arm(args) -> None:
             "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
+            "cpu_baseline_reference_style": cpu_reference_style_throughput(),
             "note": "the reference is pure Python (numpy/scipy/numba) and cannot travel to the GPU box; this arm times "
                     "the oracle's C port of the same algorithm on all host cores (kind=port)"}
     print(json.dumps(line), flush=True)
@@ -300,6 +317,7 @@ def run_gpu(args) -> None:
             "k1_ms": k1_ms, "k2_ms": k2_ms,
             "roofline": roofline, "roofline_smem": roofline_smem, "roofline_k2": roofline_k2,
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+            "cpu_baseline_reference_style": (cpu_reference_style_throughput() if cpu else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"],
                     "d2h_bytes_per_step": moved["d2h_bytes"], "ms_per_step": e2e_ms.item(), "steps": e2e_steps,
                     "path": "Ensemble.run_to_host: pinned host inputs -> K1 -> K2 -> frames + images + instance "

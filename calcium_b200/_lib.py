@@ -23,7 +23,7 @@ ST_BADGEOM = 2
 #: every symbol include/cab200.h declares (tests check the library exports all of them)
 EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
            "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_sim_layout",
-           "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask",
+           "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
            "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_selftest_division"]
 
 
@@ -73,6 +73,8 @@ def load() -> ctypes.CDLL:
         c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cab200_cells_mask.restype = c_int
     lib.cab200_cells_mask.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.cab200_paint_label_map.restype = c_int
+    lib.cab200_paint_label_map.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.cab200_peak_fp64.restype = c_int
     lib.cab200_peak_fp64.argtypes = [c_int, f64p, c_void_p]
     lib.cab200_peak_hbm_write.restype = c_int

@@ -9,6 +9,7 @@
 // 4 bytes written per pixel (image 2 + instance 2), +4 when the int32 active mask is requested;
 // the label maps (4 bytes read per pixel) stay L2 resident per geometry.
 #include <algorithm>
+#include <climits>
 #include <vector>
 
 #include "common.cuh"
@@ -259,6 +260,107 @@ __global__ void __launch_bounds__(128) cells_mask_kernel(int n_cells, const int3
     }
 }
 
+// ---- K0b: paint-order label map with OpenCV's fillPoly rule -------------------------------------
+// generate_image paints every cell with cv2.fillPoly in cell order (core/pouch.py:441-453); which
+// cell owns a pixel in the end is "the highest id whose fillPoly touches it".  For one polygon with
+// integer vertices (shift 0, 8-connected, not anti-aliased) OpenCV's fillPoly is
+//   (1) every edge drawn with cv::LineIterator, endpoints ordered left to right (CollectPolyEdges),
+//   (2) scanline fill (FillEdgeCollection): an edge is active on rows y0 <= y < y1, its x advances
+//       by dx = trunc(((x1 - x0) << 16) / (y1 - y0)) per row in 16.16 fixed point, and between
+//       consecutive pairs of x-sorted active edges the pixels ceil(x_left) .. floor(x_right) are set.
+// Restated here; tests compare it with the real cv2.fillPoly on every geometry / output size used
+// and on random concave polygons.
+__device__ __forceinline__ void label_max(uint32_t *label32, int W, int x, int y, uint32_t id)
+{
+    const size_t px = (size_t)y * W + x;
+    uint32_t *word = label32 + (px >> 1);
+    const uint32_t sh = (px & 1) * 16;
+    uint32_t old = *word;
+    while (((old >> sh) & 0xffffu) < id) {
+        const uint32_t want = (old & ~(0xffffu << sh)) | (id << sh);
+        const uint32_t prev = atomicCAS(word, old, want);
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
+__global__ void __launch_bounds__(128) paint_label_kernel(int n_cells, const int32_t *poly_off,
+                                                          const int32_t *pts, int H, int W,
+                                                          uint32_t *label32)
+{
+    constexpr int MAXV = 64;
+    __shared__ int vx[MAXV], vy[MAXV];
+    __shared__ int s_ymin, s_ymax;
+    const int cell = blockIdx.x;
+    const int b = poly_off[cell], nv = min(poly_off[cell + 1] - b, MAXV);
+    if (nv <= 0) return;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) { vx[i] = pts[2 * (b + i)]; vy[i] = pts[2 * (b + i) + 1]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int lo = INT_MAX, hi = INT_MIN;
+        for (int i = 0; i < nv; ++i) { lo = min(lo, vy[i]); hi = max(hi, vy[i]); }
+        s_ymin = lo; s_ymax = hi;
+    }
+    __syncthreads();
+    const uint32_t id = (uint32_t)cell + 1u;
+    // (1) outlines: one thread per edge, cv::LineIterator (8-connected, left to right)
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        int x0 = vx[(i + nv - 1) % nv], y0 = vy[(i + nv - 1) % nv], x1 = vx[i], y1 = vy[i];
+        int dx = x1 - x0, dy = y1 - y0;
+        if (dx < 0) { x0 = x1; y0 = y1; dx = -dx; dy = -dy; }
+        const int sy = dy >= 0 ? 1 : -1;
+        dy = abs(dy);
+        int x = x0, y = y0;
+        if (dy > dx) {
+            int err = dy - (dx + dx);
+            const int plus = dy + dy, minus = -(dx + dx);
+            for (int c = 0; c <= dy; ++c) {
+                if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) label_max(label32, W, x, y, id);
+                const bool m = err < 0;
+                err += minus + (m ? plus : 0);
+                y += sy;
+                if (m) x += 1;
+            }
+        } else {
+            int err = dx - (dy + dy);
+            const int plus = dx + dx, minus = -(dy + dy);
+            for (int c = 0; c <= dx; ++c) {
+                if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) label_max(label32, W, x, y, id);
+                const bool m = err < 0;
+                err += minus + (m ? plus : 0);
+                x += 1;
+                if (m) y += sy;
+            }
+        }
+    }
+    // (2) interior: one thread per scanline
+    const int ymin = max(s_ymin, 0), ymax = min(s_ymax, H);
+    for (int y = ymin + threadIdx.x; y < ymax; y += blockDim.x) {
+        long long xs[MAXV];
+        int cnt = 0;
+        for (int i = 0; i < nv; ++i) {
+            int xa = vx[(i + nv - 1) % nv], ya = vy[(i + nv - 1) % nv], xb = vx[i], yb = vy[i];
+            if (ya == yb) continue;
+            const long long num = ((long long)(xb - xa)) << 16;
+            const long long slope = num / (yb - ya);                 // C++ division truncates toward zero
+            if (ya > yb) { const int t = ya; ya = yb; yb = t; xa = xb; }
+            if (y < ya || y >= yb) continue;
+            const long long xv = ((long long)xa << 16) + (long long)(y - ya) * slope;
+            int j = cnt++;
+            while (j > 0 && xs[j - 1] > xv) { xs[j] = xs[j - 1]; --j; }   // insertion sort by x
+            xs[j] = xv;
+        }
+        for (int k = 0; k + 1 < cnt; k += 2) {
+            long long a = (xs[k] + 65535) >> 16, bq = xs[k + 1] >> 16;
+            if (a < W && bq >= 0) {
+                if (a < 0) a = 0;
+                if (bq >= W) bq = W - 1;
+                for (long long x = a; x <= bq; ++x) label_max(label32, W, (int)x, y, id);
+            }
+        }
+    }
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace cab200
@@ -324,6 +426,22 @@ extern "C" int cab200_raster_batch(
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (pf * tiles > 0x7fffffffLL) { set_error("cab200_raster_batch: too many frames"); return CAB200_ESIZE; }
     raster_kernel<<<(unsigned)(pf * tiles), RT, smem, stream>>>(a);
+    CAB_CUDA(cudaGetLastError());
+    return CAB200_OK;
+}
+
+extern "C" int cab200_paint_label_map(int n_cells, const int32_t *poly_off, const int32_t *pts, int H,
+                                      int W, uint16_t *label_out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_cells <= 0 || n_cells > 65534 || H <= 0 || W <= 0 || !poly_off || !pts || !label_out) {
+        set_error("cab200_paint_label_map: bad argument");
+        return CAB200_EINVAL;
+    }
+    if (((size_t)H * W) & 1) { set_error("cab200_paint_label_map: H*W must be even"); return CAB200_EINVAL; }
+    CAB_CUDA(cudaMemsetAsync(label_out, 0, sizeof(uint16_t) * (size_t)H * W, stream));
+    paint_label_kernel<<<n_cells, 128, 0, stream>>>(n_cells, poly_off, pts, H, W,
+                                                    reinterpret_cast<uint32_t *>(label_out));
     CAB_CUDA(cudaGetLastError());
     return CAB200_OK;
 }

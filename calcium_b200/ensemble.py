@@ -199,15 +199,14 @@ def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
 
 def build_label_maps(geo: Geometry, output_size: Tuple[int, int], device: torch.device
                      ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """The two static uint16 label maps of one (geometry, output size), on ``device``.
+    """The two static uint16 label maps of one (geometry, output size), both built on ``device``.
 
-    ``label_mask`` = ``Pouch.cells_mask`` (reference ``core/pouch.py:260-287``), computed on the GPU
-    by K0 (``cab200_cells_mask``, scikit-image's polygon rule).
+    ``label_mask`` = ``Pouch.cells_mask`` (reference ``core/pouch.py:260-287``): K0,
+    ``cab200_cells_mask`` (scikit-image's polygon rule).
     ``label_img`` = which cell's ``cv2.fillPoly`` painted each pixel last in ``generate_image``'s
-    loop (reference ``core/pouch.py:441-453``); obtained once with the same OpenCV call the
-    reference makes per cell and frame, on an int32 canvas with the cell id as colour.
+    loop (reference ``core/pouch.py:441-453``): K0b, ``cab200_paint_label_map`` (OpenCV's fillPoly
+    rule: outlines + scanline interior).  Rendering a frame is then a pure gather (K2).
     """
-    import cv2
     dg = device_geometry(geo, device)
     key = (int(output_size[0]), int(output_size[1]))
     if key in dg.label_maps:
@@ -215,20 +214,18 @@ def build_label_maps(geo: Geometry, output_size: Tuple[int, int], device: torch.
     width, height = key
     if geo.n_cells > 65534:
         raise ValueError("label maps are uint16: at most 65534 cells")
+    if (height * width) % 2:
+        raise ValueError("output_size with an odd pixel count is not supported")
     offs, pts = geo.scaled_polygons(key)
-    canvas = np.zeros((height, width), dtype=np.int32)
-    for cell in range(geo.n_cells):
-        poly = pts[offs[cell]:offs[cell + 1]].reshape((-1, 1, 2))
-        cv2.fillPoly(canvas, [poly], color=int(cell + 1))
-    label_img = torch.from_numpy(canvas.astype(np.uint16).view(np.int16)).to(device)
-
     lib = _lib.load()
     d_offs = torch.from_numpy(offs).to(device)
     d_pts = torch.from_numpy(pts).to(device)
-    if (height * width) % 2:
-        raise ValueError("output_size with an odd pixel count is not supported")
+    label_img = torch.empty((height, width), dtype=torch.int16, device=device)
     label_mask = torch.empty((height, width), dtype=torch.int16, device=device)
     with torch.cuda.device(device):
+        _lib.check(lib.cab200_paint_label_map(geo.n_cells, d_offs.data_ptr(), d_pts.data_ptr(), height,
+                                              width, label_img.data_ptr(), _stream_ptr(device)),
+                   "cab200_paint_label_map")
         _lib.check(lib.cab200_cells_mask(geo.n_cells, d_offs.data_ptr(), d_pts.data_ptr(), height,
                                          width, label_mask.data_ptr(), _stream_ptr(device)),
                    "cab200_cells_mask")

@@ -258,6 +258,39 @@ def test_label_maps_bit_exact(env, size, out):
     assert np.array_equal(E._u16_numpy(limg), O.paint_label_map_cv2(g.vertices, out).astype(np.uint16))
 
 
+def test_paint_label_kernel_matches_cv2_on_random_polygons(env):
+    """K0b against the real cv2.fillPoly (paint order, later wins) on overlapping random polygons,
+    convex and concave, including degenerate ones (repeated / collinear vertices, zero height)."""
+    import cv2
+    torch, L, lib = env["torch"], env["L"], env["lib"]
+    rng = np.random.RandomState(3)
+    H, W = 200, 260
+    polys = []
+    for i in range(500):
+        k = rng.randint(3, 10)
+        cx, cy = rng.randint(0, W), rng.randint(0, H)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k)); rad = rng.uniform(1, 30, k)
+        p = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], 1)
+        p = np.clip(p, 0, [W - 1, H - 1]).astype(np.int32)
+        if i % 37 == 0:
+            p[1] = p[0]                      # repeated vertex
+        if i % 41 == 0:
+            p[:, 1] = p[0, 1]                # all on one row
+        polys.append(p)
+    offs = np.cumsum([0] + [len(p) for p in polys]).astype(np.int32)
+    pts = np.concatenate(polys).astype(np.int32)
+    want = np.zeros((H, W), dtype=np.int32)
+    for i, p in enumerate(polys):
+        cv2.fillPoly(want, [p.reshape(-1, 1, 2)], color=int(i + 1))
+    d_offs, d_pts = torch.from_numpy(offs).to(env["dev"]), torch.from_numpy(pts).to(env["dev"])
+    out = torch.empty((H, W), dtype=torch.int16, device=env["dev"])
+    L.check(lib.cab200_paint_label_map(len(polys), d_offs.data_ptr(), d_pts.data_ptr(), H, W, out.data_ptr(), None),
+            "cab200_paint_label_map")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint16)
+    assert np.array_equal(got, want.astype(np.uint16)), int((got != want).sum())
+
+
 @pytest.mark.parametrize("size,out,quirk,thr", [("xsmall", (512, 512), True, 0.1), ("medium", (512, 512), True, 0.1),
                                                 ("small", (160, 120), False, 0.1), ("medium", (640, 480), True, 0.35),
                                                 ("xsmall", (250, 130), True, 0.1)])
@@ -411,6 +444,31 @@ def test_full_size_medium_wave_properties(env):
     assert np.array_equal(oi, res["image"][0, 60].cpu().numpy())
     assert np.array_equal(oin, res["instance"][0, 60].cpu().numpy().view(np.uint16))
     assert np.array_equal(oa, res["active"][0, 60].cpu().numpy())
+
+
+def test_end_to_end_host_path_matches_device_results(env):
+    """Ensemble.run_to_host (pinned host in, pinned host out, chunked, copy stream) delivers exactly
+    the bytes rasterize() produces, ragged tail chunk included."""
+    E = env["E"]
+    specs = E.make_specs(7, size="xsmall", first_seed=200)
+    ens = E.Ensemble(specs, frame_steps=[0, 4000, 9000, 17999], device=env["dev"], output_size=(256, 192))
+    got = {}
+
+    def consumer(lo, hi, arrays):
+        for i in range(lo, hi):
+            got[i] = {k: v[i - lo].copy() for k, v in arrays.items()}
+
+    moved = ens.run_to_host(chunk_pouches=3, consumer=consumer)
+    ref = ens.rasterize(image=True, instance=True)
+    ens.synchronize()
+    assert sorted(got) == list(range(7))
+    for i in range(7):
+        assert np.array_equal(got[i]["image"], ref["image"][i].cpu().numpy())
+        assert np.array_equal(got[i]["instance"], ref["instance"][i].cpu().numpy())
+        assert np.array_equal(got[i]["n_active"], ref["n_active"][i].cpu().numpy())
+    assert np.array_equal(ens._h_frames.numpy(), ens.frames.cpu().numpy())
+    assert moved["d2h_bytes"] == ens.frames.numel() * 8 + 7 * 4 * 256 * 192 * 4 + 7 * 4 * 4
+    assert moved["h2d_bytes"] == (7 * 16 + 4 * 7 * 200) * 8
 
 
 # ---- batch entry points ------------------------------------------------------------------------------
