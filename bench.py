@@ -279,7 +279,7 @@ def run_gpu(args) -> None:
         plan = slot_plan(ens.geometries[0], True, 64).copy()
         lay = np.zeros(4, dtype=np.int64)
         lib.cab200_sim_layout(n_cells, 1, 64, _lib.as_i64p(lay))
-        lib.cab200_plan_slots(n_cells, _lib.as_i32p(rowptr), _lib.as_i32p(col), int(lay[2]), 0, 1, 1,
+        lib.cab200_plan_slots(n_cells, _lib.as_i32p(rowptr), _lib.as_i32p(col), int(lay[2]), int(lay[1]), 0, 1, 1,
                               plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(plan_cost))
         sm_clock_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
         wave_ld = int(plan_cost[2])

@@ -59,7 +59,7 @@ def load() -> ctypes.CDLL:
         c_int, c_int, i32p,                                    # T, n_frames, frame_steps (host)
         c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
     lib.cab200_plan_slots.restype = c_int
-    lib.cab200_plan_slots.argtypes = [c_int, i32p, i32p, c_int, ctypes.c_longlong,
+    lib.cab200_plan_slots.argtypes = [c_int, i32p, i32p, c_int, c_int, ctypes.c_longlong,
                                       ctypes.c_ulonglong, c_int, POINTER(ctypes.c_uint16), i64p]
     lib.cab200_sim_layout.restype = c_int
     lib.cab200_sim_layout.argtypes = [c_int, c_int, c_int, i64p]

@@ -34,7 +34,7 @@ int sim_copies(int n, bool unit, size_t elem2, int nslot)
 {
     if (!unit) return 1;
     const int np = (n + 31) & ~31;
-    return integrate_smem_bytes(np, nslot, elem2, 2) <= 200 * 1024 ? 2 : 1;
+    return integrate_smem_bytes(np, nslot, elem2, 2) <= 227 * 1024 ? 2 : 1;
 }
 
 static std::mutex g_plan_mu;

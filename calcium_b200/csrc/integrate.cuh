@@ -49,13 +49,15 @@ struct SimArgs {
 };
 
 // Shared-memory bytes K1 needs for a pouch padded to `np` slots.
+static inline size_t integrate_buf_stride(int np, int nslot, size_t elem2, int copies)
+{
+    const size_t fixed = ((((size_t)copies + 1) * nslot + 1) * elem2 + 127) & ~(size_t)127;
+    if (2 * fixed + 2 * (size_t)nslot + 64 <= 227 * 1024) return fixed;          // == BufGeom::STRIDE
+    return ((((size_t)copies + 1) * np + 1) * elem2 + 127) & ~(size_t)127;        // runtime stride
+}
 static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2, int copies)
 {
-    const size_t ent = ((size_t)copies + 1) * (size_t)np + 1;
-    size_t bytes = 2 * ent * elem2;          // the two step-parity buffers
-    bytes = (bytes + 15) & ~(size_t)15;
-    bytes += 2 * (size_t)nslot;              // orig_of[NSLOT] u16
-    return bytes;
+    return 2 * integrate_buf_stride(np, nslot, elem2, copies) + 2 * (size_t)nslot + 64;   // + orig_of[NSLOT]
 }
 
 // One Euler step for one cell, reference source order (core/pouch.py:77-102), every operation
@@ -118,6 +120,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
     } while (!ok);
 }
 
+// 16-byte (two-real) shared-memory accesses at [32-bit shared address + compile-time immediate]: the
+// immediate carries the step-parity buffer offset, so a gather is exactly one LDS per entry.
+template <typename R> struct Smem2;
+template <> struct Smem2<double> {
+    template <int IMM> static __device__ __forceinline__ double2 ld(uint32_t addr)
+    {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(IMM) : "memory");
+        return v;
+    }
+    template <int IMM> static __device__ __forceinline__ void st(uint32_t addr, double x, double y)
+    {
+        asm volatile("st.shared.v2.f64 [%0+%3], {%1, %2};" ::"r"(addr), "d"(x), "d"(y), "n"(IMM) : "memory");
+    }
+};
+template <> struct Smem2<float> {
+    template <int IMM> static __device__ __forceinline__ float2 ld(uint32_t addr)
+    {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(IMM) : "memory");
+        return v;
+    }
+    template <int IMM> static __device__ __forceinline__ void st(uint32_t addr, float x, float y)
+    {
+        asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(addr), "f"(x), "f"(y), "n"(IMM) : "memory");
+    }
+};
+
+// Entries per region and bytes between the two step-parity buffers.  When both buffers fit with
+// NSLOT-sized regions the stride is a compile-time constant (CSTRIDE): parity becomes an immediate
+// and slots beyond n own real (unused) entries, so nothing in the step loop is predicated on them.
+template <typename R, int NSLOT, int COPIES>
+struct BufGeom {
+    static constexpr size_t ESZ = 2 * sizeof(R);
+    static constexpr size_t STRIDE = ((((size_t)(COPIES + 1) * NSLOT + 1) * ESZ) + 127) & ~(size_t)127;
+    static constexpr bool CSTRIDE = 2 * STRIDE + 2 * (size_t)NSLOT + 64 <= 227 * 1024;
+};
+
 // EP = number of packed entry-index pairs kept in registers per cell (row length <= 2*EP).
 // UNIT: every off-diagonal value is exactly 1.0 (verified in the prologue).  !UNIT: general weights,
 // read from global/L1 each step and multiplied per entry.
@@ -126,16 +166,21 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 {
     typedef Strict<R> S;
     typedef typename S::vec2 R2;
+    typedef Smem2<R> M;
     constexpr int NSLOT = THREADS * CPT;
     constexpr int EMAX = 2 * EP;
+    typedef BufGeom<R, NSLOT, COPIES> G;
+    constexpr bool CSTRIDE = G::CSTRIDE;
+    constexpr uint32_t ESZ = (uint32_t)G::ESZ;
+    constexpr int STRIDE_IMM = CSTRIDE ? (int)G::STRIDE : 0;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int n = a.n, np = a.np;
-    const int ent = (COPIES + 1) * np + 1;
-    R2 *buf0 = reinterpret_cast<R2 *>(smem_raw);
-    R2 *buf1 = buf0 + ent;
-    uint16_t *orig_of = reinterpret_cast<uint16_t *>(
-        smem_raw + ((2 * (size_t)ent * sizeof(R2) + 15) & ~(size_t)15));          // [NSLOT]
+    const int npr = CSTRIDE ? NSLOT : np;                 // entries per region
+    const uint32_t stride = CSTRIDE ? (uint32_t)G::STRIDE
+                                    : (uint32_t)(((((size_t)(COPIES + 1) * np + 1) * ESZ) + 127) & ~(size_t)127);
+    R2 *buf1 = reinterpret_cast<R2 *>(smem_raw + stride);
+    uint16_t *orig_of = reinterpret_cast<uint16_t *>(smem_raw + 2 * (size_t)stride);   // [NSLOT]
     // prologue scratch aliases buffer 1 (initialised after the scratch is dead)
     unsigned char *scr = reinterpret_cast<unsigned char *>(buf1);
     uint8_t *rlen = scr;                                                           // [n]
@@ -143,6 +188,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     uint16_t *copy_sel = slot_of + np;                                             // [n]
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int pouch = a.pouch_list[blockIdx.x];
     const int64_t coff = a.cell_off[pouch];
     int bad = 0;
@@ -182,7 +228,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     }
     __syncthreads();
 
-    // ---- prologue 3: parameters and private per-cell state -------------------------------------
+    // ---- prologue 3: parameters ------------------------------------------------------------------
     const double *prm = a.params + (size_t)pouch * CAB200_NPARAM;
     StepConsts<R> q;
     {
@@ -199,75 +245,92 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         q.rec_den = S::recip(S::mul(tau_max, q.k_tau_4));                      // :100
     }
 
-    const uint32_t ZERO_ENT = (uint32_t)((COPIES + 1) * np);
+    // ---- prologue 4: private per-cell state ------------------------------------------------------
+    // Slot of (warp w, group k, lane l) = (w*CPT + k)*32 + l: the CPT*32 cells a warp owns are
+    // consecutive in the length-sorted order, so ONE warp-uniform trip count W serves all of them.
+    // Rows are right-aligned in EMAX positions: positions [start, start+len) hold the row's entries
+    // in CSR order (start = EMAX-W rounded down to even), everything else points at the zero entry;
+    // the step loop enters a fully unrolled position sequence at `start` through one jump.
+    // ent[k][pos] is the 32-bit shared address of the entry inside buffer 0; buffer 1 is +stride.
+    const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t zero_addr = sb0 + (uint32_t)((COPIES + 1) * npr) * ESZ;
     R c[CPT], p[CPT], s[CPT], r[CPT], vplc[CPT], dcoef[CPT];
-    uint32_t nb[CPT][EP];
-    int wlen[CPT], rowbeg[CPT];
+    uint32_t ent[CPT][EMAX];
+    uint32_t own[CPT];              // shared address (buffer 0) of the cell's own value entry
+    int rowbeg[CPT], len[CPT];
     bool live[CPT];
+    int mylen = 0;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        const int slot = k * THREADS + tid;
+        const int slot = (warp * CPT + k) * 32 + lane;
         const int cell = (slot < n) ? (int)orig_of[slot] : 0xffff;
         live[k] = (cell != 0xffff);
-        rowbeg[k] = 0;
-        int len = 0;
+        own[k] = sb0 + (uint32_t)slot * ESZ;
+        rowbeg[k] = 0; len[k] = 0;
         c[k] = p[k] = s[k] = r[k] = vplc[k] = dcoef[k] = (R)0;
-#pragma unroll
-        for (int e = 0; e < EP; ++e) nb[k][e] = ZERO_ENT | (ZERO_ENT << 16);
         if (live[k]) {
-            len = rlen[cell];
-            const uint32_t sel = copy_sel[cell];
-            const int rb = a.rowptr[cell];
-            rowbeg[k] = rb;
-#pragma unroll
-            for (int e = 0; e < EMAX; ++e) {
-                if (e < len) {
-                    const int col = a.colidx[rb + e];
-                    uint32_t j = ZERO_ENT;
-                    if (col < 0 || col >= n) bad = 1;
-                    else {
-                        j = slot_of[col];
-                        if (COPIES == 2 && ((sel >> e) & 1u)) j = (uint32_t)np + (j ^ 4u);
-                    }
-                    if (UNIT) {
-                        const double w = a.vals[rb + e];
-                        if (col == cell) { dcoef[k] = (R)w; j = (uint32_t)(COPIES * np + slot); }
-                        else if (w != 1.0) bad = 1;
-                    }
-                    const uint32_t sh = (e & 1) * 16;
-                    nb[k][e >> 1] = (nb[k][e >> 1] & ~(0xffffu << sh)) | (j << sh);
-                }
-            }
+            len[k] = rlen[cell];
+            rowbeg[k] = a.rowptr[cell];
             c[k] = (R)a.c0[coff + cell];
             p[k] = (R)a.p0[coff + cell];
             r[k] = (R)a.r0[coff + cell];
             vplc[k] = (R)a.vplc[coff + cell];
-            s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                      // core/pouch.py:322
         }
-        wlen[k] = __reduce_max_sync(0xffffffffu, len);
+        s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                          // core/pouch.py:322
+        mylen = max(mylen, len[k]);
+    }
+    const int W = __reduce_max_sync(0xffffffffu, mylen);
+    const int start = (EMAX - W) & ~1;          // even: positions are processed in pairs
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int slot = (warp * CPT + k) * 32 + lane;
+        const int cell = live[k] ? (int)orig_of[slot] : 0;
+        const uint32_t sel = live[k] ? (uint32_t)copy_sel[cell] : 0u;
+#pragma unroll
+        for (int pos = 0; pos < EMAX; ++pos) {
+            const int e = pos - start;
+            uint32_t o = zero_addr;
+            if (live[k] && e >= 0 && e < len[k]) {
+                const int col = a.colidx[rowbeg[k] + e];
+                if (col < 0 || col >= n) bad = 1;
+                else {
+                    uint32_t j = slot_of[col];
+                    if (COPIES == 2 && ((sel >> e) & 1u)) j = (uint32_t)npr + (j ^ 4u);
+                    if (UNIT) {
+                        const double w = a.vals[rowbeg[k] + e];
+                        if (col == cell) { dcoef[k] = (R)w; j = (uint32_t)(COPIES * npr + slot); }
+                        else if (w != 1.0) bad = 1;
+                    }
+                    o = sb0 + j * ESZ;
+                }
+            }
+            ent[k][pos] = o;
+        }
     }
     if (bad) atomicOr(a.status_out + pouch, CAB200_ST_BADGEOM);
     __syncthreads();   // scratch (inside buffer 1) is dead from here on
-    for (int i = tid; i < ent; i += THREADS) buf1[i] = S::make2((R)0, (R)0);
-    for (int i = tid; i < ent; i += THREADS) buf0[i] = S::make2((R)0, (R)0);
+    for (uint32_t i = tid; i < 2 * stride / 16; i += THREADS)
+        reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        if (live[k]) {
-            const int slot = k * THREADS + tid;
-            buf0[slot] = S::make2(c[k], p[k]);
-            if (COPIES == 2) buf0[np + (slot ^ 4)] = S::make2(c[k], p[k]);
-            if (UNIT) buf0[COPIES * np + slot] = S::make2(S::mul(dcoef[k], c[k]), S::mul(dcoef[k], p[k]));
-        }
+
+    const uint32_t copyb_off = (uint32_t)npr * ESZ;                 // second value copy (multiple of 128 B)
+    const uint32_t diag_off = (uint32_t)(COPIES * npr) * ESZ;       // diagonal entries
+    // Publishes a cell's new (c, p): value entry, second copy in the bank group 4 away, diagonal
+    // term.  IMM selects the step-parity buffer at compile time (CSTRIDE) -- else roff does.
+#define CAB_PUBLISH(IMM, ROFF, K, CV, PV)                                                          \
+    if (CSTRIDE || live[K]) {                                                                     \
+        M::template st<IMM>(own[K] + (ROFF), (CV), (PV));                                         \
+        if (COPIES == 2) M::template st<IMM>(((own[K] + copyb_off) ^ (4u * ESZ)) + (ROFF), (CV), (PV)); \
+        if (UNIT) M::template st<IMM>(own[K] + diag_off + (ROFF), S::mul(dcoef[K], (CV)), S::mul(dcoef[K], (PV))); \
     }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { CAB_PUBLISH(0, 0u, k, c[k], p[k]) }
     __syncthreads();
 
     R *frames = reinterpret_cast<R *>(a.frames_out) + (size_t)coff * 4 * a.n_frames;
     int fi = 0;
     int cap_t = (a.n_frames > 0) ? a.frame_steps[0] : -1;
     const int T = a.T;
-    const R2 *cur = buf0;
-    R2 *nxt = buf1;
 
     // Writes the state at the current time (c, p, s, r of every owned cell) as frame fi.
     auto capture = [&]() {
@@ -275,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
             if (live[k]) {
-                const int cell = orig_of[k * THREADS + tid];
+                const int cell = orig_of[(warp * CPT + k) * 32 + lane];
                 R *f = frames + (size_t)fi * 4 * n + cell;
                 f[0] = c[k]; f[n] = p[k]; f[2 * (size_t)n] = s[k]; f[3 * (size_t)n] = r[k];
                 nonfinite |= !(isfinite(c[k]) && isfinite(p[k]) && isfinite(s[k]) && isfinite(r[k]));
@@ -290,11 +353,9 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     // divisions, ~75 % of the FP64 work) is computed one step ahead, *between* publishing the new
     // (c, p) and waiting for everybody else's: publish -> arrive -> local work -> wait -> gather ->
     // finish -> publish ...  The barrier is split (mbarrier arrive / try_wait), so a warp rarely
-    // blocks, warps drift apart, and the shared-memory-bound gathers of some warps overlap the
-    // FP64-bound local work of others instead of all warps hammering one pipe at a time.
-    // Buffer safety: a thread overwrites buffer (t+1)&1 only after passing wait(t), i.e. after every
-    // thread has arrived for step t, which each does after its own gather of step t-1 -- the last
-    // reader of that buffer.
+    // blocks.  Buffer safety: a thread overwrites buffer (t+1)&1 only after passing wait(t), i.e.
+    // after every warp has arrived for step t, which each does after its own gather of step t-1 --
+    // the last reader of that buffer.  Slots beyond n carry harmless zeros (no NaNs arise).
     __shared__ uint64_t step_bar;
     if (tid == 0) mbar_init(&step_bar, THREADS / 32);   // one arrival per warp
     __syncthreads();
@@ -302,73 +363,88 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     R J_ch[CPT], J_S[CPT], J_PLC[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        J_ch[k] = J_S[k] = J_PLC[k] = (R)0;
-        if (live[k]) {
-            R rn;
-            step_local<R>(q, c[k], p[k], s[k], r[k], vplc[k], J_ch[k], J_S[k], J_PLC[k], rn);
-            r[k] = rn;      // r now holds r(t+1); r(t) was captured above if requested
-        }
+        R rn;
+        step_local<R>(q, c[k], p[k], s[k], r[k], vplc[k], J_ch[k], J_S[k], J_PLC[k], rn);
+        r[k] = rn;      // r now holds r(t+1); r(t) was captured above if requested
     }
-    if ((tid & 31) == 0) mbar_arrive(&step_bar);   // state(0) was published before the __syncthreads above
+    if (lane == 0) mbar_arrive(&step_bar);   // state(0) was published before the __syncthreads above
     unsigned parity = 0;
 
-    for (int t = 0; t < T - 1; ++t) {
-        mbar_wait(&step_bar, parity);
-        parity ^= 1u;
-        // ---- Laplacian rows (csr_matvec order), all owned cells interleaved ---------------------
-        R sc[CPT], sp[CPT];
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) { sc[k] = (R)0; sp[k] = (R)0; }
-#pragma unroll
-        for (int e = 0; e < EMAX; ++e) {
-#pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                if (e < wlen[k]) {   // warp-uniform
-                    const uint32_t j = (nb[k][e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-                    const R2 v = cur[j];
-                    if (UNIT) {
-                        sc[k] = S::add(sc[k], v.x);
-                        sp[k] = S::add(sp[k], v.y);
-                    } else {
-                        const R w = (j == ZERO_ENT) ? (R)0 : (R)__ldg(a.vals + rowbeg[k] + e);
-                        sc[k] = S::add(sc[k], S::mul(w, v.x));
-                        sp[k] = S::add(sp[k], S::mul(w, v.y));
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            if (live[k]) {
-                const R lap_c = S::mul(q.D_c, sc[k]);                          // :346
-                const R lap_p = S::mul(q.D_p, sp[k]);                          // :347
-                R cn, pn;
-                step_finish<R>(q, c[k], p[k], lap_c, lap_p, J_ch[k], J_S[k], J_PLC[k], cn, pn);
-                c[k] = cn; p[k] = pn;
-                const int slot = k * THREADS + tid;
-                nxt[slot] = S::make2(cn, pn);
-                if (COPIES == 2) nxt[np + (slot ^ 4)] = S::make2(cn, pn);
-                if (UNIT) nxt[COPIES * np + slot] = S::make2(S::mul(dcoef[k], cn), S::mul(dcoef[k], pn));
-            }
-        }
-        // one arrival per warp: __syncwarp orders the other lanes' stores before lane 0's release
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&step_bar);
-        // ---- own-state work for the next step, overlapping the other warps' gathers --------------
-#pragma unroll
-        for (int k = 0; k < CPT; ++k)
-            if (live[k]) s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);         // :95
-        if (t + 1 == cap_t) capture();   // uniform across the CTA; r[] holds r(t+1) here
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            if (live[k]) {
-                R rn;
-                step_local<R>(q, c[k], p[k], s[k], r[k], vplc[k], J_ch[k], J_S[k], J_PLC[k], rn);
-                r[k] = rn;
-            }
-        }
-        const R2 *tmp = cur; cur = nxt; nxt = const_cast<R2 *>(tmp);
+// One pair of row positions for every owned cell: all loads of the pair first (2*CPT independent
+// 16-byte loads in flight per thread), then the additions in position order.
+#define CAB_GATHER_PAIR(IMM, ROFF, P0)                                                            \
+    {                                                                                             \
+        R2 va[CPT], vb[CPT];                                                                      \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
+            va[k] = M::template ld<IMM>(ent[k][(P0)] + (ROFF));                                   \
+            vb[k] = M::template ld<IMM>(ent[k][(P0) + 1] + (ROFF));                               \
+        }                                                                                         \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
+            if (UNIT) {                                                                           \
+                sc[k] = S::add(sc[k], va[k].x); sp[k] = S::add(sp[k], va[k].y);                   \
+                sc[k] = S::add(sc[k], vb[k].x); sp[k] = S::add(sp[k], vb[k].y);                   \
+            } else {                                                                              \
+                const int e0 = (P0) - start;                                                      \
+                const R w0 = (e0 >= 0 && e0 < len[k]) ? (R)__ldg(a.vals + rowbeg[k] + e0) : (R)0;  \
+                const R w1 = (e0 + 1 >= 0 && e0 + 1 < len[k]) ? (R)__ldg(a.vals + rowbeg[k] + e0 + 1) : (R)0; \
+                sc[k] = S::add(sc[k], S::mul(w0, va[k].x)); sp[k] = S::add(sp[k], S::mul(w0, va[k].y)); \
+                sc[k] = S::add(sc[k], S::mul(w1, vb[k].x)); sp[k] = S::add(sp[k], S::mul(w1, vb[k].y)); \
+            }                                                                                     \
+        }                                                                                         \
     }
+
+// One time step reading the buffer at +CUR and writing the one at +NXT (immediates when CSTRIDE).
+#define CAB_STEP(CUR_IMM, NXT_IMM, CUR_R, NXT_R)                                                  \
+    {                                                                                             \
+        mbar_wait(&step_bar, parity);                                                             \
+        parity ^= 1u;                                                                             \
+        R sc[CPT], sp[CPT];                                                                       \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k) { sc[k] = (R)0; sp[k] = (R)0; }           \
+        switch (start) { /* warp-uniform entry point; every later position follows */             \
+            case 0: CAB_GATHER_PAIR(CUR_IMM, CUR_R, 0)                                            \
+            case 2: CAB_GATHER_PAIR(CUR_IMM, CUR_R, 2)                                            \
+            case 4: CAB_GATHER_PAIR(CUR_IMM, CUR_R, 4)                                            \
+            case 6: CAB_GATHER_PAIR(CUR_IMM, CUR_R, 6)                                            \
+            case 8: CAB_GATHER_PAIR(CUR_IMM, CUR_R, 8)                                            \
+            case 10: if constexpr (EMAX > 10) CAB_GATHER_PAIR(CUR_IMM, CUR_R, 10 % EMAX)          \
+            case 12: if constexpr (EMAX > 12) CAB_GATHER_PAIR(CUR_IMM, CUR_R, 12 % EMAX)          \
+            case 14: if constexpr (EMAX > 14) CAB_GATHER_PAIR(CUR_IMM, CUR_R, 14 % EMAX)          \
+            default: break;                                                                       \
+        }                                                                                         \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
+            const R lap_c = S::mul(q.D_c, sc[k]);                              /* :346 */         \
+            const R lap_p = S::mul(q.D_p, sp[k]);                              /* :347 */         \
+            R cn, pn;                                                                             \
+            step_finish<R>(q, c[k], p[k], lap_c, lap_p, J_ch[k], J_S[k], J_PLC[k], cn, pn);       \
+            c[k] = cn; p[k] = pn;                                                                 \
+            CAB_PUBLISH(NXT_IMM, NXT_R, k, cn, pn)                                                \
+        }                                                                                         \
+        /* one arrival per warp: __syncwarp orders the other lanes' stores before lane 0's release */ \
+        __syncwarp();                                                                             \
+        if (lane == 0) mbar_arrive(&step_bar);                                                    \
+        /* own-state work for the next step, overlapping the other warps' gathers */              \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k)                                           \
+            s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                      /* :95 */          \
+        if (t + 1 == cap_t) capture();   /* uniform across the CTA; r[] holds r(t+1) here */       \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
+            R rn;                                                                                 \
+            step_local<R>(q, c[k], p[k], s[k], r[k], vplc[k], J_ch[k], J_S[k], J_PLC[k], rn);     \
+            r[k] = rn;                                                                            \
+        }                                                                                         \
+    }
+
+    const uint32_t rstride = CSTRIDE ? 0u : stride;     // runtime parity offset only without CSTRIDE
+    int t = 0;
+    for (; t + 1 < T - 1; t += 2) {
+        CAB_STEP(0, STRIDE_IMM, 0u, rstride)
+        ++t;
+        CAB_STEP(STRIDE_IMM, 0, rstride, 0u)
+        --t;
+    }
+    if (t < T - 1) { CAB_STEP(0, STRIDE_IMM, 0u, rstride) }
+#undef CAB_STEP
+#undef CAB_GATHER_PAIR
+#undef CAB_PUBLISH
 }
 
 }  // namespace cab200

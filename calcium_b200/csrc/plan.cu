@@ -32,7 +32,7 @@ void default_shape(int n, int *threads, int *cpt);   // integrate.cu
 namespace {
 
 struct Planner {
-    int n, np, copies;
+    int n, np, copies, cpt;
     const int32_t *rowptr, *col;
     std::vector<int> slot_of, cell_of;        // cell_of[slot] = cell or -1
     std::vector<std::vector<int>> refs;       // refs[c] = cells whose row contains c (incl. c)
@@ -99,7 +99,7 @@ struct Planner {
 
     int group_cost(int g) const
     {
-        const int wl = wlen[g / 4];
+        const int wl = wlen[(g * 8) / (32 * cpt)];
         int cost = 0;
         for (int e = 0; e < wl; ++e) cost += phase_cost(g, e, nullptr);
         return cost;
@@ -112,12 +112,17 @@ struct Planner {
         return c;
     }
 
+    // a warp owns 32*cpt consecutive slots and runs one trip count for all of them: its longest
+    // row, rounded up to even (the kernel walks row positions in pairs)
     void compute_wlen()
     {
-        wlen.assign(n_groups / 4, 0);
-        for (int w = 0; w < n_groups / 4; ++w)
-            for (int s = w * 32; s < w * 32 + 32; ++s)
+        const int per = 32 * cpt, nw = (np + per - 1) / per;
+        wlen.assign(nw, 0);
+        for (int w = 0; w < nw; ++w) {
+            for (int s = w * per; s < std::min(np, (w + 1) * per); ++s)
                 if (cell_of[s] >= 0) wlen[w] = std::max(wlen[w], rowptr[cell_of[s] + 1] - rowptr[cell_of[s]]);
+            wlen[w] = (wlen[w] + 1) & ~1;
+        }
     }
 };
 
@@ -140,10 +145,11 @@ using namespace cab200;
 
 // See include/cab200.h.
 extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *colidx, int copies,
-                                 long long iters, unsigned long long seed, int use_input,
-                                 uint16_t *plan_out, int64_t *cost_out)
+                                 int cells_per_thread, long long iters, unsigned long long seed,
+                                 int use_input, uint16_t *plan_out, int64_t *cost_out)
 {
-    if (n <= 0 || n > 32767 || !rowptr || !colidx || !plan_out || (copies != 1 && copies != 2)) {
+    if (n <= 0 || n > 32767 || !rowptr || !colidx || !plan_out || (copies != 1 && copies != 2) ||
+        cells_per_thread < 1 || cells_per_thread > 8) {
         set_error("cab200_plan_slots: bad argument");
         return CAB200_EINVAL;
     }
@@ -156,7 +162,7 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
             if (colidx[j] < 0 || colidx[j] >= n) { set_error("cab200_plan_slots: column out of range"); return CAB200_EINVAL; }
     }
     Planner P;
-    P.n = n; P.np = (n + 31) & ~31; P.copies = copies;
+    P.n = n; P.np = (n + 31) & ~31; P.copies = copies; P.cpt = cells_per_thread;
     P.rowptr = rowptr; P.col = colidx;
     P.n_groups = P.np / 8;
     P.slot_of.assign(n, 0);
@@ -227,7 +233,7 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
     for (int i = 0; i < n; ++i) { plan_out[i] = (uint16_t)P.slot_of[i]; plan_out[n + i] = 0; }
     if (copies == 2) {
         for (int g = 0; g < P.n_groups; ++g) {
-            const int wl = P.wlen[g / 4];
+            const int wl = P.wlen[(g * 8) / (32 * P.cpt)];
             for (int e = 0; e < wl; ++e) {
                 unsigned m = 0;
                 P.phase_cost(g, e, &m);
@@ -238,8 +244,8 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
     }
     if (cost_out) {
         cost_out[0] = cost0; cost_out[1] = cost; cost_out[2] = P.total_cost();
-        long long rows = 0;
-        for (int w : P.wlen) rows += w;
+        long long rows = 0;      // LDS.128 instructions per step: per warp, trip count x groups it owns
+        for (int g = 0; g < P.n_groups; g += 4) rows += P.wlen[(g * 8) / (32 * P.cpt)];
         cost_out[3] = rows;
     }
     return CAB200_OK;

@@ -38,7 +38,7 @@ struct RasterArgs {
 
 constexpr int RT = 256;   // threads per CTA
 
-__global__ void __launch_bounds__(RT, 4) raster_kernel(const RasterArgs a)
+__global__ void __launch_bounds__(RT, 6) raster_kernel(const RasterArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[RT / 32];
@@ -140,10 +140,11 @@ __global__ void __launch_bounds__(RT, 4) raster_kernel(const RasterArgs a)
     const int g0 = tile * gper, g1 = min(g0 + gper, groups);
     const bool vec_ok = ((a.npix & 7) == 0);
     if (vec_ok) {
-        for (int g = g0 + tid; g < g1; g += RT) {
+        // two 8-pixel groups per thread and iteration: all four label loads are issued before any
+        // look-up, which doubles the bytes in flight per thread (the kernel is latency/HBM bound)
+        auto emit = [&](int g, const uint4 li, const uint4 lm) {
             const size_t px = (size_t)g * 8;
             if (a.image_out) {
-                const uint4 li = __ldg(reinterpret_cast<const uint4 *>(limg + px));
                 const uint32_t w[4] = {li.x, li.y, li.z, li.w};
                 uint32_t o[4];
 #pragma unroll
@@ -157,7 +158,6 @@ __global__ void __launch_bounds__(RT, 4) raster_kernel(const RasterArgs a)
                        make_uint4(o[0], o[1], o[2], o[3]));
             }
             if (a.instance_out || a.active_out) {
-                const uint4 lm = __ldg(reinterpret_cast<const uint4 *>(lmsk + px));
                 const uint32_t w[4] = {lm.x, lm.y, lm.z, lm.w};
                 if (a.instance_out) {
                     uint32_t o[4];
@@ -180,6 +180,19 @@ __global__ void __launch_bounds__(RT, 4) raster_kernel(const RasterArgs a)
                     __stcs(dst + 1, make_int4(o[4], o[5], o[6], o[7]));
                 }
             }
+        };
+        const bool need_img = a.image_out != nullptr;
+        const bool need_msk = a.instance_out != nullptr || a.active_out != nullptr;
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int g = g0 + tid; g < g1; g += 2 * RT) {
+            const int gb = g + RT;
+            const bool two = gb < g1;
+            const uint4 li0 = need_img ? __ldg(reinterpret_cast<const uint4 *>(limg + (size_t)g * 8)) : z4;
+            const uint4 lm0 = need_msk ? __ldg(reinterpret_cast<const uint4 *>(lmsk + (size_t)g * 8)) : z4;
+            const uint4 li1 = (need_img && two) ? __ldg(reinterpret_cast<const uint4 *>(limg + (size_t)gb * 8)) : z4;
+            const uint4 lm1 = (need_msk && two) ? __ldg(reinterpret_cast<const uint4 *>(lmsk + (size_t)gb * 8)) : z4;
+            emit(g, li0, lm0);
+            if (two) emit(gb, li1, lm1);
         }
     } else {
         const int per = (a.npix + a.tiles - 1) / a.tiles;

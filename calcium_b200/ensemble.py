@@ -125,21 +125,22 @@ PLAN_ITERS = int(os.environ.get("CALCIUM_B200_PLAN_ITERS", "300000"))
 _PLANS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "plans")
 
 
-def plan_copies(n: int, unit: bool, precision: int) -> int:
+def plan_layout(n: int, unit: bool, precision: int) -> Tuple[int, int]:
+    """(value copies, cells per thread) the library will use for an n-cell geometry."""
     lay = np.zeros(4, dtype=np.int64)
     _lib.check(_lib.load().cab200_sim_layout(n, 1 if unit else 0, precision, _lib.as_i64p(lay)),
                "cab200_sim_layout")
-    return int(lay[2])
+    return int(lay[2]), int(lay[1])
 
 
-def plan_path(geo: Geometry, copies: int, tracked: bool) -> str:
+def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool) -> str:
     """Plans are keyed by the CSR structure and the layout they were made for.  ``tracked`` plans
     (long offline annealing, scripts/make_plans.py) ship with the package under ``plans/``; others
     are computed on first use and cached next to the synthetic geometry cache."""
     rowptr, col, _ = geo.csr
     h = hashlib.sha1()
     h.update(rowptr.tobytes()); h.update(col.tobytes())
-    h.update(f"copies={copies}:v2".encode())
+    h.update(f"copies={copies}:cpt={cpt}:v3".encode())
     name = f"plan_{h.hexdigest()[:16]}.npy"
     if tracked:
         return os.path.join(_PLANS_DIR, name)
@@ -152,8 +153,8 @@ def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = 
     lib = _lib.load()
     rowptr, col, _ = geo.csr
     n = geo.n_cells
-    copies = plan_copies(n, unit, precision)
-    paths = [plan_path(geo, copies, True), plan_path(geo, copies, False)]
+    copies, cpt = plan_layout(n, unit, precision)
+    paths = [plan_path(geo, copies, cpt, True), plan_path(geo, copies, cpt, False)]
     if iters is None:
         for path in paths:
             if os.path.exists(path):
@@ -164,7 +165,7 @@ def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = 
                 except Exception:  # noqa: BLE001 - a corrupt cache entry is just recomputed
                     pass
     plan = np.zeros(2 * n, dtype=np.uint16)
-    _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies,
+    _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, cpt,
                                      PLAN_ITERS if iters is None else iters, 1, 0,
                                      plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None),
                "cab200_plan_slots")

@@ -75,7 +75,7 @@ def test_layout_and_planner(lib):
     for copies in (1, 2):
         plan = np.zeros(2 * n, dtype=np.uint16)
         cost = np.zeros(4, dtype=np.int64)
-        rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 20000, 7, 0,
+        rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 2, 20000, 7, 0,
                                    plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(cost))
         assert rc == 0
         assert sorted(plan[:n].tolist()) == list(range(n)), "slot_of must be a permutation"
