@@ -290,8 +290,12 @@ def run_gpu(args) -> None:
                     "algorithmic_flops_per_cell_step": flops_per_cell_step,
                     "peak_source": "cab200_peak_fp64 (independent DFMA chains on every SM), measured in this run; "
                                    "MEASURED_PEAKS.json has no FP64 entry",
-                    "fp64_pipe_note": "an IEEE divide is ~9 FP64-pipe instructions, so 69 algorithmic flops are "
-                                      "~89 pipe instructions; pipe utilisation from ncu is in profiles/"}
+                    "fp64_pipe_instr_per_cell_step": 89.6,
+                    "fp64_pipe_frac_est": achieved_tf * (2.0 * 89.6 / flops_per_cell_step) / peak.value,
+                    "fp64_pipe_note": "an IEEE divide is ~9 FP64-pipe instructions, so 69.3 algorithmic flops are "
+                                      "89.6 pipe instructions per cell-step (ncu instruction counts, profiles/); "
+                                      "fp64_pipe_frac_est = pipe instructions/s over the measured DFMA issue rate; "
+                                      "ncu's own sm__pipe_fp64_cycles_active is in profiles/r1_k1_v3_immaddr_ncu.txt"}
         roofline_smem = {"kernel": "integrate_kernel (K1)", "bound": "shared-memory wavefronts",
                          "wavefronts_per_step_planned": wave_ld + wave_st,
                          "frac": smem_clk / (k1_ms * 1e-3 * sm_clock_hz),

@@ -1,0 +1,95 @@
+"""Property tests (hypothesis) for the host-side pieces: partitioning, the slot planner, the
+instance-mask helper, the PNG writer.  CPU only."""
+import ctypes
+import struct
+import zlib
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(1, 4000), min_size=0, max_size=200), st.integers(1, 8))
+def test_lpt_partition_is_a_partition_and_balanced(sizes, world):
+    from calcium_b200.parallel import shard_indices
+    parts = shard_indices(sizes, 18000, world)
+    assert len(parts) == world
+    flat = sorted(i for p in parts for i in p)
+    assert flat == list(range(len(sizes)))
+    if sizes:
+        loads = [sum(sizes[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(sizes)          # LPT bound for the greedy rule
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(3, 120), st.integers(0, 2 ** 31 - 1), st.sampled_from([1, 2]), st.sampled_from([1, 2, 3, 4]))
+def test_planner_returns_permutation_that_keeps_length_classes(n, seed, copies, cpt):
+    from calcium_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    rng = np.random.RandomState(seed % (2 ** 31))
+    # random sparse symmetric graph with the diagonal in place, rows at most 10 long
+    adj = np.zeros((n, n), dtype=bool)
+    for i in range(n):
+        for j in rng.choice(n, size=min(3, n - 1), replace=False):
+            if i != j and adj[i].sum() < 8 and adj[j].sum() < 8:
+                adj[i, j] = adj[j, i] = True
+    np.fill_diagonal(adj, True)
+    rows, cols = np.nonzero(adj)
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int32)
+    col = cols.astype(np.int32)
+    plan = np.zeros(2 * n, dtype=np.uint16)
+    cost = np.zeros(4, dtype=np.int64)
+    rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, cpt, 3000, seed + 1, 0,
+                               plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(cost))
+    assert rc == 0
+    assert sorted(plan[:n].tolist()) == list(range(n))
+    lens = np.diff(rowptr)
+    assert np.all(np.diff(lens[np.argsort(plan[:n])]) <= 0)
+    assert cost[1] == cost[2] <= cost[0]
+    if copies == 1:
+        assert not plan[n:].any()
+    else:
+        for i in range(n):
+            assert plan[n + i] < (1 << lens[i])                # only real entries may select copy B
+            d = int(np.nonzero(col[rowptr[i]:rowptr[i + 1]] == i)[0][0])
+            assert not (plan[n + i] >> d) & 1                  # the diagonal entry has no second copy
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 60), st.integers(0, 2 ** 31 - 1))
+def test_instance_mask_helper_equals_reference_loop(n_cells, seed):
+    from calcium_b200.masks import create_instance_mask_from_cells
+    rng = np.random.RandomState(seed)
+    mask = rng.randint(0, n_cells + 1, (17, 23)).astype(np.int32)
+    active = sorted(rng.choice(n_cells, rng.randint(0, n_cells + 1), replace=False).tolist())
+    want = np.zeros_like(mask, dtype=np.uint16)
+    for new_id, cell_id in enumerate(active, start=1):         # utils/sam2_data_generator.py:34-35
+        want[mask == cell_id] = new_id
+    assert np.array_equal(create_instance_mask_from_cells(mask, active), want)
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(1, 40), st.integers(1, 40), st.integers(0, 2 ** 31 - 1))
+def test_png_encoder_roundtrip(h, w, seed):
+    from calcium_b200.io import encode_gray_alpha_png16
+    rng = np.random.RandomState(seed)
+    g = rng.randint(0, 1024, (h, w)).astype(np.uint16)
+    a = rng.randint(0, 65536, (h, w)).astype(np.uint16)
+    png = encode_gray_alpha_png16(g, a)
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, ihdr = 8, b"", None
+    while pos < len(png):
+        ln, tag = struct.unpack(">I", png[pos:pos + 4])[0], png[pos + 4:pos + 8]
+        data = png[pos + 8:pos + 8 + ln]
+        assert struct.unpack(">I", png[pos + 8 + ln:pos + 12 + ln])[0] == zlib.crc32(tag + data) & 0xFFFFFFFF
+        if tag == b"IHDR":
+            ihdr = struct.unpack(">IIBBBBB", data)
+        if tag == b"IDAT":
+            idat += data
+        pos += 12 + ln
+    assert ihdr == (w, h, 16, 4, 0, 0, 0)
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 4 * w)
+    assert not raw[:, 0].any()
+    px = raw[:, 1:].copy().view(">u2").reshape(h, w, 2)
+    assert np.array_equal(px[..., 0], g) and np.array_equal(px[..., 1], a)
