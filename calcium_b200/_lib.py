@@ -23,6 +23,7 @@ ST_BADGEOM = 2
 #: every symbol include/cab200.h declares (tests check the library exports all of them)
 EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
            "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_sim_layout",
+           "cab200_cluster_layout", "cab200_plan_cluster",
            "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
            "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_selftest_division"]
 
@@ -53,7 +54,7 @@ def load() -> ctypes.CDLL:
     lib.cab200_sim_batch.argtypes = [
         c_int, i32p, c_int, i32p, i32p, i32p, i64p, i64p,      # pouch/geometry tables (host)
         c_void_p, c_void_p, c_void_p,                          # rowptr, colidx, vals (device)
-        c_void_p,                                              # slot_plan (device, may be NULL)
+        i32p, i64p, c_void_p,                                  # g_cluster, g_plan_off (host), slot_plan (device)
         i64p,                                                  # cell_off (host)
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,      # params, c0, p0, r0, vplc (device)
         c_int, c_int, i32p,                                    # T, n_frames, frame_steps (host)
@@ -61,6 +62,11 @@ def load() -> ctypes.CDLL:
     lib.cab200_plan_slots.restype = c_int
     lib.cab200_plan_slots.argtypes = [c_int, i32p, i32p, c_int, c_int, ctypes.c_longlong,
                                       ctypes.c_ulonglong, c_int, POINTER(ctypes.c_uint16), i64p]
+    lib.cab200_cluster_layout.restype = c_int
+    lib.cab200_cluster_layout.argtypes = [c_int, c_int, c_int, i64p]
+    lib.cab200_plan_cluster.restype = ctypes.c_longlong
+    lib.cab200_plan_cluster.argtypes = [c_int, i32p, i32p, c_int, c_int, c_int, ctypes.c_longlong,
+                                        ctypes.c_ulonglong, POINTER(ctypes.c_uint16), ctypes.c_longlong, i64p]
     lib.cab200_sim_layout.restype = c_int
     lib.cab200_sim_layout.argtypes = [c_int, c_int, c_int, i64p]
     lib.cab200_sim_set_plan.restype = c_int

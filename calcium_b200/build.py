@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcalcium_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
-SOURCES = ["api.cu", "integrate.cu", "raster.cu", "plan.cu"]
+SOURCES = ["integrate_f64.cu", "integrate_cl64.cu", "integrate_f32.cu", "integrate_cl32.cu", "integrate.cu",
+           "api.cu", "raster.cu", "plan.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 

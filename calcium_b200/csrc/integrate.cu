@@ -3,7 +3,7 @@
 #include <mutex>
 #include <vector>
 
-#include "integrate.cuh"
+#include "integrate_pick.cuh"
 
 namespace cab200 {
 
@@ -40,41 +40,6 @@ int sim_copies(int n, bool unit, size_t elem2, int nslot)
 static std::mutex g_plan_mu;
 static int g_force_nmax = 0, g_force_threads = 0, g_force_cpt = 0;
 
-typedef void (*KernelFn)(const SimArgs);
-
-template <typename R, int THREADS, int CPT, int MINB>
-static KernelFn pick_variant(int ep, bool unit, int copies)
-{
-    if (unit) {
-        if (copies == 2) {
-            if (ep <= 5) return integrate_kernel<R, THREADS, CPT, 5, true, 2, MINB>;
-            return integrate_kernel<R, THREADS, CPT, 8, true, 2, MINB>;
-        }
-        if (ep <= 5) return integrate_kernel<R, THREADS, CPT, 5, true, 1, MINB>;
-        return integrate_kernel<R, THREADS, CPT, 8, true, 1, MINB>;
-    }
-    return integrate_kernel<R, THREADS, CPT, 8, false, 1, MINB>;
-}
-
-template <typename R>
-static KernelFn pick_kernel(int threads, int cpt, int ep, bool unit, int copies)
-{
-#define CAB_SHAPE(T_, C_, M_) \
-    if (threads == T_ && cpt == C_) return pick_variant<R, T_, C_, M_>(ep, unit, copies);
-    CAB_SHAPE(128, 1, 8)
-    CAB_SHAPE(256, 1, 4)
-    CAB_SHAPE(256, 2, 2)
-    CAB_SHAPE(512, 1, 2)
-    CAB_SHAPE(512, 2, 1)
-    CAB_SHAPE(512, 3, 1)
-    CAB_SHAPE(768, 2, 1)
-    CAB_SHAPE(1024, 2, 1)
-    CAB_SHAPE(1024, 3, 1)
-    CAB_SHAPE(1024, 4, 1)
-#undef CAB_SHAPE
-    return nullptr;
-}
-
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace cab200
@@ -85,7 +50,7 @@ extern "C" int cab200_sim_set_plan(int n_max, int threads, int cells_per_thread)
 {
     std::lock_guard<std::mutex> lk(g_plan_mu);
     if (threads == 0) { g_force_nmax = g_force_threads = g_force_cpt = 0; return CAB200_OK; }
-    if (!pick_kernel<double>(threads, cells_per_thread, 5, true, 1)) {
+    if (!pick_kernel_f64(threads, cells_per_thread, 5, true, 1)) {
         set_error("cab200_sim_set_plan: unsupported shape threads=%d cells_per_thread=%d", threads,
                   cells_per_thread);
         return CAB200_EINVAL;
@@ -116,6 +81,23 @@ extern "C" int cab200_sim_layout(int n, int unit, int precision, int64_t out[4])
     return CAB200_OK;
 }
 
+extern "C" int cab200_cluster_layout(int n, int n_cta, int precision, int64_t out[4])
+{
+    if (!out || n <= 0 || (n_cta != 2 && n_cta != 4) ||
+        (precision != CAB200_FP64_STRICT && precision != CAB200_FP32)) {
+        set_error("cab200_cluster_layout: bad argument (cluster sizes 2 and 4 are supported)");
+        return CAB200_EINVAL;
+    }
+    int threads = 0, cpt = 0;
+    cluster_shape((n + n_cta - 1) / n_cta, &threads, &cpt);
+    if (!threads) { set_error("cab200_cluster_layout: %d cells exceed %d CTAs x 1536", n, n_cta); return CAB200_ESIZE; }
+    const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
+    const int copies = integrate_smem_bytes(0, threads * cpt, elem2, 2, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
+    out[0] = threads; out[1] = cpt; out[2] = copies;
+    out[3] = (int64_t)integrate_smem_bytes(0, threads * cpt, elem2, copies, CAB_HMAX);
+    return CAB200_OK;
+}
+
 extern "C" size_t cab200_sim_scratch_bytes(int n_pouch, int n_frames)
 {
     // pouch_list [P] i32 + cell_off [P+1] i64 + frame_steps [F] i32, each 16-byte aligned
@@ -128,7 +110,7 @@ extern "C" int cab200_sim_batch(
     int n_pouch, const int32_t *geom_id, int n_geom, const int32_t *g_ncell,
     const int32_t *g_max_row, const int32_t *g_unit, const int64_t *g_rowptr_off,
     const int64_t *g_nnz_off, const int32_t *rowptr, const int32_t *colidx, const double *vals,
-    const uint16_t *slot_plan, const int64_t *cell_off, const double *params, const double *c0, const double *p0,
+    const int32_t *g_cluster, const int64_t *g_plan_off, const uint16_t *slot_plan, const int64_t *cell_off, const double *params, const double *c0, const double *p0,
     const double *r0, const double *vplc, int T, int n_frames, const int32_t *frame_steps,
     void *frames_out, int32_t *status_out, int precision, void *scratch, size_t scratch_bytes,
     void *stream_)
@@ -203,12 +185,54 @@ extern "C" int cab200_sim_batch(
         force_nmax = g_force_nmax; force_threads = g_force_threads; force_cpt = g_force_cpt;
     }
 
-    int64_t plan_off = 0;
-    for (int g = 0; g < n_geom; plan_off += 2 * (int64_t)g_ncell[g], ++g) {
+    for (int g = 0; g < n_geom; ++g) {
         const int count = g_begin[g + 1] - g_begin[g];
         if (count == 0) continue;
         const int n = g_ncell[g];
         if (n <= 0) { set_error("cab200_sim_batch: geometry %d has no cells", g); return CAB200_EINVAL; }
+        const int ncta = g_cluster ? g_cluster[g] : 1;
+        const int64_t plan_off = (slot_plan && g_plan_off) ? g_plan_off[g] : -1;
+        if (ncta > 1) {
+            // ---- pouch split over a thread-block cluster ---------------------------------------
+            if (ncta != 2 && ncta != 4) { set_error("cab200_sim_batch: geometry %d: cluster size %d (2 or 4)", g, ncta); return CAB200_EINVAL; }
+            if (plan_off < 0) { set_error("cab200_sim_batch: geometry %d: a cluster needs a cab200_plan_cluster plan", g); return CAB200_EINVAL; }
+            if (!g_unit[g]) { set_error("cab200_sim_batch: geometry %d: clusters need the unit-weight Laplacian", g); return CAB200_EINVAL; }
+            const int max_row_c = g_max_row[g];
+            if (max_row_c > 16 || max_row_c < 0) { set_error("cab200_sim_batch: geometry %d: longest CSR row %d outside [0,16]", g, max_row_c); return CAB200_ESIZE; }
+            int cth = 0, ccpt = 0;
+            cluster_shape((n + ncta - 1) / ncta, &cth, &ccpt);
+            if (!cth) { set_error("cab200_sim_batch: geometry %d: %d cells exceed %d CTAs x 1536", g, n, ncta); return CAB200_ESIZE; }
+            const size_t el2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
+            const int ccopies = integrate_smem_bytes(0, cth * ccpt, el2, 2, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
+            const int cep = (max_row_c + 1) / 2;
+            KernelFn cfn = (precision == CAB200_FP64_STRICT) ? pick_cluster_kernel_f64(cth, ccpt, ncta, cep, ccopies)
+                                                             : pick_cluster_kernel_f32(cth, ccpt, ncta, cep, ccopies);
+            if (!cfn) { set_error("cab200_sim_batch: no cluster kernel for %dx%d x%d", cth, ccpt, ncta); return CAB200_EINVAL; }
+            const size_t csmem = integrate_smem_bytes(0, cth * ccpt, el2, ccopies, CAB_HMAX);
+            CAB_CUDA(cudaFuncSetAttribute((const void *)cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+            SimArgs ca;
+            ca.pouch_list = d_list + g_begin[g];
+            ca.cell_off = d_cell_off;
+            ca.rowptr = rowptr + g_rowptr_off[g];
+            ca.colidx = colidx + g_nnz_off[g];
+            ca.vals = vals + g_nnz_off[g];
+            ca.slot_plan = slot_plan + plan_off;
+            ca.n = n; ca.np = (n + 31) & ~31;
+            ca.params = params; ca.c0 = c0; ca.p0 = p0; ca.r0 = r0; ca.vplc = vplc;
+            ca.T = T; ca.n_frames = n_frames; ca.frame_steps = d_frame_steps;
+            ca.frames_out = frames_out; ca.status_out = status_out;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(count * ncta), 1, 1);
+            cfg.blockDim = dim3((unsigned)cth, 1, 1);
+            cfg.dynamicSmemBytes = csmem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            CAB_CUDA(cudaLaunchKernelEx(&cfg, cfn, ca));
+            continue;
+        }
         int threads = 0, cpt = 0;
         if (force_threads && n <= force_nmax && force_threads * force_cpt >= n) {
             threads = force_threads; cpt = force_cpt;
@@ -229,8 +253,8 @@ extern "C" int cab200_sim_batch(
         const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
         const int np = (n + 31) & ~31;
         const int copies = sim_copies(n, unit, elem2, threads * cpt);
-        KernelFn fn = (precision == CAB200_FP64_STRICT) ? pick_kernel<double>(threads, cpt, ep, unit, copies)
-                                                        : pick_kernel<float>(threads, cpt, ep, unit, copies);
+        KernelFn fn = (precision == CAB200_FP64_STRICT) ? pick_kernel_f64(threads, cpt, ep, unit, copies)
+                                                        : pick_kernel_f32(threads, cpt, ep, unit, copies);
         if (!fn) { set_error("cab200_sim_batch: no kernel for shape %dx%d", threads, cpt); return CAB200_EINVAL; }
         const size_t smem = integrate_smem_bytes(np, threads * cpt, elem2, copies);
         if (smem > 227 * 1024) {
@@ -246,7 +270,7 @@ extern "C" int cab200_sim_batch(
         a.colidx = colidx + g_nnz_off[g];
         a.vals = vals + g_nnz_off[g];
         a.n = n;
-        a.slot_plan = slot_plan ? slot_plan + plan_off : nullptr;
+        a.slot_plan = (plan_off >= 0) ? slot_plan + plan_off : nullptr;
         a.np = np;
         a.params = params;
         a.c0 = c0; a.p0 = p0; a.r0 = r0; a.vplc = vplc;

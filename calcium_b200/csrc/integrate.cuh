@@ -37,7 +37,8 @@ struct SimArgs {
     const int32_t *rowptr;      // this geometry's CSR
     const int32_t *colidx;
     const double *vals;
-    const uint16_t *slot_plan;  // optional plan (cab200_plan_slots): slot_of[n] then copy_sel[n]
+    const uint16_t *slot_plan;  // optional plan: cab200_plan_slots (slot_of[n] | copy_sel[n]) or, for clusters,
+                                // cab200_plan_cluster (part_of[n] | slot_of[n] | copy_sel[n] | halo counts | halo lists)
     int n;
     int np;                     // n rounded up to 32: entries per region
     const double *params;
@@ -49,15 +50,15 @@ struct SimArgs {
 };
 
 // Shared-memory bytes K1 needs for a pouch padded to `np` slots.
-static inline size_t integrate_buf_stride(int np, int nslot, size_t elem2, int copies)
+static inline size_t integrate_buf_stride(int np, int nslot, size_t elem2, int copies, int hmax = 0)
 {
-    const size_t fixed = ((((size_t)copies + 1) * nslot + 1) * elem2 + 127) & ~(size_t)127;
+    const size_t fixed = ((((size_t)copies + 1) * nslot + 1 + hmax) * elem2 + 127) & ~(size_t)127;
     if (2 * fixed + 2 * (size_t)nslot + 64 <= 227 * 1024) return fixed;          // == BufGeom::STRIDE
     return ((((size_t)copies + 1) * np + 1) * elem2 + 127) & ~(size_t)127;        // runtime stride
 }
-static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2, int copies)
+static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2, int copies, int hmax = 0)
 {
-    return 2 * integrate_buf_stride(np, nslot, elem2, copies) + 2 * (size_t)nslot + 64;   // + orig_of[NSLOT]
+    return 2 * integrate_buf_stride(np, nslot, elem2, copies, hmax) + 2 * (size_t)nslot + 64;   // + orig_of[NSLOT]
 }
 
 // One Euler step for one cell, reference source order (core/pouch.py:77-102), every operation
@@ -120,6 +121,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
     } while (!ok);
 }
 
+// ---- thread-block-cluster helpers (distributed shared memory) --------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Local arrival that also announces `bytes` of asynchronous remote stores (st.async complete_tx) the
+// barrier's current phase has to wait for.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
 // 16-byte (two-real) shared-memory accesses at [32-bit shared address + compile-time immediate]: the
 // immediate carries the step-parity buffer offset, so a gather is exactly one LDS per entry.
 template <typename R> struct Smem2;
@@ -134,6 +159,16 @@ template <> struct Smem2<double> {
     {
         asm volatile("st.shared.v2.f64 [%0+%3], {%1, %2};" ::"r"(addr), "d"(x), "d"(y), "n"(IMM) : "memory");
     }
+    template <int IMM> static __device__ __forceinline__ void st_cluster(uint32_t addr, double x, double y)
+    {
+        asm volatile("st.shared::cluster.v2.f64 [%0+%3], {%1, %2};" ::"r"(addr), "d"(x), "d"(y), "n"(IMM) : "memory");
+    }
+    // asynchronous remote store that completes 16 transaction bytes on the destination CTA's mbarrier
+    template <int IMM> static __device__ __forceinline__ void st_async(uint32_t addr, double x, double y, uint32_t mbar)
+    {
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0+%4], {%1, %2}, [%3];"
+                     ::"r"(addr), "d"(x), "d"(y), "r"(mbar), "n"(IMM) : "memory");
+    }
 };
 template <> struct Smem2<float> {
     template <int IMM> static __device__ __forceinline__ float2 ld(uint32_t addr)
@@ -146,22 +181,45 @@ template <> struct Smem2<float> {
     {
         asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(addr), "f"(x), "f"(y), "n"(IMM) : "memory");
     }
+    template <int IMM> static __device__ __forceinline__ void st_cluster(uint32_t addr, float x, float y)
+    {
+        asm volatile("st.shared::cluster.v2.f32 [%0+%3], {%1, %2};" ::"r"(addr), "f"(x), "f"(y), "n"(IMM) : "memory");
+    }
+    template <int IMM> static __device__ __forceinline__ void st_async(uint32_t addr, float x, float y, uint32_t mbar)
+    {
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0+%4], {%1, %2}, [%3];"
+                     ::"r"(addr), "f"(x), "f"(y), "r"(mbar), "n"(IMM) : "memory");
+    }
 };
 
 // Entries per region and bytes between the two step-parity buffers.  When both buffers fit with
 // NSLOT-sized regions the stride is a compile-time constant (CSTRIDE): parity becomes an immediate
 // and slots beyond n own real (unused) entries, so nothing in the step loop is predicated on them.
-template <typename R, int NSLOT, int COPIES>
+template <typename R, int NSLOT, int COPIES, int HMAX = 0>
 struct BufGeom {
     static constexpr size_t ESZ = 2 * sizeof(R);
-    static constexpr size_t STRIDE = ((((size_t)(COPIES + 1) * NSLOT + 1) * ESZ) + 127) & ~(size_t)127;
+    static constexpr size_t STRIDE = ((((size_t)(COPIES + 1) * NSLOT + 1 + HMAX) * ESZ) + 127) & ~(size_t)127;
     static constexpr bool CSTRIDE = 2 * STRIDE + 2 * (size_t)NSLOT + 64 <= 227 * 1024;
 };
+
+// Halo entries a cluster CTA can hold (values of other CTAs' cells that its rows read).
+constexpr int CAB_HMAX = 384;
 
 // EP = number of packed entry-index pairs kept in registers per cell (row length <= 2*EP).
 // UNIT: every off-diagonal value is exactly 1.0 (verified in the prologue).  !UNIT: general weights,
 // read from global/L1 each step and multiplied per entry.
-template <typename R, int THREADS, int CPT, int EP, bool UNIT, int COPIES, int MINB>
+// NCTA > 1: the pouch is split over a thread-block cluster of NCTA CTAs (cab200_plan_cluster): each
+// CTA owns one part of the cells; entries of other parts are read from local *halo* entries which
+// the owner pushes through distributed shared memory when it publishes -- with st.async, whose
+// completion is counted in transaction bytes on the destination CTA's step barrier.  A CTA's
+// barrier phase therefore completes when its own warps have published AND every halo value of that
+// time has landed: no remote arrivals and no cluster-scope fences in the step loop.  Two barriers
+// alternate with the step parity because a peer may already push time t+1 while this CTA's phase t
+// is still pending (never further ahead: its push of t+2 needs this CTA's pushes of t+1, which are
+// issued after phase t completed here).  Overwriting a halo entry of buffer t&1 with time t+2 is
+// safe for the same reason: every warp that reads halo entries of a peer also owns cells pushed to
+// that peer, and the peer's phase t+1 waits for those pushes, issued after the warp's gather of t.
+template <typename R, int THREADS, int CPT, int EP, bool UNIT, int COPIES, int MINB, int NCTA = 1>
 __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs a)
 {
     typedef Strict<R> S;
@@ -169,7 +227,9 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     typedef Smem2<R> M;
     constexpr int NSLOT = THREADS * CPT;
     constexpr int EMAX = 2 * EP;
-    typedef BufGeom<R, NSLOT, COPIES> G;
+    constexpr int HMAX = (NCTA > 1) ? CAB_HMAX : 0;
+    typedef BufGeom<R, NSLOT, COPIES, HMAX> G;
+    static_assert(NCTA == 1 || (G::CSTRIDE && UNIT), "cluster kernels need the compile-time layout");
     constexpr bool CSTRIDE = G::CSTRIDE;
     constexpr uint32_t ESZ = (uint32_t)G::ESZ;
     constexpr int STRIDE_IMM = CSTRIDE ? (int)G::STRIDE : 0;
@@ -189,8 +249,9 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int pouch = a.pouch_list[blockIdx.x];
+    const int pouch = a.pouch_list[blockIdx.x / NCTA];
     const int64_t coff = a.cell_off[pouch];
+    const uint32_t rank = (NCTA > 1) ? cluster_ctarank() : 0u;
     int bad = 0;
 
     // ---- prologue 1: row lengths -------------------------------------------------------------
@@ -202,7 +263,22 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     for (int s = tid; s < NSLOT; s += THREADS) orig_of[s] = 0xffff;
     __syncthreads();
     // ---- prologue 2: cell -> slot.  Host plan if given, else stable rank by (length desc, id asc) --
-    if (a.slot_plan) {
+    uint8_t *part_of = reinterpret_cast<uint8_t *>(copy_sel + np);                 // [n] (clusters)
+    if (NCTA > 1) {
+        // cluster plan: this CTA owns the cells of part `rank`; slot_of is the slot inside the part
+        for (int i = tid; i < n; i += THREADS) {
+            const int pq = a.slot_plan[i];
+            int sl = a.slot_plan[n + i];
+            if (pq >= NCTA || sl >= NSLOT) { bad = 1; sl = 0; }
+            part_of[i] = (uint8_t)pq;
+            slot_of[i] = (uint16_t)sl;
+            copy_sel[i] = (COPIES == 2) ? a.slot_plan[2 * n + i] : (uint16_t)0;
+            if (pq == (int)rank) orig_of[sl] = (uint16_t)i;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS)
+            if (part_of[i] == rank && orig_of[slot_of[i]] != i) bad = 1;
+    } else if (a.slot_plan) {
         for (int i = tid; i < n; i += THREADS) {
             int sl = a.slot_plan[i];
             if (sl >= n) { bad = 1; sl = i; }
@@ -263,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int slot = (warp * CPT + k) * 32 + lane;
-        const int cell = (slot < n) ? (int)orig_of[slot] : 0xffff;
+        const int cell = (int)orig_of[slot];          // 0xffff: no cell in this slot
         live[k] = (cell != 0xffff);
         own[k] = sb0 + (uint32_t)slot * ESZ;
         rowbeg[k] = 0; len[k] = 0;
@@ -279,6 +355,21 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                          // core/pouch.py:322
         mylen = max(mylen, len[k]);
     }
+    // cluster: halo lists (sorted global cell ids per part) follow the three per-cell arrays
+    const uint16_t *hcount = a.slot_plan + 3 * (size_t)n;
+    const uint16_t *hlists = hcount + NCTA;
+    auto halo_find = [&](int part, int cell_id) -> int {      // index of cell_id in part's halo list, or -1
+        int base = 0;
+        for (int qq = 0; qq < part; ++qq) base += hcount[qq];
+        int lo = 0, hi = (int)hcount[part] - 1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const int v = hlists[base + mid];
+            if (v == cell_id) return mid;
+            if (v < cell_id) lo = mid + 1; else hi = mid - 1;
+        }
+        return -1;
+    };
     const int W = __reduce_max_sync(0xffffffffu, mylen);
     const int start = (EMAX - W) & ~1;          // even: positions are processed in pairs
 #pragma unroll
@@ -293,7 +384,11 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             if (live[k] && e >= 0 && e < len[k]) {
                 const int col = a.colidx[rowbeg[k] + e];
                 if (col < 0 || col >= n) bad = 1;
-                else {
+                else if (NCTA > 1 && part_of[col] != rank) {
+                    const int h = halo_find((int)rank, col);        // another CTA's cell: local halo entry
+                    if (h < 0 || h >= HMAX || a.vals[rowbeg[k] + e] != 1.0) bad = 1;
+                    else o = sb0 + (uint32_t)((COPIES + 1) * npr + 1 + h) * ESZ;
+                } else {
                     uint32_t j = slot_of[col];
                     if (COPIES == 2 && ((sel >> e) & 1u)) j = (uint32_t)npr + (j ^ 4u);
                     if (UNIT) {
@@ -307,25 +402,71 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             ent[k][pos] = o;
         }
     }
+    // cluster: where this thread's cells must be pushed (their halo entries in the other CTAs)
+    uint32_t push[CPT][NCTA > 1 ? NCTA - 1 : 1];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+#pragma unroll
+        for (int d = 0; d < (NCTA > 1 ? NCTA - 1 : 1); ++d) push[k][d] = 0u;
+        if (NCTA > 1 && live[k]) {
+            const int cell = (int)orig_of[(warp * CPT + k) * 32 + lane];
+#pragma unroll
+            for (int d = 0; d < NCTA - 1; ++d) {
+                const uint32_t q2 = (rank + 1 + d) % NCTA;
+                const int h = halo_find((int)q2, cell);
+                if (h >= HMAX) bad = 1;
+                else if (h >= 0)
+                    push[k][d] = mapa_shared(sb0 + (uint32_t)((COPIES + 1) * npr + 1 + h) * ESZ, q2);
+            }
+        }
+    }
     if (bad) atomicOr(a.status_out + pouch, CAB200_ST_BADGEOM);
     __syncthreads();   // scratch (inside buffer 1) is dead from here on
     for (uint32_t i = tid; i < 2 * stride / 16; i += THREADS)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __shared__ uint64_t step_bar[2];     // clusters alternate between two (see above); else [0] only
+    if (tid == 0) {
+        mbar_init(&step_bar[0], THREADS / 32);         // one arrival per warp
+        mbar_init(&step_bar[1], THREADS / 32);
+        if (NCTA > 1) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (NCTA > 1) cluster_sync_all();    // every CTA's buffers are zeroed and its barrier exists
 
+    // cluster: the peers' step barriers (as cluster addresses) that this thread's pushes complete on
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&step_bar[0]);
+    uint32_t bar_peer[NCTA > 1 ? NCTA - 1 : 1];
+#pragma unroll
+    for (int d = 0; d < (NCTA > 1 ? NCTA - 1 : 1); ++d)
+        bar_peer[d] = (NCTA > 1) ? mapa_shared(bar_addr, (rank + 1 + d) % NCTA) : bar_addr;
     const uint32_t copyb_off = (uint32_t)npr * ESZ;                 // second value copy (multiple of 128 B)
     const uint32_t diag_off = (uint32_t)(COPIES * npr) * ESZ;       // diagonal entries
     // Publishes a cell's new (c, p): value entry, second copy in the bank group 4 away, diagonal
     // term.  IMM selects the step-parity buffer at compile time (CSTRIDE) -- else roff does.
-#define CAB_PUBLISH(IMM, ROFF, K, CV, PV)                                                          \
+#define CAB_PUBLISH(IMM, ROFF, K, CV, PV, ASYNC_BAR)                                               \
     if (CSTRIDE || live[K]) {                                                                     \
         M::template st<IMM>(own[K] + (ROFF), (CV), (PV));                                         \
         if (COPIES == 2) M::template st<IMM>(((own[K] + copyb_off) ^ (4u * ESZ)) + (ROFF), (CV), (PV)); \
         if (UNIT) M::template st<IMM>(own[K] + diag_off + (ROFF), S::mul(dcoef[K], (CV)), S::mul(dcoef[K], (PV))); \
+        if (NCTA > 1) {                                                                           \
+            _Pragma("unroll") for (int d_ = 0; d_ < NCTA - 1; ++d_)                               \
+                if (push[K][d_]) {                                                                \
+                    if ((ASYNC_BAR) < 0) M::template st_cluster<IMM>(push[K][d_], (CV), (PV));    \
+                    else M::template st_async<IMM>(push[K][d_], (CV), (PV), bar_peer[d_] + 8u * (ASYNC_BAR)); \
+                }                                                                                 \
+        }                                                                                         \
     }
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) { CAB_PUBLISH(0, 0u, k, c[k], p[k]) }
+    for (int k = 0; k < CPT; ++k) { CAB_PUBLISH(0, 0u, k, c[k], p[k], -1) }
     __syncthreads();
+    if (NCTA > 1) cluster_sync_all();    // initial values, halo entries included, are in place
+    const uint32_t halo_bytes = (NCTA > 1) ? (uint32_t)hcount[rank] * ESZ : 0u;   // pushed to this CTA per step
+    // lane 0 of a warp: arrival on the barrier that guards the values of the NEXT time (index BAR);
+    // warp 0 also announces the halo bytes that phase has to receive
+    auto arrive_step = [&](int bar) {
+        if (NCTA > 1 && warp == 0) mbar_arrive_expect_tx(&step_bar[bar], halo_bytes);
+        else mbar_arrive(&step_bar[bar]);
+    };
 
     R *frames = reinterpret_cast<R *>(a.frames_out) + (size_t)coff * 4 * a.n_frames;
     int fi = 0;
@@ -356,9 +497,6 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     // blocks.  Buffer safety: a thread overwrites buffer (t+1)&1 only after passing wait(t), i.e.
     // after every warp has arrived for step t, which each does after its own gather of step t-1 --
     // the last reader of that buffer.  Slots beyond n carry harmless zeros (no NaNs arise).
-    __shared__ uint64_t step_bar;
-    if (tid == 0) mbar_init(&step_bar, THREADS / 32);   // one arrival per warp
-    __syncthreads();
     if (cap_t == 0) capture();
     R J_ch[CPT], J_S[CPT], J_PLC[CPT];
 #pragma unroll
@@ -367,7 +505,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         step_local<R>(q, c[k], p[k], s[k], r[k], vplc[k], J_ch[k], J_S[k], J_PLC[k], rn);
         r[k] = rn;      // r now holds r(t+1); r(t) was captured above if requested
     }
-    if (lane == 0) mbar_arrive(&step_bar);   // state(0) was published before the __syncthreads above
+    if (lane == 0) mbar_arrive(&step_bar[0]);   // state(0) was published (and pushed) before the barriers above
     unsigned parity = 0;
 
 // One pair of row positions for every owned cell: all loads of the pair first (2*CPT independent
@@ -394,10 +532,10 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     }
 
 // One time step reading the buffer at +CUR and writing the one at +NXT (immediates when CSTRIDE).
-#define CAB_STEP(CUR_IMM, NXT_IMM, CUR_R, NXT_R)                                                  \
+#define CAB_STEP(CUR_IMM, NXT_IMM, CUR_R, NXT_R, CUR_BAR, NXT_BAR)                                \
     {                                                                                             \
-        mbar_wait(&step_bar, parity);                                                             \
-        parity ^= 1u;                                                                             \
+        mbar_wait(&step_bar[CUR_BAR], parity);                                                    \
+        if (NCTA == 1 || (CUR_BAR) == 1) parity ^= 1u;   /* a cluster uses each barrier every 2nd step */ \
         R sc[CPT], sp[CPT];                                                                       \
         _Pragma("unroll") for (int k = 0; k < CPT; ++k) { sc[k] = (R)0; sp[k] = (R)0; }           \
         switch (start) { /* warp-uniform entry point; every later position follows */             \
@@ -417,11 +555,11 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             R cn, pn;                                                                             \
             step_finish<R>(q, c[k], p[k], lap_c, lap_p, J_ch[k], J_S[k], J_PLC[k], cn, pn);       \
             c[k] = cn; p[k] = pn;                                                                 \
-            CAB_PUBLISH(NXT_IMM, NXT_R, k, cn, pn)                                                \
+            CAB_PUBLISH(NXT_IMM, NXT_R, k, cn, pn, NXT_BAR)                                       \
         }                                                                                         \
         /* one arrival per warp: __syncwarp orders the other lanes' stores before lane 0's release */ \
         __syncwarp();                                                                             \
-        if (lane == 0) mbar_arrive(&step_bar);                                                    \
+        if (lane == 0) arrive_step(NXT_BAR);                                                      \
         /* own-state work for the next step, overlapping the other warps' gathers */              \
         _Pragma("unroll") for (int k = 0; k < CPT; ++k)                                           \
             s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                      /* :95 */          \
@@ -435,13 +573,19 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 
     const uint32_t rstride = CSTRIDE ? 0u : stride;     // runtime parity offset only without CSTRIDE
     int t = 0;
+    constexpr int B1 = (NCTA > 1) ? 1 : 0;     // barrier guarding odd times (clusters only)
     for (; t + 1 < T - 1; t += 2) {
-        CAB_STEP(0, STRIDE_IMM, 0u, rstride)
+        CAB_STEP(0, STRIDE_IMM, 0u, rstride, 0, B1)
         ++t;
-        CAB_STEP(STRIDE_IMM, 0, rstride, 0u)
+        CAB_STEP(STRIDE_IMM, 0, rstride, 0u, B1, 0)
         --t;
     }
-    if (t < T - 1) { CAB_STEP(0, STRIDE_IMM, 0u, rstride) }
+    if (t < T - 1) { CAB_STEP(0, STRIDE_IMM, 0u, rstride, 0, B1) }
+    if (NCTA > 1) {
+        // the last pushes (time T-1) must have landed before anybody's shared memory goes away
+        if (T > 1) mbar_wait(&step_bar[(T - 1) & 1], (unsigned)(((T - 1) >> 1) & 1));
+        cluster_sync_all();
+    }
 #undef CAB_STEP
 #undef CAB_GATHER_PAIR
 #undef CAB_PUBLISH

@@ -1,11 +1,11 @@
-// plan.cu -- host-side slot planner for K1 (no device code).
+// plan.cu -- host-side layout planner for K1 (no device code).
 //
 // K1 gathers, for every stored Laplacian entry, a 16-byte (c, p) pair from shared memory with one
 // LDS.128 per warp.  The hardware serves such a load in four phases of eight lanes; inside a phase
 // two lanes conflict when they address different 16-byte entries that live in the same group of
 // four banks (entry index mod 8).  With cells dealt to threads in arbitrary order a phase costs
-// ~2 wavefronts on average and shared-memory bandwidth, not the FP64 pipe, bounds the kernel
-// (measured: profiles/r1_k1_baseline.md).
+// ~2 wavefronts on average and shared-memory bandwidth bounds the kernel
+// (measured: profiles/r1_k1_v0_baseline_ncu.txt).
 //
 // Two static degrees of freedom remove most of that, neither of which touches the arithmetic:
 //   1. the cell -> slot map (which thread owns which cell);
@@ -17,73 +17,81 @@
 //     sum over phase groups g (8 consecutive slots) and entry positions e of
 //         max over bank groups b of #{distinct entries in bank group b addressed by g at e},
 // where the copy choice inside each (g, e) is made greedily with one refinement pass.
+//
+// For pouches too large for one CTA (or to cut single-pouch latency) the cells are first split into
+// NCTA contiguous parts along a breadth-first order of the graph (thin boundaries), one part per
+// CTA of a thread-block cluster; a row entry whose column lives in another part reads a *halo*
+// entry that the owner CTA pushes through distributed shared memory every step.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <numeric>
+#include <queue>
 #include <vector>
 
 #include "common.cuh"
 
 namespace cab200 {
 
-void default_shape(int n, int *threads, int *cpt);   // integrate.cu
-
 namespace {
 
-struct Planner {
+// One CTA's planning problem: nloc local cells; row entries are local cell ids (>= 0), or -1-h for
+// halo entry h.  The cell's own id marks the diagonal.
+struct Problem {
     int n, np, copies, cpt;
-    const int32_t *rowptr, *col;
+    std::vector<int> rowptr, ecol;
     std::vector<int> slot_of, cell_of;        // cell_of[slot] = cell or -1
-    std::vector<std::vector<int>> refs;       // refs[c] = cells whose row contains c (incl. c)
-    std::vector<int> wlen;                    // per warp (32 slots): longest row
+    std::vector<std::vector<int>> refs;       // refs[c] = local cells whose row contains c (incl. c)
+    std::vector<int> wlen;                    // per warp (32*cpt slots): longest row, rounded to even
     int n_groups;
+
+    inline int rowlen(int c) const { return rowptr[c + 1] - rowptr[c]; }
 
     // Wavefronts of phase group g at entry position e; if sel_out, also reports which lanes should
     // read copy B (bit l of *sel_out).
     inline int phase_cost(int g, int e, unsigned *sel_out) const
     {
+        const int zero_idx = (copies + 1) * np;
         int a_idx[8], b_idx[8];     // candidate entry indices (b = -1: no choice)
         for (int l = 0; l < 8; ++l) {
             const int c = cell_of[g * 8 + l];
-            a_idx[l] = (copies + 1) * np;   // zero entry
+            a_idx[l] = zero_idx;
             b_idx[l] = -1;
             if (c < 0) continue;
-            const int rb = rowptr[c], len = rowptr[c + 1] - rb;
-            if (e >= len) continue;
-            const int cc = col[rb + e];
-            if (cc == c) { a_idx[l] = copies * np + slot_of[c]; continue; }
+            const int rb = rowptr[c];
+            if (e >= rowlen(c)) continue;
+            const int cc = ecol[rb + e];
+            if (cc < 0) { a_idx[l] = zero_idx + 1 + (-1 - cc); continue; }       // halo entry
+            if (cc == c) { a_idx[l] = copies * np + slot_of[c]; continue; }      // diagonal entry
             a_idx[l] = slot_of[cc];
             if (copies == 2) b_idx[l] = np + (slot_of[cc] ^ 4);
         }
         int chosen[8];
         int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        auto present = [&](int upto, int idx, int skip) {
-            for (int j = 0; j < upto; ++j) if (j != skip && chosen[j] == idx) return true;
+        auto present = [&](int idx, int skip) {
+            for (int j = 0; j < 8; ++j) if (j != skip && chosen[j] == idx) return true;
             return false;
         };
-        // forced lanes first, then the lanes with a choice (greedy: lighter bank group)
         for (int l = 0; l < 8; ++l) chosen[l] = -2;
-        for (int l = 0; l < 8; ++l)
-            if (b_idx[l] < 0) { if (!present(8, a_idx[l], l)) ++load[a_idx[l] & 7]; chosen[l] = a_idx[l]; }
-        for (int l = 0; l < 8; ++l) {
+        for (int l = 0; l < 8; ++l)      // lanes without a choice first
+            if (b_idx[l] < 0) { if (!present(a_idx[l], l)) ++load[a_idx[l] & 7]; chosen[l] = a_idx[l]; }
+        for (int l = 0; l < 8; ++l) {    // greedy: the lighter bank group (or an address already read)
             if (b_idx[l] < 0) continue;
             int pick;
-            if (present(8, a_idx[l], l)) pick = a_idx[l];
-            else if (present(8, b_idx[l], l)) pick = b_idx[l];
+            if (present(a_idx[l], l)) pick = a_idx[l];
+            else if (present(b_idx[l], l)) pick = b_idx[l];
             else pick = (load[a_idx[l] & 7] <= load[b_idx[l] & 7]) ? a_idx[l] : b_idx[l];
-            if (!present(8, pick, l)) ++load[pick & 7];
+            if (!present(pick, l)) ++load[pick & 7];
             chosen[l] = pick;
         }
-        // one refinement pass: move a lane off the heaviest bank group if that helps
-        for (int l = 0; l < 8; ++l) {
+        for (int l = 0; l < 8; ++l) {    // one refinement pass
             if (b_idx[l] < 0) continue;
             const int cur = chosen[l], alt = (cur == a_idx[l]) ? b_idx[l] : a_idx[l];
-            if (present(8, cur, l)) continue;                 // shared address: moving gains nothing
-            const int lc = load[cur & 7], la = load[alt & 7] + (present(8, alt, l) ? 0 : 1);
+            if (present(cur, l)) continue;
+            const int lc = load[cur & 7], la = load[alt & 7] + (present(alt, l) ? 0 : 1);
             if (la < lc) {
                 --load[cur & 7];
-                if (!present(8, alt, l)) ++load[alt & 7];
+                if (!present(alt, l)) ++load[alt & 7];
                 chosen[l] = alt;
             }
         }
@@ -120,9 +128,31 @@ struct Planner {
         wlen.assign(nw, 0);
         for (int w = 0; w < nw; ++w) {
             for (int s = w * per; s < std::min(np, (w + 1) * per); ++s)
-                if (cell_of[s] >= 0) wlen[w] = std::max(wlen[w], rowptr[cell_of[s] + 1] - rowptr[cell_of[s]]);
+                if (cell_of[s] >= 0) wlen[w] = std::max(wlen[w], rowlen(cell_of[s]));
             wlen[w] = (wlen[w] + 1) & ~1;
         }
+    }
+
+    // order: cell at each slot (a permutation of 0..n-1)
+    void set_order(const std::vector<int> &order)
+    {
+        np = (n + 31) & ~31;
+        n_groups = np / 8;
+        slot_of.assign(n, 0);
+        cell_of.assign(np, -1);
+        for (int s = 0; s < n; ++s) { slot_of[order[s]] = s; cell_of[s] = order[s]; }
+        compute_wlen();
+        refs.assign(n, {});
+        for (int i = 0; i < n; ++i)
+            for (int j = rowptr[i]; j < rowptr[i + 1]; ++j)
+                if (ecol[j] >= 0) refs[ecol[j]].push_back(i);
+    }
+
+    long long gather_instructions() const
+    {
+        long long rows = 0;
+        for (int g = 0; g < n_groups; g += 4) rows += wlen[(g * 8) / (32 * cpt)];
+        return rows;
     }
 };
 
@@ -138,67 +168,19 @@ struct Rng {
     double unit() { return (next() >> 11) * (1.0 / 9007199254740992.0); }
 };
 
-}  // namespace
-}  // namespace cab200
-
-using namespace cab200;
-
-// See include/cab200.h.
-extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *colidx, int copies,
-                                 int cells_per_thread, long long iters, unsigned long long seed,
-                                 int use_input, uint16_t *plan_out, int64_t *cost_out)
+// Simulated annealing over swaps inside row-length classes.  Returns the final cost.
+long long anneal(Problem &P, long long iters, uint64_t seed, long long *cost0_out)
 {
-    if (n <= 0 || n > 32767 || !rowptr || !colidx || !plan_out || (copies != 1 && copies != 2) ||
-        cells_per_thread < 1 || cells_per_thread > 8) {
-        set_error("cab200_plan_slots: bad argument");
-        return CAB200_EINVAL;
-    }
-    for (int i = 0; i < n; ++i) {
-        if (rowptr[i + 1] < rowptr[i] || rowptr[i + 1] - rowptr[i] > 16) {
-            set_error("cab200_plan_slots: row %d: length outside [0,16]", i);
-            return CAB200_EINVAL;
-        }
-        for (int j = rowptr[i]; j < rowptr[i + 1]; ++j)
-            if (colidx[j] < 0 || colidx[j] >= n) { set_error("cab200_plan_slots: column out of range"); return CAB200_EINVAL; }
-    }
-    Planner P;
-    P.n = n; P.np = (n + 31) & ~31; P.copies = copies; P.cpt = cells_per_thread;
-    P.rowptr = rowptr; P.col = colidx;
-    P.n_groups = P.np / 8;
-    P.slot_of.assign(n, 0);
-    P.cell_of.assign(P.np, -1);
-    // start: stable sort by row length, descending (what the kernel does on its own)
-    std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return (rowptr[a + 1] - rowptr[a]) > (rowptr[b + 1] - rowptr[b]);
-    });
-    if (use_input) {
-        std::vector<char> seen(n, 0);
-        for (int i = 0; i < n; ++i) {
-            const int sl = plan_out[i];
-            if (sl >= n || seen[sl]) { set_error("cab200_plan_slots: input is not a permutation"); return CAB200_EINVAL; }
-            seen[sl] = 1;
-            order[sl] = i;
-        }
-    }
-    for (int s = 0; s < n; ++s) { P.slot_of[order[s]] = s; P.cell_of[s] = order[s]; }
-    P.compute_wlen();
-    P.refs.assign(n, {});
-    for (int i = 0; i < n; ++i)
-        for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) P.refs[colidx[j]].push_back(i);
-
-    // length classes: a swap never changes which row lengths a warp holds
+    const int n = P.n;
     std::vector<std::vector<int>> class_slots(32);
     std::vector<int> class_of(n);
     for (int s = 0; s < n; ++s) {
-        const int len = rowptr[order[s] + 1] - rowptr[order[s]];
+        const int len = std::min(31, P.rowlen(P.cell_of[s]));
         class_of[s] = len;
         class_slots[len].push_back(s);
     }
-
     long long cost = P.total_cost();
-    const long long cost0 = cost;
+    if (cost0_out) *cost0_out = cost;
     Rng rng{seed ? seed : 0x5EEDull};
     std::vector<int> touched;
     const double t_start = 0.8, t_end = 0.02;
@@ -229,24 +211,176 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
             P.cell_of[sa] = a; P.cell_of[sb] = b;
         }
     }
-    // emit: slot_of[n], then per-cell copy-selection bit masks (bit e: entry e reads copy B)
-    for (int i = 0; i < n; ++i) { plan_out[i] = (uint16_t)P.slot_of[i]; plan_out[n + i] = 0; }
-    if (copies == 2) {
-        for (int g = 0; g < P.n_groups; ++g) {
-            const int wl = P.wlen[(g * 8) / (32 * P.cpt)];
-            for (int e = 0; e < wl; ++e) {
-                unsigned m = 0;
-                P.phase_cost(g, e, &m);
-                for (int l = 0; l < 8; ++l)
-                    if ((m >> l) & 1u) plan_out[n + P.cell_of[g * 8 + l]] |= (uint16_t)(1u << e);
-            }
+    return cost;
+}
+
+// copy-selection bit masks (bit e: entry e reads copy B) for the problem's final order
+void emit_sel(const Problem &P, std::vector<uint16_t> &sel)
+{
+    sel.assign(P.n, 0);
+    if (P.copies != 2) return;
+    for (int g = 0; g < P.n_groups; ++g) {
+        const int wl = P.wlen[(g * 8) / (32 * P.cpt)];
+        for (int e = 0; e < wl; ++e) {
+            unsigned m = 0;
+            P.phase_cost(g, e, &m);
+            for (int l = 0; l < 8; ++l)
+                if ((m >> l) & 1u) sel[P.cell_of[g * 8 + l]] |= (uint16_t)(1u << e);
         }
     }
-    if (cost_out) {
-        cost_out[0] = cost0; cost_out[1] = cost; cost_out[2] = P.total_cost();
-        long long rows = 0;      // LDS.128 instructions per step: per warp, trip count x groups it owns
-        for (int g = 0; g < P.n_groups; g += 4) rows += P.wlen[(g * 8) / (32 * P.cpt)];
-        cost_out[3] = rows;
+}
+
+int check_csr(int n, const int32_t *rowptr, const int32_t *colidx, const char *who)
+{
+    for (int i = 0; i < n; ++i) {
+        if (rowptr[i + 1] < rowptr[i] || rowptr[i + 1] - rowptr[i] > 16) {
+            set_error("%s: row %d: length outside [0,16]", who, i);
+            return CAB200_EINVAL;
+        }
+        for (int j = rowptr[i]; j < rowptr[i + 1]; ++j)
+            if (colidx[j] < 0 || colidx[j] >= n) { set_error("%s: column out of range", who); return CAB200_EINVAL; }
     }
     return CAB200_OK;
+}
+
+std::vector<int> length_sorted_order(const Problem &P)
+{
+    std::vector<int> order(P.n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return P.rowlen(a) > P.rowlen(b); });
+    return order;
+}
+
+}  // namespace
+}  // namespace cab200
+
+using namespace cab200;
+
+// See include/cab200.h.
+extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *colidx, int copies,
+                                 int cells_per_thread, long long iters, unsigned long long seed,
+                                 int use_input, uint16_t *plan_out, int64_t *cost_out)
+{
+    if (n <= 0 || n > 32767 || !rowptr || !colidx || !plan_out || (copies != 1 && copies != 2) ||
+        cells_per_thread < 1 || cells_per_thread > 8) {
+        set_error("cab200_plan_slots: bad argument");
+        return CAB200_EINVAL;
+    }
+    if (int rc = check_csr(n, rowptr, colidx, "cab200_plan_slots")) return rc;
+    Problem P;
+    P.n = n; P.copies = copies; P.cpt = cells_per_thread;
+    P.rowptr.assign(rowptr, rowptr + n + 1);
+    P.ecol.assign(colidx, colidx + rowptr[n]);
+    std::vector<int> order = length_sorted_order(P);
+    if (use_input) {
+        std::vector<char> seen(n, 0);
+        for (int i = 0; i < n; ++i) {
+            const int sl = plan_out[i];
+            if (sl >= n || seen[sl]) { set_error("cab200_plan_slots: input is not a permutation"); return CAB200_EINVAL; }
+            seen[sl] = 1;
+            order[sl] = i;
+        }
+    }
+    P.set_order(order);
+    long long cost0 = 0;
+    const long long cost = anneal(P, iters, seed, &cost0);
+    std::vector<uint16_t> sel;
+    emit_sel(P, sel);
+    for (int i = 0; i < n; ++i) { plan_out[i] = (uint16_t)P.slot_of[i]; plan_out[n + i] = sel[i]; }
+    if (cost_out) {
+        cost_out[0] = cost0; cost_out[1] = cost; cost_out[2] = P.total_cost();
+        cost_out[3] = P.gather_instructions();
+    }
+    return CAB200_OK;
+}
+
+// See include/cab200.h.
+extern "C" long long cab200_plan_cluster(int n, const int32_t *rowptr, const int32_t *colidx, int n_cta,
+                                         int copies, int cells_per_thread, long long iters,
+                                         unsigned long long seed, uint16_t *plan_out,
+                                         long long plan_capacity, int64_t *cost_out)
+{
+    if (n <= 0 || n > 32767 || !rowptr || !colidx || n_cta < 2 || n_cta > 8 || (copies != 1 && copies != 2) ||
+        cells_per_thread < 1 || cells_per_thread > 8) {
+        set_error("cab200_plan_cluster: bad argument");
+        return CAB200_EINVAL;
+    }
+    if (int rc = check_csr(n, rowptr, colidx, "cab200_plan_cluster")) return rc;
+    // ---- 1. breadth-first order from a pseudo-peripheral cell; parts = equal contiguous chunks ----
+    auto bfs = [&](int src, std::vector<int> &order) {
+        std::vector<char> seen(n, 0);
+        order.clear();
+        std::queue<int> q;
+        auto run = [&](int s0) {
+            q.push(s0); seen[s0] = 1;
+            while (!q.empty()) {
+                const int u = q.front(); q.pop();
+                order.push_back(u);
+                for (int j = rowptr[u]; j < rowptr[u + 1]; ++j)
+                    if (!seen[colidx[j]]) { seen[colidx[j]] = 1; q.push(colidx[j]); }
+            }
+        };
+        run(src);
+        for (int i = 0; i < n; ++i) if (!seen[i]) run(i);      // other components, in id order
+    };
+    std::vector<int> order;
+    bfs(0, order);
+    bfs(order.back(), order);
+    bfs(order.back(), order);
+    std::vector<int> part_of(n);
+    for (int i = 0; i < n; ++i) part_of[order[i]] = (int)((long long)i * n_cta / n);
+    // ---- 2. per part: local ids, halo list, plan ------------------------------------------------
+    std::vector<uint16_t> out;
+    out.resize(3 * (size_t)n + n_cta);          // part_of | slot_of | sel | halo_count[n_cta] | halo lists
+    long long c0 = 0, c1 = 0, rows = 0, halo_total = 0;
+    std::vector<std::vector<int>> halos(n_cta);
+    for (int q = 0; q < n_cta; ++q) {
+        std::vector<int> cells;                 // global ids of this part, ascending
+        for (int i = 0; i < n; ++i) if (part_of[i] == q) cells.push_back(i);
+        std::vector<int> local_of(n, -1);
+        for (size_t k = 0; k < cells.size(); ++k) local_of[cells[k]] = (int)k;
+        std::vector<int> &halo = halos[q];
+        for (int c : cells)
+            for (int j = rowptr[c]; j < rowptr[c + 1]; ++j)
+                if (part_of[colidx[j]] != q) halo.push_back(colidx[j]);
+        std::sort(halo.begin(), halo.end());
+        halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+        Problem P;
+        P.n = (int)cells.size(); P.copies = copies; P.cpt = cells_per_thread;
+        P.rowptr.assign(1, 0);
+        for (int c : cells) {
+            for (int j = rowptr[c]; j < rowptr[c + 1]; ++j) {
+                const int cc = colidx[j];
+                if (part_of[cc] == q) P.ecol.push_back(local_of[cc]);
+                else P.ecol.push_back(-1 - (int)(std::lower_bound(halo.begin(), halo.end(), cc) - halo.begin()));
+            }
+            P.rowptr.push_back((int)P.ecol.size());
+        }
+        if (P.n == 0) { set_error("cab200_plan_cluster: empty part"); return CAB200_EINVAL; }
+        P.set_order(length_sorted_order(P));
+        long long cost0 = 0;
+        c1 += anneal(P, iters / n_cta, seed + 977 * (q + 1), &cost0);
+        c0 += cost0;
+        rows += P.gather_instructions();
+        std::vector<uint16_t> sel;
+        emit_sel(P, sel);
+        for (int k = 0; k < P.n; ++k) {
+            out[cells[k]] = (uint16_t)q;
+            out[n + cells[k]] = (uint16_t)P.slot_of[k];
+            out[2 * (size_t)n + cells[k]] = sel[k];
+        }
+        out[3 * (size_t)n + q] = (uint16_t)halo.size();
+        halo_total += (long long)halo.size();
+    }
+    for (int q = 0; q < n_cta; ++q)
+        for (int h : halos[q]) out.push_back((uint16_t)h);
+    if (cost_out) { cost_out[0] = c0; cost_out[1] = c1; cost_out[2] = halo_total; cost_out[3] = rows; }
+    if (plan_out) {
+        if ((long long)out.size() > plan_capacity) {
+            set_error("cab200_plan_cluster: plan needs %zu uint16, capacity %lld", out.size(), plan_capacity);
+            return CAB200_ESIZE;
+        }
+        std::copy(out.begin(), out.end(), plan_out);
+    }
+    return (long long)out.size();
 }

@@ -108,17 +108,25 @@ class _DeviceGeometry:
         self.col = torch.from_numpy(col).to(device)
         self.val = torch.from_numpy(val).to(device)
         self.label_maps: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
-        self.plans: Dict[int, torch.Tensor] = {}
+        self.plans: Dict[Tuple[int, int], torch.Tensor] = {}
 
-    def plan(self, precision: int) -> torch.Tensor:
-        """Device copy of the K1 slot plan (``cab200_plan_slots``) for this geometry; the plan is
-        pure layout (bank-conflict avoidance), computed once on the host and cached on disk."""
-        t = self.plans.get(precision)
+    def plan(self, precision: int, n_cta: int = 1) -> torch.Tensor:
+        """Device copy of the K1 layout plan (``cab200_plan_slots`` / ``cab200_plan_cluster``) for this
+        geometry; pure layout (bank-conflict avoidance, cluster partition), computed once on the host
+        and cached on disk."""
+        t = self.plans.get((precision, n_cta))
         if t is None:
-            t = torch.from_numpy(slot_plan(self.geo, self.unit, precision).view(np.int16)).to(
+            t = torch.from_numpy(slot_plan(self.geo, self.unit, precision, n_cta=n_cta).view(np.int16)).to(
                 self.rowptr.device)
-            self.plans[precision] = t
+            self.plans[(precision, n_cta)] = t
         return t
+
+    def auto_cluster(self) -> int:
+        """CTAs per pouch when the caller leaves the choice to the library: one CTA up to 1536 cells
+        (what a 512-thread CTA holds without spilling), else a cluster of 2 or 4."""
+        if not self.unit or self.n <= 1536:
+            return 1
+        return 2 if self.n <= 3072 else 4
 
 
 PLAN_ITERS = int(os.environ.get("CALCIUM_B200_PLAN_ITERS", "300000"))
@@ -133,14 +141,15 @@ def plan_layout(n: int, unit: bool, precision: int) -> Tuple[int, int]:
     return int(lay[2]), int(lay[1])
 
 
-def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool) -> str:
+def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool, n_cta: int = 1) -> str:
     """Plans are keyed by the CSR structure and the layout they were made for.  ``tracked`` plans
     (long offline annealing, scripts/make_plans.py) ship with the package under ``plans/``; others
     are computed on first use and cached next to the synthetic geometry cache."""
     rowptr, col, _ = geo.csr
     h = hashlib.sha1()
     h.update(rowptr.tobytes()); h.update(col.tobytes())
-    h.update(f"copies={copies}:cpt={cpt}:v3".encode())
+    h.update(f"copies={copies}:cpt={cpt}:v3".encode() if n_cta == 1
+             else f"copies={copies}:cpt={cpt}:ncta={n_cta}:v1".encode())
     name = f"plan_{h.hexdigest()[:16]}.npy"
     if tracked:
         return os.path.join(_PLANS_DIR, name)
@@ -148,27 +157,45 @@ def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool) -> str:
     return os.path.join(os.path.dirname(_synthetic_cache_path("x")), name)
 
 
-def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = None) -> np.ndarray:
-    """uint16[2n] plan for ``geo`` (see ``cab200_plan_slots`` in include/cab200.h)."""
+def cluster_layout(n: int, n_cta: int, precision: int) -> Tuple[int, int]:
+    lay = np.zeros(4, dtype=np.int64)
+    _lib.check(_lib.load().cab200_cluster_layout(n, n_cta, precision, _lib.as_i64p(lay)),
+               "cab200_cluster_layout")
+    return int(lay[2]), int(lay[1])
+
+
+def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = None,
+              n_cta: int = 1) -> np.ndarray:
+    """uint16 plan for ``geo``: ``cab200_plan_slots`` (one CTA per pouch, ``[2n]``) or
+    ``cab200_plan_cluster`` (``n_cta`` CTAs per pouch); see include/cab200.h."""
     lib = _lib.load()
     rowptr, col, _ = geo.csr
     n = geo.n_cells
-    copies, cpt = plan_layout(n, unit, precision)
-    paths = [plan_path(geo, copies, cpt, True), plan_path(geo, copies, cpt, False)]
+    copies, cpt = plan_layout(n, unit, precision) if n_cta == 1 else cluster_layout(n, n_cta, precision)
+    paths = [plan_path(geo, copies, cpt, True, n_cta), plan_path(geo, copies, cpt, False, n_cta)]
     if iters is None:
         for path in paths:
             if os.path.exists(path):
                 try:
                     plan = np.load(path)
-                    if plan.shape == (2 * n,) and plan.dtype == np.uint16:
+                    if plan.dtype == np.uint16 and plan.ndim == 1 and (n_cta > 1 or plan.shape == (2 * n,)):
                         return plan
                 except Exception:  # noqa: BLE001 - a corrupt cache entry is just recomputed
                     pass
-    plan = np.zeros(2 * n, dtype=np.uint16)
-    _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, cpt,
-                                     PLAN_ITERS if iters is None else iters, 1, 0,
-                                     plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None),
-               "cab200_plan_slots")
+    n_it = PLAN_ITERS if iters is None else iters
+    if n_cta == 1:
+        plan = np.zeros(2 * n, dtype=np.uint16)
+        _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, cpt, n_it, 1, 0,
+                                         plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None),
+                   "cab200_plan_slots")
+    else:
+        cap = 3 * n + n_cta + n_cta * n
+        plan = np.zeros(cap, dtype=np.uint16)
+        got = lib.cab200_plan_cluster(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), n_cta, copies, cpt, n_it, 1,
+                                      plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), cap, None)
+        if got < 0:
+            _lib.check(int(got), "cab200_plan_cluster")
+        plan = plan[:int(got)].copy()
     if iters is None:
         try:
             os.makedirs(os.path.dirname(paths[1]), exist_ok=True)
@@ -252,7 +279,7 @@ class Ensemble:
     def __init__(self, specs: Sequence[PouchSpec], *, output_size: Tuple[int, int] = (512, 512),
                  T: int = T_DEFAULT, frame_steps: Optional[Sequence[int]] = None,
                  device: Optional[torch.device] = None, precision: int = _lib.FP64_STRICT,
-                 dt: float = DT, use_plan: bool = True):
+                 dt: float = DT, use_plan: bool = True, cluster="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("calcium_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -299,10 +326,21 @@ class Ensemble:
         ncell = self.g_ncell[gid].astype(np.int64)
         self.cell_off = np.concatenate([[0], np.cumsum(ncell)]).astype(np.int64)
         self.total_cells = int(self.cell_off[-1])
+        # CTAs per pouch: "auto" (one CTA up to 1536 cells, else a cluster), or 1 / 2 / 4 for all
+        self.g_cluster = np.array([d.auto_cluster() if cluster == "auto" else (int(cluster) if d.unit else 1)
+                                   for d in self.dgeo], dtype=np.int32)
         self.use_plan = use_plan
         self.d_plan: Optional[torch.Tensor] = None
-        if use_plan:
-            plans = [d.plan(precision) for d in self.dgeo]
+        self.g_plan_off = np.full(len(self.dgeo), -1, dtype=np.int64)
+        plans, off = [], 0
+        for gi, d in enumerate(self.dgeo):
+            nc = int(self.g_cluster[gi])
+            if use_plan or nc > 1:          # a cluster cannot run without its partition plan
+                t = d.plan(precision, nc)
+                self.g_plan_off[gi] = off
+                plans.append(t)
+                off += int(t.numel())
+        if plans:
             self.d_plan = plans[0] if len(plans) == 1 else torch.cat(plans)
 
         # host staging (pinned) for the per-pouch inputs: params | c0 | p0 | r0 | vplc
@@ -366,6 +404,7 @@ class Ensemble:
                 _lib.as_i32p(self.g_max_row), _lib.as_i32p(self.g_unit),
                 _lib.as_i64p(self.g_rowptr_off), _lib.as_i64p(self.g_nnz_off),
                 self.d_rowptr.data_ptr(), self.d_col.data_ptr(), self.d_val.data_ptr(),
+                _lib.as_i32p(self.g_cluster), _lib.as_i64p(self.g_plan_off),
                 self.d_plan.data_ptr() if self.d_plan is not None else None,
                 _lib.as_i64p(self.cell_off),
                 base, base + 8 * np_, base + 8 * (np_ + tc), base + 8 * (np_ + 2 * tc),

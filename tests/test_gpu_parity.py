@@ -110,6 +110,38 @@ def test_layout_choices_never_change_results(env):
     assert np.array_equal(want, ref.reshape(-1)[1500 * 4 * 3: 2 * 1500 * 4 * 3].reshape(3, 4, 1500))
 
 
+@pytest.mark.parametrize("size,n_cta,count,T", [("xsmall", 2, 3, 4000), ("small", 2, 3, 4000), ("medium", 2, 3, 6000),
+                                                  ("medium", 4, 5, 6000), ("large", 4, 2, 5000)])
+def test_cluster_path_bit_exact(env, size, n_cta, count, T):
+    """A pouch split over a thread-block cluster (halo entries pushed through distributed shared
+    memory, cluster-wide step barrier) produces the same bits as the oracle."""
+    E, O = env["E"], env["O"]
+    specs = E.make_specs(count, size=size, first_seed=60)
+    steps = [0, 1, 2, T // 2, T - 1]
+    ens = E.Ensemble(specs, T=T, frame_steps=steps, device=env["dev"], cluster=n_cta)
+    assert ens.g_cluster.tolist() == [n_cta]
+    ens.simulate(); ens.synchronize()
+    assert not ens.check_status().any()
+    for i, s in enumerate(specs):
+        want = _oracle_frames(O, s, T, steps)
+        got = ens.frames_of(i).cpu().numpy()
+        assert np.array_equal(want, got), f"{size} x{n_cta} [{i}] max abs diff {np.abs(want - got).max():.3e}"
+
+
+def test_cluster_auto_for_large_and_mixed_ensembles(env):
+    """cluster="auto": large pouches take 4-CTA clusters, the rest one CTA, in one call."""
+    E, O = env["E"], env["O"]
+    specs = E.make_specs(2, size="large", first_seed=5) + E.make_specs(3, size="medium", first_seed=9) + \
+        E.make_specs(2, size="xsmall", first_seed=1)
+    T, steps = 3000, [0, 1500, 2999]
+    ens = E.Ensemble(specs, T=T, frame_steps=steps, device=env["dev"])
+    assert sorted(ens.g_cluster.tolist()) == [1, 1, 4]
+    ens.simulate()
+    assert not ens.check_status().any()
+    for i, s in enumerate(specs):
+        assert np.array_equal(_oracle_frames(O, s, T, steps), ens.frames_of(i).cpu().numpy()), i
+
+
 def _weighted_geometry(n=300, seed=5):
     from calcium_b200.geometry import Geometry, make_synthetic_geometry
     g = make_synthetic_geometry("w", n_cells=n, seed=seed)

@@ -53,7 +53,7 @@ def test_argument_validation_needs_no_gpu(lib):
     z32 = np.zeros(4, dtype=np.int32); z64 = np.zeros(4, dtype=np.int64)
     rc = lib.cab200_sim_batch(1, _lib.as_i32p(z32), 0, _lib.as_i32p(z32), _lib.as_i32p(z32),
                               _lib.as_i32p(z32), _lib.as_i64p(z64), _lib.as_i64p(z64), None, None, None,
-                              None, _lib.as_i64p(z64), None, None, None, None, None, 10, 0,
+                              None, None, None, _lib.as_i64p(z64), None, None, None, None, None, 10, 0,
                               _lib.as_i32p(z32), None, None, 64, None, 0, None)
     assert rc == -1 and b"bad sizes" in lib.cab200_last_error()
     assert lib.cab200_sim_set_plan(2000, 333, 2) == -1
@@ -84,6 +84,46 @@ def test_layout_and_planner(lib):
         order = np.argsort(plan[:n])
         assert np.all(np.diff(lens[order]) <= 0), "cells stay sorted by row length"
         assert np.all(plan[n:] < (1 << lens.max())) and (copies == 2 or not plan[n:].any())
+
+
+def test_cluster_planner(lib):
+    """cab200_plan_cluster: parts cover the cells evenly, slots are unique inside a part, halo lists
+    are exactly the other-part columns of each part's rows (sorted), and boundaries are thin."""
+    from calcium_b200 import _lib
+    from calcium_b200.geometry import get_geometry
+    lay = np.zeros(4, dtype=np.int64)
+    for size, n_cta in (("medium", 2), ("medium", 4), ("large", 4)):
+        g = get_geometry(size)
+        rowptr, col, _ = g.csr
+        n = g.n_cells
+        lay = np.zeros(4, dtype=np.int64)
+        assert lib.cab200_cluster_layout(n, n_cta, 64, _lib.as_i64p(lay)) == 0
+        threads, cpt, copies, smem = lay.tolist()
+        assert threads * cpt * n_cta >= n and smem <= 227 * 1024
+        cap = 3 * n + n_cta + n_cta * n
+        plan = np.zeros(cap, dtype=np.uint16)
+        cost = np.zeros(4, dtype=np.int64)
+        got = lib.cab200_plan_cluster(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), n_cta, copies, cpt, 5000, 3,
+                                      plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), cap, _lib.as_i64p(cost))
+        assert got > 3 * n + n_cta
+        part, slot = plan[:n].astype(int), plan[n:2 * n].astype(int)
+        counts = np.bincount(part, minlength=n_cta)
+        assert counts.max() - counts.min() <= 1 and counts.sum() == n
+        hcount = plan[3 * n:3 * n + n_cta].astype(int)
+        assert got == 3 * n + n_cta + hcount.sum() and cost[2] == hcount.sum()
+        hl = plan[3 * n + n_cta:got].astype(int)
+        off = 0
+        for q in range(n_cta):
+            mine = np.nonzero(part == q)[0]
+            assert sorted(slot[mine].tolist()) == list(range(len(mine)))       # a permutation inside the part
+            want = sorted({int(c) for i in mine for c in col[rowptr[i]:rowptr[i + 1]] if part[c] != q})
+            assert hl[off:off + hcount[q]].tolist() == want
+            off += hcount[q]
+            assert hcount[q] <= 384                                            # CAB_HMAX
+        assert hcount.sum() < 0.25 * n                                         # thin boundaries
+    assert lib.cab200_cluster_layout(1500, 3, 64, _lib.as_i64p(lay)) == -1
+    assert lib.cab200_cluster_layout(3255, 2, 64, _lib.as_i64p(lay)) == -3      # 1628 cells per CTA > 1536
+    assert lib.cab200_cluster_layout(20000, 4, 64, _lib.as_i64p(lay)) == -3
 
 
 def test_parameters_api():
