@@ -130,44 +130,90 @@ def run_reference_arm(args) -> None:
 # --------------------------------------------------------------------------------------------------
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every few ms from a
+    thread (``nvidia-smi -lms`` needs ~1 s to print its first row, longer than a short timed region);
+    ``nvidia-smi`` is the fallback when NVML cannot be loaded."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.rows = []
+    def __init__(self, index: int, uuid: str = None, period_s: float = 0.004):
+        self.rows = []            # (t, sm_mhz, sm_max_mhz, [reason names])
         self.proc = None
+        self.nvml = None
+        self._stop = threading.Event()
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:  # noqa: BLE001
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.handle, self.period = pynvml, h, period_s
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001 - fall back to nvidia-smi
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                 else 0x8),
+                ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:  # noqa: BLE001
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((time.perf_counter(), sm, self.mx, [n for n, b in bits if mask & b]))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
-
-    def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
-        sm, mx, reasons = [], [], set()
-        for r in rows:
+            c = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                self.rows.append((time.perf_counter(), float(c[0]), float(c[1]),
+                                  [n for n, v in zip(self.NAMES, c[3:7]) if v.lower().startswith("active")]))
             except (ValueError, IndexError):
                 continue
-            for name, val in zip(self.NAMES, r[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        rows = inside or list(self.rows)
+        sm = [r[1] for r in rows]
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "reasons": reasons, "samples": len(sm), "samples_in_timed_region": len(inside), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -219,7 +265,14 @@ def run_gpu(args) -> None:
     # ---- device-resident timed region: exactly K steps --------------------------------------------
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    sampler = None
+    if rank == 0:
+        try:
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+        except Exception:  # noqa: BLE001
+            uuid = None
+        sampler = ClockSampler(local, uuid)
     barrier()
     t_host0 = time.perf_counter()
     start.record()
@@ -230,7 +283,7 @@ def run_gpu(args) -> None:
         ev[k][1].record()
         raster_all()
         ev[k][2].record()
-        launches += 1 + (P + chunk - 1) // chunk
+        launches += 1 + (P + chunk - 1) // chunk          # one K1 launch + one K2 launch per raster chunk
     stop.record()
     barrier()
     t_host1 = time.perf_counter()
@@ -247,20 +300,57 @@ def run_gpu(args) -> None:
     work_per_gpu = n_cells * P * (T_STEPS - 1)
     value = work_per_gpu * world / (ms_per_step * 1e-3)
 
+    # ---- K3 alone (device resident): rasterise + encode every frame into .png / .npz files ---------
+    enc_out = {}
+    def encode_all():
+        for lo in range(0, P, chunk):
+            hi = min(lo + chunk, P)
+            ens.encode(pouches=(lo, hi), out=enc_out)
+    encode_all()
+    barrier()
+    s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s3.record()
+    for _ in range(args.steps):
+        encode_all()
+    e3.record()
+    barrier()
+    k3_ms = s3.elapsed_time(e3) / args.steps
+    enc_out.clear()
+    out.clear()
+    torch.cuda.empty_cache()
+
     # ---- end to end through the public API, host buffers both sides --------------------------------
+    # (a) the batch path's product: every frame as a finished .png + .npz in host memory (K1 -> K3)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    moved = ens.run_to_host(chunk_pouches=args.e2e_chunk)       # warm: allocates the pinned rings
-    barrier()
-    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s2.record()
-    for _ in range(e2e_steps):
-        moved = ens.run_to_host(chunk_pouches=args.e2e_chunk)
-    e2.record()
-    barrier()
-    e2e_ms = torch.tensor([s2.elapsed_time(e2) / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = work_per_gpu * world / (e2e_ms.item() * 1e-3)
+
+    def timed_e2e(fn, finish=None):
+        moved = fn()                                             # warm: allocates the pinned rings
+        if finish:
+            finish()
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        h2d = d2h = 0
+        for _ in range(e2e_steps):
+            moved = fn()
+            h2d += moved["h2d_bytes"]; d2h += moved["d2h_bytes"]
+        if finish:
+            d2h += finish()                                      # every byte is in host memory before the clock stops
+        e2.record()
+        barrier()
+        ms = torch.tensor([s2.elapsed_time(e2) / e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return {"h2d_bytes": h2d // e2e_steps, "d2h_bytes": d2h // e2e_steps}, ms.item()
+
+    # steps are pipelined: the copy-out of a step's last chunks overlaps the next step's integration
+    moved, e2e_ms_v = timed_e2e(lambda: ens.run_files_to_host(chunk_pouches=chunk, wait=False), ens.flush_files)
+    e2e_value = work_per_gpu * world / (e2e_ms_v * 1e-3)
+    if hasattr(ens, "_fring"):
+        del ens._fring
+    # (b) the same with raw arrays (images + instance masks uncompressed): PCIe bound
+    moved_raw, e2e_raw_ms = timed_e2e(lambda: ens.run_to_host(chunk_pouches=args.e2e_chunk))
+    e2e_raw_value = work_per_gpu * world / (e2e_raw_ms * 1e-3)
 
     if rank == 0:
         # ---- rooflines ------------------------------------------------------------------------------
@@ -323,9 +413,16 @@ def run_gpu(args) -> None:
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "cpu_baseline_reference_style": (cpu_reference_style_throughput() if cpu else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"],
-                    "d2h_bytes_per_step": moved["d2h_bytes"], "ms_per_step": e2e_ms.item(), "steps": e2e_steps,
-                    "path": "Ensemble.run_to_host: pinned host inputs -> K1 -> K2 -> frames + images + instance "
-                            "masks copied to pinned host memory (copy stream overlaps K2)"},
+                    "d2h_bytes_per_step": moved["d2h_bytes"], "ms_per_step": e2e_ms_v, "steps": e2e_steps,
+                    "path": "Ensemble.run_files_to_host (what generate_simulation_batch runs): pinned host inputs -> K1 -> "
+                            "K3 (rasterise + DEFLATE-encode on the device) -> float64 frames + every frame's finished "
+                            ".png (16-bit gray+alpha) and .npz (instance mask) copied to pinned host memory; "
+                            "decoding them gives bit for bit the arrays of e2e_raw_arrays"},
+            "e2e_raw_arrays": {"value": e2e_raw_value, "unit": UNIT, "h2d_bytes_per_step": moved_raw["h2d_bytes"],
+                               "d2h_bytes_per_step": moved_raw["d2h_bytes"], "ms_per_step": e2e_raw_ms,
+                               "path": "Ensemble.run_to_host: K1 -> K2 -> frames + uncompressed images + instance "
+                                       "masks to pinned host memory (PCIe bound)"},
+            "k3_ms": k3_ms,
             "gpu_launches": launches, "clocks": clocks, "status_nonzero": status_bad,
         }
         print(json.dumps(line), flush=True)
@@ -342,7 +439,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pouches-per-gpu", type=int, default=POUCHES_PER_GPU)
     ap.add_argument("--raster-chunk", type=int, default=37)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunk", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -19,12 +19,15 @@ PARAM_SLOTS = ["k_1", "k_a", "k_p", "k_2", "V_SERCA", "K_SERCA", "K_PLC", "K_5",
                "k_tau", "tau_max", "k_i", "D_c", "D_p", "dt"]
 ST_NONFINITE = 1
 ST_BADGEOM = 2
+ENC_OK, ENC_STAGE_FULL, ENC_ARENA_FULL, ENC_SKIPPED = 1, 2, 4, 8
 
 #: every symbol include/cab200.h declares (tests check the library exports all of them)
 EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
            "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_sim_layout",
            "cab200_cluster_layout", "cab200_plan_cluster",
            "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
+           "cab200_encode_tables_bytes", "cab200_encode_tables", "cab200_encode_scratch_bytes", "cab200_encode_batch",
+           "cab200_encode_geometry_bytes", "cab200_encode_geometry", "cab200_publish_to_host",
            "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_selftest_division"]
 
 
@@ -77,6 +80,25 @@ def load() -> ctypes.CDLL:
     lib.cab200_raster_batch.argtypes = [
         c_int, i32p, i32p, i64p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
         c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.cab200_encode_tables_bytes.restype = c_size_t
+    lib.cab200_encode_tables_bytes.argtypes = []
+    lib.cab200_encode_tables.restype = c_int
+    lib.cab200_encode_tables.argtypes = [c_int, c_int, c_void_p]
+    lib.cab200_encode_scratch_bytes.restype = c_size_t
+    lib.cab200_encode_scratch_bytes.argtypes = [c_int, c_int]
+    lib.cab200_encode_geometry_bytes.restype = c_size_t
+    lib.cab200_encode_geometry_bytes.argtypes = [c_int]
+    lib.cab200_encode_geometry.restype = c_int
+    lib.cab200_encode_geometry.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.cab200_encode_batch.restype = c_int
+    lib.cab200_encode_batch.argtypes = [
+        c_int, i32p, c_int, i32p, i64p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+        c_double, c_int, c_int, c_int,                         # threshold, quirk, want_image, want_mask
+        c_void_p, c_void_p, i64p,                              # tables, geom_tabs, g_tab_off
+        c_void_p, c_size_t, c_void_p,                          # arena, arena_bytes, cursor
+        c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
+    lib.cab200_publish_to_host.restype = c_int
+    lib.cab200_publish_to_host.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cab200_cells_mask.restype = c_int
     lib.cab200_cells_mask.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.cab200_paint_label_map.restype = c_int

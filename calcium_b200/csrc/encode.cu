@@ -1,0 +1,903 @@
+// encode.cu -- K3: rasterise AND losslessly encode every (pouch, frame) on the device, so that what
+// crosses PCIe is the file the reference's batch path stores, not the raw pixels.
+//
+// Replaces, per sampled frame of the batch path (reference main.py:270-330):
+//   Pouch.generate_image + save_image(..., format='png')   core/pouch.py:412-453,
+//        utils/image_processing.py:252-269  (gray*4 | alpha*257, 16-bit gray+alpha PNG)
+//   process_batch_for_sam2's mask branch                   utils/sam2_data_generator.py:315-335
+//        (get_active_cells, get_cell_masks(active_only), create_instance_mask_from_cells,
+//         np.savez_compressed(path, mask=instance_mask); no file when no cell is active)
+// Output per frame: one complete .png byte string and one complete .npz byte string in a device
+// arena, plus a record (offset, size).  A 512x512 frame is 1.5 MiB of raw pixels; encoded it is
+// typically 30-60 KiB, which is what makes the end-to-end path compute- instead of PCIe-bound.
+//
+// One CTA per (pouch, frame).  It builds the per-frame look-up tables (frame_lut.cuh), then encodes
+// the two streams one after the other into a shared-memory staging buffer:
+//   * the pixel rows are never materialised: a warp handles one 512-pixel row segment, a lane 16
+//     consecutive pixels, read from the static label map (L2 resident) through the LUT;
+//   * LZ77 parse restricted to two match distances: the previous pixel (runs inside a cell) and the
+//     pixel above (rows of flat-shaded polygons mostly repeat the row above).  Per pixel the mode is
+//     "up" if it equals the pixel above, else "left" if it equals the previous pixel, else literal;
+//     a token is a maximal run of one mode, cut at multiples of 256 bytes and at segment ends;
+//   * DEFLATE with the fixed Huffman code (one final block): token bit lengths are known from small
+//     tables, a warp scan + a CTA scan over the 16 rows of a pass give every token its bit
+//     position, and the bits are OR-ed into the zeroed staging buffer with shared-memory atomics;
+//   * checksums on the fly: Adler-32 of the PNG scanlines (plain sums), CRC-32 of the .npy bytes
+//     (per-lane table CRC, moved to its place in the message by multiplication with x^(8k) mod P in
+//     GF(2)[x] -- CRC is linear), CRC-32 of the finished IDAT chunk (pieces combined the same way);
+//   * the finished file is copied to the arena at a cursor advanced with one atomicAdd.
+// A frame whose encoding does not fit the staging buffer is flagged; the host falls back to K2 + a
+// host encoder for it (never observed for polygon images; covered by a test with a tiny buffer).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "frame_lut.cuh"
+
+namespace cab200 {
+
+constexpr int ENC_NT = 512;
+constexpr int ENC_NW = ENC_NT / 32;
+constexpr int ENC_MAXDIM = 2048;
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+
+struct EncStream {
+    uint8_t prefix[64];
+    uint8_t suffix[96];
+    uint8_t head[192];       // uncompressed bytes in front of the pixel rows (.npy header), sent as literals
+    uint16_t head_off[192];  // bit offset of head byte j's literal; head_bits = all of them
+    int head_bits;
+    int prefix_len, suffix_len, head_len;
+    uint32_t dist_left, dist_up;   // distance code + extra bits (low 24 bits) | bit count << 24; count 0 = unusable
+    int bpp;                 // bytes per pixel in the uncompressed stream
+    int seg_lanes;           // a forced token start every seg_lanes lanes (16 pixels each): 256 bytes
+    int row_lead;            // PNG: one filter byte (0) in front of every row
+    uint32_t crc_const;      // npz: CRC-32 terms that do not depend on the pixels
+    uint32_t raw_len;        // length of the uncompressed stream
+    int p_len_prefix;        // PNG: position of the big-endian IDAT length in the prefix
+    int p_crc_prefix, p_csize_prefix;                    // zip local header fields (little endian)
+    int p_crc_suffix, p_csize_suffix, p_cdoff_suffix;    // zip central directory / end record
+};
+
+struct EncTables {
+    uint32_t lit[256];       // fixed-Huffman literal: reversed code | bits << 24
+    uint32_t len[260];       // match length 3..258: reversed code + extra bits | bits << 24
+    uint32_t crc[256];       // reflected CRC-32 table
+    uint32_t pow8[32];       // x^(8 * 2^k) mod P
+    uint32_t rowshift[ENC_MAXDIM];        // mask: x^(8 * bytes after row y)
+    uint32_t colshift[ENC_MAXDIM / 16];   // mask: x^(8 * bytes after 16-pixel chunk c inside its row)
+    EncStream img, msk;
+    int H, W;
+};
+
+struct EncRecord {
+    unsigned long long offset;
+    uint32_t size;
+    uint32_t flags;
+};
+
+struct EncodeArgs {
+    const PouchEntry *pouches;
+    const uint16_t *label_img, *label_mask;
+    const double *ca_frames;
+    const EncTables *tab;
+    const unsigned char *geom_tabs;   // per-geometry checksum tables (enc_geometry_kernel)
+    const long long *geom_tab_off;    // [G] byte offsets into geom_tabs
+    int n_frames, H, W;
+    double threshold;
+    int quirk, want_img, want_msk;
+    int lut_bytes, stage_cap;
+    uint8_t *arena;
+    unsigned long long *cursor;
+    unsigned long long arena_bytes;
+    EncRecord *records;      // [P*F][2]: image, mask
+    int32_t *n_active_out;
+};
+
+// ---- GF(2)[x] mod the CRC-32 polynomial, reflected representation (bit 31 = x^0) ------------------
+__host__ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+#pragma unroll
+    for (int i = 31; i >= 0; --i) {
+        p ^= b & (0u - ((a >> i) & 1u));
+        b = (b >> 1) ^ (CRC_POLY & (0u - (b & 1u)));
+    }
+    return p;
+}
+
+// x^(8*n) from the table of x^(8*2^k)
+__device__ __forceinline__ uint32_t gf2_xpow8(const uint32_t *pow8, uint32_t n)
+{
+    uint32_t r = 0x80000000u;   // x^0
+    for (int k = 0; n; ++k, n >>= 1)
+        if (n & 1u) r = gf2_mulmod(r, pow8[k]);
+    return r;
+}
+
+__device__ __forceinline__ void put_bits(uint32_t *w, uint32_t pos, unsigned long long val, int nb)
+{
+    const uint32_t idx = pos >> 5, sh = pos & 31u;
+    const unsigned long long v0 = val << sh;
+    atomicOr(&w[idx], (uint32_t)v0);
+    if (sh + nb > 32) atomicOr(&w[idx + 1], (uint32_t)(v0 >> 32));
+    if (sh + nb > 64) atomicOr(&w[idx + 2], (uint32_t)(val >> (64 - sh)));
+}
+
+__device__ __forceinline__ void put_le32(uint8_t *p, uint32_t v)
+{
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+__device__ __forceinline__ void put_be32(uint8_t *p, uint32_t v)
+{
+    p[3] = (uint8_t)v; p[2] = (uint8_t)(v >> 8); p[1] = (uint8_t)(v >> 16); p[0] = (uint8_t)(v >> 24);
+}
+
+// Static per-(geometry, H, W) checksum tables, one block per geometry:
+//   Q[n+1] u32 | cnt[n+1] u32 | (8-byte aligned) M[n+1] u64      (see encode_stream's finalisation)
+struct GeomTab {
+    const uint32_t *Q, *cnt;
+    const unsigned long long *M;
+};
+__host__ __device__ inline size_t geom_tab_bytes(int n) { return (((size_t)(n + 1) * 8 + 7) & ~(size_t)7) + (size_t)(n + 1) * 8; }
+__device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n)
+{
+    GeomTab t;
+    t.Q = reinterpret_cast<const uint32_t *>(p);
+    t.cnt = t.Q + (n + 1);
+    t.M = reinterpret_cast<const unsigned long long *>(p + (((size_t)(n + 1) * 8 + 7) & ~(size_t)7));
+    return t;
+}
+
+// Fills one geometry's block (zeroed by the caller).  One thread per pixel, atomics on ~n addresses;
+// runs once per (geometry, output size).
+__global__ void __launch_bounds__(256) enc_geometry_kernel(const uint16_t *label_img, const uint16_t *label_mask, int H,
+                                                           int W, int n, const EncTables *tab, unsigned char *out)
+{
+    extern __shared__ uint32_t colpx[];     // [W] x^(8 * bytes after pixel x inside its row)
+    for (int x = threadIdx.x; x < W; x += blockDim.x) colpx[x] = gf2_xpow8(tab->pow8, 2u * (uint32_t)(W - 1 - x));
+    __syncthreads();
+    uint32_t *Q = reinterpret_cast<uint32_t *>(out);
+    uint32_t *cnt = Q + (n + 1);
+    unsigned long long *M = reinterpret_cast<unsigned long long *>(out + (((size_t)(n + 1) * 8 + 7) & ~(size_t)7));
+    const unsigned long long N = tab->img.raw_len;
+    const unsigned long long row_bytes = 1ull + 4ull * (unsigned long long)W;
+    const int npix = H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        const int li = label_img[i], lm = label_mask[i];
+        if (li > 0 && li <= n) {
+            atomicAdd(&cnt[li], 1u);
+            atomicAdd(&M[li], N - ((unsigned long long)y * row_bytes + 1ull + 4ull * (unsigned long long)x));
+        }
+        if (lm <= n) atomicXor(&Q[lm], gf2_mulmod(tab->rowshift[y], colpx[x]));
+    }
+}
+
+// shared-memory tables of one CTA
+struct EncSmem {
+    unsigned long long *lit64;   // [512] image pixel (gray | alpha flag << 8) -> 4 literals: bits | count << 58
+    uint32_t *len_s, *lit_s, *crc_s;
+    uint8_t *stage;
+};
+
+// 16 labels of one lane -> 8 packed keys (two 16-bit keys per word)
+template <bool IMG>
+__device__ __forceinline__ void load_keys(const uint16_t *row, int xl, int nvalid, bool vec_ok, const FrameLut &lut,
+                                          uint32_t k[8])
+{
+    uint32_t w[8];
+    if (nvalid == 16 && vec_ok) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(row + xl));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(row + xl) + 1);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t l0 = (2 * q < nvalid) ? (uint32_t)__ldg(row + xl + 2 * q) : 0u;
+            const uint32_t l1 = (2 * q + 1 < nvalid) ? (uint32_t)__ldg(row + xl + 2 * q + 1) : 0u;
+            w[q] = l0 | (l1 << 16);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t l0 = w[q] & 0xffffu, l1 = w[q] >> 16;
+        const uint16_t *kl = IMG ? lut.rank1 : lut.inst_lut;    // image: key LUT built over the rank scratch
+        k[q] = (uint32_t)kl[l0] | ((uint32_t)kl[l1] << 16);
+    }
+}
+
+template <bool IMG>
+__device__ __forceinline__ uint32_t one_key(const uint16_t *p, const FrameLut &lut)
+{
+    const uint32_t l = __ldg(p);
+    return IMG ? lut.rank1[l] : lut.inst_lut[l];
+}
+
+// Encodes one stream into sm.stage.  Returns the total file size in bytes, or 0 when the staging
+// buffer is too small (uniform over the CTA).
+template <bool IMG>
+__device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const EncSmem &sm, const FrameLut &lut,
+                                  const uint16_t *lmap, const GeomTab &gt, int n)
+{
+    __shared__ uint32_t rowbits[2][ENC_NW];
+    __shared__ unsigned long long red64[2][ENC_NW];
+    __shared__ uint32_t pc[ENC_NT];
+    __shared__ uint32_t s_crc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.H, W = a.W;
+    uint32_t *stage32 = reinterpret_cast<uint32_t *>(sm.stage);
+    const uint32_t *lit_s = sm.lit_s, *len_s = sm.len_s, *crc_s = sm.crc_s;
+
+    // ---- zero the staging buffer, place the container prefix ------------------------------------
+    for (int i = tid; i < a.stage_cap / 16; i += ENC_NT)
+        reinterpret_cast<uint4 *>(sm.stage)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) s_crc = 0;
+    __syncthreads();
+    for (int i = tid; i < d.prefix_len; i += ENC_NT) sm.stage[i] = d.prefix[i];
+    __syncthreads();
+    uint32_t bitpos = 8u * (uint32_t)d.prefix_len;
+    if (tid == 0) put_bits(stage32, bitpos, 3ull, 3);          // BFINAL = 1, BTYPE = 01 (fixed Huffman)
+    bitpos += 3;
+    // uncompressed head bytes (.npy header) as literals
+    if (tid < d.head_len) {
+        const uint32_t t = lit_s[d.head[tid]];
+        put_bits(stage32, bitpos + d.head_off[tid], (unsigned long long)(t & 0xffffffu), (int)(t >> 24));
+    }
+    bitpos += (uint32_t)d.head_bits;
+
+    const int nseg = (W + 511) / 512;
+    const int nitems = H * nseg;
+    const bool vec_ok = (W % 8) == 0;
+    constexpr int BPP = IMG ? 4 : 2;                 // == d.bpp
+    constexpr int SEG_LANES = IMG ? 4 : 8;           // == d.seg_lanes: a forced cut every 256 bytes
+    const uint32_t dist_up = d.dist_up, dist_left = d.dist_left;
+    const uint32_t tail_room = (uint32_t)d.suffix_len + 24u;
+    const bool use_up = (dist_up >> 24) != 0;
+    const uint32_t filt = lit_s[0];                               // the PNG filter byte 0 as a literal
+    bool overflow = false;
+    int par = 0;
+
+    for (int item0 = 0; item0 < nitems; item0 += ENC_NW, par ^= 1) {
+        const int item = item0 + warp;
+        const bool valid = item < nitems;
+        const int y = valid ? (nseg == 1 ? item : item / nseg) : 0;
+        const int x0 = (valid && nseg > 1) ? (item % nseg) * 512 : 0;
+        const int xl = x0 + 16 * lane;
+        const int nvalid = valid ? max(0, min(16, W - xl)) : 0;
+        const int xend = min(W, x0 + 512);
+
+        // ---- phase A: keys, modes, token starts ------------------------------------------------
+        uint32_t kc[8];
+        uint32_t mU = 0, mL = 0;
+        const uint32_t V = (nvalid >= 16) ? 0xffffu : ((1u << nvalid) - 1u);
+        if (nvalid > 0) load_keys<IMG>(lmap + (size_t)y * W, xl, nvalid, vec_ok, lut, kc);
+        else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) kc[q] = 0;
+        }
+        if (nvalid > 0 && y > 0 && use_up) {
+            uint32_t ku[8];
+            load_keys<IMG>(lmap + (size_t)(y - 1) * W, xl, nvalid, vec_ok, lut, ku);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t x = kc[q] ^ ku[q];
+                mU |= ((x & 0xffffu) == 0u ? 1u : 0u) << (2 * q);
+                mU |= ((x >> 16) == 0u ? 1u : 0u) << (2 * q + 1);
+            }
+            mU &= V;
+        }
+        {
+            // previous pixel of this lane's first pixel: the previous lane's last key, or (first lane of
+            // a later segment) the pixel in front of the segment; none at the start of a row
+            uint32_t prev = __shfl_up_sync(0xffffffffu, kc[7] >> 16, 1);
+            bool has_prev = true;
+            if (lane == 0) {
+                has_prev = valid && x0 > 0;
+                prev = has_prev ? one_key<IMG>(lmap + (size_t)y * W + x0 - 1, lut) : 0u;
+            }
+            uint32_t pk = prev;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t lo = kc[q] & 0xffffu, hi = kc[q] >> 16;
+                mL |= (lo == pk ? 1u : 0u) << (2 * q);
+                mL |= (hi == lo ? 1u : 0u) << (2 * q + 1);
+                pk = hi;
+            }
+            if (!has_prev) mL &= ~1u;
+            mL &= V & ~mU;
+        }
+        // token starts: literal pixels, mode changes, forced cuts every 256 bytes / at the segment start
+        uint32_t S;
+        {
+            const uint32_t cu = __shfl_up_sync(0xffffffffu, mU >> 15, 1) & 1u;
+            const uint32_t cl = __shfl_up_sync(0xffffffffu, mL >> 15, 1) & 1u;
+            const uint32_t pU = (mU << 1) | (lane ? cu : 0u);
+            const uint32_t pL = (mL << 1) | (lane ? cl : 0u);
+            S = (V & ~mU & ~mL) | (mU & ~pU) | (mL & ~pL);
+            if ((lane & (SEG_LANES - 1)) == 0) S |= 1u;
+            S &= V;
+        }
+        // end of a token that runs past this lane: the first start in a later lane, or the segment end
+        int nxt;
+        {
+            int fs = S ? (xl + __ffs((int)S) - 1) : 0x7fffffff;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, fs, o);
+                if (lane + o < 32) fs = min(fs, t);
+            }
+            nxt = __shfl_down_sync(0xffffffffu, fs, 1);
+            if (lane == 31) nxt = 0x7fffffff;
+            nxt = min(nxt, xend);
+        }
+
+        // token walk: WRITE = false sums the bit counts, WRITE = true ORs the bits in at `pos`
+        auto walk = [&](bool write, uint32_t pos) -> uint32_t {
+            uint32_t bits = 0;
+            if (IMG && lane == 0 && x0 == 0 && valid) {
+                if (write) put_bits(stage32, pos, (unsigned long long)(filt & 0xffffffu), (int)(filt >> 24));
+                bits += filt >> 24;
+            }
+            uint32_t rest = S;
+            while (rest) {
+                const int j = __ffs((int)rest) - 1;
+                rest &= rest - 1;
+                const int len = (rest ? (__ffs((int)rest) - 1) : (nxt - xl)) - j;
+                const bool isU = (mU >> j) & 1u, isL = (mL >> j) & 1u;
+                unsigned long long val;
+                int nb;
+                if ((isU || isL) && len * BPP >= 3) {
+                    const uint32_t lt = len_s[len * BPP];
+                    const uint32_t dd = isU ? dist_up : dist_left;
+                    const int ln = (int)(lt >> 24);
+                    val = (unsigned long long)(lt & 0xffffffu) | ((unsigned long long)(dd & 0xffffffu) << ln);
+                    nb = ln + (int)(dd >> 24);
+                } else {
+                    // literal pixel (a one-pixel match of a 2-byte pixel is too short for DEFLATE)
+                    const int q = j >> 1;
+                    uint32_t w = kc[0];
+                    w = (q == 1) ? kc[1] : w; w = (q == 2) ? kc[2] : w; w = (q == 3) ? kc[3] : w;
+                    w = (q == 4) ? kc[4] : w; w = (q == 5) ? kc[5] : w; w = (q == 6) ? kc[6] : w;
+                    w = (q == 7) ? kc[7] : w;
+                    const uint32_t key = (j & 1) ? (w >> 16) : (w & 0xffffu);
+                    if (IMG) {
+                        const unsigned long long t = sm.lit64[key & 0x1ffu];
+                        val = t & ((1ull << 58) - 1ull);
+                        nb = (int)(t >> 58);
+                    } else {
+                        const uint32_t t0 = lit_s[key & 0xffu], t1 = lit_s[key >> 8];
+                        const int n0 = (int)(t0 >> 24);
+                        val = (unsigned long long)(t0 & 0xffffffu) | ((unsigned long long)(t1 & 0xffffffu) << n0);
+                        nb = n0 + (int)(t1 >> 24);
+                    }
+                }
+                if (write) put_bits(stage32, pos + bits, val, nb);
+                bits += (uint32_t)nb;
+            }
+            return bits;
+        };
+        const uint32_t lanebits = walk(false, 0u);
+        uint32_t incl = lanebits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) rowbits[par][warp] = incl;
+
+        // ---- phase B: bit position of every row of this pass ---------------------------------------
+        __syncthreads();
+        uint32_t before, total;
+        {
+            const uint32_t mine = (lane < ENC_NW) ? rowbits[par][lane] : 0u;
+            uint32_t sc = mine;
+#pragma unroll
+            for (int o = 1; o < ENC_NW; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o);
+                if (lane >= o) sc += t;
+            }
+            before = __shfl_sync(0xffffffffu, sc - mine, warp);
+            total = __shfl_sync(0xffffffffu, sc, ENC_NW - 1);
+        }
+        if ((bitpos + total + 7u + 7u) / 8u + tail_room > (uint32_t)a.stage_cap) {
+            overflow = true;
+            break;
+        }
+        // ---- phase C: write the tokens ----------------------------------------------------------------
+        if (valid) walk(true, bitpos + before + incl - lanebits);
+        bitpos += total;
+    }
+    __syncthreads();
+    if (overflow) return 0u;
+
+    // end-of-block code: seven zero bits (already zero), then pad to a byte
+    bitpos += 7;
+    const uint32_t plen = (uint32_t)d.prefix_len;
+    const uint32_t L = (bitpos - 8u * plen + 7u) / 8u;          // deflate bytes
+    uint32_t total_bytes;
+    if (IMG) {
+        // Adler-32 of the scanlines (big endian, ends the zlib stream) without touching a pixel:
+        // a = 1 + sum_i d_i and b = N + sum_i (N - i) d_i are sums over pixels of terms that depend only
+        // on the pixel's label (through its gray level) and position, so with the static per-label pixel
+        // count cnt_l and position weight M_l = sum_{px in l} (N - pos_px):
+        //   sum d = sum_l cnt_l * S(g_l),   sum (N - i) d_i = sum_l (M_l * S(g_l) - cnt_l * w(g_l))
+        // S = byte sum of a pixel, w = sum_k k * byte_k.  Background pixels are all-zero bytes.
+        unsigned long long ad1 = 0, ad2 = 0;
+        for (int l = 1 + tid; l <= n; l += ENC_NT) {
+            const uint32_t g = lut.gray_lut[l];
+            const uint32_t b1 = (g << 2) & 0xffu;
+            const unsigned long long S = (g >> 6) + b1 + 510u, w = b1 + 1275u;
+            const unsigned long long cnt = gt.cnt[l];
+            ad1 += cnt * S;
+            ad2 += gt.M[l] * S - cnt * w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ad1 += __shfl_xor_sync(0xffffffffu, ad1, o);
+            ad2 += __shfl_xor_sync(0xffffffffu, ad2, o);
+        }
+        if (lane == 0) { red64[0][warp] = ad1; red64[1][warp] = ad2; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long s1 = 1, s2 = d.raw_len;
+            for (int w = 0; w < ENC_NW; ++w) { s1 += red64[0][w]; s2 += red64[1][w]; }
+            const uint32_t adler = (uint32_t)(s1 % 65521ull) | ((uint32_t)(s2 % 65521ull) << 16);
+            put_be32(sm.stage + plen + L, adler);
+            put_be32(sm.stage + d.p_len_prefix, L + 6u);          // zlib header 2 + deflate + Adler 4
+        }
+        __syncthreads();
+        // CRC-32 of the IDAT chunk (type + data): equal pieces aligned to the END of the range (leading
+        // zeros do not change a CRC started from 0), combined pairwise with x^(8*piece) powers
+        const uint32_t r0 = (uint32_t)d.p_len_prefix + 4u, r1 = plen + L + 4u;
+        const uint32_t Lr = r1 - r0;
+        const uint32_t C = (Lr + ENC_NT - 1) / ENC_NT;
+        {
+            const long long e = (long long)r1 - (long long)(ENC_NT - 1 - tid) * C;
+            long long b = e - C;
+            if (b < (long long)r0) b = r0;
+            uint32_t c = 0;
+            for (long long i = b; i < e; ++i) c = crc_s[(c ^ sm.stage[i]) & 0xffu] ^ (c >> 8);
+            pc[tid] = c;
+        }
+        // g_k = x^(8*C*2^k), k = 0..8, computed once (sequential squarings) by warp 0
+        __shared__ uint32_t gpow[9];
+        if (warp == 0) {
+            uint32_t g = gf2_xpow8(a.tab->pow8, C);
+            for (int k = 0; k < 9; ++k) {
+                if (lane == 0) gpow[k] = g;
+                g = gf2_mulmod(g, g);
+            }
+        }
+        __syncthreads();
+        // crc0(A | B) = crc0(A) * x^(8|B|) ^ crc0(B): up-sweep inside each warp with shuffles ...
+        uint32_t c = pc[tid];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int s = 1 << k;
+            const uint32_t left = __shfl_up_sync(0xffffffffu, c, s);
+            if ((lane & (2 * s - 1)) == 2 * s - 1) c ^= gf2_mulmod(left, gpow[k]);
+        }
+        __syncthreads();
+        if (lane == 31) pc[warp] = c;
+        __syncthreads();
+        // ... then over the 16 warp results
+        if (warp == 0) {
+            uint32_t cw = (lane < ENC_NW) ? pc[lane] : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int s = 1 << k;
+                const uint32_t left = __shfl_up_sync(0xffffffffu, cw, s);
+                if (lane < ENC_NW && (lane & (2 * s - 1)) == 2 * s - 1) cw ^= gf2_mulmod(left, gpow[5 + k]);
+            }
+            if (lane == ENC_NW - 1) pc[ENC_NT - 1] = cw;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // CRC(M) = crc0(M) ^ CRC(zeros(|M|));  CRC(zeros(n)) = (0xFFFFFFFF * x^(8n)) ^ 0xFFFFFFFF
+            const uint32_t aff = gf2_mulmod(0xffffffffu, gf2_xpow8(a.tab->pow8, Lr)) ^ 0xffffffffu;
+            put_be32(sm.stage + r1, pc[ENC_NT - 1] ^ aff);
+            for (int i = 0; i < d.suffix_len; ++i) sm.stage[r1 + 4 + i] = d.suffix[i];
+        }
+        total_bytes = r1 + 4u + (uint32_t)d.suffix_len;
+    } else {
+        // CRC-32 of the .npy bytes without touching a pixel: CRC is linear over GF(2), so the pixels
+        // of one label value v contribute crc0(bytes of id_v) * Q_v with the static polynomial
+        // Q_v = sum_{px with label v} x^(8 * bytes after px) mod P
+        uint32_t crc_acc = 0;
+        for (int v = tid; v <= n; v += ENC_NT) {
+            const uint32_t id = lut.inst_lut[v];
+            if (id) {
+                uint32_t c = crc_s[id & 0xffu];
+                c = crc_s[(c ^ (id >> 8)) & 0xffu] ^ (c >> 8);
+                crc_acc ^= gf2_mulmod(c, gt.Q[v]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) crc_acc ^= __shfl_xor_sync(0xffffffffu, crc_acc, o);
+        if (lane == 0 && crc_acc) atomicXor(&s_crc, crc_acc);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t crc = s_crc ^ d.crc_const;
+            uint8_t *suf = sm.stage + plen + L;
+            for (int i = 0; i < d.suffix_len; ++i) suf[i] = d.suffix[i];
+            put_le32(sm.stage + d.p_crc_prefix, crc);
+            put_le32(sm.stage + d.p_csize_prefix, L);
+            put_le32(suf + d.p_crc_suffix, crc);
+            put_le32(suf + d.p_csize_suffix, L);
+            put_le32(suf + d.p_cdoff_suffix, plen + L);
+        }
+        total_bytes = plen + L + (uint32_t)d.suffix_len;
+    }
+    __syncthreads();
+    return total_bytes;
+}
+
+// Copies a finished file from the staging buffer into the arena and fills its record.
+__device__ void emit_file(const EncodeArgs &a, const uint8_t *stage, uint32_t total, EncRecord *rec)
+{
+    __shared__ unsigned long long s_off;
+    const int tid = threadIdx.x;
+    const uint32_t total16 = (total + 15u) & ~15u;
+    if (tid == 0) {
+        unsigned long long off = ~0ull;
+        uint32_t flags = CAB200_ENC_STAGE_FULL;
+        if (total) {
+            off = atomicAdd(a.cursor, (unsigned long long)total16);
+            flags = CAB200_ENC_OK;
+            if (off + total16 > a.arena_bytes) { off = ~0ull; flags = CAB200_ENC_ARENA_FULL; }
+        }
+        s_off = off;
+        rec->offset = (off == ~0ull) ? 0ull : off;
+        rec->size = (off == ~0ull) ? 0u : total;
+        rec->flags = flags;
+    }
+    __syncthreads();
+    const unsigned long long off = s_off;
+    if (off != ~0ull) {
+        uint4 *dst = reinterpret_cast<uint4 *>(a.arena + off);
+        const uint4 *src = reinterpret_cast<const uint4 *>(stage);
+        for (uint32_t i = tid; i < total16 / 16; i += ENC_NT) dst[i] = src[i];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ENC_NT, 2) encode_kernel(const EncodeArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int pf = blockIdx.x;
+    const int f = pf % a.n_frames;
+    const int pi = pf / a.n_frames;
+    const PouchEntry pe = a.pouches[pi];
+    const int n = pe.n;
+    const double *ca = a.ca_frames + (size_t)pe.cell_off * 4 * a.n_frames + (size_t)f * 4 * n;
+
+    const FrameLut lut = frame_lut_carve(smem_raw, n);
+    EncSmem sm;
+    unsigned char *p = smem_raw + a.lut_bytes;
+    sm.lit64 = reinterpret_cast<unsigned long long *>(p); p += 512 * 8;
+    sm.len_s = reinterpret_cast<uint32_t *>(p); p += 260 * 4;
+    sm.lit_s = reinterpret_cast<uint32_t *>(p); p += 256 * 4;
+    sm.crc_s = reinterpret_cast<uint32_t *>(p); p += 256 * 4;
+    sm.stage = p;                                   // 16-byte aligned: lut_bytes is, 260*4 = 65*16
+
+    const int n_active = frame_lut_build<ENC_NT>(lut, ca, n, a.threshold, a.quirk);
+    if (tid == 0 && a.n_active_out) a.n_active_out[pf] = n_active;
+    for (int i = tid; i < 260; i += ENC_NT) sm.len_s[i] = a.tab->len[i];
+    for (int i = tid; i < 256; i += ENC_NT) { sm.lit_s[i] = a.tab->lit[i]; sm.crc_s[i] = a.tab->crc[i]; }
+    // image pixel key per label value: gray | 0x100 (alpha set), 0 for the background; the rank
+    // scratch of the LUT build is free now
+    for (int v = tid; v <= n; v += ENC_NT) lut.rank1[v] = v ? (uint16_t)(lut.gray_lut[v] | 0x100u) : (uint16_t)0;
+    __syncthreads();
+    // the four literals of a 16-bit gray+alpha pixel: gray*4 and alpha*257, big endian
+    for (int key = tid; key < 512; key += ENC_NT) {
+        const uint32_t g = key & 0xff, al = (key >> 8) ? 255u : 0u;
+        const uint32_t b[4] = {g >> 6, (g << 2) & 0xffu, al, al};
+        unsigned long long v = 0;
+        int nb = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t t = sm.lit_s[b[i]];
+            v |= (unsigned long long)(t & 0xffffffu) << nb;
+            nb += (int)(t >> 24);
+        }
+        sm.lit64[key] = v | ((unsigned long long)nb << 58);
+    }
+    __syncthreads();
+
+    EncRecord *rec = a.records + (size_t)pf * 2;
+    const size_t gbase = (size_t)pe.geom * a.H * a.W;
+    const GeomTab gt = geom_tab_carve(a.geom_tabs + a.geom_tab_off[pe.geom], n);
+    if (a.want_img) {
+        const uint32_t total = encode_stream<true>(a, a.tab->img, sm, lut, a.label_img + gbase, gt, n);
+        emit_file(a, sm.stage, total, rec);
+    } else if (tid == 0) {
+        rec[0].offset = 0; rec[0].size = 0; rec[0].flags = CAB200_ENC_SKIPPED;
+    }
+    if (a.want_msk && n_active > 0) {           // the reference writes no mask file for a frame without active cells
+        const uint32_t total = encode_stream<false>(a, a.tab->msk, sm, lut, a.label_mask + gbase, gt, n);
+        emit_file(a, sm.stage, total, rec + 1);
+    } else if (tid == 0) {
+        rec[1].offset = 0; rec[1].size = 0; rec[1].flags = CAB200_ENC_SKIPPED;
+    }
+}
+
+// Device -> pinned host memory with plain stores (zero copy) instead of the DMA engine: the few
+// bytes the host must see before it can size a chunk's copy-out must not queue behind megabytes of
+// earlier copies on the same engine.
+__global__ void __launch_bounds__(256) publish_kernel(uint4 *dst, const uint4 *src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+// ---- host side: tables and container templates -----------------------------------------------------
+static uint32_t rev_bits(uint32_t v, int n)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+}
+
+// fixed Huffman code of literal/length symbol `sym` (RFC 1951, 3.2.6): reversed code | bits << 24
+static uint32_t fixed_sym(int sym)
+{
+    uint32_t code; int nb;
+    if (sym <= 143) { code = 0x30 + sym; nb = 8; }
+    else if (sym <= 255) { code = 0x190 + (sym - 144); nb = 9; }
+    else if (sym <= 279) { code = sym - 256; nb = 7; }
+    else { code = 0xC0 + (sym - 280); nb = 8; }
+    return rev_bits(code, nb) | ((uint32_t)nb << 24);
+}
+
+static uint32_t length_entry(int len)
+{
+    static const int base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99,
+                                 115, 131, 163, 195, 227, 258};
+    static const int extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    int i = 28;
+    while (len < base[i]) --i;
+    const uint32_t s = fixed_sym(257 + i);
+    const int nb = (int)(s >> 24);
+    return (s & 0xffffffu) | ((uint32_t)(len - base[i]) << nb) | ((uint32_t)(nb + extra[i]) << 24);
+}
+
+static uint32_t dist_entry(int dist)
+{
+    static const int base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025,
+                                 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const int extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12,
+                                  12, 13, 13};
+    if (dist < 1 || dist > 32768) return 0u;
+    int i = 29;
+    while (dist < base[i]) --i;
+    return rev_bits((uint32_t)i, 5) | ((uint32_t)(dist - base[i]) << 5) | ((uint32_t)(5 + extra[i]) << 24);
+}
+
+static uint32_t host_crc0(const uint32_t *tab, const uint8_t *p, size_t n, uint32_t c = 0)
+{
+    for (size_t i = 0; i < n; ++i) c = tab[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+    return c;
+}
+static uint32_t host_crc(const uint32_t *tab, const uint8_t *p, size_t n)
+{
+    return host_crc0(tab, p, n, 0xffffffffu) ^ 0xffffffffu;
+}
+static uint32_t host_xpow8(const uint32_t *pow8, unsigned long long n)
+{
+    uint32_t r = 0x80000000u;
+    for (int k = 0; n; ++k, n >>= 1)
+        if (n & 1ull) r = gf2_mulmod(r, pow8[k]);
+    return r;
+}
+static void h_le16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+static void h_le32(uint8_t *p, uint32_t v) { h_le16(p, v); h_le16(p + 2, v >> 16); }
+static void h_be32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+
+static void build_tables(int H, int W, EncTables *t)
+{
+    memset(t, 0, sizeof(*t));
+    t->H = H; t->W = W;
+    for (int i = 0; i < 256; ++i) t->lit[i] = fixed_sym(i);
+    for (int l = 3; l <= 258; ++l) t->len[l] = length_entry(l);
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ CRC_POLY : c >> 1;
+        t->crc[i] = c;
+    }
+    t->pow8[0] = 0x00800000u;                     // x^8
+    for (int k = 1; k < 32; ++k) t->pow8[k] = gf2_mulmod(t->pow8[k - 1], t->pow8[k - 1]);
+    for (int y = 0; y < H; ++y) t->rowshift[y] = host_xpow8(t->pow8, 2ull * W * (unsigned long long)(H - 1 - y));
+    for (int c = 0; c * 16 < W; ++c) t->colshift[c] = host_xpow8(t->pow8, 2ull * (unsigned long long)(W - std::min(W, 16 * (c + 1))));
+
+    // ---- PNG, colour type 4 (gray + alpha), 16 bit: signature | IHDR | IDAT(zlib) | IEND ---------------
+    EncStream &g = t->img;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    uint8_t *p = g.prefix;
+    memcpy(p, sig, 8); p += 8;
+    h_be32(p, 13); memcpy(p + 4, "IHDR", 4); h_be32(p + 8, (uint32_t)W); h_be32(p + 12, (uint32_t)H);
+    p[16] = 16; p[17] = 4; p[18] = 0; p[19] = 0; p[20] = 0;
+    h_be32(p + 21, host_crc(t->crc, p + 4, 17)); p += 25;
+    g.p_len_prefix = (int)(p - g.prefix);
+    h_be32(p, 0); memcpy(p + 4, "IDAT", 4); p += 8;
+    p[0] = 0x78; p[1] = 0x01; p += 2;             // zlib header: deflate, 32K window, fastest
+    g.prefix_len = (int)(p - g.prefix);
+    static const uint8_t iend[12] = {0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xae, 0x42, 0x60, 0x82};
+    memcpy(g.suffix, iend, 12); g.suffix_len = 12;
+    g.head_len = 0;
+    g.bpp = 4; g.seg_lanes = 4; g.row_lead = 1;
+    g.dist_left = dist_entry(4); g.dist_up = dist_entry(1 + 4 * W);
+    g.raw_len = (uint32_t)((size_t)H * (1 + 4 * (size_t)W));
+    g.p_crc_prefix = g.p_csize_prefix = g.p_crc_suffix = g.p_csize_suffix = g.p_cdoff_suffix = -1;
+
+    // ---- NPZ: zip archive with one deflated member "mask.npy" (np.savez_compressed(path, mask=...)) -----
+    EncStream &m = t->msk;
+    char dict[160];
+    snprintf(dict, sizeof(dict), "{'descr': '<u2', 'fortran_order': False, 'shape': (%d, %d), }", H, W);
+    int dl = (int)strlen(dict);
+    const int pad = 64 - ((10 + dl + 1) % 64);     // numpy.lib.format: header block is a multiple of 64 bytes
+    const int hl = dl + (pad % 64) + 1;
+    uint8_t *h = m.head;
+    h[0] = 0x93; memcpy(h + 1, "NUMPY", 5); h[6] = 1; h[7] = 0; h_le16(h + 8, (uint32_t)hl);
+    memcpy(h + 10, dict, dl); memset(h + 10 + dl, ' ', hl - dl - 1); h[10 + hl - 1] = '\n';
+    m.head_len = 10 + hl;
+    for (int j = 0; j < m.head_len; ++j) { m.head_off[j] = (uint16_t)m.head_bits; m.head_bits += (int)(t->lit[m.head[j]] >> 24); }
+    const unsigned long long data_len = 2ull * H * W;
+    m.raw_len = (uint32_t)(m.head_len + data_len);
+    // CRC(M) = crc0(head) * x^(8*|data|) ^ crc0(data) ^ CRC(zeros(|M|)): the first and last term are constant
+    const uint32_t aff = gf2_mulmod(0xffffffffu, host_xpow8(t->pow8, m.raw_len)) ^ 0xffffffffu;
+    m.crc_const = gf2_mulmod(host_crc0(t->crc, m.head, m.head_len), host_xpow8(t->pow8, data_len)) ^ aff;
+    static const char name[] = "mask.npy";
+    p = m.prefix;
+    h_le32(p, 0x04034b50u); h_le16(p + 4, 20); h_le16(p + 6, 0); h_le16(p + 8, 8); h_le16(p + 10, 0);
+    h_le16(p + 12, 0x21);                          // 1980-01-01 00:00
+    m.p_crc_prefix = 14; m.p_csize_prefix = 18;
+    h_le32(p + 14, 0); h_le32(p + 18, 0); h_le32(p + 22, m.raw_len); h_le16(p + 26, 8); h_le16(p + 28, 0);
+    memcpy(p + 30, name, 8);
+    m.prefix_len = 38;
+    p = m.suffix;
+    h_le32(p, 0x02014b50u); h_le16(p + 4, 20); h_le16(p + 6, 20); h_le16(p + 8, 0); h_le16(p + 10, 8);
+    h_le16(p + 12, 0); h_le16(p + 14, 0x21);
+    m.p_crc_suffix = 16; m.p_csize_suffix = 20;
+    h_le32(p + 16, 0); h_le32(p + 20, 0); h_le32(p + 24, m.raw_len); h_le16(p + 28, 8); h_le16(p + 30, 0);
+    h_le16(p + 32, 0); h_le16(p + 34, 0); h_le16(p + 36, 0); h_le32(p + 38, 0x01800000u); h_le32(p + 42, 0);
+    memcpy(p + 46, name, 8);
+    p += 54;
+    h_le32(p, 0x06054b50u); h_le16(p + 4, 0); h_le16(p + 6, 0); h_le16(p + 8, 1); h_le16(p + 10, 1);
+    h_le32(p + 12, 54); h_le32(p + 16, 0); h_le16(p + 20, 0);
+    m.p_cdoff_suffix = 54 + 16;
+    m.suffix_len = 54 + 22;
+    m.bpp = 2; m.seg_lanes = 8; m.row_lead = 0;
+    m.dist_left = dist_entry(2); m.dist_up = dist_entry(2 * W);
+    m.p_len_prefix = -1;
+}
+
+static inline size_t enc_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static size_t enc_fixed_smem(int n_max) { return enc_align(frame_lut_bytes(n_max), 16) + 512 * 8 + 260 * 4 + 256 * 4 + 256 * 4; }
+
+}  // namespace cab200
+
+using namespace cab200;
+
+extern "C" size_t cab200_encode_tables_bytes(void) { return sizeof(EncTables); }
+
+extern "C" int cab200_encode_tables(int H, int W, void *tables_host_out)
+{
+    if (H <= 0 || W <= 0 || H > ENC_MAXDIM || W > ENC_MAXDIM || !tables_host_out) {
+        set_error("cab200_encode_tables: H and W must be in [1, %d]", ENC_MAXDIM);
+        return CAB200_EINVAL;
+    }
+    build_tables(H, W, (EncTables *)tables_host_out);
+    return CAB200_OK;
+}
+
+extern "C" size_t cab200_encode_scratch_bytes(int n_pouch, int n_geom)
+{
+    return enc_align(sizeof(PouchEntry) * (size_t)std::max(n_pouch, 1), 16) +
+           enc_align(sizeof(long long) * (size_t)std::max(n_geom, 1), 16);
+}
+
+extern "C" size_t cab200_encode_geometry_bytes(int n_cells) { return enc_align(geom_tab_bytes(n_cells), 16); }
+
+extern "C" int cab200_encode_geometry(int n_cells, const uint16_t *label_img, const uint16_t *label_mask, int H, int W,
+                                      const void *tables, void *geom_out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_cells <= 0 || n_cells > 65534 || H <= 0 || W <= 0 || H > ENC_MAXDIM || W > ENC_MAXDIM || !label_img ||
+        !label_mask || !tables || !geom_out) {
+        set_error("cab200_encode_geometry: bad argument");
+        return CAB200_EINVAL;
+    }
+    CAB_CUDA(cudaMemsetAsync(geom_out, 0, cab200_encode_geometry_bytes(n_cells), stream));
+    enc_geometry_kernel<<<148 * 4, 256, sizeof(uint32_t) * (size_t)W, stream>>>(
+        label_img, label_mask, H, W, n_cells, (const EncTables *)tables, (unsigned char *)geom_out);
+    CAB_CUDA(cudaGetLastError());
+    return CAB200_OK;
+}
+
+extern "C" int cab200_encode_batch(
+    int n_pouch, const int32_t *geom_id, int n_geom, const int32_t *g_ncell, const int64_t *cell_off,
+    const uint16_t *label_img, const uint16_t *label_mask, int H, int W, int n_frames,
+    const double *ca_frames, double threshold, int quirk_mode, int want_image, int want_mask,
+    const void *tables, const void *geom_tabs, const int64_t *g_tab_off, uint8_t *arena, size_t arena_bytes, unsigned long long *cursor,
+    void *records_out, int32_t *n_active_out, int stage_bytes, void *scratch, size_t scratch_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pouch < 0 || H <= 0 || W <= 0 || H > ENC_MAXDIM || W > ENC_MAXDIM || n_frames < 0) {
+        set_error("cab200_encode_batch: bad sizes (H, W in [1, %d])", ENC_MAXDIM);
+        return CAB200_EINVAL;
+    }
+    if (n_pouch == 0 || n_frames == 0) return CAB200_OK;
+    if (!geom_id || !g_ncell || !cell_off || !label_img || !label_mask || !ca_frames || !tables || !geom_tabs ||
+        !g_tab_off || !arena || !cursor || !records_out || !scratch || n_geom <= 0) {
+        set_error("cab200_encode_batch: null pointer argument");
+        return CAB200_EINVAL;
+    }
+    if (((uintptr_t)arena & 15u) != 0) { set_error("cab200_encode_batch: arena must be 16-byte aligned"); return CAB200_EINVAL; }
+    if (scratch_bytes < cab200_encode_scratch_bytes(n_pouch, n_geom)) {
+        set_error("cab200_encode_batch: scratch too small");
+        return CAB200_ESIZE;
+    }
+    std::vector<PouchEntry> tab(n_pouch);
+    int n_max = 0;
+    for (int p = 0; p < n_pouch; ++p) {
+        tab[p].cell_off = cell_off[p];
+        tab[p].geom = geom_id[p];
+        if (geom_id[p] < 0 || geom_id[p] >= n_geom) { set_error("cab200_encode_batch: pouch %d: bad geom_id", p); return CAB200_EINVAL; }
+        tab[p].n = g_ncell[geom_id[p]];
+        if (tab[p].n > 65534 || tab[p].n <= 0 || cell_off[p + 1] - cell_off[p] != tab[p].n) {
+            set_error("cab200_encode_batch: pouch %d: bad cell count", p);
+            return CAB200_EINVAL;
+        }
+        n_max = std::max(n_max, tab[p].n);
+    }
+    const long long pf = (long long)n_pouch * n_frames;
+    if (pf > 0x7fffffffLL) { set_error("cab200_encode_batch: too many frames"); return CAB200_ESIZE; }
+    const size_t fixed = enc_fixed_smem(n_max);
+    // staging: by default half of an SM's shared memory per CTA (two CTAs per SM)
+    size_t cap = (stage_bytes > 0) ? (size_t)stage_bytes : (size_t)(112 * 1024) - fixed - 4608;
+    cap &= ~(size_t)15;
+    if ((stage_bytes <= 0 && fixed + 4608 + 4096 > 112 * 1024) || cap < 1024 || fixed + cap > 224 * 1024) {
+        set_error("cab200_encode_batch: staging buffer of %zu bytes does not fit (tables take %zu)", cap, fixed);
+        return CAB200_ESIZE;
+    }
+    CAB_CUDA(cudaMemcpyAsync(scratch, tab.data(), sizeof(PouchEntry) * (size_t)n_pouch, cudaMemcpyHostToDevice, stream));
+    long long *d_tab_off = (long long *)((unsigned char *)scratch + enc_align(sizeof(PouchEntry) * (size_t)n_pouch, 16));
+    CAB_CUDA(cudaMemcpyAsync(d_tab_off, g_tab_off, sizeof(long long) * (size_t)n_geom, cudaMemcpyHostToDevice, stream));
+    EncodeArgs a;
+    a.geom_tabs = (const unsigned char *)geom_tabs;
+    a.geom_tab_off = d_tab_off;
+    a.pouches = (const PouchEntry *)scratch;
+    a.label_img = label_img; a.label_mask = label_mask; a.ca_frames = ca_frames;
+    a.tab = (const EncTables *)tables;
+    a.n_frames = n_frames; a.H = H; a.W = W;
+    a.threshold = threshold; a.quirk = quirk_mode; a.want_img = want_image; a.want_msk = want_mask;
+    a.lut_bytes = (int)enc_align(frame_lut_bytes(n_max), 16);
+    a.stage_cap = (int)cap;
+    a.arena = arena; a.cursor = cursor; a.arena_bytes = arena_bytes;
+    a.records = (EncRecord *)records_out;
+    a.n_active_out = n_active_out;
+    const size_t smem = fixed + cap;
+    CAB_CUDA(cudaFuncSetAttribute((const void *)encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    encode_kernel<<<(unsigned)pf, ENC_NT, smem, stream>>>(a);
+    CAB_CUDA(cudaGetLastError());
+    return CAB200_OK;
+}
+
+extern "C" int cab200_publish_to_host(void *dst_pinned_host, const void *src_device, size_t bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (bytes == 0) return CAB200_OK;
+    if (!dst_pinned_host || !src_device || (bytes & 15u) || ((uintptr_t)dst_pinned_host & 15u) || ((uintptr_t)src_device & 15u)) {
+        set_error("cab200_publish_to_host: pointers and size must be 16-byte aligned");
+        return CAB200_EINVAL;
+    }
+    void *dst_dev = nullptr;
+    CAB_CUDA(cudaHostGetDevicePointer(&dst_dev, dst_pinned_host, 0));
+    const size_t n16 = bytes / 16;
+    const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 148 * 2);
+    publish_kernel<<<grid, 256, 0, stream>>>((uint4 *)dst_dev, (const uint4 *)src_device, n16);
+    CAB_CUDA(cudaGetLastError());
+    return CAB200_OK;
+}

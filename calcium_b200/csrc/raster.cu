@@ -13,14 +13,9 @@
 #include <vector>
 
 #include "common.cuh"
+#include "frame_lut.cuh"
 
 namespace cab200 {
-
-struct PouchEntry {
-    int64_t cell_off;
-    int32_t n;
-    int32_t geom;
-};
 
 struct RasterArgs {
     const PouchEntry *pouches;   // [P]
@@ -41,10 +36,6 @@ constexpr int RT = 256;   // threads per CTA
 __global__ void __launch_bounds__(RT, 6) raster_kernel(const RasterArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[RT / 32];
-    __shared__ int wsum[RT / 32];
-    __shared__ double s_vmax;
-    __shared__ int s_total;
 
     const int tile = blockIdx.x % a.tiles;
     const int pf = blockIdx.x / a.tiles;
@@ -54,81 +45,13 @@ __global__ void __launch_bounds__(RT, 6) raster_kernel(const RasterArgs a)
     const int n = pe.n;
     const double *ca = a.ca_frames + (size_t)pe.cell_off * 4 * a.n_frames + (size_t)f * 4 * n;
 
-    // LUTs indexed by label value v in [0, n]
-    uint16_t *inst_lut = reinterpret_cast<uint16_t *>(smem_raw);                 // [n+1]
-    uint16_t *rank1 = inst_lut + ((n + 2 + 7) & ~7);                            // [n+1] scratch
-    uint8_t *gray_lut = reinterpret_cast<uint8_t *>(rank1 + ((n + 2 + 7) & ~7)); // [n+1]
-    uint8_t *act8 = gray_lut + ((n + 2 + 15) & ~15);                            // [n+1] act8[v]=active(cell v-1)
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // ---- vmax = max(np.max(ca), 0.5)  (core/pouch.py:421-422) --------------------------------
-    double mx = -INFINITY;
-    for (int i = tid; i < n; i += RT) mx = fmax(mx, ca[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        double m = red[0];
-        for (int w = 1; w < RT / 32; ++w) m = fmax(m, red[w]);
-        s_vmax = (0.5 > m) ? 0.5 : m;
-    }
-    __syncthreads();
-    const double vmax = s_vmax;
-
-    // ---- per-cell gray level, active flag, 1-based rank among active cells ---------------------
-    // contiguous chunk per thread so the scan keeps ascending cell order (np.where, :564)
-    const int chunk = (n + RT - 1) / RT;
-    const int beg = min(tid * chunk, n), end = min(beg + chunk, n);
-    int cnt = 0;
-    for (int i = beg; i < end; ++i) {
-        const double v = ca[i];
-        double nv = __ddiv_rn(__dsub_rn(v, 0.0), __dsub_rn(vmax, 0.0));        // :426
-        nv = (nv < 0.0) ? 0.0 : ((nv > 1.0) ? 1.0 : nv);                       // np.clip
-        gray_lut[i + 1] = (uint8_t)(int)__dmul_rn(255.0, nv);                  // int(255*x), :427
-        const int act = v > a.threshold;                                        // strict >, :564
-        act8[i + 1] = (uint8_t)act;
-        cnt += act;
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int w = 0; w < RT / 32; ++w) { const int t = wsum[w]; wsum[w] = run; run += t; }
-        s_total = run;
-        gray_lut[0] = 0; act8[0] = 0;
-    }
-    __syncthreads();
-    int run = wsum[warp] + incl - cnt;
-    for (int i = beg; i < end; ++i) {
-        const int act = act8[i + 1];
-        run += act;
-        rank1[i] = (uint16_t)(act ? run : 0);      // rank1[cell], 1-based
-    }
-    if (tid == 0) rank1[n] = 0;
-    __syncthreads();
-    // instance id per label value
-    for (int v = tid; v <= n; v += RT) {
-        uint16_t id;
-        if (a.quirk) {
-            // reference semantics: masked value m = v if cell v-1 active else 0; then the loop
-            // `instance[mask == cell_id] = new_id` over 0-based active ids (D5)
-            const int m = (v > 0 && act8[v]) ? v : 0;
-            id = (m < n && act8[m + 1]) ? rank1[m] : 0;
-        } else {
-            id = (v > 0 && act8[v]) ? rank1[v - 1] : 0;
-        }
-        inst_lut[v] = id;
-    }
-    if (tid == 0 && tile == 0 && a.n_active_out) a.n_active_out[pf] = s_total;
-    __syncthreads();
+    // LUTs indexed by label value v in [0, n] (frame_lut.cuh)
+    const FrameLut lut = frame_lut_carve(smem_raw, n);
+    const uint16_t *inst_lut = lut.inst_lut;
+    const uint8_t *gray_lut = lut.gray_lut, *act8 = lut.act8;
+    const int tid = threadIdx.x;
+    const int n_active = frame_lut_build<RT>(lut, ca, n, a.threshold, a.quirk);
+    if (tid == 0 && tile == 0 && a.n_active_out) a.n_active_out[pf] = n_active;
 
     // ---- stream the pixels ---------------------------------------------------------------------
     const size_t gbase = (size_t)pe.geom * a.npix;
@@ -433,7 +356,7 @@ extern "C" int cab200_raster_batch(
     int tiles = 1;
     while ((long long)tiles * pf < 148 * 8 && tiles < 32) tiles *= 2;
     a.tiles = tiles;
-    const size_t smem = 2 * (size_t)((n_max + 2 + 7) & ~7) * 2 + 2 * (size_t)((n_max + 2 + 15) & ~15);
+    const size_t smem = frame_lut_bytes(n_max);
     if (smem > 48 * 1024)
         CAB_CUDA(cudaFuncSetAttribute((const void *)raster_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

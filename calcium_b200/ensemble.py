@@ -363,10 +363,13 @@ class Ensemble:
         self.status: Optional[torch.Tensor] = None
         self._scratch = torch.empty(
             int(self.lib.cab200_sim_scratch_bytes(self.P, self.F)
-                + self.lib.cab200_raster_scratch_bytes(self.P)) + 64,
+                + self.lib.cab200_raster_scratch_bytes(self.P)
+                + self.lib.cab200_encode_scratch_bytes(self.P, len(self.dgeo))) + 96,
             dtype=torch.uint8, device=self.device)
         self._label_img: Optional[torch.Tensor] = None
         self._label_mask: Optional[torch.Tensor] = None
+        self._enc_tables: Optional[torch.Tensor] = None
+        self._enc_geom: Optional[Tuple[torch.Tensor, np.ndarray]] = None
 
     # -- sizes ---------------------------------------------------------------------------------
     @property
@@ -492,6 +495,244 @@ class Ensemble:
             _lib.check(rc, "cab200_raster_batch")
         return res
 
+    # -- K3 ------------------------------------------------------------------------------------
+    def encode_tables(self) -> torch.Tensor:
+        """Device copy of ``cab200_encode_tables`` for this ensemble's output size."""
+        if self._enc_tables is None:
+            w, h = self.output_size
+            nb = int(self.lib.cab200_encode_tables_bytes())
+            host = np.zeros(nb, dtype=np.uint8)
+            _lib.check(self.lib.cab200_encode_tables(h, w, host.ctypes.data), "cab200_encode_tables")
+            self._enc_tables = torch.from_numpy(host).to(self.device)
+        return self._enc_tables
+
+    def encode_geometry_tables(self) -> Tuple[torch.Tensor, np.ndarray]:
+        """Static per-geometry checksum tables (``cab200_encode_geometry``) and their byte offsets."""
+        if getattr(self, "_enc_geom", None) is None:
+            w, h = self.output_size
+            limg, lmsk = self.label_maps()
+            tabs = self.encode_tables()
+            sizes = [int(self.lib.cab200_encode_geometry_bytes(int(n))) for n in self.g_ncell]
+            off = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+            buf = torch.empty(int(sum(sizes)), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                for g, n in enumerate(self.g_ncell):
+                    _lib.check(self.lib.cab200_encode_geometry(
+                        int(n), limg[g].data_ptr(), lmsk[g].data_ptr(), h, w, tabs.data_ptr(),
+                        buf.data_ptr() + int(off[g]), _stream_ptr(self.device)), "cab200_encode_geometry")
+            self._enc_geom = (buf, off)
+        return self._enc_geom
+
+    def encode(self, image: bool = True, mask: bool = True, pouches: Optional[Tuple[int, int]] = None,
+               threshold: float = 0.1, quirk: bool = True, out: Optional[Dict[str, torch.Tensor]] = None,
+               arena_bytes: Optional[int] = None, stage_bytes: int = 0) -> Dict[str, torch.Tensor]:
+        """K3 over pouches ``[a, b)``: every frame rasterised and encoded on the device into the files
+        the reference's batch path stores -- a 16-bit gray+alpha ``.png`` (``save_image``,
+        utils/image_processing.py:252-269) and a ``.npz`` holding ``mask`` (the instance mask,
+        utils/sam2_data_generator.py:203).  Returns device tensors ``arena`` (uint8), ``cursor``
+        (int64[1], bytes used), ``records`` (int64 ``[p, F, 2, 2]``: for image / mask the arena offset
+        and ``size | flags << 32``) and ``n_active [p, F]``.  See :func:`records_to_host`."""
+        if self.frames is None:
+            raise RuntimeError("simulate() first")
+        if self.precision != _lib.FP64_STRICT:
+            raise RuntimeError("encode() reads float64 frames; run the FP64 mode")
+        a, b = (0, self.P) if pouches is None else pouches
+        cnt = b - a
+        w, h = self.output_size
+        limg, lmsk = self.label_maps()
+        tabs = self.encode_tables()
+        gtab, gtab_off = self.encode_geometry_tables()
+        res: Dict[str, torch.Tensor] = {} if out is None else out
+        if arena_bytes is None:
+            # a flat-shaded polygon frame encodes to ~1/10 of its raw size; 1/3 leaves ample room
+            arena_bytes = max(1 << 20, cnt * self.F * h * w * 6 // 3)
+        arena_bytes = (int(arena_bytes) + 15) // 16 * 16
+        with torch.cuda.device(self.device):
+            arena = res.get("arena")
+            if arena is None or arena.numel() < arena_bytes:
+                arena = torch.empty(arena_bytes, dtype=torch.uint8, device=self.device)
+                res["arena"] = arena
+            cursor = res.get("cursor")
+            if cursor is None:
+                res["cursor16"] = torch.zeros(2, dtype=torch.int64, device=self.device)   # 16 bytes: publishable
+                cursor = res["cursor16"][:1]
+                res["cursor"] = cursor
+            else:
+                cursor.zero_()
+            rec = res.get("records")
+            if rec is None or tuple(rec.shape) != (cnt, self.F, 2, 2):
+                rec = torch.empty((cnt, self.F, 2, 2), dtype=torch.int64, device=self.device)
+                res["records"] = rec
+            nact = res.get("n_active")
+            if nact is None or tuple(nact.shape) != (cnt, self.F):
+                pad = torch.zeros((cnt * self.F + 3) // 4 * 4, dtype=torch.int32, device=self.device)
+                nact = pad[: cnt * self.F].view(cnt, self.F)       # storage padded to 16 bytes
+                res["n_active"], res["n_active16"] = nact, pad
+            gid = np.ascontiguousarray(self.geom_id[a:b])
+            coff = np.ascontiguousarray(self.cell_off[a:b + 1])
+            scr_off = int(self.lib.cab200_sim_scratch_bytes(self.P, self.F)) + int(
+                self.lib.cab200_raster_scratch_bytes(self.P))
+            scr_off = (scr_off + 15) // 16 * 16
+            rc = self.lib.cab200_encode_batch(
+                cnt, _lib.as_i32p(gid), len(self.dgeo), _lib.as_i32p(self.g_ncell), _lib.as_i64p(coff),
+                limg.data_ptr(), lmsk.data_ptr(), h, w, self.F, self.frames.data_ptr(),
+                float(threshold), 1 if quirk else 0, 1 if image else 0, 1 if mask else 0,
+                tabs.data_ptr(), gtab.data_ptr(), _lib.as_i64p(gtab_off),
+                arena.data_ptr(), arena.numel(), cursor.data_ptr(),
+                rec.data_ptr(), nact.data_ptr(), int(stage_bytes),
+                self._scratch.data_ptr() + scr_off, self.lib.cab200_encode_scratch_bytes(cnt, len(self.dgeo)),
+                _stream_ptr(self.device))
+            _lib.check(rc, "cab200_encode_batch")
+        return res
+
+    @staticmethod
+    def records_to_host(records: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """``records`` (int64 [..., 2]) -> (offset, size, flags) arrays."""
+        off = records[..., 0]
+        size = records[..., 1] & 0xFFFFFFFF
+        flags = (records[..., 1] >> 32) & 0xFFFFFFFF
+        return off, size, flags
+
+    def encoded_files(self, enc: Dict[str, torch.Tensor]) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """Host copies ``(arena[:used], offset, size, flags)`` of an :meth:`encode` result (synchronises).
+        The file of pouch i, frame f, kind k (0 image, 1 mask) is ``arena[offset[i,f,k]:][:size[i,f,k]]``."""
+        used = int(enc["cursor"].item())
+        arena = enc["arena"][: min(used, enc["arena"].numel())].cpu().numpy()
+        off, size, flags = self.records_to_host(enc["records"].cpu().numpy())
+        if np.any(flags & _lib.ENC_ARENA_FULL):
+            raise _lib.Cab200Error(f"encode arena too small ({enc['arena'].numel()} bytes for {used} needed)")
+        return arena, off, size, flags
+
+    def run_files_to_host(self, chunk_pouches: int = 37, image: bool = True, mask: bool = True,
+                           consumer=None, threshold: float = 0.1, quirk: bool = True,
+                           arena_bytes_per_pixel: float = 0.75, wait: bool = True,
+                           stage_bytes: int = 0) -> Dict[str, int]:
+        """The whole hot path with HOST buffers on both sides, in the form the reference's batch path
+        stores its results: pinned host inputs -> device, K1, then K3 chunk by chunk -- every sampled
+        frame as a finished ``.png`` and ``.npz`` byte string -- copied into pinned host memory together
+        with the float64 frames and the per-frame records.  Four ring slots: while K3 encodes chunk k,
+        the host learns the size of chunk k-1 (a 16-byte read) and queues its copy-out on a second
+        stream.  ``consumer(chunk: EncodedChunk)`` is called once a chunk has landed.  With
+        ``wait=False`` the last chunks are left in flight (their copy-out then overlaps whatever the
+        caller queues next, e.g. the next ensemble's integration); :meth:`flush_files` completes them.
+        Returns the byte counts moved (with ``wait=False``: of the copies queued during this call)."""
+        dev = self.device
+        w, h = self.output_size
+        cur = torch.cuda.current_stream(dev)
+        cp = max(1, min(chunk_pouches, self.P))
+        cap = (int(cp * self.F * h * w * arena_bytes_per_pixel) + (1 << 20) + 15) // 16 * 16
+        key = (cp, cap, image, mask)
+        st = getattr(self, "_fring", None)
+        if st is None or st["key"] != key:
+            self.flush_files()
+            st = {"key": key, "cs": torch.cuda.Stream(device=dev), "fs": torch.cuda.Stream(device=dev),
+                  "slots": [], "launched": [], "copying": [],
+                  "frames_done": torch.cuda.Event(),
+                  "h_frames": torch.empty(max(self.frame_elems, 1), dtype=torch.float64, pin_memory=True)}
+            for _ in range(4):
+                st["slots"].append({
+                    "dev": {}, "h_arena": torch.empty(cap, dtype=torch.uint8, pin_memory=True),
+                    "h_rec": torch.empty((cp, self.F, 2, 2), dtype=torch.int64, pin_memory=True),
+                    "h_cur": torch.empty(2, dtype=torch.int64, pin_memory=True),
+                    "h_nact": torch.empty((cp * self.F + 3) // 4 * 4, dtype=torch.int32, pin_memory=True),
+                    "meta": torch.cuda.Event(), "data": torch.cuda.Event(), "busy": None})
+            self._fring = st
+        cs = st["cs"]
+        d2h = 0
+        launched: List[Dict[str, Any]] = st["launched"]      # K3 queued, size not yet known to the host
+        copying: List[Dict[str, Any]] = st["copying"]        # copy-out queued
+
+        def queue_copy(e):
+            nonlocal d2h
+            slot = e["slot"]
+            slot["meta"].synchronize()
+            used = int(slot["h_cur"][0])
+            if used > cap:
+                raise _lib.Cab200Error(f"encode arena too small: {used} > {cap} bytes "
+                                       f"(raise arena_bytes_per_pixel above {arena_bytes_per_pixel})")
+            e["used"] = used
+            with torch.cuda.stream(cs):
+                if used:
+                    slot["h_arena"][:used].copy_(slot["dev"]["arena"][:used], non_blocking=True)
+                slot["data"].record(cs)
+            d2h += used
+            copying.append(e)
+
+        def finish(e):
+            slot = e["slot"]
+            slot["data"].synchronize()
+            consumer, threshold, quirk = e["consumer"]
+            if consumer is not None:
+                n = e["hi"] - e["lo"]
+                consumer(EncodedChunk(self, e["lo"], e["hi"], slot["h_arena"][: e["used"]].numpy(),
+                                      slot["h_rec"][:n].numpy(),
+                                      slot["h_nact"][: n * self.F].view(n, self.F).numpy(), threshold, quirk))
+            slot["busy"] = None
+
+        st["queue_copy"], st["finish"] = queue_copy, finish
+        with torch.cuda.device(dev):
+            cur.wait_event(st["frames_done"])        # a previous call's frame copy-out reads self.frames
+            self.simulate(upload=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            fs = st["fs"]                            # own stream: waits for K1, and an arena copy of the
+            fs.wait_event(ev)                        # previous call must not queue behind that wait
+            with torch.cuda.stream(fs):
+                st["h_frames"].copy_(self.frames, non_blocking=True)
+                st["frames_done"].record(fs)
+            d2h += self.frames.numel() * self.frames.element_size()
+            k = st.get("k", 0)
+            for lo in range(0, self.P, cp):
+                hi = min(lo + cp, self.P)
+                slot = st["slots"][k % 4]
+                if slot["busy"] is not None:             # its previous chunk must be out of the way
+                    e = slot["busy"]
+                    if e in launched:
+                        launched.remove(e); queue_copy(e)
+                    if e in copying:
+                        copying.remove(e); finish(e)
+                cur.wait_event(slot["data"])
+                enc = self.encode(image=image, mask=mask, pouches=(lo, hi), threshold=threshold, quirk=quirk,
+                                  out=slot["dev"], arena_bytes=cap, stage_bytes=stage_bytes)
+                n = hi - lo
+                # the sizes reach the host by zero-copy stores, not through the copy engine (it is busy
+                # with megabytes of earlier chunks, and the host needs these bytes to queue the next copy)
+                for dst, src in ((slot["h_rec"], enc["records"]), (slot["h_nact"], enc["n_active16"]),
+                                 (slot["h_cur"], enc["cursor16"])):
+                    nbytes = src.numel() * src.element_size()
+                    _lib.check(self.lib.cab200_publish_to_host(dst.data_ptr(), src.data_ptr(), nbytes // 16 * 16,
+                                                               _stream_ptr(dev)), "cab200_publish_to_host")
+                slot["meta"].record(cur)
+                d2h += 8 + enc["records"].numel() * 8 + enc["n_active"].numel() * 4
+                e = {"lo": lo, "hi": hi, "slot": slot, "consumer": (consumer, threshold, quirk)}
+                slot["busy"] = e
+                launched.append(e)
+                if len(launched) >= 2:
+                    queue_copy(launched.pop(0))
+                k += 1
+            st["k"] = k
+            if wait:
+                self.flush_files()
+        return {"h2d_bytes": self.h2d_bytes, "d2h_bytes": d2h}
+
+    def flush_files(self) -> int:
+        """Completes every chunk :meth:`run_files_to_host` left in flight (copy-out finished, consumer
+        called); returns the bytes of the chunks whose size was only learnt here."""
+        st = getattr(self, "_fring", None)
+        if st is None or "queue_copy" not in st:
+            return 0
+        late = 0
+        with torch.cuda.device(self.device):
+            while st["launched"]:
+                e = st["launched"].pop(0)
+                st["queue_copy"](e)
+                late += int(e["used"])
+            while st["copying"]:
+                st["finish"](st["copying"].pop(0))
+            st["cs"].synchronize()
+            st["fs"].synchronize()
+        return late
+
     def synchronize(self) -> None:
         torch.cuda.current_stream(self.device).synchronize()
 
@@ -564,6 +805,50 @@ class Ensemble:
                     pslot["done"].synchronize()
                     consumer(plo, phi, {n_: t[: phi - plo].numpy() for n_, t in pslot["host"].items()})
         return {"h2d_bytes": self.h2d_bytes, "d2h_bytes": d2h}
+
+
+class EncodedChunk:
+    """The files of pouches ``[lo, hi)`` as K3 left them in (pinned) host memory.  Valid until the
+    ring slot is reused, i.e. until the consumer callback returns."""
+
+    def __init__(self, ens: "Ensemble", lo: int, hi: int, arena: np.ndarray, records: np.ndarray,
+                 n_active: np.ndarray, threshold: float, quirk: bool):
+        self.ens, self.lo, self.hi = ens, lo, hi
+        self.arena = arena
+        self.offset, self.size, self.flags = Ensemble.records_to_host(records)
+        self.n_active = n_active
+        self._threshold, self._quirk = threshold, quirk
+        self._raw: Dict[int, Dict[str, np.ndarray]] = {}
+
+    def file(self, i: int, f: int, kind: int):
+        """Bytes of the ``.png`` (kind 0) / ``.npz`` (kind 1) of chunk-local pouch i, frame f; ``None``
+        when there is none (not requested, or a mask of a frame without active cells)."""
+        fl = int(self.flags[i, f, kind])
+        if fl & _lib.ENC_OK:
+            o = int(self.offset[i, f, kind])
+            return self.arena[o:o + int(self.size[i, f, kind])]
+        if fl & _lib.ENC_SKIPPED:
+            return None
+        if fl & _lib.ENC_STAGE_FULL:
+            return self._host_encoded(i, f, kind)
+        raise _lib.Cab200Error(f"frame ({self.lo + i}, {f}) kind {kind}: encode flags {fl}")
+
+    def _host_encoded(self, i: int, f: int, kind: int) -> bytes:
+        """A file that did not fit K3's staging buffer: rasterise the pouch with K2 and encode on the host."""
+        import io as _io
+        from . import io as cio
+        raw = self._raw.get(i)
+        if raw is None:
+            out = self.ens.rasterize(image=True, instance=True, pouches=(self.lo + i, self.lo + i + 1),
+                                     threshold=self._threshold, quirk=self._quirk)
+            raw = {"image": out["image"][0].cpu().numpy(), "instance": _u16_numpy(out["instance"][0])}
+            self._raw[i] = raw
+        if kind == 0:
+            img = raw["image"][f]
+            return cio.encode_gray_alpha_png16(img[..., 0].astype(np.uint16) << 2, img[..., 1].astype(np.uint16) * 257)
+        buf = _io.BytesIO()
+        np.savez_compressed(buf, mask=raw["instance"][f])
+        return buf.getvalue()
 
 
 def make_specs(n: int, size: str = "medium", sim_types: Optional[Sequence[str]] = None,

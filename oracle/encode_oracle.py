@@ -1,0 +1,200 @@
+"""TEST INFRASTRUCTURE -- CPU restatement of K3's file encoder (calcium_b200/csrc/encode.cu).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module; the product
+never does.
+
+What it pins, and against what:
+  * the *content* of the files is pinned to the reference: decoding the PNG gives the array the
+    reference builds in utils/image_processing.py:256-265 (gray*4 as big-endian uint16, alpha*257)
+    from Pouch.generate_image's output, and ``np.load(npz)['mask']`` gives the array
+    utils/sam2_data_generator.py:203 stores -- both checked with independent decoders (zlib, numpy's
+    own npz reader, cv2.imdecode);
+  * the *bytes* of the files are this repo's own choice (any DEFLATE parse is a valid PNG/zip), so
+    the byte-exact comparison is GPU encoder vs this restatement of the same parse rules, written
+    independently in numpy with zlib's crc32/adler32 as the checksum authority.
+
+Parse rules (the same as encode.cu): rows are cut into 512-pixel segments; per pixel the mode is
+"up" when it equals the pixel above, else "left" when it equals the previous pixel of the row, else
+literal; a token is a maximal run of one mode, additionally cut every 256 bytes from the segment
+start; a match shorter than 3 bytes is sent as a literal pixel; one final fixed-Huffman block.
+"""
+from __future__ import annotations
+
+import struct
+import zlib
+from typing import List, Tuple
+
+import numpy as np
+
+_LEN_BASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+_LEN_EXTRA = [0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0]
+_DIST_BASE = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073,
+              4097, 6145, 8193, 12289, 16385, 24577]
+_DIST_EXTRA = [0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13]
+
+
+def _rev(v: int, n: int) -> int:
+    return int(format(v, f"0{n}b")[::-1], 2)
+
+
+def fixed_symbol(sym: int) -> Tuple[int, int]:
+    """(bits in stream order, count) of literal/length symbol ``sym`` in the fixed Huffman code (RFC 1951 3.2.6)."""
+    if sym <= 143:
+        code, nb = 0b00110000 + sym, 8
+    elif sym <= 255:
+        code, nb = 0b110010000 + (sym - 144), 9
+    elif sym <= 279:
+        code, nb = sym - 256, 7
+    else:
+        code, nb = 0b11000000 + (sym - 280), 8
+    return _rev(code, nb), nb
+
+
+def length_token(length: int) -> Tuple[int, int]:
+    i = max(k for k in range(29) if _LEN_BASE[k] <= length)
+    v, nb = fixed_symbol(257 + i)
+    return v | ((length - _LEN_BASE[i]) << nb), nb + _LEN_EXTRA[i]
+
+
+def dist_token(dist: int) -> Tuple[int, int]:
+    i = max(k for k in range(30) if _DIST_BASE[k] <= dist)
+    return _rev(i, 5) | ((dist - _DIST_BASE[i]) << 5), 5 + _DIST_EXTRA[i]
+
+
+def _pack(tokens: List[Tuple[int, int]]) -> bytes:
+    """Concatenate (value, bit count) pairs LSB first."""
+    vals = np.array([t[0] for t in tokens], dtype=np.uint64)
+    nbs = np.array([t[1] for t in tokens], dtype=np.int64)
+    k = np.arange(64, dtype=np.uint64)
+    bits = ((vals[:, None] >> k[None, :]) & np.uint64(1)).astype(np.uint8)
+    keep = np.arange(64)[None, :] < nbs[:, None]
+    return np.packbits(bits[keep], bitorder="little").tobytes()
+
+
+def deflate_rows(keys: np.ndarray, pixel_bytes, bpp: int, row_lead: int, head: bytes = b"") -> bytes:
+    """Raw DEFLATE stream of ``head`` + rows of pixels.  ``keys`` (H, W) integers identify pixel
+    values; ``pixel_bytes(key)`` gives the ``bpp`` bytes of a pixel; every row is preceded by
+    ``row_lead`` zero bytes (the PNG filter byte)."""
+    H, W = keys.shape
+    maxpix = 256 // bpp
+    up_dist = row_lead + bpp * W
+    use_up = up_dist <= 32768
+    lit = [fixed_symbol(b) for b in range(256)]
+    tok: List[Tuple[int, int]] = [(3, 3)]                      # BFINAL=1, BTYPE=01
+    tok += [lit[b] for b in head]
+    d_left, d_up = dist_token(bpp), (dist_token(up_dist) if use_up else (0, 0))
+
+    def literal_pixel(key):
+        v, nb = 0, 0
+        for b in pixel_bytes(int(key)):
+            v |= lit[b][0] << nb
+            nb += lit[b][1]
+        return v, nb
+
+    for y in range(H):
+        row = keys[y]
+        eq_up = (row == keys[y - 1]) if (y > 0 and use_up) else np.zeros(W, bool)
+        eq_left = np.zeros(W, bool)
+        eq_left[1:] = row[1:] == row[:-1]
+        mode = np.where(eq_up, 2, np.where(eq_left, 1, 0))
+        for _ in range(row_lead):
+            tok.append(lit[0])
+        for x0 in range(0, W, 512):
+            x1 = min(W, x0 + 512)
+            m = mode[x0:x1]
+            n = x1 - x0
+            start = np.zeros(n, bool)
+            start[0] = True
+            start[1:] = m[1:] != m[:-1]
+            start |= m == 0
+            start[np.arange(0, n, maxpix)] = True
+            pos = np.flatnonzero(start)
+            ends = np.append(pos[1:], n)
+            for s, e in zip(pos, ends):
+                ln = int(e - s)
+                md = int(m[s])
+                if md != 0 and ln * bpp >= 3:
+                    lv, lnb = length_token(ln * bpp)
+                    dv, dnb = d_up if md == 2 else d_left
+                    tok.append((lv | (dv << lnb), lnb + dnb))
+                else:
+                    assert ln == 1
+                    tok.append(literal_pixel(row[x0 + s]))
+    tok.append(fixed_symbol(256))                               # end of block
+    return _pack(tok)
+
+
+def _png_chunk(tag: bytes, data: bytes) -> bytes:
+    return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+
+def png_scanlines(image: np.ndarray) -> bytes:
+    """Filter-0 scanlines of the 16-bit gray+alpha picture the reference builds from an (H, W, 2)
+    uint8 frame (utils/image_processing.py:256-265): gray*4, alpha*257, big endian."""
+    h, w, _ = image.shape
+    px = np.empty((h, w, 2), dtype=">u2")
+    px[..., 0] = image[..., 0].astype(np.uint16) * 4
+    px[..., 1] = image[..., 1].astype(np.uint16) * 257
+    raw = np.zeros((h, 1 + 4 * w), dtype=np.uint8)
+    raw[:, 1:] = px.view(np.uint8).reshape(h, 4 * w)
+    return raw.tobytes()
+
+
+def encode_png(image: np.ndarray) -> bytes:
+    """The .png K3 writes for ``image`` = Pouch.generate_image's (H, W, 2) uint8 array."""
+    h, w, _ = image.shape
+    keys = image[..., 0].astype(np.int64) | ((image[..., 1] != 0).astype(np.int64) << 8)
+
+    def pixel_bytes(key):
+        g, a = key & 255, 255 if key >> 8 else 0
+        return [g >> 6, (g << 2) & 255, a, a]
+
+    z = b"\x78\x01" + deflate_rows(keys, pixel_bytes, 4, 1) + struct.pack(">I", zlib.adler32(png_scanlines(image)))
+    return (b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 16, 4, 0, 0, 0))
+            + _png_chunk(b"IDAT", z) + _png_chunk(b"IEND", b""))
+
+
+def npy_bytes(mask: np.ndarray) -> bytes:
+    """.npy (format 1.0) bytes of a C-contiguous uint16 array, as numpy.lib.format writes them."""
+    h, w = mask.shape
+    d = "{'descr': '<u2', 'fortran_order': False, 'shape': (%d, %d), }" % (h, w)
+    pad = (64 - ((10 + len(d) + 1) % 64)) % 64
+    hdr = d + " " * pad + "\n"
+    return b"\x93NUMPY\x01\x00" + struct.pack("<H", len(hdr)) + hdr.encode("latin1") + mask.astype("<u2").tobytes()
+
+
+def encode_npz(mask: np.ndarray) -> bytes:
+    """The .npz K3 writes for an instance mask: a zip archive with the single deflated member
+    ``mask.npy`` (what np.savez_compressed(path, mask=mask) stores)."""
+    h, w = mask.shape
+    raw = npy_bytes(mask)
+    head = raw[: len(raw) - 2 * h * w]
+    comp = deflate_rows(mask.astype(np.int64), lambda k: [k & 255, k >> 8], 2, 0, head=head)
+    crc = zlib.crc32(raw) & 0xFFFFFFFF
+    name = b"mask.npy"
+    local = struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0, 8, 0, 0x21, crc, len(comp), len(raw), len(name), 0) + name
+    central = struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 20, 20, 0, 8, 0, 0x21, crc, len(comp), len(raw),
+                          len(name), 0, 0, 0, 0, 0x01800000, 0) + name
+    end = struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, 1, 1, len(central), len(local) + len(comp), 0)
+    return local + comp + central + end
+
+
+def decode_png(data: bytes) -> np.ndarray:
+    """Independent decoder for the PNG subset above -> (H, W, 2) uint16 (gray16, alpha16).  Checks
+    every chunk CRC and lets zlib check the Adler-32."""
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w = 8, b"", None
+    while pos < len(data):
+        (ln,), tag = struct.unpack(">I", data[pos:pos + 4]), data[pos + 4:pos + 8]
+        body = data[pos + 8:pos + 8 + ln]
+        (crc,) = struct.unpack(">I", data[pos + 8 + ln:pos + 12 + ln])
+        assert crc == (zlib.crc32(tag + body) & 0xFFFFFFFF), f"bad CRC in {tag!r}"
+        if tag == b"IHDR":
+            w, h, depth, ctype, _, _, interlace = struct.unpack(">IIBBBBB", body)
+            assert (depth, ctype, interlace) == (16, 4, 0)
+        elif tag == b"IDAT":
+            idat += body
+        pos += 12 + ln
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 4 * w)
+    assert not raw[:, 0].any()
+    return raw[:, 1:].copy().view(">u2").reshape(h, w, 2).astype(np.uint16)

@@ -1,0 +1,292 @@
+"""K3 (rasterise + encode on the device, csrc/encode.cu) against its oracle and independent decoders.
+
+Content parity (what the reference would store): decoding the PNG gives gray*4 / alpha*257 of
+``generate_image`` (utils/image_processing.py:256-265), ``np.load(npz)['mask']`` gives
+``create_instance_mask_from_cells`` of the active-cell mask (utils/sam2_data_generator.py:315-335),
+no mask file for frames without active cells (:318-319).  Byte parity: GPU files == the numpy
+restatement of the same parse (oracle/encode_oracle.py), which uses zlib for every checksum.
+"""
+import io
+import struct
+import zipfile
+import zlib
+
+import numpy as np
+import pytest
+
+TAB_WORDS = 256 + 260 + 256 + 32 + 2048 + 128
+
+
+def _tables(lib, L, H, W):
+    nb = int(lib.cab200_encode_tables_bytes())
+    host = np.zeros(nb, dtype=np.uint8)
+    L.check(lib.cab200_encode_tables(H, W, host.ctypes.data), "cab200_encode_tables")
+    u32 = host[: 4 * TAB_WORDS].view(np.uint32)
+    t = dict(lit=u32[:256], len=u32[256:516], crc=u32[516:772], pow8=u32[772:804], rowshift=u32[804:804 + 2048],
+             colshift=u32[804 + 2048:TAB_WORDS])
+    streams = []
+    base = 4 * TAB_WORDS
+    for _ in range(2):
+        blob = host[base:base + 804]
+        ints = blob[736:].view(np.int32)
+        names = ["head_bits", "prefix_len", "suffix_len", "head_len", "dist_left", "dist_up", "bpp", "seg_lanes", "row_lead",
+                 "crc_const", "raw_len", "p_len_prefix", "p_crc_prefix", "p_csize_prefix", "p_crc_suffix",
+                 "p_csize_suffix", "p_cdoff_suffix"]
+        d = {n: int(v) for n, v in zip(names, ints)}
+        d["prefix"] = bytes(blob[:64][: d["prefix_len"]])
+        d["suffix"] = bytes(blob[64:160][: d["suffix_len"]])
+        d["head"] = bytes(blob[160:352][: d["head_len"]])
+        streams.append(d)
+        base += 804
+    t["img"], t["msk"] = streams
+    return t
+
+
+def _mulmod(a, b):
+    p = 0
+    for i in range(31, -1, -1):
+        if (a >> i) & 1:
+            p ^= b
+        b = (b >> 1) ^ (0xEDB88320 if b & 1 else 0)
+    return p
+
+
+def _crc0_slow(data, c):
+    # CRC register started from c, no final xor: crc32(data, c') = ~reg(data, ~c')
+    return (zlib.crc32(bytes(data), c ^ 0xFFFFFFFF) ^ 0xFFFFFFFF) & 0xFFFFFFFF
+
+
+# ---- CPU: oracle round trips, host tables ------------------------------------------------------------
+
+def _random_label_picture(rng, H, W, n_labels):
+    # blocky picture with vertical coherence, literals, long runs and one-pixel runs
+    ys = np.sort(rng.integers(0, H, 6)); xs = np.sort(rng.integers(0, W, 9))
+    lab = (np.searchsorted(ys, np.arange(H))[:, None] * 10 + np.searchsorted(xs, np.arange(W))[None, :]) % n_labels
+    noise = rng.random((H, W)) < 0.03
+    lab[noise] = rng.integers(0, n_labels, int(noise.sum()))
+    return lab
+
+
+@pytest.mark.parametrize("H,W", [(64, 48), (75, 100), (33, 530), (128, 1030)])
+def test_oracle_files_decode_with_independent_readers(H, W):
+    from oracle import encode_oracle as EO
+    rng = np.random.default_rng(H * 1000 + W)
+    lab = _random_label_picture(rng, H, W, 300)
+    gray = (lab * 7 % 256).astype(np.uint8)
+    img = np.stack([np.where(lab > 0, gray, 0), np.where(lab > 0, 255, 0)], axis=-1).astype(np.uint8)
+    inst = np.where(lab % 3 == 0, lab * 211 % 65536, 0).astype(np.uint16)
+    png, npz = EO.encode_png(img), EO.encode_npz(inst)
+    dec = EO.decode_png(png)
+    assert np.array_equal(dec[..., 0], img[..., 0].astype(np.uint16) * 4)
+    assert np.array_equal(dec[..., 1], img[..., 1].astype(np.uint16) * 257)
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    if cv2 is not None:
+        cvd = cv2.imdecode(np.frombuffer(png, np.uint8), cv2.IMREAD_UNCHANGED)
+        assert cvd.dtype == np.uint16 and np.array_equal(cvd[..., 0], dec[..., 0]) and np.array_equal(cvd[..., -1], dec[..., 1])
+    assert zipfile.ZipFile(io.BytesIO(npz)).testzip() is None
+    m = np.load(io.BytesIO(npz))["mask"]
+    assert m.dtype == np.uint16 and np.array_equal(m, inst)
+    # the .npy member is what numpy itself writes
+    ref = io.BytesIO(); np.save(ref, inst)
+    assert EO.npy_bytes(inst) == ref.getvalue()
+
+
+def test_host_tables_match_the_oracle_and_zlib():
+    """cab200_encode_tables is host code: Huffman tables, CRC machinery and container templates."""
+    from calcium_b200 import _lib as L, build
+    from oracle import encode_oracle as EO
+    build.build()
+    lib = L.load()
+    H, W = 96, 200
+    t = _tables(lib, L, H, W)
+    for b in range(256):
+        v, n = EO.fixed_symbol(b)
+        assert t["lit"][b] == (v | n << 24)
+        assert t["crc"][b] == _crc0_slow(bytes([b]), 0)
+    for ln in range(3, 259):
+        v, n = EO.length_token(ln)
+        assert t["len"][ln] == (v | n << 24)
+    for name, dist in (("img", (4, 1 + 4 * W)), ("msk", (2, 2 * W))):
+        for key, d in zip(("dist_left", "dist_up"), dist):
+            v, n = EO.dist_token(d)
+            assert (t[name][key] & 0xFFFFFFFF) == (v | n << 24)
+    # x^(8*2^k), and CRC(zeros(n)) = (0xFFFFFFFF * x^(8n)) ^ 0xFFFFFFFF
+    x = 0x00800000
+    for k in range(20):
+        assert int(t["pow8"][k]) == x
+        n = 1 << k
+        assert (_mulmod(0xFFFFFFFF, x) ^ 0xFFFFFFFF) == (zlib.crc32(bytes(n)) & 0xFFFFFFFF)
+        x = _mulmod(x, x)
+    # the mask CRC exactly as the kernel assembles it: per 16-pixel chunk crc0, shifted into place
+    rng = np.random.default_rng(5)
+    inst = np.where(rng.random((H, W)) < 0.3, rng.integers(0, 65536, (H, W)), 0).astype("<u2")
+    acc = 0
+    for y in range(H):
+        rowc = 0
+        for c in range((W + 15) // 16):
+            chunk = inst[y, 16 * c:16 * c + 16].tobytes()
+            rowc ^= _mulmod(_crc0_slow(chunk, 0), int(t["colshift"][c]))
+        acc ^= _mulmod(rowc, int(t["rowshift"][y]))
+    crc = acc ^ (t["msk"]["crc_const"] & 0xFFFFFFFF)
+    assert crc == (zlib.crc32(EO.npy_bytes(inst)) & 0xFFFFFFFF)
+    # container templates: the oracle's files start / end with them (variable fields zero in the template)
+    img = np.zeros((H, W, 2), np.uint8)
+    png = EO.encode_png(img)
+    p = t["img"]
+    assert png[:p["p_len_prefix"]] == p["prefix"][:p["p_len_prefix"]] and png[p["p_len_prefix"] + 4:p["prefix_len"]] == p["prefix"][p["p_len_prefix"] + 4:]
+    assert png[-12:] == p["suffix"] and p["raw_len"] == H * (1 + 4 * W)
+    npz = EO.encode_npz(inst)
+    m = t["msk"]
+    assert m["head"] == EO.npy_bytes(inst)[:m["head_len"]] and m["raw_len"] == m["head_len"] + 2 * H * W
+    assert npz[:14] == m["prefix"][:14] and npz[22:38] == m["prefix"][22:38]
+    tail = npz[-m["suffix_len"]:]
+    for a, b in ((0, 16), (24, 54 + 16), (54 + 20, m["suffix_len"])):
+        assert tail[a:b] == m["suffix"][a:b]
+
+
+# ---- GPU -------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def env(cuda_device, oracle):
+    import torch
+    from calcium_b200 import _lib, build
+    build.build()
+    from calcium_b200 import ensemble
+    from oracle import encode_oracle
+    return dict(dev=cuda_device, O=oracle, EO=encode_oracle, lib=_lib.load(), L=_lib, E=ensemble, torch=torch)
+
+
+def _run(env, size, count, out, T=4000, every=400, **kw):
+    E = env["E"]
+    specs = E.make_specs(count, size=size, first_seed=40)
+    ens = E.Ensemble(specs, T=T, frame_steps=list(range(0, T, every)), output_size=out, device=env["dev"])
+    ens.simulate()
+    raw = ens.rasterize(image=True, instance=True)
+    enc = ens.encode(**kw)
+    ens.synchronize()
+    arena, off, size_, flags = ens.encoded_files(enc)
+    return ens, raw, enc, arena, off, size_, flags
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,count,out", [("small", 4, (256, 256)), ("medium", 4, (512, 512)), ("xsmall", 4, (100, 75)),
+                                            ("small", 2, (640, 480)), ("small", 1, (1030, 40))])
+def test_k3_files_decode_to_k2_arrays_and_match_oracle_bytes(env, size, count, out):
+    EO, L = env["EO"], env["L"]
+    ens, raw, enc, arena, off, size_, flags = _run(env, size, count, out)
+    image = raw["image"].cpu().numpy()
+    inst = raw["instance"].cpu().numpy().view(np.uint16)
+    nact = raw["n_active"].cpu().numpy()
+    assert np.array_equal(enc["n_active"].cpu().numpy(), nact)
+    n_bytes_checked = 0
+    for i in range(ens.P):
+        for f in range(ens.F):
+            assert flags[i, f, 0] == L.ENC_OK
+            png = arena[off[i, f, 0]: off[i, f, 0] + size_[i, f, 0]].tobytes()
+            dec = EO.decode_png(png)                      # checks chunk CRCs and the Adler-32
+            assert np.array_equal(dec[..., 0], image[i, f, :, :, 0].astype(np.uint16) * 4)
+            assert np.array_equal(dec[..., 1], image[i, f, :, :, 1].astype(np.uint16) * 257)
+            if nact[i, f] == 0:
+                assert flags[i, f, 1] == L.ENC_SKIPPED and size_[i, f, 1] == 0
+            else:
+                assert flags[i, f, 1] == L.ENC_OK
+                npz = arena[off[i, f, 1]: off[i, f, 1] + size_[i, f, 1]].tobytes()
+                assert zipfile.ZipFile(io.BytesIO(npz)).testzip() is None       # zip CRC-32 of the .npy
+                m = np.load(io.BytesIO(npz))["mask"]
+                assert m.dtype == np.uint16 and np.array_equal(m, inst[i, f])
+            if (i * ens.F + f) % 7 == 0:                  # byte parity with the oracle's parse on a sample
+                assert png == EO.encode_png(image[i, f])
+                if nact[i, f]:
+                    assert npz == EO.encode_npz(inst[i, f])
+                n_bytes_checked += 1
+    assert n_bytes_checked >= 2
+    assert int(enc["cursor"].item()) == int(((size_ + 15) // 16 * 16).sum())
+
+
+@pytest.mark.gpu
+def test_k3_png_is_readable_by_opencv(env):
+    cv2 = pytest.importorskip("cv2")
+    ens, raw, enc, arena, off, size_, flags = _run(env, "small", 1, (256, 256))
+    image = raw["image"].cpu().numpy()
+    for f in range(ens.F):
+        png = arena[off[0, f, 0]: off[0, f, 0] + size_[0, f, 0]]
+        cvd = cv2.imdecode(png, cv2.IMREAD_UNCHANGED)
+        assert cvd is not None and cvd.dtype == np.uint16
+        assert np.array_equal(cvd[..., 0], image[0, f, :, :, 0].astype(np.uint16) * 4)
+        assert np.array_equal(cvd[..., -1], image[0, f, :, :, 1].astype(np.uint16) * 257)
+
+
+@pytest.mark.gpu
+def test_k3_flags_frames_that_do_not_fit_the_staging_buffer(env):
+    L = env["L"]
+    ens, raw, enc, arena, off, size_, flags = _run(env, "small", 1, (256, 256), stage_bytes=4096)
+    assert (flags[..., 0] == L.ENC_STAGE_FULL).all() and (size_[..., 0] == 0).all()
+    with pytest.raises(L.Cab200Error):
+        e2 = ens.encode(arena_bytes=4096)
+        ens.encoded_files(e2)
+
+
+@pytest.mark.gpu
+def test_k3_intended_ids_mode_and_threshold(env):
+    """quirk=False (intended rank-of-active-cell ids) and a non-default threshold go through the same LUTs as K2."""
+    E = env["E"]
+    specs = E.make_specs(2, size="small", first_seed=3)
+    ens = E.Ensemble(specs, T=3000, frame_steps=[0, 1500, 2999], output_size=(256, 256), device=env["dev"])
+    ens.simulate()
+    raw = ens.rasterize(image=False, instance=True, quirk=False, threshold=0.05)
+    enc = ens.encode(image=False, quirk=False, threshold=0.05)
+    arena, off, size_, flags = ens.encoded_files(enc)
+    inst = raw["instance"].cpu().numpy().view(np.uint16)
+    assert (flags[..., 0] == env["L"].ENC_SKIPPED).all()
+    for i in range(2):
+        for f in range(3):
+            if flags[i, f, 1] == env["L"].ENC_OK:
+                m = np.load(io.BytesIO(arena[off[i, f, 1]: off[i, f, 1] + size_[i, f, 1]].tobytes()))["mask"]
+                assert np.array_equal(m, inst[i, f])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stage_bytes,wait", [(0, True), (0, False), (4096, True)])
+def test_files_pipeline_delivers_every_frame_to_the_host(env, stage_bytes, wait):
+    """Ensemble.run_files_to_host (host in, host out; three-slot ring, ragged last chunk), called twice
+    back to back like the benchmark does; with a tiny staging buffer every frame takes the K2 + host
+    encoder fall-back.  Every file decodes to the arrays of the raw path."""
+    E, EO, L = env["E"], env["EO"], env["L"]
+    specs = E.make_specs(5, size="small", first_seed=11)
+    ens = E.Ensemble(specs, T=3000, frame_steps=[0, 700, 1400, 2999], output_size=(256, 256), device=env["dev"])
+    got = {}
+
+    def consumer(ch):
+        for i in range(ch.hi - ch.lo):
+            for f in range(ens.F):
+                for kind in (0, 1):
+                    b = ch.file(i, f, kind)
+                    got[(len(got_calls), ch.lo + i, f, kind)] = None if b is None else bytes(b)
+        assert ch.n_active.shape == (ch.hi - ch.lo, ens.F)
+
+    got_calls = []
+    for _ in range(2):
+        moved = ens.run_files_to_host(chunk_pouches=2, consumer=consumer, wait=wait, stage_bytes=stage_bytes)
+        if not wait:
+            ens.flush_files()
+        got_calls.append(1)
+        assert moved["h2d_bytes"] == ens.h2d_bytes and moved["d2h_bytes"] > 0
+    raw = ens.rasterize(image=True, instance=True)
+    image = raw["image"].cpu().numpy()
+    inst = raw["instance"].cpu().numpy().view(np.uint16)
+    nact = raw["n_active"].cpu().numpy()
+    assert len(got) == 2 * 5 * ens.F * 2
+    for (call, i, f, kind), b in got.items():
+        if kind == 0:
+            dec = EO.decode_png(b)
+            assert np.array_equal(dec[..., 0], image[i, f, :, :, 0].astype(np.uint16) * 4)
+            assert np.array_equal(dec[..., 1], image[i, f, :, :, 1].astype(np.uint16) * 257)
+        elif nact[i, f] == 0:
+            assert b is None
+        else:
+            assert np.array_equal(np.load(io.BytesIO(b))["mask"], inst[i, f])
+    frames_host = ens._fring["h_frames"].numpy()
+    assert np.array_equal(frames_host, ens.frames.cpu().numpy())
