@@ -23,7 +23,7 @@ ENC_OK, ENC_STAGE_FULL, ENC_ARENA_FULL, ENC_SKIPPED = 1, 2, 4, 8
 
 #: every symbol include/cab200.h declares (tests check the library exports all of them)
 EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
-           "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_sim_layout",
+           "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_frames_tmp_bytes", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_sim_layout",
            "cab200_cluster_layout", "cab200_plan_cluster",
            "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
            "cab200_encode_tables_bytes", "cab200_encode_tables", "cab200_encode_scratch_bytes", "cab200_encode_batch",
@@ -61,7 +61,9 @@ def load() -> ctypes.CDLL:
         i64p,                                                  # cell_off (host)
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,      # params, c0, p0, r0, vplc (device)
         c_int, c_int, i32p,                                    # T, n_frames, frame_steps (host)
-        c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
+        c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]
+    lib.cab200_sim_frames_tmp_bytes.restype = c_size_t
+    lib.cab200_sim_frames_tmp_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
     lib.cab200_plan_slots.restype = c_int
     lib.cab200_plan_slots.argtypes = [c_int, i32p, i32p, c_int, c_int, ctypes.c_longlong,
                                       ctypes.c_ulonglong, c_int, POINTER(ctypes.c_uint16), i64p]

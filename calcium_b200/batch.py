@@ -114,32 +114,65 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     per_pouch_bytes = max(1, len(steps)) * h * w * (2 + (2 if generate_masks else 0))
     chunk = max(1, int(max_chunk_bytes // per_pouch_bytes))
 
+    def _write_bytes(path: str, data: bytes) -> str:
+        with open(path, "wb") as fh:
+            fh.write(data)
+        return path
+
     try:
         for c0 in range(0, len(drawn), chunk):
             part = drawn[c0:c0 + chunk]
             ens = Ensemble([d["spec"] for d in part], output_size=output_size, T=T,
                            frame_steps=steps, device=device)
-            ens.simulate()
-            status = ens.check_status()
-            out = ens.rasterize(image=True, instance=bool(generate_masks)) if steps else {}
-            ens.synchronize()
-            img = out["image"].cpu().numpy() if steps else None
-            ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and generate_masks) else None
-            nact = out["n_active"].cpu().numpy() if steps else None
+            names = {li: [f"{d['name']}_t{t:05d}_{batch_run_id}" for t in steps] for li, d in enumerate(part)}
+            image_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
+            mask_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
+            img = ins = nact = None
+            if steps and not keep_arrays:
+                # K1 -> K3: every frame arrives on the host as the finished .png / .npz byte string
+                # (cab200_encode_batch); writing a file is a plain write of those bytes.
+                def consumer(ch):
+                    for i in range(ch.hi - ch.lo):
+                        li = ch.lo + i
+                        for fi in range(len(steps)):
+                            base = names[li][fi]
+                            ipath = os.path.join(img_dir, base + ".png")
+                            image_files[li].append(ipath)
+                            if pool is not None:
+                                pending.append(pool.submit(_write_bytes, ipath, bytes(ch.file(i, fi, 0))))
+                            mb = ch.file(i, fi, 1) if generate_masks else None
+                            if mb is not None:     # no active cell -> no mask (sam2_data_generator.py:318-319)
+                                mpath = os.path.join(mask_dir, base + ".npz")
+                                mask_files[li].append(mpath)
+                                mappings.append((os.path.basename(ipath), os.path.basename(mpath)))
+                                if pool is not None:
+                                    pending.append(pool.submit(_write_bytes, mpath, bytes(mb)))
+                ens.run_files_to_host(chunk_pouches=min(len(part), 37), image=True, mask=bool(generate_masks),
+                                      consumer=consumer)
+                status = ens.check_status()
+            else:
+                ens.simulate()
+                status = ens.check_status()
+                out = ens.rasterize(image=True, instance=bool(generate_masks)) if steps else {}
+                ens.synchronize()
+                img = out["image"].cpu().numpy() if steps else None
+                ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and generate_masks) else None
+                nact = out["n_active"].cpu().numpy() if steps else None
+                del out
             for li, d in enumerate(part):
-                image_files, mask_files = [], []
-                for fi, t in enumerate(steps):
-                    base = f"{d['name']}_t{t:05d}_{batch_run_id}"
-                    ipath = os.path.join(img_dir, base + ".png")
-                    image_files.append(ipath)
-                    if pool is not None:
-                        pending.append(pool.submit(cio.save_gray_alpha_png, img[li, fi], ipath, 10))
-                    if generate_masks and nact[li, fi] > 0:      # no active cell -> no mask (sam2_data_generator.py:318-319)
-                        mpath = os.path.join(mask_dir, base + ".npz")
-                        mask_files.append(mpath)
-                        mappings.append((os.path.basename(ipath), os.path.basename(mpath)))
+                if img is not None:
+                    for fi, t in enumerate(steps):
+                        base = names[li][fi]
+                        ipath = os.path.join(img_dir, base + ".png")
+                        image_files[li].append(ipath)
                         if pool is not None:
-                            pending.append(pool.submit(cio.save_instance_mask, ins[li, fi], mpath))
+                            pending.append(pool.submit(cio.save_gray_alpha_png, img[li, fi], ipath, 10))
+                        if generate_masks and nact[li, fi] > 0:      # no active cell -> no mask (sam2_data_generator.py:318-319)
+                            mpath = os.path.join(mask_dir, base + ".npz")
+                            mask_files[li].append(mpath)
+                            mappings.append((os.path.basename(ipath), os.path.basename(mpath)))
+                            if pool is not None:
+                                pending.append(pool.submit(cio.save_instance_mask, ins[li, fi], mpath))
                 if keep_arrays:
                     arrays[d["sim_idx"]] = {
                         "time_steps": list(steps), "image": img[li].copy() if img is not None else None,
@@ -156,9 +189,9 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 results["simulations"].append({
                     "simulation_id": d["sim_idx"], "simulation_name": d["name"],
                     "simulation_type": d["type"], "pouch_size": d["size"], "parameters": d["params"],
-                    "image_count": len(image_files), "image_dir": img_dir, "mask_dir": mask_dir,
-                    "mask_count": len(mask_files), "pouch": pouch_obj})
-            del ens, out
+                    "image_count": len(image_files[li]), "image_dir": img_dir, "mask_dir": mask_dir,
+                    "mask_count": len(mask_files[li]), "pouch": pouch_obj})
+            del ens
     finally:
         if pool is not None:
             for f in pending:

@@ -37,6 +37,26 @@ int sim_copies(int n, bool unit, size_t elem2, int nslot)
     return integrate_smem_bytes(np, nslot, elem2, 2) <= 227 * 1024 ? 2 : 1;
 }
 
+// frames_tmp (slot order, see integrate.cuh) -> frames_out (original cell order).  One CTA per
+// (frame, pouch of the launch): gathers inside one 4*NS-element block (L1/L2 resident), writes coalesced.
+template <typename R>
+__global__ void __launch_bounds__(256) unpermute_kernel(const R *tmp, R *out, const int32_t *pouch_list,
+                                                        const int64_t *cell_off, const uint16_t *plan, int n, int ncta,
+                                                        int nslot, int n_frames)
+{
+    const int q = blockIdx.y, fi = blockIdx.x;
+    const int64_t coff = cell_off[pouch_list[q]];
+    const size_t ns = (size_t)ncta * nslot;
+    const R *src = tmp + ((size_t)q * n_frames + fi) * 4 * ns;
+    R *dst = out + (size_t)coff * 4 * n_frames + (size_t)fi * 4 * n;
+    for (int cell = threadIdx.x; cell < n; cell += blockDim.x) {
+        // cluster plan: part_of[n] | slot_of[n] | ...;  single-CTA plan: slot_of[n] | ...
+        const size_t g = (ncta > 1) ? (size_t)plan[cell] * nslot + plan[n + cell] : (size_t)plan[cell];
+#pragma unroll
+        for (int st = 0; st < 4; ++st) dst[(size_t)st * n + cell] = src[st * ns + g];
+    }
+}
+
 static std::mutex g_plan_mu;
 static int g_force_nmax = 0, g_force_threads = 0, g_force_cpt = 0;
 
@@ -98,6 +118,15 @@ extern "C" int cab200_cluster_layout(int n, int n_cta, int precision, int64_t ou
     return CAB200_OK;
 }
 
+extern "C" size_t cab200_sim_frames_tmp_bytes(int n_cells, int n_cta, int unit, int precision, int n_pouch, int n_frames)
+{
+    int64_t lay[4];
+    const int rc = (n_cta > 1) ? cab200_cluster_layout(n_cells, n_cta, precision, lay) : cab200_sim_layout(n_cells, unit, precision, lay);
+    if (rc != CAB200_OK || n_pouch <= 0 || n_frames <= 0) return 0;
+    const size_t ns = (size_t)(n_cta > 1 ? n_cta : 1) * (size_t)lay[0] * (size_t)lay[1];
+    return (size_t)n_pouch * n_frames * 4 * ns * (precision == CAB200_FP64_STRICT ? 8 : 4);
+}
+
 extern "C" size_t cab200_sim_scratch_bytes(int n_pouch, int n_frames)
 {
     // pouch_list [P] i32 + cell_off [P+1] i64 + frame_steps [F] i32, each 16-byte aligned
@@ -113,7 +142,7 @@ extern "C" int cab200_sim_batch(
     const int32_t *g_cluster, const int64_t *g_plan_off, const uint16_t *slot_plan, const int64_t *cell_off, const double *params, const double *c0, const double *p0,
     const double *r0, const double *vplc, int T, int n_frames, const int32_t *frame_steps,
     void *frames_out, int32_t *status_out, int precision, void *scratch, size_t scratch_bytes,
-    void *stream_)
+    void *frames_tmp, size_t frames_tmp_bytes, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_pouch < 0 || n_geom <= 0 || T < 1 || n_frames < 0) {
@@ -221,6 +250,8 @@ extern "C" int cab200_sim_batch(
             ca.params = params; ca.c0 = c0; ca.p0 = p0; ca.r0 = r0; ca.vplc = vplc;
             ca.T = T; ca.n_frames = n_frames; ca.frame_steps = d_frame_steps;
             ca.frames_out = frames_out; ca.status_out = status_out;
+            const size_t tmp_need = (size_t)count * n_frames * 4 * ((size_t)ncta * cth * ccpt) * (el2 / 2);
+            ca.frames_tmp = (frames_tmp && n_frames > 0 && tmp_need <= frames_tmp_bytes) ? frames_tmp : nullptr;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(count * ncta), 1, 1);
             cfg.blockDim = dim3((unsigned)cth, 1, 1);
@@ -231,6 +262,16 @@ extern "C" int cab200_sim_batch(
             attr[0].val.clusterDim.x = (unsigned)ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
             CAB_CUDA(cudaLaunchKernelEx(&cfg, cfn, ca));
+            if (ca.frames_tmp) {
+                const dim3 ug((unsigned)n_frames, (unsigned)count);
+                if (precision == CAB200_FP64_STRICT)
+                    unpermute_kernel<double><<<ug, 256, 0, stream>>>((const double *)frames_tmp, (double *)frames_out, ca.pouch_list,
+                                                                     d_cell_off, ca.slot_plan, n, ncta, cth * ccpt, n_frames);
+                else
+                    unpermute_kernel<float><<<ug, 256, 0, stream>>>((const float *)frames_tmp, (float *)frames_out, ca.pouch_list,
+                                                                    d_cell_off, ca.slot_plan, n, ncta, cth * ccpt, n_frames);
+                CAB_CUDA(cudaGetLastError());
+            }
             continue;
         }
         int threads = 0, cpt = 0;
@@ -278,8 +319,21 @@ extern "C" int cab200_sim_batch(
         a.frame_steps = d_frame_steps;
         a.frames_out = frames_out;
         a.status_out = status_out;
+        const size_t tmp_need = (size_t)count * n_frames * 4 * (size_t)(threads * cpt) * (elem2 / 2);
+        a.frames_tmp = (frames_tmp && n_frames > 0 && a.slot_plan && tmp_need <= frames_tmp_bytes && count <= 65535)
+                           ? frames_tmp : nullptr;
         fn<<<count, threads, smem, stream>>>(a);
         CAB_CUDA(cudaGetLastError());
+        if (a.frames_tmp) {
+            const dim3 ug((unsigned)n_frames, (unsigned)count);
+            if (precision == CAB200_FP64_STRICT)
+                unpermute_kernel<double><<<ug, 256, 0, stream>>>((const double *)frames_tmp, (double *)frames_out, a.pouch_list,
+                                                                 d_cell_off, a.slot_plan, n, 1, threads * cpt, n_frames);
+            else
+                unpermute_kernel<float><<<ug, 256, 0, stream>>>((const float *)frames_tmp, (float *)frames_out, a.pouch_list,
+                                                                d_cell_off, a.slot_plan, n, 1, threads * cpt, n_frames);
+            CAB_CUDA(cudaGetLastError());
+        }
     }
     return CAB200_OK;
 }

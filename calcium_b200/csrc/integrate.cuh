@@ -46,6 +46,10 @@ struct SimArgs {
     int T, n_frames;
     const int32_t *frame_steps;
     void *frames_out;
+    void *frames_tmp;           // optional: frames are written HERE in slot order (fully coalesced), blocks of
+                                // [n_frames][4][NCTA*NSLOT] per pouch of this launch; unpermute_kernel then fills
+                                // frames_out.  For captures of (nearly) every step, where the scattered
+                                // cell-order stores would dominate the step.
     int32_t *status_out;
 };
 
@@ -473,16 +477,31 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     int cap_t = (a.n_frames > 0) ? a.frame_steps[0] : -1;
     const int T = a.T;
 
-    // Writes the state at the current time (c, p, s, r of every owned cell) as frame fi.
+    // Writes the state at the current time (c, p, s, r of every owned cell) as frame fi: in original
+    // cell order (scattered 8-byte stores; fine for a few frames), or -- frames_tmp -- in slot order,
+    // one fully coalesced store per state and slot group.
+    R *ftmp = a.frames_tmp ? reinterpret_cast<R *>(a.frames_tmp) + (size_t)(blockIdx.x / NCTA) * a.n_frames * 4 * (NCTA * NSLOT)
+                                 + (size_t)rank * NSLOT + (size_t)warp * CPT * 32 + lane
+                           : nullptr;
     auto capture = [&]() {
         int nonfinite = 0;
+        if (ftmp) {
+            R *f = ftmp + (size_t)fi * 4 * (NCTA * NSLOT);
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            if (live[k]) {
-                const int cell = orig_of[(warp * CPT + k) * 32 + lane];
-                R *f = frames + (size_t)fi * 4 * n + cell;
-                f[0] = c[k]; f[n] = p[k]; f[2 * (size_t)n] = s[k]; f[3 * (size_t)n] = r[k];
+            for (int k = 0; k < CPT; ++k) {
+                f[k * 32] = c[k]; f[k * 32 + NCTA * NSLOT] = p[k];
+                f[k * 32 + 2 * (NCTA * NSLOT)] = s[k]; f[k * 32 + 3 * (NCTA * NSLOT)] = r[k];
                 nonfinite |= !(isfinite(c[k]) && isfinite(p[k]) && isfinite(s[k]) && isfinite(r[k]));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                if (live[k]) {
+                    const int cell = orig_of[(warp * CPT + k) * 32 + lane];
+                    R *f = frames + (size_t)fi * 4 * n + cell;
+                    f[0] = c[k]; f[n] = p[k]; f[2 * (size_t)n] = s[k]; f[3 * (size_t)n] = r[k];
+                    nonfinite |= !(isfinite(c[k]) && isfinite(p[k]) && isfinite(s[k]) && isfinite(r[k]));
+                }
             }
         }
         if (nonfinite) atomicOr(a.status_out + pouch, CAB200_ST_NONFINITE);

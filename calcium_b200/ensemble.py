@@ -279,7 +279,7 @@ class Ensemble:
     def __init__(self, specs: Sequence[PouchSpec], *, output_size: Tuple[int, int] = (512, 512),
                  T: int = T_DEFAULT, frame_steps: Optional[Sequence[int]] = None,
                  device: Optional[torch.device] = None, precision: int = _lib.FP64_STRICT,
-                 dt: float = DT, use_plan: bool = True, cluster="auto"):
+                 dt: float = DT, use_plan: bool = True, cluster="auto", coalesced_capture="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("calcium_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -330,6 +330,8 @@ class Ensemble:
         self.g_cluster = np.array([d.auto_cluster() if cluster == "auto" else (int(cluster) if d.unit else 1)
                                    for d in self.dgeo], dtype=np.int32)
         self.use_plan = use_plan
+        self.coalesced_capture = coalesced_capture      # "auto" | True | False, see _alloc_frames_tmp
+        self._frames_tmp: Optional[torch.Tensor] = None
         self.d_plan: Optional[torch.Tensor] = None
         self.g_plan_off = np.full(len(self.dgeo), -1, dtype=np.int64)
         plans, off = [], 0
@@ -382,6 +384,26 @@ class Ensemble:
         return self.total_cells * 4 * self.F
 
     # -- K1 ------------------------------------------------------------------------------------
+    def _alloc_frames_tmp(self) -> Optional[torch.Tensor]:
+        """Staging for the coalesced capture path (``frames_tmp`` of ``cab200_sim_batch``): used when a
+        large share of the steps is captured (the reference's full ``disc_dynamics`` history), if the
+        slot-ordered copy of the largest same-geometry group fits in free device memory."""
+        if self.coalesced_capture is False or self.F == 0:
+            return None
+        if self.coalesced_capture == "auto" and self.F * 8 < self.T:
+            return None
+        need = 0
+        for g, d in enumerate(self.dgeo):
+            if self.g_plan_off[g] < 0:
+                continue
+            cnt = int((self.geom_id == g).sum())
+            need = max(need, int(self.lib.cab200_sim_frames_tmp_bytes(d.n, int(self.g_cluster[g]), int(d.unit),
+                                                                      self.precision, cnt, self.F)))
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if need == 0 or need > free - (2 << 30):
+            return None
+        return torch.empty(need, dtype=torch.uint8, device=self.device)
+
     def upload(self) -> None:
         """Host -> device copy of params / initial state (from pinned memory, async)."""
         with torch.cuda.device(self.device):
@@ -398,6 +420,7 @@ class Ensemble:
             if self.frames is None or self.frames.dtype != real:
                 self.frames = torch.empty(max(self.frame_elems, 1), dtype=real, device=self.device)
                 self.status = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+                self._frames_tmp = self._alloc_frames_tmp()
             d = self._d_in
             np_ = self.P * _lib.NPARAM
             tc = self.total_cells
@@ -415,6 +438,8 @@ class Ensemble:
                 self.T, self.F, _lib.as_i32p(self.frame_steps),
                 self.frames.data_ptr(), self.status.data_ptr(), self.precision,
                 self._scratch.data_ptr(), self.lib.cab200_sim_scratch_bytes(self.P, self.F),
+                self._frames_tmp.data_ptr() if self._frames_tmp is not None else None,
+                self._frames_tmp.numel() if self._frames_tmp is not None else 0,
                 _stream_ptr(self.device))
             _lib.check(rc, "cab200_sim_batch")
         return self.frames

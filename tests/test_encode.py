@@ -290,3 +290,35 @@ def test_files_pipeline_delivers_every_frame_to_the_host(env, stage_bytes, wait)
             assert np.array_equal(np.load(io.BytesIO(b))["mask"], inst[i, f])
     frames_host = ens._fring["h_frames"].numpy()
     assert np.array_equal(frames_host, ens.frames.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_batch_path_writes_the_encoded_frames(env, tmp_path):
+    """generate_simulation_batch stores K3's byte strings: the files decode to the arrays of the raw path."""
+    import glob
+    import os
+    import random
+    from calcium_b200 import generate_simulation_batch
+    EO = env["EO"]
+    kw = dict(pouch_sizes=["xsmall", "small"], time_steps=[0, 5000, 9000], image_size="256x256")
+    random.seed(9)
+    ra = generate_simulation_batch(3, str(tmp_path / "a"), keep_arrays=True, write_files=False, **kw)
+    random.seed(9)
+    rb = generate_simulation_batch(3, str(tmp_path / "b"), **kw)
+    assert [s["simulation_name"] for s in ra["simulations"]] == [s["simulation_name"] for s in rb["simulations"]]
+    n_masks = 0
+    for sim in rb["simulations"]:
+        arr = ra["arrays"][sim["simulation_id"]]
+        assert sim["image_count"] == 3
+        for fi, t in enumerate(arr["time_steps"]):
+            (png,) = glob.glob(os.path.join(sim["image_dir"], f"{sim['simulation_name']}_t{t:05d}_*.png"))
+            dec = EO.decode_png(open(png, "rb").read())
+            assert np.array_equal(dec[..., 0], arr["image"][fi][..., 0].astype(np.uint16) * 4)
+            assert np.array_equal(dec[..., 1], arr["image"][fi][..., 1].astype(np.uint16) * 257)
+            npz = glob.glob(os.path.join(sim["mask_dir"], f"{sim['simulation_name']}_t{t:05d}_*.npz"))
+            assert len(npz) == (1 if arr["n_active"][fi] > 0 else 0)
+            if npz:
+                assert np.array_equal(np.load(npz[0])["mask"], arr["instance"][fi])
+                n_masks += 1
+        assert sim["mask_count"] == int((arr["n_active"] > 0).sum())
+    assert rb["stats"]["total_masks"] == n_masks

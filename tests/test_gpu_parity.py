@@ -551,3 +551,28 @@ def test_generate_simulation_batch_and_controller(env, tmp_path):
     assert out["success"] and len(out["simulations"]) == 4
     bad = ctl.run_batch_generation({"num_simulations": "x"}, str(tmp_path / "e"))
     assert bad["success"] is False and bad["error"].startswith("Batch generation error:")
+
+
+# ---- coalesced capture (frames_tmp): every-step histories ---------------------------------------------
+
+@pytest.mark.parametrize("size,count,cluster,prec", [("medium", 3, 1, 64), ("large", 2, 4, 64), ("small", 5, 2, 64),
+                                                     ("medium", 2, 1, 32)])
+def test_every_step_capture_through_slot_order_staging(env, size, count, cluster, prec):
+    """Capturing every step (the reference's full disc_dynamics history, core/pouch.py:203) goes through
+    coalesced slot-order stores + an un-permute kernel; the frames are the same bits as the direct path."""
+    E = env["E"]
+    T = 600
+    specs = E.make_specs(count, size=size, first_seed=23)
+    a = E.Ensemble(specs, T=T, frame_steps=range(T), device=env["dev"], cluster=cluster, precision=prec,
+                   coalesced_capture=True)
+    a.simulate(); a.synchronize()
+    assert a._frames_tmp is not None
+    b = E.Ensemble(specs, T=T, frame_steps=range(T), device=env["dev"], cluster=cluster, precision=prec,
+                   coalesced_capture=False)
+    b.simulate(); b.synchronize()
+    assert b._frames_tmp is None
+    assert not a.check_status().any()
+    assert env["torch"].equal(a.frames, b.frames)
+    if prec == 64:
+        want = _oracle_frames(env["O"], specs[0], T, list(range(T)))
+        assert np.array_equal(want, a.frames_of(0).cpu().numpy())
