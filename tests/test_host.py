@@ -54,8 +54,17 @@ def test_argument_validation_needs_no_gpu(lib):
     rc = lib.cab200_sim_batch(1, _lib.as_i32p(z32), 0, _lib.as_i32p(z32), _lib.as_i32p(z32),
                               _lib.as_i32p(z32), _lib.as_i64p(z64), _lib.as_i64p(z64), None, None, None,
                               None, None, None, _lib.as_i64p(z64), None, None, None, None, None, 10, 0,
-                              _lib.as_i32p(z32), None, None, 64, None, 0, None)
+                              _lib.as_i32p(z32), None, None, 64, None, 0, None, 0, None)
     assert rc == -1 and b"bad sizes" in lib.cab200_last_error()
+    # K3's argument checks and host-side table builder need no GPU either
+    assert lib.cab200_encode_tables(4096, 64, None) == -1 and b"[1, 2048]" in lib.cab200_last_error()
+    rc = lib.cab200_encode_batch(1, _lib.as_i32p(z32), 1, _lib.as_i32p(z32), _lib.as_i64p(z64), None, None, 64, 64, 3,
+                                 None, 0.1, 1, 1, 1, None, None, _lib.as_i64p(z64), None, 0, None, None, None, 0,
+                                 None, 0, None)
+    assert rc == -1 and b"null pointer" in lib.cab200_last_error()
+    assert lib.cab200_publish_to_host(None, None, 16, None) == -1
+    assert lib.cab200_sim_frames_tmp_bytes(1500, 1, 1, 64, 2, 10) == 2 * 10 * 4 * 1536 * 8
+    assert lib.cab200_sim_frames_tmp_bytes(3255, 4, 1, 64, 1, 10) == 10 * 4 * 4096 * 8
     assert lib.cab200_sim_set_plan(2000, 333, 2) == -1
     assert lib.cab200_sim_set_plan(0, 0, 0) == 0
 
