@@ -89,14 +89,14 @@ def load() -> ctypes.CDLL:
     lib.cab200_encode_scratch_bytes.restype = c_size_t
     lib.cab200_encode_scratch_bytes.argtypes = [c_int, c_int]
     lib.cab200_encode_geometry_bytes.restype = c_size_t
-    lib.cab200_encode_geometry_bytes.argtypes = [c_int]
+    lib.cab200_encode_geometry_bytes.argtypes = [c_int, c_int, c_int]
     lib.cab200_encode_geometry.restype = c_int
-    lib.cab200_encode_geometry.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.cab200_encode_geometry.argtypes = [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, i32p, c_void_p]
     lib.cab200_encode_batch.restype = c_int
     lib.cab200_encode_batch.argtypes = [
         c_int, i32p, c_int, i32p, i64p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
         c_double, c_int, c_int, c_int,                         # threshold, quirk, want_image, want_mask
-        c_void_p, c_void_p, i64p,                              # tables, geom_tabs, g_tab_off
+        c_void_p, c_void_p, i64p, i32p,                        # tables, geom_tabs, g_tab_off, g_max_events
         c_void_p, c_size_t, c_void_p,                          # arena, arena_bytes, cursor
         c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
     lib.cab200_publish_to_host.restype = c_int

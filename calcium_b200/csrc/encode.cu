@@ -124,6 +124,26 @@ __device__ __forceinline__ void put_bits(uint32_t *w, uint32_t pos, unsigned lon
     if (sh + nb > 64) atomicOr(&w[idx + 2], (uint32_t)(val >> (64 - sh)));
 }
 
+// Table look-ups through explicit 32-bit shared addresses: with generic pointers the compiler rebuilds the
+// shared window base (S2R + LEA + ...) in front of every predicated load -- 6 instructions per look-up.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __device__ __forceinline__ void put_le32(uint8_t *p, uint32_t v)
 {
     p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
@@ -138,15 +158,54 @@ __device__ __forceinline__ void put_be32(uint8_t *p, uint32_t v)
 struct GeomTab {
     const uint32_t *Q, *cnt;
     const unsigned long long *M;
+    const uint2 *ev_img, *ev_msk;      // static event lists (enc_events_kernel), [H * nseg][ENC_ECAP] each
 };
-__host__ __device__ inline size_t geom_tab_bytes(int n) { return (((size_t)(n + 1) * 8 + 7) & ~(size_t)7) + (size_t)(n + 1) * 8; }
-__device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n)
+constexpr int ENC_ECAP = 256;
+__host__ __device__ inline size_t geom_tab_sums_bytes(int n) { return ((((size_t)(n + 1) * 8 + 7) & ~(size_t)7) + (size_t)(n + 1) * 8 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t geom_tab_events_bytes(int H, int W) { return (size_t)H * ((W + 511) / 512) * ENC_ECAP * sizeof(uint2); }
+__host__ __device__ inline size_t geom_tab_bytes(int n, int H, int W) { return geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W); }
+__device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n, int H, int W)
 {
     GeomTab t;
     t.Q = reinterpret_cast<const uint32_t *>(p);
     t.cnt = t.Q + (n + 1);
     t.M = reinterpret_cast<const unsigned long long *>(p + (((size_t)(n + 1) * 8 + 7) & ~(size_t)7));
+    t.ev_img = reinterpret_cast<const uint2 *>(p + geom_tab_sums_bytes(n));
+    t.ev_msk = reinterpret_cast<const uint2 *>(p + geom_tab_sums_bytes(n) + geom_tab_events_bytes(H, W));
     return t;
+}
+
+// Static event list of one label map: per 512-pixel row segment the pixels whose label differs from the
+// left or the upper neighbour, plus the forced cut positions (every `maxpix` pixels), ENC_ECAP slots:
+// x = {x | label << 16}, y = {label_left | label_up << 16} (0xffff = no such neighbour); padding slots
+// have x = segment end.  Every other pixel has the label of both neighbours, hence -- whatever a frame's
+// values -- the mode "up" (or "left" where no row above is usable).  One warp per segment; max_count
+// receives the largest number of events in a segment (a list is truncated at ENC_ECAP: the caller
+// then must not use it).
+__global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, int H, int W, int maxpix, int use_up,
+                                                         uint2 *events, int *max_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int nseg = (W + 511) / 512;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= H * nseg) return;
+    const int y = item / nseg, x0 = (item % nseg) * 512, xend = min(W, x0 + 512);
+    uint2 *out = events + (size_t)item * ENC_ECAP;
+    int count = 0;
+    for (int c = x0; c < xend; c += 32) {
+        const int x = c + lane;
+        const bool inb = x < xend;
+        const uint32_t lab = inb ? label[(size_t)y * W + x] : 0u;
+        const uint32_t labL = (inb && x > 0) ? label[(size_t)y * W + x - 1] : 0xffffu;
+        const uint32_t labU = (inb && y > 0 && use_up) ? label[(size_t)(y - 1) * W + x] : 0xffffu;
+        const bool isev = inb && ((x % maxpix) == 0 || labL == 0xffffu || lab != labL || (labU != 0xffffu && lab != labU));
+        const unsigned b = __ballot_sync(0xffffffffu, isev);
+        const int idx = count + __popc(b & ((1u << lane) - 1u));
+        if (isev && idx < ENC_ECAP) out[idx] = make_uint2((uint32_t)x | (lab << 16), labL | (labU << 16));
+        count += __popc(b);
+    }
+    for (int j = min(count, ENC_ECAP) + lane; j < ENC_ECAP; j += 32) out[j] = make_uint2((uint32_t)xend | 0xffff0000u, 0xffffffffu);
+    if (lane == 0) atomicMax(max_count, count);
 }
 
 // Fills one geometry's block (zeroed by the caller).  One thread per pixel, atomics on ~n addresses;
@@ -175,10 +234,13 @@ __global__ void __launch_bounds__(256) enc_geometry_kernel(const uint16_t *label
 }
 
 // shared-memory tables of one CTA
+constexpr int ENC_TCAP = 64;     // token descriptors per warp and batch (event parse)
 struct EncSmem {
     unsigned long long *lit64;   // [512] image pixel (gray | alpha flag << 8) -> 4 literals: bits | count << 58
     uint32_t *len_s, *lit_s, *crc_s;
+    uint32_t *toklist;           // [ENC_NW][ENC_TCAP]
     uint8_t *stage;
+    uint32_t len_a, lit_a, tok_a;   // the same tables as 32-bit shared addresses (lds_u32)
 };
 
 // 16 labels of one lane -> 8 packed keys (two 16-bit keys per word)
@@ -186,6 +248,7 @@ template <bool IMG>
 __device__ __forceinline__ void load_keys(const uint16_t *row, int xl, int nvalid, bool vec_ok, const FrameLut &lut,
                                           uint32_t k[8])
 {
+    const uint32_t kl_a = smem_addr(IMG ? lut.rank1 : lut.inst_lut);    // image: key LUT built over the rank scratch
     uint32_t w[8];
     if (nvalid == 16 && vec_ok) {
         const uint4 a = __ldg(reinterpret_cast<const uint4 *>(row + xl));
@@ -202,8 +265,7 @@ __device__ __forceinline__ void load_keys(const uint16_t *row, int xl, int nvali
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const uint32_t l0 = w[q] & 0xffffu, l1 = w[q] >> 16;
-        const uint16_t *kl = IMG ? lut.rank1 : lut.inst_lut;    // image: key LUT built over the rank scratch
-        k[q] = (uint32_t)kl[l0] | ((uint32_t)kl[l1] << 16);
+        k[q] = lds_u16(kl_a + 2u * l0) | (lds_u16(kl_a + 2u * l1) << 16);
     }
 }
 
@@ -211,14 +273,78 @@ template <bool IMG>
 __device__ __forceinline__ uint32_t one_key(const uint16_t *p, const FrameLut &lut)
 {
     const uint32_t l = __ldg(p);
-    return IMG ? lut.rank1[l] : lut.inst_lut[l];
+    return lds_u16(smem_addr(IMG ? lut.rank1 : lut.inst_lut) + 2u * l);
 }
 
 // Encodes one stream into sm.stage.  Returns the total file size in bytes, or 0 when the staging
 // buffer is too small (uniform over the CTA).
-template <bool IMG>
+// Phase B of a pass: every lane knows the bit count of its tokens; a warp scan and a scan over the 16
+// rows of the pass give the lane's absolute bit position.  false = the staging buffer would overflow
+// (uniform over the CTA).
+__device__ __forceinline__ bool place_rows(uint32_t lanebits, uint32_t *rowbits, uint32_t bitpos, uint32_t tail_room,
+                                           uint32_t cap, uint32_t &pos, uint32_t &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = lanebits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) rowbits[warp] = incl;
+    __syncthreads();
+    const uint32_t mine = (lane < ENC_NW) ? rowbits[lane] : 0u;
+    uint32_t sc = mine;
+#pragma unroll
+    for (int o = 1; o < ENC_NW; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o);
+        if (lane >= o) sc += t;
+    }
+    const uint32_t before = __shfl_sync(0xffffffffu, sc - mine, warp);
+    total = __shfl_sync(0xffffffffu, sc, ENC_NW - 1);
+    pos = bitpos + before + incl - lanebits;
+    return (bitpos + total + 7u + 7u) / 8u + tail_room <= cap;
+}
+
+// One token -> (bits, count).  A match of `len` pixels in mode up/left, or the literal pixel `key`
+// (also for a one-pixel match of a 2-byte pixel, which is too short for DEFLATE).
+template <bool IMG, bool LIT64>
+__device__ __forceinline__ void make_token(const EncSmem &sm, bool is_match, bool is_up, int len, uint32_t key,
+                                           uint32_t dist_up, uint32_t dist_left, unsigned long long &val, int &nb)
+{
+    constexpr int BPP = IMG ? 4 : 2;
+    if (is_match && len * BPP >= 3) {
+        const uint32_t lt = lds_u32(sm.len_a + 4u * (uint32_t)(len * BPP));
+        const uint32_t dd = is_up ? dist_up : dist_left;
+        const int ln = (int)(lt >> 24);
+        val = (unsigned long long)(lt & 0xffffffu) | ((unsigned long long)(dd & 0xffffffu) << ln);
+        nb = ln + (int)(dd >> 24);
+    } else if (IMG && LIT64) {
+        const unsigned long long t = sm.lit64[key & 0x1ffu];
+        val = t & ((1ull << 58) - 1ull);
+        nb = (int)(t >> 58);
+    } else if (IMG) {
+        // 16-bit gray*4 and alpha*257, big endian: four literals
+        const uint32_t g = key & 0xffu, al = (key >> 8) ? 255u : 0u;
+        const uint32_t t0 = lds_u32(sm.lit_a + 4u * (g >> 6)), t1 = lds_u32(sm.lit_a + 4u * ((g << 2) & 0xffu)),
+                       t2 = lds_u32(sm.lit_a + 4u * al);
+        const int n0 = (int)(t0 >> 24), n1 = (int)(t1 >> 24), n2 = (int)(t2 >> 24);
+        val = (unsigned long long)(t0 & 0xffffffu) | ((unsigned long long)(t1 & 0xffffffu) << n0) |
+              ((unsigned long long)(t2 & 0xffffffu) << (n0 + n1)) | ((unsigned long long)(t2 & 0xffffffu) << (n0 + n1 + n2));
+        nb = n0 + n1 + 2 * n2;
+    } else {
+        const uint32_t t0 = lds_u32(sm.lit_a + 4u * (key & 0xffu)), t1 = lds_u32(sm.lit_a + 4u * (key >> 8));
+        const int n0 = (int)(t0 >> 24);
+        val = (unsigned long long)(t0 & 0xffffffu) | ((unsigned long long)(t1 & 0xffffffu) << n0);
+        nb = n0 + (int)(t1 >> 24);
+    }
+}
+
+// K = 0: parse every pixel of a row segment (16 per lane).  K > 0: parse only the static events of the
+// segment (K per lane); same tokens, a fraction of the look-ups.
+template <bool IMG, int K>
 __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const EncSmem &sm, const FrameLut &lut,
-                                  const uint16_t *lmap, const GeomTab &gt, int n)
+                                  const uint16_t *lmap, const uint2 *events, const GeomTab &gt, int n)
 {
     __shared__ uint32_t rowbits[2][ENC_NW];
     __shared__ unsigned long long red64[2][ENC_NW];
@@ -227,7 +353,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W;
     uint32_t *stage32 = reinterpret_cast<uint32_t *>(sm.stage);
-    const uint32_t *lit_s = sm.lit_s, *len_s = sm.len_s, *crc_s = sm.crc_s;
+    const uint32_t *lit_s = sm.lit_s, *crc_s = sm.crc_s;
 
     // ---- zero the staging buffer, place the container prefix ------------------------------------
     for (int i = tid; i < a.stage_cap / 16; i += ENC_NT)
@@ -251,6 +377,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
     const bool vec_ok = (W % 8) == 0;
     constexpr int BPP = IMG ? 4 : 2;                 // == d.bpp
     constexpr int SEG_LANES = IMG ? 4 : 8;           // == d.seg_lanes: a forced cut every 256 bytes
+    constexpr int MAXPIX = 256 / BPP;                // the same cut in pixels
     const uint32_t dist_up = d.dist_up, dist_left = d.dist_left;
     const uint32_t tail_room = (uint32_t)d.suffix_len + 24u;
     const bool use_up = (dist_up >> 24) != 0;
@@ -266,147 +393,247 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
         const int xl = x0 + 16 * lane;
         const int nvalid = valid ? max(0, min(16, W - xl)) : 0;
         const int xend = min(W, x0 + 512);
+        uint32_t pass_bits = 0;
 
-        // ---- phase A: keys, modes, token starts ------------------------------------------------
-        uint32_t kc[8];
-        uint32_t mU = 0, mL = 0;
-        const uint32_t V = (nvalid >= 16) ? 0xffffu : ((1u << nvalid) - 1u);
-        if (nvalid > 0) load_keys<IMG>(lmap + (size_t)y * W, xl, nvalid, vec_ok, lut, kc);
-        else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) kc[q] = 0;
-        }
-        if (nvalid > 0 && y > 0 && use_up) {
-            uint32_t ku[8];
-            load_keys<IMG>(lmap + (size_t)(y - 1) * W, xl, nvalid, vec_ok, lut, ku);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint32_t x = kc[q] ^ ku[q];
-                mU |= ((x & 0xffffu) == 0u ? 1u : 0u) << (2 * q);
-                mU |= ((x >> 16) == 0u ? 1u : 0u) << (2 * q + 1);
+        if constexpr (K == 0) {
+            // ---- phase A: keys, modes, token starts ------------------------------------------------
+            uint32_t kc[8];
+            uint32_t mU = 0, mL = 0;
+            const uint32_t V = (nvalid >= 16) ? 0xffffu : ((1u << nvalid) - 1u);
+            if (nvalid > 0) load_keys<IMG>(lmap + (size_t)y * W, xl, nvalid, vec_ok, lut, kc);
+            else {
+    #pragma unroll
+                for (int q = 0; q < 8; ++q) kc[q] = 0;
             }
-            mU &= V;
-        }
-        {
-            // previous pixel of this lane's first pixel: the previous lane's last key, or (first lane of
-            // a later segment) the pixel in front of the segment; none at the start of a row
-            uint32_t prev = __shfl_up_sync(0xffffffffu, kc[7] >> 16, 1);
-            bool has_prev = true;
-            if (lane == 0) {
-                has_prev = valid && x0 > 0;
-                prev = has_prev ? one_key<IMG>(lmap + (size_t)y * W + x0 - 1, lut) : 0u;
+            if (nvalid > 0 && y > 0 && use_up) {
+                uint32_t ku[8];
+                load_keys<IMG>(lmap + (size_t)(y - 1) * W, xl, nvalid, vec_ok, lut, ku);
+    #pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t x = kc[q] ^ ku[q];
+                    mU |= ((x & 0xffffu) == 0u ? 1u : 0u) << (2 * q);
+                    mU |= ((x >> 16) == 0u ? 1u : 0u) << (2 * q + 1);
+                }
+                mU &= V;
             }
-            uint32_t pk = prev;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint32_t lo = kc[q] & 0xffffu, hi = kc[q] >> 16;
-                mL |= (lo == pk ? 1u : 0u) << (2 * q);
-                mL |= (hi == lo ? 1u : 0u) << (2 * q + 1);
-                pk = hi;
+            {
+                // previous pixel of this lane's first pixel: the previous lane's last key, or (first lane of
+                // a later segment) the pixel in front of the segment; none at the start of a row
+                uint32_t prev = __shfl_up_sync(0xffffffffu, kc[7] >> 16, 1);
+                bool has_prev = true;
+                if (lane == 0) {
+                    has_prev = valid && x0 > 0;
+                    prev = has_prev ? one_key<IMG>(lmap + (size_t)y * W + x0 - 1, lut) : 0u;
+                }
+                uint32_t pk = prev;
+    #pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t lo = kc[q] & 0xffffu, hi = kc[q] >> 16;
+                    mL |= (lo == pk ? 1u : 0u) << (2 * q);
+                    mL |= (hi == lo ? 1u : 0u) << (2 * q + 1);
+                    pk = hi;
+                }
+                if (!has_prev) mL &= ~1u;
+                mL &= V & ~mU;
             }
-            if (!has_prev) mL &= ~1u;
-            mL &= V & ~mU;
-        }
-        // token starts: literal pixels, mode changes, forced cuts every 256 bytes / at the segment start
-        uint32_t S;
-        {
-            const uint32_t cu = __shfl_up_sync(0xffffffffu, mU >> 15, 1) & 1u;
-            const uint32_t cl = __shfl_up_sync(0xffffffffu, mL >> 15, 1) & 1u;
-            const uint32_t pU = (mU << 1) | (lane ? cu : 0u);
-            const uint32_t pL = (mL << 1) | (lane ? cl : 0u);
-            S = (V & ~mU & ~mL) | (mU & ~pU) | (mL & ~pL);
-            if ((lane & (SEG_LANES - 1)) == 0) S |= 1u;
-            S &= V;
-        }
-        // end of a token that runs past this lane: the first start in a later lane, or the segment end
-        int nxt;
-        {
-            int fs = S ? (xl + __ffs((int)S) - 1) : 0x7fffffff;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_down_sync(0xffffffffu, fs, o);
-                if (lane + o < 32) fs = min(fs, t);
+            // token starts: literal pixels, mode changes, forced cuts every 256 bytes / at the segment start
+            uint32_t S;
+            {
+                const uint32_t cu = __shfl_up_sync(0xffffffffu, mU >> 15, 1) & 1u;
+                const uint32_t cl = __shfl_up_sync(0xffffffffu, mL >> 15, 1) & 1u;
+                const uint32_t pU = (mU << 1) | (lane ? cu : 0u);
+                const uint32_t pL = (mL << 1) | (lane ? cl : 0u);
+                S = (V & ~mU & ~mL) | (mU & ~pU) | (mL & ~pL);
+                if ((lane & (SEG_LANES - 1)) == 0) S |= 1u;
+                S &= V;
             }
-            nxt = __shfl_down_sync(0xffffffffu, fs, 1);
-            if (lane == 31) nxt = 0x7fffffff;
-            nxt = min(nxt, xend);
-        }
+            // end of a token that runs past this lane: the first start in a later lane, or the segment end
+            int nxt;
+            {
+                int fs = S ? (xl + __ffs((int)S) - 1) : 0x7fffffff;
+    #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_down_sync(0xffffffffu, fs, o);
+                    if (lane + o < 32) fs = min(fs, t);
+                }
+                nxt = __shfl_down_sync(0xffffffffu, fs, 1);
+                if (lane == 31) nxt = 0x7fffffff;
+                nxt = min(nxt, xend);
+            }
 
-        // token walk: WRITE = false sums the bit counts, WRITE = true ORs the bits in at `pos`
-        auto walk = [&](bool write, uint32_t pos) -> uint32_t {
-            uint32_t bits = 0;
-            if (IMG && lane == 0 && x0 == 0 && valid) {
-                if (write) put_bits(stage32, pos, (unsigned long long)(filt & 0xffffffu), (int)(filt >> 24));
-                bits += filt >> 24;
-            }
-            uint32_t rest = S;
-            while (rest) {
-                const int j = __ffs((int)rest) - 1;
-                rest &= rest - 1;
-                const int len = (rest ? (__ffs((int)rest) - 1) : (nxt - xl)) - j;
-                const bool isU = (mU >> j) & 1u, isL = (mL >> j) & 1u;
-                unsigned long long val;
-                int nb;
-                if ((isU || isL) && len * BPP >= 3) {
-                    const uint32_t lt = len_s[len * BPP];
-                    const uint32_t dd = isU ? dist_up : dist_left;
-                    const int ln = (int)(lt >> 24);
-                    val = (unsigned long long)(lt & 0xffffffu) | ((unsigned long long)(dd & 0xffffffu) << ln);
-                    nb = ln + (int)(dd >> 24);
-                } else {
-                    // literal pixel (a one-pixel match of a 2-byte pixel is too short for DEFLATE)
+            // token walk: WRITE = false sums the bit counts, WRITE = true ORs the bits in at `pos`
+            auto walk = [&](bool write, uint32_t pos) -> uint32_t {
+                uint32_t bits = 0;
+                if (IMG && lane == 0 && x0 == 0 && valid) {
+                    if (write) put_bits(stage32, pos, (unsigned long long)(filt & 0xffffffu), (int)(filt >> 24));
+                    bits += filt >> 24;
+                }
+                uint32_t rest = S;
+                while (rest) {
+                    const int j = __ffs((int)rest) - 1;
+                    rest &= rest - 1;
+                    const int len = (rest ? (__ffs((int)rest) - 1) : (nxt - xl)) - j;
+                    const bool isU = (mU >> j) & 1u, isL = (mL >> j) & 1u;
                     const int q = j >> 1;
                     uint32_t w = kc[0];
                     w = (q == 1) ? kc[1] : w; w = (q == 2) ? kc[2] : w; w = (q == 3) ? kc[3] : w;
                     w = (q == 4) ? kc[4] : w; w = (q == 5) ? kc[5] : w; w = (q == 6) ? kc[6] : w;
                     w = (q == 7) ? kc[7] : w;
                     const uint32_t key = (j & 1) ? (w >> 16) : (w & 0xffffu);
-                    if (IMG) {
-                        const unsigned long long t = sm.lit64[key & 0x1ffu];
-                        val = t & ((1ull << 58) - 1ull);
-                        nb = (int)(t >> 58);
-                    } else {
-                        const uint32_t t0 = lit_s[key & 0xffu], t1 = lit_s[key >> 8];
-                        const int n0 = (int)(t0 >> 24);
-                        val = (unsigned long long)(t0 & 0xffffffu) | ((unsigned long long)(t1 & 0xffffffu) << n0);
-                        nb = n0 + (int)(t1 >> 24);
+                    unsigned long long val;
+                    int nb;
+                    make_token<IMG, true>(sm, isU || isL, isU, len, key, dist_up, dist_left, val, nb);
+                    if (write) put_bits(stage32, pos + bits, val, nb);
+                    bits += (uint32_t)nb;
+                }
+                return bits;
+            };
+            const uint32_t lanebits = walk(false, 0u);
+            uint32_t pos;
+            if (!place_rows(lanebits, rowbits[par], bitpos, tail_room, (uint32_t)a.stage_cap, pos, pass_bits)) { overflow = true; break; }
+            if (valid) walk(true, pos);
+        } else {
+            // ---- phase A (events): K static events per lane; values only decide each event's own mode ------
+            const uint32_t gm = (y > 0 && use_up) ? 2u : 1u;            // mode of every non-event pixel: up, else left
+            uint32_t info[K];                                           // x | mode << 12 | key << 16
+            uint32_t ex[K];
+            {
+                const uint2 *ev = events + (size_t)item * ENC_ECAP + lane * K;
+                const uint32_t kl_a = smem_addr(IMG ? lut.rank1 : lut.inst_lut);
+    #pragma unroll
+                for (int e = 0; e < K; e += 2) {
+                    uint4 r = make_uint4((uint32_t)xend | 0xffff0000u, 0xffffffffu, (uint32_t)xend | 0xffff0000u, 0xffffffffu);
+                    if (valid) r = __ldg(reinterpret_cast<const uint4 *>(ev + e));
+                    const uint32_t rx[2] = {r.x, r.z}, ry[2] = {r.y, r.w};
+    #pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t x = rx[h] & 0xffffu, lab = rx[h] >> 16, labL = ry[h] & 0xffffu, labU = ry[h] >> 16;
+                        // padding slots and missing neighbours carry label 0xffff: read entry 0 instead and
+                        // discard, so the three look-ups are unconditional
+                        const uint32_t k = lds_u16(kl_a + 2u * (lab == 0xffffu ? 0u : lab));
+                        const uint32_t kL = lds_u16(kl_a + 2u * (labL == 0xffffu ? 0u : labL));
+                        const uint32_t kU = lds_u16(kl_a + 2u * (labU == 0xffffu ? 0u : labU));
+                        const uint32_t m = (labU != 0xffffu && k == kU) ? 2u : ((labL != 0xffffu && k == kL) ? 1u : 0u);
+                        ex[e + h] = x;
+                        info[e + h] = x | (m << 12) | (k << 16);
                     }
                 }
-                if (write) put_bits(stage32, pos + bits, val, nb);
-                bits += (uint32_t)nb;
             }
-            return bits;
-        };
-        const uint32_t lanebits = walk(false, 0u);
-        uint32_t incl = lanebits;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) rowbits[par][warp] = incl;
-
-        // ---- phase B: bit position of every row of this pass ---------------------------------------
-        __syncthreads();
-        uint32_t before, total;
-        {
-            const uint32_t mine = (lane < ENC_NW) ? rowbits[par][lane] : 0u;
-            uint32_t sc = mine;
-#pragma unroll
-            for (int o = 1; o < ENC_NW; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o);
-                if (lane >= o) sc += t;
+            // token starts: slot 2e = at the event pixel (forced cut, literal, or mode differs from the pixel
+            // before), slot 2e+1 = at the pixel after it (the gap's static mode differs from the event's)
+            uint32_t S = 0;
+            {
+                const uint32_t pinfo = __shfl_up_sync(0xffffffffu, info[K - 1], 1);
+                uint32_t nx0 = __shfl_down_sync(0xffffffffu, ex[0], 1);
+                if (lane == 31) nx0 = (uint32_t)xend;
+                uint32_t px = pinfo & 0xfffu, pm = (pinfo >> 12) & 3u;
+    #pragma unroll
+                for (int e = 0; e < K; ++e) {
+                    const uint32_t x = ex[e], m = (info[e] >> 12) & 3u;
+                    const bool isev = (int)x < xend;
+                    const uint32_t before = (x - px > 1u) ? gm : pm;     // mode of pixel x-1
+                    const bool forced = ((x & (uint32_t)(MAXPIX - 1)) == 0u);
+                    const uint32_t nx = (e + 1 < K) ? ex[(e + 1 < K) ? e + 1 : e] : nx0;
+                    if (isev && (forced || m == 0u || m != before)) S |= 1u << (2 * e);
+                    if (isev && nx - x > 1u && m != gm) S |= 2u << (2 * e);
+                    px = x; pm = m;
+                }
             }
-            before = __shfl_sync(0xffffffffu, sc - mine, warp);
-            total = __shfl_sync(0xffffffffu, sc, ENC_NW - 1);
+            // ---- tokens, compacted.  A lane's events start 0..2K tokens (most: none), so walking them
+            // per lane would cost every lane the longest walk of the warp.  Instead each lane drops its
+            // token descriptors (pixels | mode << 12 | key << 16) at their rank into a per-warp list and
+            // the warp then handles them 32 at a time, one token per lane.
+            uint32_t desc[2 * K];
+            {
+                // first token start at or after the next lane's first event: the end of this lane's last token
+                int fs = 0x7fffffff;
+#pragma unroll
+                for (int sidx = 2 * K - 1; sidx >= 0; --sidx)
+                    if ((S >> sidx) & 1u) fs = (int)ex[sidx >> 1] + (sidx & 1);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_down_sync(0xffffffffu, fs, o);
+                    if (lane + o < 32) fs = min(fs, t);
+                }
+                int nextpos = __shfl_down_sync(0xffffffffu, fs, 1);
+                if (lane == 31) nextpos = 0x7fffffff;
+                nextpos = min(nextpos, xend);
+#pragma unroll
+                for (int sidx = 2 * K - 1; sidx >= 0; --sidx) {
+                    const int pos = (int)ex[sidx >> 1] + (sidx & 1);
+                    const uint32_t m = (sidx & 1) ? gm : ((info[sidx >> 1] >> 12) & 3u);
+                    desc[sidx] = ((uint32_t)(nextpos - pos) & 0xfffu) | (m << 12) | (info[sidx >> 1] & 0xffff0000u);
+                    if ((S >> sidx) & 1u) nextpos = pos;
+                }
+            }
+            const bool lead = IMG && lane == 0 && x0 == 0 && valid;           // the PNG filter byte of the row
+            int ntok, rank0;
+            {
+                const int mine = __popc(S) + (lead ? 1 : 0);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                ntok = __shfl_sync(0xffffffffu, incl, 31);
+                rank0 = incl - mine;
+            }
+            const uint32_t list_a = sm.tok_a + (uint32_t)(warp * ENC_TCAP) * 4u;
+            // descriptors with rank in [b0, b0 + ENC_TCAP) -> list (rows with more tokens go batch by batch);
+            // the rank of slot s is rank0 + (lead) + the number of starts below it
+            auto fill = [&](int b0) {
+                const int base = rank0 - b0 + (lead ? 1 : 0);
+                if (lead && (unsigned)(rank0 - b0) < (unsigned)ENC_TCAP) sts_u32(list_a + 4u * (uint32_t)(rank0 - b0), 0xffffffffu);
+#pragma unroll
+                for (int sidx = 0; sidx < 2 * K; ++sidx) {
+                    const int at = base + __popc(S & ((1u << sidx) - 1u));
+                    if (((S >> sidx) & 1u) && (unsigned)at < (unsigned)ENC_TCAP) sts_u32(list_a + 4u * (uint32_t)at, desc[sidx]);
+                }
+                __syncwarp();
+            };
+            auto token_at = [&](int t, unsigned long long &val, int &nb) {
+                const uint32_t dsc = lds_u32(list_a + 4u * (uint32_t)t);
+                if (dsc == 0xffffffffu) { val = filt & 0xffffffu; nb = (int)(filt >> 24); return; }
+                const uint32_t m = (dsc >> 12) & 3u;
+                make_token<IMG, K == 0>(sm, m != 0u, m == 2u, (int)(dsc & 0xfffu), dsc >> 16, dist_up, dist_left, val, nb);
+            };
+            // bit counts, one token per lane and round
+            uint32_t lanebits = 0;
+            for (int b0 = 0; b0 < ntok; b0 += ENC_TCAP) {
+                if (b0) __syncwarp();
+                fill(b0);
+                const int nt = min(ntok - b0, ENC_TCAP);
+                for (int t = lane; t < nt; t += 32) {
+                    unsigned long long val; int nb;
+                    token_at(t, val, nb);
+                    lanebits += (uint32_t)nb;
+                }
+            }
+            uint32_t pos;
+            if (!place_rows(lanebits, rowbits[par], bitpos, tail_room, (uint32_t)a.stage_cap, pos, pass_bits)) { overflow = true; break; }
+            // tokens are interleaved over the lanes by round, not contiguous per lane: take the row's start
+            // (lane 0's position) and scan round by round
+            uint32_t rowpos = __shfl_sync(0xffffffffu, pos, 0);
+            for (int b0 = 0; b0 < ntok; b0 += ENC_TCAP) {
+                if (ntok > ENC_TCAP) { __syncwarp(); fill(b0); }       // a single batch is still in the list
+                const int nt = min(ntok - b0, ENC_TCAP);
+                for (int r0 = 0; r0 < nt; r0 += 32) {
+                    const int t = r0 + lane;
+                    unsigned long long val = 0; int nb = 0;
+                    if (t < nt) token_at(t, val, nb);
+                    uint32_t inc = (uint32_t)nb;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += u;
+                    }
+                    if (t < nt && valid) put_bits(stage32, rowpos + inc - (uint32_t)nb, val, nb);
+                    rowpos += __shfl_sync(0xffffffffu, inc, 31);
+                }
+            }
         }
-        if ((bitpos + total + 7u + 7u) / 8u + tail_room > (uint32_t)a.stage_cap) {
-            overflow = true;
-            break;
-        }
-        // ---- phase C: write the tokens ----------------------------------------------------------------
-        if (valid) walk(true, bitpos + before + incl - lanebits);
-        bitpos += total;
+        bitpos += pass_bits;
     }
     __syncthreads();
     if (overflow) return 0u;
@@ -562,6 +789,7 @@ __device__ void emit_file(const EncodeArgs &a, const uint8_t *stage, uint32_t to
     __syncthreads();
 }
 
+template <int K>
 __global__ void __launch_bounds__(ENC_NT, 2) encode_kernel(const EncodeArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -576,11 +804,13 @@ __global__ void __launch_bounds__(ENC_NT, 2) encode_kernel(const EncodeArgs a)
     const FrameLut lut = frame_lut_carve(smem_raw, n);
     EncSmem sm;
     unsigned char *p = smem_raw + a.lut_bytes;
-    sm.lit64 = reinterpret_cast<unsigned long long *>(p); p += 512 * 8;
+    sm.lit64 = reinterpret_cast<unsigned long long *>(p); p += (K == 0 ? 512 * 8 : 0);
     sm.len_s = reinterpret_cast<uint32_t *>(p); p += 260 * 4;
     sm.lit_s = reinterpret_cast<uint32_t *>(p); p += 256 * 4;
     sm.crc_s = reinterpret_cast<uint32_t *>(p); p += 256 * 4;
+    sm.toklist = reinterpret_cast<uint32_t *>(p); p += (K > 0 ? ENC_NW * ENC_TCAP * 4 : 0);
     sm.stage = p;                                   // 16-byte aligned: lut_bytes is, 260*4 = 65*16
+    sm.len_a = smem_addr(sm.len_s); sm.lit_a = smem_addr(sm.lit_s); sm.tok_a = smem_addr(sm.toklist);
 
     const int n_active = frame_lut_build<ENC_NT>(lut, ca, n, a.threshold, a.quirk);
     if (tid == 0 && a.n_active_out) a.n_active_out[pf] = n_active;
@@ -591,7 +821,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) encode_kernel(const EncodeArgs a)
     for (int v = tid; v <= n; v += ENC_NT) lut.rank1[v] = v ? (uint16_t)(lut.gray_lut[v] | 0x100u) : (uint16_t)0;
     __syncthreads();
     // the four literals of a 16-bit gray+alpha pixel: gray*4 and alpha*257, big endian
-    for (int key = tid; key < 512; key += ENC_NT) {
+    for (int key = tid; key < (K == 0 ? 512 : 0); key += ENC_NT) {
         const uint32_t g = key & 0xff, al = (key >> 8) ? 255u : 0u;
         const uint32_t b[4] = {g >> 6, (g << 2) & 0xffu, al, al};
         unsigned long long v = 0;
@@ -608,15 +838,15 @@ __global__ void __launch_bounds__(ENC_NT, 2) encode_kernel(const EncodeArgs a)
 
     EncRecord *rec = a.records + (size_t)pf * 2;
     const size_t gbase = (size_t)pe.geom * a.H * a.W;
-    const GeomTab gt = geom_tab_carve(a.geom_tabs + a.geom_tab_off[pe.geom], n);
+    const GeomTab gt = geom_tab_carve(a.geom_tabs + a.geom_tab_off[pe.geom], n, a.H, a.W);
     if (a.want_img) {
-        const uint32_t total = encode_stream<true>(a, a.tab->img, sm, lut, a.label_img + gbase, gt, n);
+        const uint32_t total = encode_stream<true, K>(a, a.tab->img, sm, lut, a.label_img + gbase, gt.ev_img, gt, n);
         emit_file(a, sm.stage, total, rec);
     } else if (tid == 0) {
         rec[0].offset = 0; rec[0].size = 0; rec[0].flags = CAB200_ENC_SKIPPED;
     }
     if (a.want_msk && n_active > 0) {           // the reference writes no mask file for a frame without active cells
-        const uint32_t total = encode_stream<false>(a, a.tab->msk, sm, lut, a.label_mask + gbase, gt, n);
+        const uint32_t total = encode_stream<false, K>(a, a.tab->msk, sm, lut, a.label_mask + gbase, gt.ev_msk, gt, n);
         emit_file(a, sm.stage, total, rec + 1);
     } else if (tid == 0) {
         rec[1].offset = 0; rec[1].size = 0; rec[1].flags = CAB200_ENC_SKIPPED;
@@ -774,7 +1004,10 @@ static void build_tables(int H, int W, EncTables *t)
 }
 
 static inline size_t enc_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
-static size_t enc_fixed_smem(int n_max) { return enc_align(frame_lut_bytes(n_max), 16) + 512 * 8 + 260 * 4 + 256 * 4 + 256 * 4; }
+static size_t enc_fixed_smem(int n_max, bool events)
+{
+    return enc_align(frame_lut_bytes(n_max), 16) + 260 * 4 + 256 * 4 + 256 * 4 + (events ? ENC_NW * ENC_TCAP * 4 : 512 * 8);
+}
 
 }  // namespace cab200
 
@@ -798,21 +1031,38 @@ extern "C" size_t cab200_encode_scratch_bytes(int n_pouch, int n_geom)
            enc_align(sizeof(long long) * (size_t)std::max(n_geom, 1), 16);
 }
 
-extern "C" size_t cab200_encode_geometry_bytes(int n_cells) { return enc_align(geom_tab_bytes(n_cells), 16); }
+extern "C" size_t cab200_encode_geometry_bytes(int n_cells, int H, int W) { return enc_align(geom_tab_bytes(n_cells, H, W), 16); }
 
 extern "C" int cab200_encode_geometry(int n_cells, const uint16_t *label_img, const uint16_t *label_mask, int H, int W,
-                                      const void *tables, void *geom_out, void *stream_)
+                                      const void *tables, void *geom_out, int32_t *max_events_out, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_cells <= 0 || n_cells > 65534 || H <= 0 || W <= 0 || H > ENC_MAXDIM || W > ENC_MAXDIM || !label_img ||
-        !label_mask || !tables || !geom_out) {
+        !label_mask || !tables || !geom_out || !max_events_out) {
         set_error("cab200_encode_geometry: bad argument");
         return CAB200_EINVAL;
     }
-    CAB_CUDA(cudaMemsetAsync(geom_out, 0, cab200_encode_geometry_bytes(n_cells), stream));
+    unsigned char *out = (unsigned char *)geom_out;
+    CAB_CUDA(cudaMemsetAsync(out, 0, geom_tab_sums_bytes(n_cells), stream));
     enc_geometry_kernel<<<148 * 4, 256, sizeof(uint32_t) * (size_t)W, stream>>>(
-        label_img, label_mask, H, W, n_cells, (const EncTables *)tables, (unsigned char *)geom_out);
+        label_img, label_mask, H, W, n_cells, (const EncTables *)tables, out);
     CAB_CUDA(cudaGetLastError());
+    // static event lists; the first 4 bytes of each list double as its max counter until it is written
+    int *d_max = nullptr;
+    CAB_CUDA(cudaMallocAsync((void **)&d_max, 2 * sizeof(int), stream));
+    CAB_CUDA(cudaMemsetAsync(d_max, 0, 2 * sizeof(int), stream));
+    const int items = H * ((W + 511) / 512);
+    const bool up_img = 1 + 4 * W <= 32768, up_msk = 2 * W <= 32768;     // the distances DEFLATE can express
+    uint2 *ev_img = (uint2 *)(out + geom_tab_sums_bytes(n_cells));
+    uint2 *ev_msk = (uint2 *)(out + geom_tab_sums_bytes(n_cells) + geom_tab_events_bytes(H, W));
+    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_img, H, W, 64, up_img ? 1 : 0, ev_img, d_max);
+    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_mask, H, W, 128, up_msk ? 1 : 0, ev_msk, d_max + 1);
+    CAB_CUDA(cudaGetLastError());
+    int h_max[2] = {0, 0};
+    CAB_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
+    CAB_CUDA(cudaStreamSynchronize(stream));
+    CAB_CUDA(cudaFreeAsync(d_max, stream));
+    *max_events_out = std::max(h_max[0], h_max[1]);
     return CAB200_OK;
 }
 
@@ -820,7 +1070,7 @@ extern "C" int cab200_encode_batch(
     int n_pouch, const int32_t *geom_id, int n_geom, const int32_t *g_ncell, const int64_t *cell_off,
     const uint16_t *label_img, const uint16_t *label_mask, int H, int W, int n_frames,
     const double *ca_frames, double threshold, int quirk_mode, int want_image, int want_mask,
-    const void *tables, const void *geom_tabs, const int64_t *g_tab_off, uint8_t *arena, size_t arena_bytes, unsigned long long *cursor,
+    const void *tables, const void *geom_tabs, const int64_t *g_tab_off, const int32_t *g_max_events, uint8_t *arena, size_t arena_bytes, unsigned long long *cursor,
     void *records_out, int32_t *n_active_out, int stage_bytes, void *scratch, size_t scratch_bytes, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -854,7 +1104,12 @@ extern "C" int cab200_encode_batch(
     }
     const long long pf = (long long)n_pouch * n_frames;
     if (pf > 0x7fffffffLL) { set_error("cab200_encode_batch: too many frames"); return CAB200_ESIZE; }
-    const size_t fixed = enc_fixed_smem(n_max);
+    // events per lane: the largest static event count of a row segment over the geometries of this call
+    // (4 or 8 per lane); unknown or above 256 -> the per-pixel parse
+    int max_ev = g_max_events ? 0 : ENC_ECAP + 1;
+    if (g_max_events)
+        for (int p = 0; p < n_pouch; ++p) max_ev = std::max(max_ev, g_max_events[geom_id[p]] > 0 ? g_max_events[geom_id[p]] : ENC_ECAP + 1);
+    const size_t fixed = enc_fixed_smem(n_max, max_ev <= ENC_ECAP);
     // staging: by default half of an SM's shared memory per CTA (two CTAs per SM)
     size_t cap = (stage_bytes > 0) ? (size_t)stage_bytes : (size_t)(112 * 1024) - fixed - 4608;
     cap &= ~(size_t)15;
@@ -879,8 +1134,9 @@ extern "C" int cab200_encode_batch(
     a.records = (EncRecord *)records_out;
     a.n_active_out = n_active_out;
     const size_t smem = fixed + cap;
-    CAB_CUDA(cudaFuncSetAttribute((const void *)encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    encode_kernel<<<(unsigned)pf, ENC_NT, smem, stream>>>(a);
+    void (*kern)(const EncodeArgs) = (max_ev <= 128) ? encode_kernel<4> : (max_ev <= 256) ? encode_kernel<8> : encode_kernel<0>;
+    CAB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)pf, ENC_NT, smem, stream>>>(a);
     CAB_CUDA(cudaGetLastError());
     return CAB200_OK;
 }

@@ -371,7 +371,7 @@ class Ensemble:
         self._label_img: Optional[torch.Tensor] = None
         self._label_mask: Optional[torch.Tensor] = None
         self._enc_tables: Optional[torch.Tensor] = None
-        self._enc_geom: Optional[Tuple[torch.Tensor, np.ndarray]] = None
+        self._enc_geom: Optional[Tuple[torch.Tensor, np.ndarray, np.ndarray]] = None
 
     # -- sizes ---------------------------------------------------------------------------------
     @property
@@ -531,32 +531,39 @@ class Ensemble:
             self._enc_tables = torch.from_numpy(host).to(self.device)
         return self._enc_tables
 
-    def encode_geometry_tables(self) -> Tuple[torch.Tensor, np.ndarray]:
-        """Static per-geometry checksum tables (``cab200_encode_geometry``) and their byte offsets."""
+    def encode_geometry_tables(self) -> Tuple[torch.Tensor, np.ndarray, np.ndarray]:
+        """Static per-geometry tables of K3 (``cab200_encode_geometry``: checksum sums and event lists),
+        their byte offsets and the largest event count per row segment."""
         if getattr(self, "_enc_geom", None) is None:
             w, h = self.output_size
             limg, lmsk = self.label_maps()
             tabs = self.encode_tables()
-            sizes = [int(self.lib.cab200_encode_geometry_bytes(int(n))) for n in self.g_ncell]
+            sizes = [int(self.lib.cab200_encode_geometry_bytes(int(n), h, w)) for n in self.g_ncell]
             off = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
             buf = torch.empty(int(sum(sizes)), dtype=torch.uint8, device=self.device)
+            max_ev = np.zeros(len(sizes), dtype=np.int32)
             with torch.cuda.device(self.device):
                 for g, n in enumerate(self.g_ncell):
+                    one = np.zeros(1, dtype=np.int32)
                     _lib.check(self.lib.cab200_encode_geometry(
                         int(n), limg[g].data_ptr(), lmsk[g].data_ptr(), h, w, tabs.data_ptr(),
-                        buf.data_ptr() + int(off[g]), _stream_ptr(self.device)), "cab200_encode_geometry")
-            self._enc_geom = (buf, off)
+                        buf.data_ptr() + int(off[g]), _lib.as_i32p(one), _stream_ptr(self.device)),
+                        "cab200_encode_geometry")
+                    max_ev[g] = one[0]
+            self._enc_geom = (buf, off, max_ev)
         return self._enc_geom
 
     def encode(self, image: bool = True, mask: bool = True, pouches: Optional[Tuple[int, int]] = None,
                threshold: float = 0.1, quirk: bool = True, out: Optional[Dict[str, torch.Tensor]] = None,
-               arena_bytes: Optional[int] = None, stage_bytes: int = 0) -> Dict[str, torch.Tensor]:
+               arena_bytes: Optional[int] = None, stage_bytes: int = 0, parse: str = "events"
+               ) -> Dict[str, torch.Tensor]:
         """K3 over pouches ``[a, b)``: every frame rasterised and encoded on the device into the files
         the reference's batch path stores -- a 16-bit gray+alpha ``.png`` (``save_image``,
         utils/image_processing.py:252-269) and a ``.npz`` holding ``mask`` (the instance mask,
         utils/sam2_data_generator.py:203).  Returns device tensors ``arena`` (uint8), ``cursor``
         (int64[1], bytes used), ``records`` (int64 ``[p, F, 2, 2]``: for image / mask the arena offset
-        and ``size | flags << 32``) and ``n_active [p, F]``.  See :func:`records_to_host`."""
+        and ``size | flags << 32``) and ``n_active [p, F]``.  See :func:`records_to_host`.
+        ``parse="pixels"`` forces the per-pixel parse (same files; the event parse is the fast path)."""
         if self.frames is None:
             raise RuntimeError("simulate() first")
         if self.precision != _lib.FP64_STRICT:
@@ -566,7 +573,7 @@ class Ensemble:
         w, h = self.output_size
         limg, lmsk = self.label_maps()
         tabs = self.encode_tables()
-        gtab, gtab_off = self.encode_geometry_tables()
+        gtab, gtab_off, gmax_ev = self.encode_geometry_tables()
         res: Dict[str, torch.Tensor] = {} if out is None else out
         if arena_bytes is None:
             # a flat-shaded polygon frame encodes to ~1/10 of its raw size; 1/3 leaves ample room
@@ -603,6 +610,7 @@ class Ensemble:
                 limg.data_ptr(), lmsk.data_ptr(), h, w, self.F, self.frames.data_ptr(),
                 float(threshold), 1 if quirk else 0, 1 if image else 0, 1 if mask else 0,
                 tabs.data_ptr(), gtab.data_ptr(), _lib.as_i64p(gtab_off),
+                _lib.as_i32p(gmax_ev) if parse == "events" else None,
                 arena.data_ptr(), arena.numel(), cursor.data_ptr(),
                 rec.data_ptr(), nact.data_ptr(), int(stage_bytes),
                 self._scratch.data_ptr() + scr_off, self.lib.cab200_encode_scratch_bytes(cnt, len(self.dgeo)),
@@ -630,7 +638,7 @@ class Ensemble:
 
     def run_files_to_host(self, chunk_pouches: int = 37, image: bool = True, mask: bool = True,
                            consumer=None, threshold: float = 0.1, quirk: bool = True,
-                           arena_bytes_per_pixel: float = 0.75, wait: bool = True,
+                           arena_bytes_per_pixel: float = 0.5, wait: bool = True,
                            stage_bytes: int = 0) -> Dict[str, int]:
         """The whole hot path with HOST buffers on both sides, in the form the reference's batch path
         stores its results: pinned host inputs -> device, K1, then K3 chunk by chunk -- every sampled

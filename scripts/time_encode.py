@@ -10,6 +10,7 @@ ens.simulate(); ens.synchronize()
 out, enc = {}, {}
 for name, fn in (("K2 raw", lambda: ens.rasterize(image=True, instance=True, out=out)),
                  ("K3 img+mask", lambda: ens.encode(out=enc)),
+                 ("K3 per-pixel", lambda: ens.encode(out=enc, parse="pixels")),
                  ("K3 img only", lambda: ens.encode(mask=False, out=enc)),
                  ("K3 mask only", lambda: ens.encode(image=False, out=enc))):
     fn(); ens.synchronize()

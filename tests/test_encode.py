@@ -172,11 +172,16 @@ def _run(env, size, count, out, T=4000, every=400, **kw):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("parse", ["events", "pixels"])
 @pytest.mark.parametrize("size,count,out", [("small", 4, (256, 256)), ("medium", 4, (512, 512)), ("xsmall", 4, (100, 75)),
-                                            ("small", 2, (640, 480)), ("small", 1, (1030, 40))])
-def test_k3_files_decode_to_k2_arrays_and_match_oracle_bytes(env, size, count, out):
+                                            ("small", 2, (640, 480)), ("small", 1, (1030, 40)), ("large", 1, (512, 512)),
+                                            ("large", 1, (200, 160))])
+def test_k3_files_decode_to_k2_arrays_and_match_oracle_bytes(env, size, count, out, parse):
+    """Both parses (static events: the fast path; every pixel: the general one) write the same bytes."""
     EO, L = env["EO"], env["L"]
-    ens, raw, enc, arena, off, size_, flags = _run(env, size, count, out)
+    ens, raw, enc, arena, off, size_, flags = _run(env, size, count, out, parse=parse)
+    if parse == "events":
+        assert (ens.encode_geometry_tables()[2] > 0).all()
     image = raw["image"].cpu().numpy()
     inst = raw["instance"].cpu().numpy().view(np.uint16)
     nact = raw["n_active"].cpu().numpy()
