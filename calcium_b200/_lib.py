@@ -27,7 +27,7 @@ EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
            "cab200_cluster_layout", "cab200_plan_cluster",
            "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
            "cab200_encode_tables_bytes", "cab200_encode_tables", "cab200_encode_scratch_bytes", "cab200_encode_batch",
-           "cab200_encode_geometry_bytes", "cab200_encode_geometry", "cab200_publish_to_host",
+           "cab200_encode_geometry_bytes", "cab200_encode_geometry", "cab200_publish_to_host", "cab200_edt_scratch_bytes", "cab200_edt_classes",
            "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_selftest_division"]
 
 
@@ -99,6 +99,10 @@ def load() -> ctypes.CDLL:
         c_void_p, c_void_p, i64p, i32p,                        # tables, geom_tabs, g_tab_off, g_max_events
         c_void_p, c_size_t, c_void_p,                          # arena, arena_bytes, cursor
         c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
+    lib.cab200_edt_scratch_bytes.restype = c_size_t
+    lib.cab200_edt_scratch_bytes.argtypes = [c_int, c_int, c_int]
+    lib.cab200_edt_classes.restype = c_int
+    lib.cab200_edt_classes.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cab200_publish_to_host.restype = c_int
     lib.cab200_publish_to_host.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cab200_cells_mask.restype = c_int

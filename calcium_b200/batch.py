@@ -61,12 +61,15 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                               generate_labels=False, image_size="512x512", jpeg_quality=90,
                               save_pouch=False, dataset_split="train", *, geometry_dir=None,
                               device=None, write_files=True, keep_arrays=False,
-                              max_chunk_bytes=4 << 30, writer_threads=8):
+                              max_chunk_bytes=4 << 30, writer_threads=8, generate_prompts=True):
     """Generate a batch of simulations with images and instance masks (see module docstring).
 
     Extra keyword-only arguments: ``geometry_dir``, ``device``, ``write_files`` (False: compute only),
     ``keep_arrays`` (return the images / masks in ``results['arrays']``), ``max_chunk_bytes`` (device
-    memory budget for one chunk's raster outputs), ``writer_threads``.
+    memory budget for one chunk's raster outputs), ``writer_threads``, ``generate_prompts`` (with
+    ``generate_masks``: the per-frame prompt JSON of ``process_batch_for_sam2``,
+    ``utils/sam2_data_generator.py:325-341`` -- K4 distance transforms + the reference's own draws from
+    the global numpy generator, continued from the state the pouch's own draws left it in).
     """
     os.makedirs(output_dir, exist_ok=True)
     if pouch_sizes is None:
@@ -98,7 +101,9 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             spec = PouchSpec.draw(sim_params, size=pouch_size, sim_number=sim_idx,
                                   geometry_dir=geometry_dir)
             drawn.append({"sim_idx": sim_idx, "spec": spec, "type": sim_type, "size": pouch_size,
-                          "name": f"{sim_type.replace(' ', '_')}_{sim_idx}", "params": sim_params})
+                          "name": f"{sim_type.replace(' ', '_')}_{sim_idx}", "params": sim_params,
+                          # the reference's frame loop continues the generator its Pouch seeded (core/pouch.py:317)
+                          "rng_state": np.random.get_state()})
             print(f"Running simulation {sim_idx+1}/{num_simulations}: {sim_type} on {pouch_size} pouch")
         except Exception as e:  # noqa: BLE001 - the reference skips a failing simulation (main.py:388-390)
             print(f"Error in simulation {sim_idx}: {str(e)}")
@@ -159,6 +164,25 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and generate_masks) else None
                 nact = out["n_active"].cpu().numpy() if steps else None
                 del out
+            prompt_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
+            if steps and generate_masks and generate_prompts:
+                from .prompts import PromptTables, frame_prompts, save_prompts
+                lmsk = ens.label_maps()[1]
+                tables: Dict[int, Any] = {}
+                for li, d in enumerate(part):
+                    g = int(ens.geom_id[li])
+                    if g not in tables:
+                        tables[g] = PromptTables(lmsk[g], int(ens.g_ncell[g]))
+                    ca_all = ens.frames_of(li)[:, 0, :].cpu().numpy()
+                    np.random.set_state(d["rng_state"])
+                    for fi in range(len(steps)):
+                        if not (ca_all[fi] > 0.1).any():          # no active cell: nothing is written (:318-319)
+                            continue
+                        pos, neg = frame_prompts(tables[g], ca_all[fi])
+                        ppath = os.path.join(prompt_dir, names[li][fi] + ".json")
+                        prompt_files[li].append(ppath)
+                        if write_files:
+                            save_prompts(pos, ppath, neg)
             for li, d in enumerate(part):
                 if img is not None:
                     for fi, t in enumerate(steps):
@@ -190,7 +214,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     "simulation_id": d["sim_idx"], "simulation_name": d["name"],
                     "simulation_type": d["type"], "pouch_size": d["size"], "parameters": d["params"],
                     "image_count": len(image_files[li]), "image_dir": img_dir, "mask_dir": mask_dir,
-                    "mask_count": len(mask_files[li]), "pouch": pouch_obj})
+                    "mask_count": len(mask_files[li]), "prompt_count": len(prompt_files[li]), "pouch": pouch_obj})
             del ens
     finally:
         if pool is not None:

@@ -16,6 +16,9 @@ Fixtures
   raster_xsmall.npz       cells_mask, generate_image(t), get_active_cells, get_cell_masks(active_only), instance masks
                           at 160x120 and 512x512, from the reference's own methods on the xsmall run
   geometry_xsmall.npz     the synthetic xsmall geometry itself (drift check for the generator)
+  prompts_small.npz/json  generate_point_prompts_from_mask + generate_negative_prompts (utils/sam2_data_generator.py)
+                          on instance masks of a small "Fluttering" pouch (reference pipeline, 256x256), with
+                          np.random.seed(k) in front of each frame; the calcium frames are stored as inputs
 """
 from __future__ import annotations
 
@@ -149,6 +152,30 @@ def main() -> None:
     np.savez(os.path.join(OUT, "traj_medium_flutter.npz"), steps=np.array(steps_m),
              vplc=po.V_PLC.flatten(), r0=po.disc_dynamics[:, 3, 0].copy(),
              frames=frames_of(po, steps_m), geometry_sha256=np.array(geometry_digest(gm)))
+    # ---- prompts: the reference's own functions on its own instance masks ------------------
+    from utils.sam2_data_generator import generate_point_prompts_from_mask, generate_negative_prompts
+    prm = ns.SimulationParameters("Fluttering").generate_random_params(seed=3)
+    pf = ns.Pouch(params=prm, size="small", sim_number=3, geometry_dir=gdir, output_size=(256, 256))
+    pf.simulate()
+    ts = [2000, 9000, 16000]
+    pj2, pz = {}, {"t": np.array(ts), "ca": np.ascontiguousarray(pf.disc_dynamics[:, 0, ts].T),
+                   "cells_mask": pf.cells_mask.astype(np.uint16)}
+    for k, t in enumerate(ts):
+        # threshold 0.1 is the default; 0.0 makes (almost) every cell active, cell 0 included: the id
+        # mismatch then labels the whole background as instance 1
+        for thr in (0.1, 0.0):
+            act = pf.get_active_cells(t, threshold=thr)
+            am = pf.get_cell_masks(active_only=True, time_step=t, threshold=thr)
+            inst = ns.create_instance_mask_from_cells(am, act)
+            np.random.seed(40 + k)
+            pos = generate_point_prompts_from_mask(inst, strategy="distance_based")
+            neg = generate_negative_prompts(inst, num_negative=5)
+            pj2[f"{t}_{thr}"] = {"positive": {str(i): v for i, v in pos.items()}, "negative": neg,
+                                  "n_active": len(act), "seed": 40 + k}
+            pz[f"instance_{t}_{thr}"] = inst
+    np.savez_compressed(os.path.join(OUT, "prompts_small.npz"), **pz)
+    with open(os.path.join(OUT, "prompts_small.json"), "w") as fh:
+        json.dump(pj2, fh, indent=1, sort_keys=True)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f"  {f:32s} {os.path.getsize(os.path.join(OUT, f)) / 1024:8.1f} KiB")

@@ -326,4 +326,13 @@ def test_batch_path_writes_the_encoded_frames(env, tmp_path):
                 assert np.array_equal(np.load(npz[0])["mask"], arr["instance"][fi])
                 n_masks += 1
         assert sim["mask_count"] == int((arr["n_active"] > 0).sum())
+        assert sim["prompt_count"] == sim["mask_count"]
     assert rb["stats"]["total_masks"] == n_masks
+    # prompt files: the reference's JSON layout (utils/sam2_data_generator.py:227-232), one per mask
+    import json
+    pj = sorted(glob.glob(os.path.join(str(tmp_path / "b"), "prompts", "train", "*.json")))
+    assert len(pj) == n_masks
+    for path in pj[:3]:
+        data = json.load(open(path))
+        assert set(data) == {"positive_prompts", "negative_prompts", "num_cells", "version"}
+        assert data["num_cells"] == len(data["positive_prompts"]) and len(data["negative_prompts"]) <= 5
