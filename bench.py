@@ -415,9 +415,9 @@ def run_gpu(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"],
                     "d2h_bytes_per_step": moved["d2h_bytes"], "ms_per_step": e2e_ms_v, "steps": e2e_steps,
                     "path": "Ensemble.run_files_to_host (what generate_simulation_batch runs): pinned host inputs -> K1 -> "
-                            "K3 (rasterise + DEFLATE-encode on the device) -> float64 frames + every frame's finished "
-                            ".png (16-bit gray+alpha) and .npz (instance mask) copied to pinned host memory; "
-                            "decoding them gives bit for bit the arrays of e2e_raw_arrays"},
+                            "K3 (rasterise + DEFLATE-encode on the device) -> every frame's finished .png (16-bit gray+alpha) "
+                            "and .npz (instance mask) + the sampled float64 calcium state copied to pinned host memory; "
+                            "decoding the files gives bit for bit the arrays of e2e_raw_arrays"},
             "e2e_raw_arrays": {"value": e2e_raw_value, "unit": UNIT, "h2d_bytes_per_step": moved_raw["h2d_bytes"],
                                "d2h_bytes_per_step": moved_raw["d2h_bytes"], "ms_per_step": e2e_raw_ms,
                                "path": "Ensemble.run_to_host: K1 -> K2 -> frames + uncompressed images + instance "

@@ -20,6 +20,7 @@ PARAM_SLOTS = ["k_1", "k_a", "k_p", "k_2", "V_SERCA", "K_SERCA", "K_PLC", "K_5",
 ST_NONFINITE = 1
 ST_BADGEOM = 2
 ENC_OK, ENC_STAGE_FULL, ENC_ARENA_FULL, ENC_SKIPPED = 1, 2, 4, 8
+HUFFMAN_FIXED, HUFFMAN_TUNED = 0, 1
 
 #: every symbol include/cab200.h declares (tests check the library exports all of them)
 EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
@@ -85,7 +86,7 @@ def load() -> ctypes.CDLL:
     lib.cab200_encode_tables_bytes.restype = c_size_t
     lib.cab200_encode_tables_bytes.argtypes = []
     lib.cab200_encode_tables.restype = c_int
-    lib.cab200_encode_tables.argtypes = [c_int, c_int, c_void_p]
+    lib.cab200_encode_tables.argtypes = [c_int, c_int, c_int, c_void_p]
     lib.cab200_encode_scratch_bytes.restype = c_size_t
     lib.cab200_encode_scratch_bytes.argtypes = [c_int, c_int]
     lib.cab200_encode_geometry_bytes.restype = c_size_t

@@ -42,6 +42,11 @@ constexpr int ENC_MAXDIM = 2048;
 constexpr uint32_t CRC_POLY = 0xEDB88320u;
 
 struct EncStream {
+    uint32_t lit[256];       // literal: reversed Huffman code | bits << 24
+    uint32_t len[260];       // match length 3..258: reversed code + extra bits | bits << 24
+    uint32_t hdr[96];        // DEFLATE block header (BFINAL, BTYPE and, for a dynamic block, the code lengths), LSB first
+    int hdr_bits;
+    uint32_t eob;            // end-of-block symbol: reversed code | bits << 24
     uint8_t prefix[64];
     uint8_t suffix[96];
     uint8_t head[192];       // uncompressed bytes in front of the pixel rows (.npy header), sent as literals
@@ -60,8 +65,6 @@ struct EncStream {
 };
 
 struct EncTables {
-    uint32_t lit[256];       // fixed-Huffman literal: reversed code | bits << 24
-    uint32_t len[260];       // match length 3..258: reversed code + extra bits | bits << 24
     uint32_t crc[256];       // reflected CRC-32 table
     uint32_t pow8[32];       // x^(8 * 2^k) mod P
     uint32_t rowshift[ENC_MAXDIM];        // mask: x^(8 * bytes after row y)
@@ -236,7 +239,6 @@ __global__ void __launch_bounds__(256) enc_geometry_kernel(const uint16_t *label
 // shared-memory tables of one CTA
 constexpr int ENC_TCAP = 64;     // token descriptors per warp and batch (event parse)
 struct EncSmem {
-    unsigned long long *lit64;   // [512] image pixel (gray | alpha flag << 8) -> 4 literals: bits | count << 58
     uint32_t *len_s, *lit_s, *crc_s;
     uint32_t *toklist;           // [ENC_NW][ENC_TCAP]
     uint8_t *stage;
@@ -308,7 +310,7 @@ __device__ __forceinline__ bool place_rows(uint32_t lanebits, uint32_t *rowbits,
 
 // One token -> (bits, count).  A match of `len` pixels in mode up/left, or the literal pixel `key`
 // (also for a one-pixel match of a 2-byte pixel, which is too short for DEFLATE).
-template <bool IMG, bool LIT64>
+template <bool IMG>
 __device__ __forceinline__ void make_token(const EncSmem &sm, bool is_match, bool is_up, int len, uint32_t key,
                                            uint32_t dist_up, uint32_t dist_left, unsigned long long &val, int &nb)
 {
@@ -319,10 +321,6 @@ __device__ __forceinline__ void make_token(const EncSmem &sm, bool is_match, boo
         const int ln = (int)(lt >> 24);
         val = (unsigned long long)(lt & 0xffffffu) | ((unsigned long long)(dd & 0xffffffu) << ln);
         nb = ln + (int)(dd >> 24);
-    } else if (IMG && LIT64) {
-        const unsigned long long t = sm.lit64[key & 0x1ffu];
-        val = t & ((1ull << 58) - 1ull);
-        nb = (int)(t >> 58);
     } else if (IMG) {
         // 16-bit gray*4 and alpha*257, big endian: four literals
         const uint32_t g = key & 0xffu, al = (key >> 8) ? 255u : 0u;
@@ -361,10 +359,17 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
     if (tid == 0) s_crc = 0;
     __syncthreads();
     for (int i = tid; i < d.prefix_len; i += ENC_NT) sm.stage[i] = d.prefix[i];
+    // this stream's Huffman tables
+    for (int i = tid; i < 260; i += ENC_NT) sm.len_s[i] = d.len[i];
+    for (int i = tid; i < 256; i += ENC_NT) sm.lit_s[i] = d.lit[i];
     __syncthreads();
     uint32_t bitpos = 8u * (uint32_t)d.prefix_len;
-    if (tid == 0) put_bits(stage32, bitpos, 3ull, 3);          // BFINAL = 1, BTYPE = 01 (fixed Huffman)
-    bitpos += 3;
+    // block header: BFINAL = 1 and either BTYPE = 01 (fixed code) or BTYPE = 10 + the code lengths
+    if (tid < (d.hdr_bits + 31) / 32) {
+        const int nb = min(32, d.hdr_bits - 32 * tid);
+        put_bits(stage32, bitpos + 32u * (uint32_t)tid, (unsigned long long)d.hdr[tid], nb);
+    }
+    bitpos += (uint32_t)d.hdr_bits;
     // uncompressed head bytes (.npy header) as literals
     if (tid < d.head_len) {
         const uint32_t t = lit_s[d.head[tid]];
@@ -482,7 +487,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                     const uint32_t key = (j & 1) ? (w >> 16) : (w & 0xffffu);
                     unsigned long long val;
                     int nb;
-                    make_token<IMG, true>(sm, isU || isL, isU, len, key, dist_up, dist_left, val, nb);
+                    make_token<IMG>(sm, isU || isL, isU, len, key, dist_up, dist_left, val, nb);
                     if (write) put_bits(stage32, pos + bits, val, nb);
                     bits += (uint32_t)nb;
                 }
@@ -596,7 +601,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                 const uint32_t dsc = lds_u32(list_a + 4u * (uint32_t)t);
                 if (dsc == 0xffffffffu) { val = filt & 0xffffffu; nb = (int)(filt >> 24); return; }
                 const uint32_t m = (dsc >> 12) & 3u;
-                make_token<IMG, K == 0>(sm, m != 0u, m == 2u, (int)(dsc & 0xfffu), dsc >> 16, dist_up, dist_left, val, nb);
+                make_token<IMG>(sm, m != 0u, m == 2u, (int)(dsc & 0xfffu), dsc >> 16, dist_up, dist_left, val, nb);
             };
             // bit counts, one token per lane and round
             uint32_t lanebits = 0;
@@ -638,8 +643,10 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
     __syncthreads();
     if (overflow) return 0u;
 
-    // end-of-block code: seven zero bits (already zero), then pad to a byte
-    bitpos += 7;
+    // end-of-block symbol, then pad to a byte
+    if (tid == 0) put_bits(stage32, bitpos, (unsigned long long)(d.eob & 0xffffffu), (int)(d.eob >> 24));
+    bitpos += d.eob >> 24;
+    __syncthreads();
     const uint32_t plen = (uint32_t)d.prefix_len;
     const uint32_t L = (bitpos - 8u * plen + 7u) / 8u;          // deflate bytes
     uint32_t total_bytes;
@@ -804,7 +811,6 @@ __global__ void __launch_bounds__(ENC_NT, 2) encode_kernel(const EncodeArgs a)
     const FrameLut lut = frame_lut_carve(smem_raw, n);
     EncSmem sm;
     unsigned char *p = smem_raw + a.lut_bytes;
-    sm.lit64 = reinterpret_cast<unsigned long long *>(p); p += (K == 0 ? 512 * 8 : 0);
     sm.len_s = reinterpret_cast<uint32_t *>(p); p += 260 * 4;
     sm.lit_s = reinterpret_cast<uint32_t *>(p); p += 256 * 4;
     sm.crc_s = reinterpret_cast<uint32_t *>(p); p += 256 * 4;
@@ -814,28 +820,11 @@ __global__ void __launch_bounds__(ENC_NT, 2) encode_kernel(const EncodeArgs a)
 
     const int n_active = frame_lut_build<ENC_NT>(lut, ca, n, a.threshold, a.quirk);
     if (tid == 0 && a.n_active_out) a.n_active_out[pf] = n_active;
-    for (int i = tid; i < 260; i += ENC_NT) sm.len_s[i] = a.tab->len[i];
-    for (int i = tid; i < 256; i += ENC_NT) { sm.lit_s[i] = a.tab->lit[i]; sm.crc_s[i] = a.tab->crc[i]; }
+    for (int i = tid; i < 256; i += ENC_NT) sm.crc_s[i] = a.tab->crc[i];
     // image pixel key per label value: gray | 0x100 (alpha set), 0 for the background; the rank
     // scratch of the LUT build is free now
     for (int v = tid; v <= n; v += ENC_NT) lut.rank1[v] = v ? (uint16_t)(lut.gray_lut[v] | 0x100u) : (uint16_t)0;
     __syncthreads();
-    // the four literals of a 16-bit gray+alpha pixel: gray*4 and alpha*257, big endian
-    for (int key = tid; key < (K == 0 ? 512 : 0); key += ENC_NT) {
-        const uint32_t g = key & 0xff, al = (key >> 8) ? 255u : 0u;
-        const uint32_t b[4] = {g >> 6, (g << 2) & 0xffu, al, al};
-        unsigned long long v = 0;
-        int nb = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t t = sm.lit_s[b[i]];
-            v |= (unsigned long long)(t & 0xffffffu) << nb;
-            nb += (int)(t >> 24);
-        }
-        sm.lit64[key] = v | ((unsigned long long)nb << 58);
-    }
-    __syncthreads();
-
     EncRecord *rec = a.records + (size_t)pf * 2;
     const size_t gbase = (size_t)pe.geom * a.H * a.W;
     const GeomTab gt = geom_tab_carve(a.geom_tabs + a.geom_tab_off[pe.geom], n, a.H, a.W);
@@ -870,39 +859,144 @@ static uint32_t rev_bits(uint32_t v, int n)
     return r;
 }
 
-// fixed Huffman code of literal/length symbol `sym` (RFC 1951, 3.2.6): reversed code | bits << 24
-static uint32_t fixed_sym(int sym)
+// fixed Huffman code lengths of the literal/length alphabet (RFC 1951, 3.2.6)
+static int fixed_len(int sym) { return sym <= 143 ? 8 : sym <= 255 ? 9 : sym <= 279 ? 7 : 8; }
+
+// Huffman code lengths for weights w[0..n) (all > 0), at most maxlen bits.  Deterministic so that the
+// oracle can restate it: priority queue ordered by (weight, id), leaves have ids 0..n-1, internal nodes get
+// the next ids in creation order; if the deepest leaf exceeds maxlen all weights are halved (rounding up)
+// and the construction is repeated.
+static void huffman_lengths(const uint32_t *w, int n, int maxlen, int *len_out)
 {
-    uint32_t code; int nb;
-    if (sym <= 143) { code = 0x30 + sym; nb = 8; }
-    else if (sym <= 255) { code = 0x190 + (sym - 144); nb = 9; }
-    else if (sym <= 279) { code = sym - 256; nb = 7; }
-    else { code = 0xC0 + (sym - 280); nb = 8; }
-    return rev_bits(code, nb) | ((uint32_t)nb << 24);
+    std::vector<unsigned long long> f(w, w + n);
+    for (;;) {
+        struct Node { unsigned long long w; int id; };
+        auto cmp = [](const Node &a, const Node &b) { return a.w != b.w ? a.w > b.w : a.id > b.id; };
+        std::vector<Node> heap;
+        std::vector<int> parent(2 * n, -1);
+        for (int i = 0; i < n; ++i) heap.push_back({f[i], i});
+        std::make_heap(heap.begin(), heap.end(), cmp);
+        int next = n;
+        while (heap.size() > 1) {
+            std::pop_heap(heap.begin(), heap.end(), cmp); Node a = heap.back(); heap.pop_back();
+            std::pop_heap(heap.begin(), heap.end(), cmp); Node b = heap.back(); heap.pop_back();
+            parent[a.id] = next; parent[b.id] = next;
+            heap.push_back({a.w + b.w, next++});
+            std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+        int deepest = 0;
+        for (int i = 0; i < n; ++i) {
+            int d = 0;
+            for (int p = parent[i]; p >= 0; p = parent[p]) ++d;
+            len_out[i] = (n == 1) ? 1 : d;
+            deepest = std::max(deepest, len_out[i]);
+        }
+        if (deepest <= maxlen) return;
+        for (int i = 0; i < n; ++i) f[i] = (f[i] + 1) / 2;
+    }
 }
 
-static uint32_t length_entry(int len)
+// canonical codes (RFC 1951, 3.2.2) for lengths len[0..n) (0 = unused); code_out holds the code MSB first
+static void canonical_codes(const int *len, int n, uint32_t *code_out)
 {
-    static const int base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99,
+    int bl_count[16] = {0};
+    for (int i = 0; i < n; ++i) bl_count[len[i]]++;
+    bl_count[0] = 0;
+    uint32_t next_code[16] = {0}, code = 0;
+    for (int b = 1; b <= 15; ++b) { code = (code + bl_count[b - 1]) << 1; next_code[b] = code; }
+    for (int i = 0; i < n; ++i) code_out[i] = len[i] ? next_code[len[i]]++ : 0u;
+}
+
+struct BitWriter {
+    uint32_t *w; int cap_bits; int n = 0;
+    void put(uint32_t v, int nb) { for (int i = 0; i < nb; ++i, ++n) if (n < cap_bits && ((v >> i) & 1u)) w[n >> 5] |= 1u << (n & 31); }
+};
+
+static const int kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99,
                                  115, 131, 163, 195, 227, 258};
-    static const int extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-    int i = 28;
-    while (len < base[i]) --i;
-    const uint32_t s = fixed_sym(257 + i);
-    const int nb = (int)(s >> 24);
-    return (s & 0xffffffu) | ((uint32_t)(len - base[i]) << nb) | ((uint32_t)(nb + extra[i]) << 24);
-}
+static const int kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static const int kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025,
+                                  1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static const int kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12,
+                                   12, 13, 13};
+static int dist_symbol(int dist) { int i = 29; while (dist < kDistBase[i]) --i; return i; }
 
-static uint32_t dist_entry(int dist)
+#include "enc_freq.inc"
+
+// Fills a stream's code tables, block header and distance entries.  tuned: a dynamic-Huffman block whose
+// code lengths come from the measured symbol frequencies of enc_freq.inc (static per stream kind, so the
+// kernel stays table driven); else the fixed code of RFC 1951 3.2.6.
+static void build_codes(EncStream &d, int dist_left, int dist_up, const uint32_t *freq_ll, const uint32_t *freq_d2, bool tuned)
 {
-    static const int base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025,
-                                 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-    static const int extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12,
-                                  12, 13, 13};
-    if (dist < 1 || dist > 32768) return 0u;
-    int i = 29;
-    while (dist < base[i]) --i;
-    return rev_bits((uint32_t)i, 5) | ((uint32_t)(dist - base[i]) << 5) | ((uint32_t)(5 + extra[i]) << 24);
+    int ll_len[286], d_len[30];
+    uint32_t ll_code[286], d_code[30];
+    if (tuned) {
+        uint32_t fd[30];
+        for (int i = 0; i < 30; ++i) fd[i] = 1;
+        fd[dist_symbol(dist_left)] = freq_d2[0];
+        if (dist_up >= 1 && dist_up <= 32768) fd[dist_symbol(dist_up)] = freq_d2[1];
+        huffman_lengths(freq_ll, 286, 15, ll_len);
+        huffman_lengths(fd, 30, 15, d_len);
+    } else {
+        for (int i = 0; i < 286; ++i) ll_len[i] = fixed_len(i);
+        for (int i = 0; i < 30; ++i) d_len[i] = 5;
+    }
+    if (tuned) {
+        canonical_codes(ll_len, 286, ll_code);
+        canonical_codes(d_len, 30, d_code);
+    } else {
+        int full[288];
+        uint32_t fc[288];
+        for (int i = 0; i < 288; ++i) full[i] = fixed_len(i);
+        canonical_codes(full, 288, fc);                  // the fixed code is canonical over all 288 symbols
+        for (int i = 0; i < 286; ++i) ll_code[i] = fc[i];
+        for (int i = 0; i < 30; ++i) d_code[i] = (uint32_t)i;
+    }
+    for (int i = 0; i < 256; ++i) d.lit[i] = rev_bits(ll_code[i], ll_len[i]) | ((uint32_t)ll_len[i] << 24);
+    d.eob = rev_bits(ll_code[256], ll_len[256]) | ((uint32_t)ll_len[256] << 24);
+    for (int l = 3; l <= 258; ++l) {
+        int i = 28;
+        while (l < kLenBase[i]) --i;
+        const int nb = ll_len[257 + i];
+        d.len[l] = rev_bits(ll_code[257 + i], nb) | ((uint32_t)(l - kLenBase[i]) << nb) | ((uint32_t)(nb + kLenExtra[i]) << 24);
+    }
+    auto dist_entry = [&](int dist) -> uint32_t {
+        if (dist < 1 || dist > 32768) return 0u;
+        const int i = dist_symbol(dist), nb = d_len[i];
+        if (nb + kDistExtra[i] > 24) return 0u;          // does not fit the entry: that distance is not used
+        return rev_bits(d_code[i], nb) | ((uint32_t)(dist - kDistBase[i]) << nb) | ((uint32_t)(nb + kDistExtra[i]) << 24);
+    };
+    d.dist_left = dist_entry(dist_left);
+    d.dist_up = dist_entry(dist_up);
+    // block header
+    memset(d.hdr, 0, sizeof(d.hdr));
+    BitWriter bw{d.hdr, (int)sizeof(d.hdr) * 8};
+    bw.put(1, 1);                                        // BFINAL
+    if (!tuned) {
+        bw.put(1, 2);                                    // BTYPE = 01
+    } else {
+        bw.put(2, 2);                                    // BTYPE = 10: HLIT, HDIST, HCLEN, code-length code, lengths
+        bw.put(286 - 257, 5); bw.put(30 - 1, 5); bw.put(19 - 4, 4);
+        // code-length alphabet: the 316 lengths are sent one by one (no repeat codes 16-18)
+        uint32_t clf[19] = {0};
+        for (int i = 0; i < 286; ++i) clf[ll_len[i]]++;
+        for (int i = 0; i < 30; ++i) clf[d_len[i]]++;
+        int used[19], nused = 0;
+        for (int v = 0; v < 19; ++v) if (clf[v]) used[nused++] = v;
+        if (nused == 1) { used[nused++] = (used[0] == 0) ? 1 : 0; clf[used[1]] = 1; std::sort(used, used + nused); }
+        uint32_t uw[19]; int ul[19];
+        for (int k = 0; k < nused; ++k) uw[k] = clf[used[k]];
+        huffman_lengths(uw, nused, 7, ul);
+        int cl_len[19] = {0};
+        uint32_t cl_code[19];
+        for (int k = 0; k < nused; ++k) cl_len[used[k]] = ul[k];
+        canonical_codes(cl_len, 19, cl_code);
+        static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        for (int k = 0; k < 19; ++k) bw.put((uint32_t)cl_len[order[k]], 3);
+        for (int i = 0; i < 286; ++i) bw.put(rev_bits(cl_code[ll_len[i]], cl_len[ll_len[i]]), cl_len[ll_len[i]]);
+        for (int i = 0; i < 30; ++i) bw.put(rev_bits(cl_code[d_len[i]], cl_len[d_len[i]]), cl_len[d_len[i]]);
+    }
+    d.hdr_bits = bw.n;
 }
 
 static uint32_t host_crc0(const uint32_t *tab, const uint8_t *p, size_t n, uint32_t c = 0)
@@ -925,12 +1019,10 @@ static void h_le16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)
 static void h_le32(uint8_t *p, uint32_t v) { h_le16(p, v); h_le16(p + 2, v >> 16); }
 static void h_be32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
 
-static void build_tables(int H, int W, EncTables *t)
+static void build_tables(int H, int W, bool tuned, EncTables *t)
 {
     memset(t, 0, sizeof(*t));
     t->H = H; t->W = W;
-    for (int i = 0; i < 256; ++i) t->lit[i] = fixed_sym(i);
-    for (int l = 3; l <= 258; ++l) t->len[l] = length_entry(l);
     for (uint32_t i = 0; i < 256; ++i) {
         uint32_t c = i;
         for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ CRC_POLY : c >> 1;
@@ -957,7 +1049,7 @@ static void build_tables(int H, int W, EncTables *t)
     memcpy(g.suffix, iend, 12); g.suffix_len = 12;
     g.head_len = 0;
     g.bpp = 4; g.seg_lanes = 4; g.row_lead = 1;
-    g.dist_left = dist_entry(4); g.dist_up = dist_entry(1 + 4 * W);
+    build_codes(g, 4, 1 + 4 * W, kFreqImgLL, kFreqImgD, tuned);
     g.raw_len = (uint32_t)((size_t)H * (1 + 4 * (size_t)W));
     g.p_crc_prefix = g.p_csize_prefix = g.p_crc_suffix = g.p_csize_suffix = g.p_cdoff_suffix = -1;
 
@@ -972,7 +1064,6 @@ static void build_tables(int H, int W, EncTables *t)
     h[0] = 0x93; memcpy(h + 1, "NUMPY", 5); h[6] = 1; h[7] = 0; h_le16(h + 8, (uint32_t)hl);
     memcpy(h + 10, dict, dl); memset(h + 10 + dl, ' ', hl - dl - 1); h[10 + hl - 1] = '\n';
     m.head_len = 10 + hl;
-    for (int j = 0; j < m.head_len; ++j) { m.head_off[j] = (uint16_t)m.head_bits; m.head_bits += (int)(t->lit[m.head[j]] >> 24); }
     const unsigned long long data_len = 2ull * H * W;
     m.raw_len = (uint32_t)(m.head_len + data_len);
     // CRC(M) = crc0(head) * x^(8*|data|) ^ crc0(data) ^ CRC(zeros(|M|)): the first and last term are constant
@@ -999,14 +1090,15 @@ static void build_tables(int H, int W, EncTables *t)
     m.p_cdoff_suffix = 54 + 16;
     m.suffix_len = 54 + 22;
     m.bpp = 2; m.seg_lanes = 8; m.row_lead = 0;
-    m.dist_left = dist_entry(2); m.dist_up = dist_entry(2 * W);
+    build_codes(m, 2, 2 * W, kFreqMskLL, kFreqMskD, tuned);
+    for (int j = 0; j < m.head_len; ++j) { m.head_off[j] = (uint16_t)m.head_bits; m.head_bits += (int)(m.lit[m.head[j]] >> 24); }
     m.p_len_prefix = -1;
 }
 
 static inline size_t enc_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t enc_fixed_smem(int n_max, bool events)
 {
-    return enc_align(frame_lut_bytes(n_max), 16) + 260 * 4 + 256 * 4 + 256 * 4 + (events ? ENC_NW * ENC_TCAP * 4 : 512 * 8);
+    return enc_align(frame_lut_bytes(n_max), 16) + 260 * 4 + 256 * 4 + 256 * 4 + (events ? ENC_NW * ENC_TCAP * 4 : 0);
 }
 
 }  // namespace cab200
@@ -1015,13 +1107,14 @@ using namespace cab200;
 
 extern "C" size_t cab200_encode_tables_bytes(void) { return sizeof(EncTables); }
 
-extern "C" int cab200_encode_tables(int H, int W, void *tables_host_out)
+extern "C" int cab200_encode_tables(int H, int W, int huffman, void *tables_host_out)
 {
     if (H <= 0 || W <= 0 || H > ENC_MAXDIM || W > ENC_MAXDIM || !tables_host_out) {
         set_error("cab200_encode_tables: H and W must be in [1, %d]", ENC_MAXDIM);
         return CAB200_EINVAL;
     }
-    build_tables(H, W, (EncTables *)tables_host_out);
+    if (huffman != CAB200_HUFFMAN_FIXED && huffman != CAB200_HUFFMAN_TUNED) { set_error("cab200_encode_tables: huffman must be CAB200_HUFFMAN_FIXED or CAB200_HUFFMAN_TUNED"); return CAB200_EINVAL; }
+    build_tables(H, W, huffman == CAB200_HUFFMAN_TUNED, (EncTables *)tables_host_out);
     return CAB200_OK;
 }
 

@@ -279,7 +279,8 @@ class Ensemble:
     def __init__(self, specs: Sequence[PouchSpec], *, output_size: Tuple[int, int] = (512, 512),
                  T: int = T_DEFAULT, frame_steps: Optional[Sequence[int]] = None,
                  device: Optional[torch.device] = None, precision: int = _lib.FP64_STRICT,
-                 dt: float = DT, use_plan: bool = True, cluster="auto", coalesced_capture="auto"):
+                 dt: float = DT, use_plan: bool = True, cluster="auto", coalesced_capture="auto",
+                 huffman: str = "tuned"):
         if not torch.cuda.is_available():
             raise RuntimeError("calcium_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -330,6 +331,7 @@ class Ensemble:
         self.g_cluster = np.array([d.auto_cluster() if cluster == "auto" else (int(cluster) if d.unit else 1)
                                    for d in self.dgeo], dtype=np.int32)
         self.use_plan = use_plan
+        self.huffman = huffman                          # K3's DEFLATE code: "tuned" (static dynamic-Huffman block) | "fixed"
         self.coalesced_capture = coalesced_capture      # "auto" | True | False, see _alloc_frames_tmp
         self._frames_tmp: Optional[torch.Tensor] = None
         self.d_plan: Optional[torch.Tensor] = None
@@ -527,7 +529,8 @@ class Ensemble:
             w, h = self.output_size
             nb = int(self.lib.cab200_encode_tables_bytes())
             host = np.zeros(nb, dtype=np.uint8)
-            _lib.check(self.lib.cab200_encode_tables(h, w, host.ctypes.data), "cab200_encode_tables")
+            _lib.check(self.lib.cab200_encode_tables(h, w, _lib.HUFFMAN_TUNED if self.huffman == "tuned"
+                                                     else _lib.HUFFMAN_FIXED, host.ctypes.data), "cab200_encode_tables")
             self._enc_tables = torch.from_numpy(host).to(self.device)
         return self._enc_tables
 
@@ -639,7 +642,7 @@ class Ensemble:
     def run_files_to_host(self, chunk_pouches: int = 37, image: bool = True, mask: bool = True,
                            consumer=None, threshold: float = 0.1, quirk: bool = True,
                            arena_bytes_per_pixel: float = 0.5, wait: bool = True,
-                           stage_bytes: int = 0) -> Dict[str, int]:
+                           stage_bytes: int = 0, frames: str = "ca") -> Dict[str, int]:
         """The whole hot path with HOST buffers on both sides, in the form the reference's batch path
         stores its results: pinned host inputs -> device, K1, then K3 chunk by chunk -- every sampled
         frame as a finished ``.png`` and ``.npz`` byte string -- copied into pinned host memory together
@@ -648,20 +651,32 @@ class Ensemble:
         stream.  ``consumer(chunk: EncodedChunk)`` is called once a chunk has landed.  With
         ``wait=False`` the last chunks are left in flight (their copy-out then overlaps whatever the
         caller queues next, e.g. the next ensemble's integration); :meth:`flush_files` completes them.
-        Returns the byte counts moved (with ``wait=False``: of the copies queued during this call)."""
+        ``frames``: which part of the sampled float64 state also goes to the host (``_fring["h_frames"]``):
+        ``"ca"`` -- the calcium state ``[P, F, n]``, what labels and prompts are computed from (default;
+        ensembles of one pouch size, otherwise like ``"all"``), ``"all"`` -- c, p, s, r as laid out on the
+        device, ``"none"``.  Returns the byte counts moved (with ``wait=False``: of the copies queued
+        during this call)."""
         dev = self.device
         w, h = self.output_size
         cur = torch.cuda.current_stream(dev)
         cp = max(1, min(chunk_pouches, self.P))
         cap = (int(cp * self.F * h * w * arena_bytes_per_pixel) + (1 << 20) + 15) // 16 * 16
-        key = (cp, cap, image, mask)
+        uniform = len(set(int(x) for x in self.g_ncell[self.geom_id])) == 1
+        if frames == "ca" and not uniform:
+            frames = "all"
+        if frames not in ("ca", "all", "none"):
+            raise ValueError(f"frames must be 'ca', 'all' or 'none', got {frames!r}")
+        key = (cp, cap, image, mask, frames)
         st = getattr(self, "_fring", None)
         if st is None or st["key"] != key:
             self.flush_files()
             st = {"key": key, "cs": torch.cuda.Stream(device=dev), "fs": torch.cuda.Stream(device=dev),
                   "slots": [], "launched": [], "copying": [],
                   "frames_done": torch.cuda.Event(),
-                  "h_frames": torch.empty(max(self.frame_elems, 1), dtype=torch.float64, pin_memory=True)}
+                  "h_frames": (torch.empty(max(self.frame_elems, 1), dtype=torch.float64, pin_memory=True)
+                               if frames == "all" else
+                               torch.empty((self.P, self.F, int(self.g_ncell[0])), dtype=torch.float64, pin_memory=True)
+                               if frames == "ca" else None)}
             for _ in range(4):
                 st["slots"].append({
                     "dev": {}, "h_arena": torch.empty(cap, dtype=torch.uint8, pin_memory=True),
@@ -711,9 +726,16 @@ class Ensemble:
             fs = st["fs"]                            # own stream: waits for K1, and an arena copy of the
             fs.wait_event(ev)                        # previous call must not queue behind that wait
             with torch.cuda.stream(fs):
-                st["h_frames"].copy_(self.frames, non_blocking=True)
+                if frames == "all":
+                    st["h_frames"].copy_(self.frames, non_blocking=True)
+                elif frames == "ca":
+                    n0 = int(self.g_ncell[0])
+                    ca = self.frames.view(self.P, self.F, 4, n0)[:, :, 0, :].contiguous()
+                    ca.record_stream(fs)
+                    st["h_frames"].copy_(ca, non_blocking=True)
                 st["frames_done"].record(fs)
-            d2h += self.frames.numel() * self.frames.element_size()
+            if st["h_frames"] is not None:
+                d2h += st["h_frames"].numel() * 8
             k = st.get("k", 0)
             for lo in range(0, self.P, cp):
                 hi = min(lo + cp, self.P)

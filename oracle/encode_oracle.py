@@ -16,7 +16,16 @@ What it pins, and against what:
 Parse rules (the same as encode.cu): rows are cut into 512-pixel segments; per pixel the mode is
 "up" when it equals the pixel above, else "left" when it equals the previous pixel of the row, else
 literal; a token is a maximal run of one mode, additionally cut every 256 bytes from the segment
-start; a match shorter than 3 bytes is sent as a literal pixel; one final fixed-Huffman block.
+start; a match shorter than 3 bytes is sent as a literal pixel; one final block.
+
+Huffman code: ``"fixed"`` (RFC 1951 3.2.6) or ``"tuned"`` -- a dynamic-Huffman block whose code
+lengths are static per stream kind: Huffman lengths (<= 15 bits) over the symbol frequencies in
+``calcium_b200/csrc/enc_freq.inc`` (shared DATA; the two "distance" weights go to the symbols of the
+left / up distance of the actual image width, every other distance symbol weighs 1), built with a
+priority queue ordered by (weight, id) -- leaves 0..n-1, internal nodes numbered in creation order --
+halving all weights (rounding up) while the deepest leaf exceeds the limit; canonical codes; the
+block header sends all 316 code lengths one by one (no repeat codes) with a <= 7-bit code-length code
+built the same way over the length values in use.
 """
 from __future__ import annotations
 
@@ -50,15 +59,113 @@ def fixed_symbol(sym: int) -> Tuple[int, int]:
     return _rev(code, nb), nb
 
 
-def length_token(length: int) -> Tuple[int, int]:
+def length_token(length: int, code=None) -> Tuple[int, int]:
     i = max(k for k in range(29) if _LEN_BASE[k] <= length)
-    v, nb = fixed_symbol(257 + i)
+    v, nb = fixed_symbol(257 + i) if code is None else code.ll[257 + i]
     return v | ((length - _LEN_BASE[i]) << nb), nb + _LEN_EXTRA[i]
 
 
-def dist_token(dist: int) -> Tuple[int, int]:
-    i = max(k for k in range(30) if _DIST_BASE[k] <= dist)
-    return _rev(i, 5) | ((dist - _DIST_BASE[i]) << 5), 5 + _DIST_EXTRA[i]
+def dist_symbol(dist: int) -> int:
+    return max(k for k in range(30) if _DIST_BASE[k] <= dist)
+
+
+def dist_token(dist: int, code=None) -> Tuple[int, int]:
+    i = dist_symbol(dist)
+    v, nb = (_rev(i, 5), 5) if code is None else code.d[i]
+    return v | ((dist - _DIST_BASE[i]) << nb), nb + _DIST_EXTRA[i]
+
+
+def _freq_tables():
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "calcium_b200", "csrc", "enc_freq.inc")
+    text = open(path).read()
+    out = {}
+    for name in ("kFreqImgLL", "kFreqImgD", "kFreqMskLL", "kFreqMskD"):
+        body = re.search(r"%s\[\d+\] = \{(.*?)\};" % name, text, re.S).group(1)
+        out[name] = [int(x) for x in re.findall(r"\d+", body)]
+    return out
+
+
+def huffman_lengths(weights: List[int], maxlen: int) -> List[int]:
+    import heapq
+    f = list(weights)
+    n = len(f)
+    if n == 1:
+        return [1]
+    while True:
+        heap = [(w, i) for i, w in enumerate(f)]
+        heapq.heapify(heap)
+        parent = {}
+        nxt = n
+        while len(heap) > 1:
+            a = heapq.heappop(heap)
+            b = heapq.heappop(heap)
+            parent[a[1]] = parent[b[1]] = nxt
+            heapq.heappush(heap, (a[0] + b[0], nxt))
+            nxt += 1
+        lens = []
+        for i in range(n):
+            d, p = 0, i
+            while p in parent:
+                p = parent[p]
+                d += 1
+            lens.append(d)
+        if max(lens) <= maxlen:
+            return lens
+        f = [(w + 1) // 2 for w in f]
+
+
+def canonical(lens: List[int]) -> List[Tuple[int, int]]:
+    """(stream-order bits, count) per symbol from code lengths (RFC 1951 3.2.2)."""
+    count = [0] * 16
+    for ln in lens:
+        count[ln] += 1
+    count[0] = 0
+    code, nxt = 0, [0] * 16
+    for b in range(1, 16):
+        code = (code + count[b - 1]) << 1
+        nxt[b] = code
+    out = []
+    for ln in lens:
+        if ln:
+            out.append((_rev(nxt[ln], ln), ln))
+            nxt[ln] += 1
+        else:
+            out.append((0, 0))
+    return out
+
+
+class TunedCode:
+    """The static dynamic-Huffman code of one stream kind ('img' | 'msk') at a given left / up distance."""
+
+    def __init__(self, kind: str, dist_left: int, dist_up: int):
+        fr = _freq_tables()
+        ll_w = fr["kFreqImgLL" if kind == "img" else "kFreqMskLL"]
+        d2 = fr["kFreqImgD" if kind == "img" else "kFreqMskD"]
+        d_w = [1] * 30
+        d_w[dist_symbol(dist_left)] = d2[0]
+        if 1 <= dist_up <= 32768:
+            d_w[dist_symbol(dist_up)] = d2[1]
+        ll_len, d_len = huffman_lengths(ll_w, 15), huffman_lengths(d_w, 15)
+        self.ll, self.d = canonical(ll_len), canonical(d_len)
+        # block header: BFINAL=1, BTYPE=10, HLIT, HDIST, HCLEN, code-length code, the 316 lengths
+        hdr: List[Tuple[int, int]] = [(1, 1), (2, 2), (286 - 257, 5), (30 - 1, 5), (19 - 4, 4)]
+        every = ll_len + d_len
+        used = sorted(set(every))
+        weights = [every.count(v) for v in used]
+        if len(used) == 1:
+            used = sorted(used + [1 if used[0] == 0 else 0])
+            weights = [every.count(v) or 1 for v in used]
+        ul = huffman_lengths(weights, 7)
+        cl_len = [0] * 19
+        for v, ln in zip(used, ul):
+            cl_len[v] = ln
+        cl = canonical(cl_len)
+        for k in (16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15):
+            hdr.append((cl_len[k], 3))
+        hdr += [cl[v] for v in every]
+        self.header = hdr
 
 
 def _pack(tokens: List[Tuple[int, int]]) -> bytes:
@@ -71,7 +178,8 @@ def _pack(tokens: List[Tuple[int, int]]) -> bytes:
     return np.packbits(bits[keep], bitorder="little").tobytes()
 
 
-def deflate_rows(keys: np.ndarray, pixel_bytes, bpp: int, row_lead: int, head: bytes = b"") -> bytes:
+def deflate_rows(keys: np.ndarray, pixel_bytes, bpp: int, row_lead: int, head: bytes = b"", kind: str = "img",
+                 huffman: str = "tuned") -> bytes:
     """Raw DEFLATE stream of ``head`` + rows of pixels.  ``keys`` (H, W) integers identify pixel
     values; ``pixel_bytes(key)`` gives the ``bpp`` bytes of a pixel; every row is preceded by
     ``row_lead`` zero bytes (the PNG filter byte)."""
@@ -79,10 +187,11 @@ def deflate_rows(keys: np.ndarray, pixel_bytes, bpp: int, row_lead: int, head: b
     maxpix = 256 // bpp
     up_dist = row_lead + bpp * W
     use_up = up_dist <= 32768
-    lit = [fixed_symbol(b) for b in range(256)]
-    tok: List[Tuple[int, int]] = [(3, 3)]                      # BFINAL=1, BTYPE=01
+    code = TunedCode(kind, bpp, up_dist) if huffman == "tuned" else None
+    lit = [fixed_symbol(b) if code is None else code.ll[b] for b in range(256)]
+    tok: List[Tuple[int, int]] = [(3, 3)] if code is None else list(code.header)   # fixed: BFINAL=1, BTYPE=01
     tok += [lit[b] for b in head]
-    d_left, d_up = dist_token(bpp), (dist_token(up_dist) if use_up else (0, 0))
+    d_left, d_up = dist_token(bpp, code), (dist_token(up_dist, code) if use_up else (0, 0))
 
     def literal_pixel(key):
         v, nb = 0, 0
@@ -114,13 +223,13 @@ def deflate_rows(keys: np.ndarray, pixel_bytes, bpp: int, row_lead: int, head: b
                 ln = int(e - s)
                 md = int(m[s])
                 if md != 0 and ln * bpp >= 3:
-                    lv, lnb = length_token(ln * bpp)
+                    lv, lnb = length_token(ln * bpp, code)
                     dv, dnb = d_up if md == 2 else d_left
                     tok.append((lv | (dv << lnb), lnb + dnb))
                 else:
                     assert ln == 1
                     tok.append(literal_pixel(row[x0 + s]))
-    tok.append(fixed_symbol(256))                               # end of block
+    tok.append(fixed_symbol(256) if code is None else code.ll[256])   # end of block
     return _pack(tok)
 
 
@@ -140,7 +249,7 @@ def png_scanlines(image: np.ndarray) -> bytes:
     return raw.tobytes()
 
 
-def encode_png(image: np.ndarray) -> bytes:
+def encode_png(image: np.ndarray, huffman: str = "tuned") -> bytes:
     """The .png K3 writes for ``image`` = Pouch.generate_image's (H, W, 2) uint8 array."""
     h, w, _ = image.shape
     keys = image[..., 0].astype(np.int64) | ((image[..., 1] != 0).astype(np.int64) << 8)
@@ -149,7 +258,7 @@ def encode_png(image: np.ndarray) -> bytes:
         g, a = key & 255, 255 if key >> 8 else 0
         return [g >> 6, (g << 2) & 255, a, a]
 
-    z = b"\x78\x01" + deflate_rows(keys, pixel_bytes, 4, 1) + struct.pack(">I", zlib.adler32(png_scanlines(image)))
+    z = b"\x78\x01" + deflate_rows(keys, pixel_bytes, 4, 1, kind="img", huffman=huffman) + struct.pack(">I", zlib.adler32(png_scanlines(image)))
     return (b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 16, 4, 0, 0, 0))
             + _png_chunk(b"IDAT", z) + _png_chunk(b"IEND", b""))
 
@@ -163,13 +272,13 @@ def npy_bytes(mask: np.ndarray) -> bytes:
     return b"\x93NUMPY\x01\x00" + struct.pack("<H", len(hdr)) + hdr.encode("latin1") + mask.astype("<u2").tobytes()
 
 
-def encode_npz(mask: np.ndarray) -> bytes:
+def encode_npz(mask: np.ndarray, huffman: str = "tuned") -> bytes:
     """The .npz K3 writes for an instance mask: a zip archive with the single deflated member
     ``mask.npy`` (what np.savez_compressed(path, mask=mask) stores)."""
     h, w = mask.shape
     raw = npy_bytes(mask)
     head = raw[: len(raw) - 2 * h * w]
-    comp = deflate_rows(mask.astype(np.int64), lambda k: [k & 255, k >> 8], 2, 0, head=head)
+    comp = deflate_rows(mask.astype(np.int64), lambda k: [k & 255, k >> 8], 2, 0, head=head, kind="msk", huffman=huffman)
     crc = zlib.crc32(raw) & 0xFFFFFFFF
     name = b"mask.npy"
     local = struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0, 8, 0, 0x21, crc, len(comp), len(raw), len(name), 0) + name

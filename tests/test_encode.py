@@ -14,31 +14,41 @@ import zlib
 import numpy as np
 import pytest
 
-TAB_WORDS = 256 + 260 + 256 + 32 + 2048 + 128
+import ctypes
 
 
-def _tables(lib, L, H, W):
-    nb = int(lib.cab200_encode_tables_bytes())
-    host = np.zeros(nb, dtype=np.uint8)
-    L.check(lib.cab200_encode_tables(H, W, host.ctypes.data), "cab200_encode_tables")
-    u32 = host[: 4 * TAB_WORDS].view(np.uint32)
-    t = dict(lit=u32[:256], len=u32[256:516], crc=u32[516:772], pow8=u32[772:804], rowshift=u32[804:804 + 2048],
-             colshift=u32[804 + 2048:TAB_WORDS])
-    streams = []
-    base = 4 * TAB_WORDS
-    for _ in range(2):
-        blob = host[base:base + 804]
-        ints = blob[736:].view(np.int32)
-        names = ["head_bits", "prefix_len", "suffix_len", "head_len", "dist_left", "dist_up", "bpp", "seg_lanes", "row_lead",
-                 "crc_const", "raw_len", "p_len_prefix", "p_crc_prefix", "p_csize_prefix", "p_crc_suffix",
-                 "p_csize_suffix", "p_cdoff_suffix"]
-        d = {n: int(v) for n, v in zip(names, ints)}
-        d["prefix"] = bytes(blob[:64][: d["prefix_len"]])
-        d["suffix"] = bytes(blob[64:160][: d["suffix_len"]])
-        d["head"] = bytes(blob[160:352][: d["head_len"]])
-        streams.append(d)
-        base += 804
-    t["img"], t["msk"] = streams
+class _EncStream(ctypes.Structure):        # mirror of csrc/encode.cu: struct EncStream
+    _fields_ = [("lit", ctypes.c_uint32 * 256), ("len", ctypes.c_uint32 * 260), ("hdr", ctypes.c_uint32 * 96),
+                ("hdr_bits", ctypes.c_int), ("eob", ctypes.c_uint32),
+                ("prefix", ctypes.c_uint8 * 64), ("suffix", ctypes.c_uint8 * 96), ("head", ctypes.c_uint8 * 192),
+                ("head_off", ctypes.c_uint16 * 192), ("head_bits", ctypes.c_int),
+                ("prefix_len", ctypes.c_int), ("suffix_len", ctypes.c_int), ("head_len", ctypes.c_int),
+                ("dist_left", ctypes.c_uint32), ("dist_up", ctypes.c_uint32), ("bpp", ctypes.c_int),
+                ("seg_lanes", ctypes.c_int), ("row_lead", ctypes.c_int), ("crc_const", ctypes.c_uint32),
+                ("raw_len", ctypes.c_uint32), ("p_len_prefix", ctypes.c_int), ("p_crc_prefix", ctypes.c_int),
+                ("p_csize_prefix", ctypes.c_int), ("p_crc_suffix", ctypes.c_int), ("p_csize_suffix", ctypes.c_int),
+                ("p_cdoff_suffix", ctypes.c_int)]
+
+
+class _EncTables(ctypes.Structure):        # struct EncTables
+    _fields_ = [("crc", ctypes.c_uint32 * 256), ("pow8", ctypes.c_uint32 * 32), ("rowshift", ctypes.c_uint32 * 2048),
+                ("colshift", ctypes.c_uint32 * 128), ("img", _EncStream), ("msk", _EncStream),
+                ("H", ctypes.c_int), ("W", ctypes.c_int)]
+
+
+def _tables(lib, L, H, W, huffman=1):
+    assert int(lib.cab200_encode_tables_bytes()) == ctypes.sizeof(_EncTables)
+    raw = _EncTables()
+    L.check(lib.cab200_encode_tables(H, W, huffman, ctypes.addressof(raw)), "cab200_encode_tables")
+    t = dict(crc=np.array(raw.crc), pow8=np.array(raw.pow8), rowshift=np.array(raw.rowshift), colshift=np.array(raw.colshift))
+    for name in ("img", "msk"):
+        st = getattr(raw, name)
+        d = {k: getattr(st, k) for k, _ in _EncStream._fields_ if not hasattr(getattr(st, k), "__len__")}
+        d["lit"], d["len"], d["hdr"] = np.array(st.lit), np.array(st.len), np.array(st.hdr)
+        d["prefix"] = bytes(st.prefix)[: st.prefix_len]
+        d["suffix"] = bytes(st.suffix)[: st.suffix_len]
+        d["head"] = bytes(st.head)[: st.head_len]
+        t[name] = d
     return t
 
 
@@ -101,18 +111,29 @@ def test_host_tables_match_the_oracle_and_zlib():
     build.build()
     lib = L.load()
     H, W = 96, 200
-    t = _tables(lib, L, H, W)
+    for huffman, hname in ((0, "fixed"), (1, "tuned")):
+        t = _tables(lib, L, H, W, huffman)
+        for name, bpp, up in (("img", 4, 1 + 4 * W), ("msk", 2, 2 * W)):
+            code = EO.TunedCode(name, bpp, up) if hname == "tuned" else None
+            for b in range(256):
+                v, n = EO.fixed_symbol(b) if code is None else code.ll[b]
+                assert t[name]["lit"][b] == (v | n << 24)
+            for ln in range(3, 259):
+                v, n = EO.length_token(ln, code)
+                assert t[name]["len"][ln] == (v | n << 24)
+            for key, d in (("dist_left", bpp), ("dist_up", up)):
+                v, n = EO.dist_token(d, code)
+                assert (t[name][key] & 0xFFFFFFFF) == (v | n << 24)
+            v, n = EO.fixed_symbol(256) if code is None else code.ll[256]
+            assert t[name]["eob"] == (v | n << 24)
+            hdr = [(3, 3)] if code is None else code.header
+            packed = EO._pack(hdr)
+            want = np.frombuffer(packed + bytes(8 - len(packed) % 4), dtype="<u4")
+            nbits = sum(nb for _, nb in hdr)
+            assert t[name]["hdr_bits"] == nbits
+            assert np.array_equal(t[name]["hdr"][: (nbits + 31) // 32], want[: (nbits + 31) // 32])
     for b in range(256):
-        v, n = EO.fixed_symbol(b)
-        assert t["lit"][b] == (v | n << 24)
         assert t["crc"][b] == _crc0_slow(bytes([b]), 0)
-    for ln in range(3, 259):
-        v, n = EO.length_token(ln)
-        assert t["len"][ln] == (v | n << 24)
-    for name, dist in (("img", (4, 1 + 4 * W)), ("msk", (2, 2 * W))):
-        for key, d in zip(("dist_left", "dist_up"), dist):
-            v, n = EO.dist_token(d)
-            assert (t[name][key] & 0xFFFFFFFF) == (v | n << 24)
     # x^(8*2^k), and CRC(zeros(n)) = (0xFFFFFFFF * x^(8n)) ^ 0xFFFFFFFF
     x = 0x00800000
     for k in range(20):
@@ -159,10 +180,11 @@ def env(cuda_device, oracle):
     return dict(dev=cuda_device, O=oracle, EO=encode_oracle, lib=_lib.load(), L=_lib, E=ensemble, torch=torch)
 
 
-def _run(env, size, count, out, T=4000, every=400, **kw):
+def _run(env, size, count, out, T=4000, every=400, huffman="tuned", **kw):
     E = env["E"]
     specs = E.make_specs(count, size=size, first_seed=40)
-    ens = E.Ensemble(specs, T=T, frame_steps=list(range(0, T, every)), output_size=out, device=env["dev"])
+    ens = E.Ensemble(specs, T=T, frame_steps=list(range(0, T, every)), output_size=out, device=env["dev"],
+                     huffman=huffman)
     ens.simulate()
     raw = ens.rasterize(image=True, instance=True)
     enc = ens.encode(**kw)
@@ -212,6 +234,25 @@ def test_k3_files_decode_to_k2_arrays_and_match_oracle_bytes(env, size, count, o
 
 
 @pytest.mark.gpu
+def test_k3_fixed_huffman_mode(env):
+    """huffman="fixed": one fixed-Huffman block (RFC 1951 3.2.6) instead of the static tuned code; same content."""
+    EO = env["EO"]
+    ens, raw, enc, arena, off, size_, flags = _run(env, "small", 2, (256, 256), huffman="fixed")
+    image = raw["image"].cpu().numpy()
+    inst = raw["instance"].cpu().numpy().view(np.uint16)
+    tuned_bytes = _run(env, "small", 2, (256, 256))[5].sum()
+    assert size_.sum() > 1.2 * tuned_bytes                      # the tuned code is what makes the files small
+    for i in range(2):
+        for f in (1, 5, 9):
+            png = arena[off[i, f, 0]: off[i, f, 0] + size_[i, f, 0]].tobytes()
+            assert png == EO.encode_png(image[i, f], huffman="fixed")
+            if size_[i, f, 1]:
+                npz = arena[off[i, f, 1]: off[i, f, 1] + size_[i, f, 1]].tobytes()
+                assert npz == EO.encode_npz(inst[i, f], huffman="fixed")
+                assert np.array_equal(np.load(io.BytesIO(npz))["mask"], inst[i, f])
+
+
+@pytest.mark.gpu
 def test_k3_png_is_readable_by_opencv(env):
     cv2 = pytest.importorskip("cv2")
     ens, raw, enc, arena, off, size_, flags = _run(env, "small", 1, (256, 256))
@@ -228,7 +269,9 @@ def test_k3_png_is_readable_by_opencv(env):
 def test_k3_flags_frames_that_do_not_fit_the_staging_buffer(env):
     L = env["L"]
     ens, raw, enc, arena, off, size_, flags = _run(env, "small", 1, (256, 256), stage_bytes=4096)
-    assert (flags[..., 0] == L.ENC_STAGE_FULL).all() and (size_[..., 0] == 0).all()
+    full = flags[..., 0] == L.ENC_STAGE_FULL
+    assert full.any() and (size_[..., 0][full] == 0).all()
+    assert ((flags[..., 0] == L.ENC_OK) | full).all()          # the nearly empty first frames still fit
     with pytest.raises(L.Cab200Error):
         e2 = ens.encode(arena_bytes=4096)
         ens.encoded_files(e2)
@@ -293,8 +336,11 @@ def test_files_pipeline_delivers_every_frame_to_the_host(env, stage_bytes, wait)
             assert b is None
         else:
             assert np.array_equal(np.load(io.BytesIO(b))["mask"], inst[i, f])
-    frames_host = ens._fring["h_frames"].numpy()
-    assert np.array_equal(frames_host, ens.frames.cpu().numpy())
+    ca_host = ens._fring["h_frames"].numpy()            # default frames="ca": the calcium state [P, F, n]
+    dev_frames = ens.frames.cpu().numpy().reshape(ens.P, ens.F, 4, -1)
+    assert np.array_equal(ca_host, dev_frames[:, :, 0, :])
+    ens.run_files_to_host(chunk_pouches=5, frames="all")
+    assert np.array_equal(ens._fring["h_frames"].numpy(), ens.frames.cpu().numpy())
 
 
 @pytest.mark.gpu

@@ -57,7 +57,7 @@ def test_argument_validation_needs_no_gpu(lib):
                               _lib.as_i32p(z32), None, None, 64, None, 0, None, 0, None)
     assert rc == -1 and b"bad sizes" in lib.cab200_last_error()
     # K3's argument checks and host-side table builder need no GPU either
-    assert lib.cab200_encode_tables(4096, 64, None) == -1 and b"[1, 2048]" in lib.cab200_last_error()
+    assert lib.cab200_encode_tables(4096, 64, 1, None) == -1 and b"[1, 2048]" in lib.cab200_last_error()
     rc = lib.cab200_encode_batch(1, _lib.as_i32p(z32), 1, _lib.as_i32p(z32), _lib.as_i64p(z64), None, None, 64, 64, 3,
                                  None, 0.1, 1, 1, 1, None, None, _lib.as_i64p(z64), None, None, 0, None, None, None, 0,
                                  None, 0, None)
