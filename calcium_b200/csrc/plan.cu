@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <numeric>
 #include <queue>
 #include <vector>
@@ -183,7 +184,9 @@ long long anneal(Problem &P, long long iters, uint64_t seed, long long *cost0_ou
     if (cost0_out) *cost0_out = cost;
     Rng rng{seed ? seed : 0x5EEDull};
     std::vector<int> touched;
-    const double t_start = 0.8, t_end = 0.02;
+    // CALCIUM_B200_PLAN_T0: start temperature (default 0.8); a low value polishes an existing plan (use_input)
+    const char *t0_env = getenv("CALCIUM_B200_PLAN_T0");
+    const double t_start = (t0_env && atof(t0_env) > 0.0) ? atof(t0_env) : 0.8, t_end = 0.02;
     for (long long it = 0; it < iters; ++it) {
         const int sa = (int)(rng.next() % (uint64_t)n);
         const std::vector<int> &cls = class_slots[class_of[sa]];

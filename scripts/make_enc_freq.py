@@ -1,7 +1,7 @@
 """Offline: measures the symbol frequencies of K3's token streams on sample frames (oracle parse) and writes
 calcium_b200/csrc/enc_freq.inc, the data the static Huffman codes are built from."""
-import sys, heapq, collections
-sys.path.insert(0, "/root/repo")
+import os, sys, heapq, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from oracle import pouch_oracle as O, encode_oracle as EO
 from calcium_b200.ensemble import make_specs, DEFAULT_FRAME_STEPS
@@ -69,7 +69,7 @@ out = []
 for name, cnt, n in (("kFreqImgLL", LLi, 286), ("kFreqImgD", DSi, 30), ("kFreqMskLL", LLm, 286), ("kFreqMskD", DSm, 30)):
     t = table(cnt, n)
     out.append(f"static const uint32_t {name}[{n}] = {{\n" + "\n".join("    " + ", ".join(str(v) for v in t[i:i+16]) + "," for i in range(0, n, 16)) + "\n};\n")
-open("/root/repo/calcium_b200/csrc/enc_freq.inc", "w").write(
+open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "calcium_b200", "csrc", "enc_freq.inc"), "w").write(
 "// enc_freq.inc -- symbol frequencies K3's static Huffman codes are built from (DEFLATE literal/length and\n"
 "// distance alphabets, image and mask stream), measured on 32 frames of medium pouches of the four sim\n"
 "// types with the token parse of encode.cu, scaled to a maximum of 65536 with a floor of 1 (every symbol\n"
