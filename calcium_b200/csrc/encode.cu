@@ -166,7 +166,7 @@ struct GeomTab {
 constexpr int ENC_ECAP = 256;
 __host__ __device__ inline size_t geom_tab_sums_bytes(int n) { return ((((size_t)(n + 1) * 8 + 7) & ~(size_t)7) + (size_t)(n + 1) * 8 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t geom_tab_events_bytes(int H, int W) { return (size_t)H * ((W + 511) / 512) * ENC_ECAP * sizeof(uint2); }
-__host__ __device__ inline size_t geom_tab_bytes(int n, int H, int W) { return geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W); }
+__host__ __device__ inline size_t geom_tab_bytes(int n, int H, int W) { return geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16; }   // + two event counters
 __device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n, int H, int W)
 {
     GeomTab t;
@@ -1140,9 +1140,8 @@ extern "C" int cab200_encode_geometry(int n_cells, const uint16_t *label_img, co
     enc_geometry_kernel<<<148 * 4, 256, sizeof(uint32_t) * (size_t)W, stream>>>(
         label_img, label_mask, H, W, n_cells, (const EncTables *)tables, out);
     CAB_CUDA(cudaGetLastError());
-    // static event lists; the first 4 bytes of each list double as its max counter until it is written
-    int *d_max = nullptr;
-    CAB_CUDA(cudaMallocAsync((void **)&d_max, 2 * sizeof(int), stream));
+    // static event lists; the two counters (largest event count of a segment) live at the end of the block
+    int *d_max = (int *)(out + geom_tab_sums_bytes(n_cells) + 2 * geom_tab_events_bytes(H, W));
     CAB_CUDA(cudaMemsetAsync(d_max, 0, 2 * sizeof(int), stream));
     const int items = H * ((W + 511) / 512);
     const bool up_img = 1 + 4 * W <= 32768, up_msk = 2 * W <= 32768;     // the distances DEFLATE can express
@@ -1154,7 +1153,6 @@ extern "C" int cab200_encode_geometry(int n_cells, const uint16_t *label_img, co
     int h_max[2] = {0, 0};
     CAB_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
     CAB_CUDA(cudaStreamSynchronize(stream));
-    CAB_CUDA(cudaFreeAsync(d_max, stream));
     *max_events_out = std::max(h_max[0], h_max[1]);
     return CAB200_OK;
 }

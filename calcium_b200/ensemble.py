@@ -121,12 +121,23 @@ class _DeviceGeometry:
             self.plans[(precision, n_cta)] = t
         return t
 
-    def auto_cluster(self) -> int:
-        """CTAs per pouch when the caller leaves the choice to the library: one CTA up to 1536 cells
-        (what a 512-thread CTA holds without spilling), else a cluster of 2 or 4."""
-        if not self.unit or self.n <= 1536:
+    def auto_cluster(self, count: int = 1 << 30, n_sm: int = 148) -> int:
+        """CTAs per pouch when the caller leaves the choice to the library.  Above 1536 cells (what a
+        512-thread CTA holds without spilling) always a cluster of 4.  Medium-sized pouches (> 1024
+        cells) take one CTA each when there are enough of them to fill the machine, and a cluster of 2
+        or 4 when fewer than half / a quarter of the SMs would otherwise be busy -- a lone medium pouch
+        finishes in 13 ms instead of 25.  Smaller pouches are latency bound per step (a cluster's halo
+        exchange would only add to that) and stay on one CTA."""
+        if not self.unit:
             return 1
-        return 2 if self.n <= 3072 else 4
+        if self.n > 1536:
+            return 4
+        if self.n > 1024:
+            if 4 * count <= n_sm:
+                return 4
+            if 2 * count <= n_sm:
+                return 2
+        return 1
 
 
 PLAN_ITERS = int(os.environ.get("CALCIUM_B200_PLAN_ITERS", "300000"))
@@ -328,8 +339,11 @@ class Ensemble:
         self.cell_off = np.concatenate([[0], np.cumsum(ncell)]).astype(np.int64)
         self.total_cells = int(self.cell_off[-1])
         # CTAs per pouch: "auto" (one CTA up to 1536 cells, else a cluster), or 1 / 2 / 4 for all
-        self.g_cluster = np.array([d.auto_cluster() if cluster == "auto" else (int(cluster) if d.unit else 1)
-                                   for d in self.dgeo], dtype=np.int32)
+        n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        counts = np.bincount(gid, minlength=len(self.dgeo))
+        self.g_cluster = np.array([d.auto_cluster(int(counts[gi]), n_sm) if cluster == "auto"
+                                   else (int(cluster) if d.unit else 1)
+                                   for gi, d in enumerate(self.dgeo)], dtype=np.int32)
         self.use_plan = use_plan
         self.huffman = huffman                          # K3's DEFLATE code: "tuned" (static dynamic-Huffman block) | "fixed"
         self.coalesced_capture = coalesced_capture      # "auto" | True | False, see _alloc_frames_tmp

@@ -225,6 +225,18 @@ def test_lpt_partition():
     assert lpt_partition([5.0], 1) == [[0]]
 
 
+def test_auto_cluster_policy():
+    """CTAs per pouch under cluster="auto": large always 4; medium by how many there are; small 1."""
+    from types import SimpleNamespace as NS
+    from calcium_b200.ensemble import _DeviceGeometry as DG
+    pick = lambda n, count, unit=True: DG.auto_cluster(NS(unit=unit, n=n), count, 148)
+    assert pick(3255, 1) == 4 and pick(3255, 1000) == 4
+    assert pick(1500, 1) == 4 and pick(1500, 37) == 4 and pick(1500, 38) == 2
+    assert pick(1500, 74) == 2 and pick(1500, 75) == 1 and pick(1500, 148) == 1
+    assert pick(500, 1) == 1 and pick(200, 3) == 1
+    assert pick(3255, 1, unit=False) == 1          # general weights: single-CTA kernel only
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "calcium_b200")
     for dirpath, _, files in os.walk(pkg):
