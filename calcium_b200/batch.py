@@ -133,7 +133,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             image_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             mask_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             img = ins = nact = None
-            if steps and not keep_arrays:
+            if steps and not keep_arrays and not edge_blur:
                 # K1 -> K3: every frame arrives on the host as the finished .png / .npz byte string
                 # (cab200_encode_batch); writing a file is a plain write of those bytes.
                 def consumer(ch):
@@ -158,7 +158,10 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             else:
                 ens.simulate()
                 status = ens.check_status()
-                out = ens.rasterize(image=True, instance=bool(generate_masks)) if steps else {}
+                # edge_blur (main.py:281-287): K2b blends the blurred frame in along the cell outlines; these
+                # frames are not flat-shaded any more, so they take the raw-array path and the host PNG writer
+                out = ens.rasterize(image=True, instance=bool(generate_masks), edge_blur=bool(edge_blur),
+                                    blur_kernel_size=int(blur_kernel_size), blur_type=blur_type) if steps else {}
                 ens.synchronize()
                 img = out["image"].cpu().numpy() if steps else None
                 ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and generate_masks) else None

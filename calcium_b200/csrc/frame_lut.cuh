@@ -19,7 +19,7 @@ struct PouchEntry {
 };
 
 // bytes of dynamic shared memory the four tables take for n cells; offsets via frame_lut_carve
-static inline size_t frame_lut_bytes(int n)
+__host__ __device__ static inline size_t frame_lut_bytes(int n)
 {
     return 2 * (size_t)((n + 2 + 7) & ~7) * 2 + 2 * (size_t)((n + 2 + 15) & ~15);
 }

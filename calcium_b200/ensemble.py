@@ -108,6 +108,7 @@ class _DeviceGeometry:
         self.col = torch.from_numpy(col).to(device)
         self.val = torch.from_numpy(val).to(device)
         self.label_maps: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.edge_maps: Dict[Tuple[int, int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.plans: Dict[Tuple[int, int], torch.Tensor] = {}
 
     def plan(self, precision: int, n_cta: int = 1) -> torch.Tensor:
@@ -273,6 +274,50 @@ def build_label_maps(geo: Geometry, output_size: Tuple[int, int], device: torch.
     return dg.label_maps[key]
 
 
+def edge_mode(with_border: bool, edge_blur: bool) -> int:
+    """K2b mode for ``generate_image``'s optional branches (reference ``core/pouch.py:458-481``); 0 = default."""
+    if edge_blur:
+        return _lib.EDGE_BLUR_BORDER if with_border else _lib.EDGE_BLUR
+    return _lib.EDGE_BORDER if with_border else 0
+
+
+def blur_code(blur_type: str) -> int:
+    """'motion' or -- like the reference's ``_create_blur_kernel`` (``:494-513``) -- mean for anything else."""
+    return _lib.BLUR_MOTION if blur_type == "motion" else _lib.BLUR_MEAN
+
+
+def build_edge_maps(geo: Geometry, output_size: Tuple[int, int], device: torch.device,
+                    blur_kernel_size: int = 3, blur_type: str = "mean"
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The three static uint8 maps of ``generate_image``'s edge branches for one (geometry, output size,
+    blur kernel), built on ``device`` by K0c (``cab200_edge_maps``): ``edges`` = the reference's
+    ``edges_mask`` (every cell outlined with ``cv2.polylines``, ``core/pouch.py:455-456``), ``dilated`` =
+    ``cv2.dilate(cv2.filter2D(edges_mask, -1, kernel), ones((3, 3)))`` (``:459-461``), whose /255 is the
+    blend weight, and ``alpha`` = channel 1 of the blended image (frame independent)."""
+    dg = device_geometry(geo, device)
+    ks, bt = int(blur_kernel_size), blur_code(blur_type)
+    key = (int(output_size[0]), int(output_size[1]), ks, bt)
+    if key in dg.edge_maps:
+        return dg.edge_maps[key]
+    width, height = key[:2]
+    offs, pts = geo.scaled_polygons(key[:2])
+    lib = _lib.load()
+    d_offs = torch.from_numpy(offs).to(device)
+    d_pts = torch.from_numpy(pts).to(device)
+    limg, _ = build_label_maps(geo, key[:2], device)
+    edges = torch.empty((height, width), dtype=torch.uint8, device=device)
+    dilated = torch.empty((height, width), dtype=torch.uint8, device=device)
+    alpha = torch.empty((height, width), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.cab200_edge_maps(geo.n_cells, d_offs.data_ptr(), d_pts.data_ptr(), limg.data_ptr(), height, width,
+                                        ks, bt, edges.data_ptr(), dilated.data_ptr(), alpha.data_ptr(),
+                                        _stream_ptr(device)),
+                   "cab200_edge_maps")
+        torch.cuda.current_stream(device).synchronize()
+    dg.edge_maps[key] = (edges, dilated, alpha)
+    return dg.edge_maps[key]
+
+
 def _u16_numpy(t: torch.Tensor) -> np.ndarray:
     return t.cpu().numpy().view(np.uint16)
 
@@ -385,6 +430,7 @@ class Ensemble:
                 + self.lib.cab200_encode_scratch_bytes(self.P, len(self.dgeo))) + 96,
             dtype=torch.uint8, device=self.device)
         self._label_img: Optional[torch.Tensor] = None
+        self._edge_maps: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
         self._label_mask: Optional[torch.Tensor] = None
         self._enc_tables: Optional[torch.Tensor] = None
         self._enc_geom: Optional[Tuple[torch.Tensor, np.ndarray, np.ndarray]] = None
@@ -493,13 +539,25 @@ class Ensemble:
         c = self.P if count is None else count
         return c * self.F * h * w * (2 * bool(image) + 2 * bool(instance) + 4 * bool(active))
 
+    def edge_maps(self, blur_kernel_size: int = 3, blur_type: str = "mean"
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Per-geometry stacks ``[G][H][W]`` u8 of the static outline, blend-weight and alpha maps (K0c)."""
+        key = (int(blur_kernel_size), blur_code(blur_type))
+        if key not in self._edge_maps:
+            maps = [build_edge_maps(g, self.output_size, self.device, key[0], blur_type) for g in self.geometries]
+            self._edge_maps[key] = tuple(torch.stack([m[k] for m in maps]).contiguous() for k in range(3))
+        return self._edge_maps[key]
+
     def rasterize(self, image: bool = True, instance: bool = True, active: bool = False,
                   pouches: Optional[Tuple[int, int]] = None, threshold: float = 0.1,
-                  quirk: bool = True, out: Optional[Dict[str, torch.Tensor]] = None
-                  ) -> Dict[str, torch.Tensor]:
+                  quirk: bool = True, out: Optional[Dict[str, torch.Tensor]] = None,
+                  with_border: bool = False, edge_blur: bool = False, blur_kernel_size: int = 3,
+                  blur_type: str = "mean") -> Dict[str, torch.Tensor]:
         """K2 over pouches ``[a, b)`` (default all).  Returns device tensors
         ``image [p,F,H,W,2] u8``, ``instance [p,F,H,W] i16 (bit pattern of uint16)``,
-        ``active [p,F,H,W] i32``, ``n_active [p,F] i32``.  ``out`` may hold preallocated tensors."""
+        ``active [p,F,H,W] i32``, ``n_active [p,F] i32``.  ``out`` may hold preallocated tensors.
+        With ``edge_blur`` / ``with_border`` (``generate_image``'s optional branches, reference
+        ``core/pouch.py:458-481``) the image comes from K2b (``cab200_raster_edges_batch``) instead."""
         if self.frames is None:
             raise RuntimeError("simulate() first")
         if self.precision != _lib.FP64_STRICT:
@@ -524,16 +582,27 @@ class Ensemble:
             coff = np.ascontiguousarray(self.cell_off[a:b + 1])
             sim_scr = int(self.lib.cab200_sim_scratch_bytes(self.P, self.F))
             sim_scr = (sim_scr + 15) // 16 * 16
+            mode = edge_mode(with_border, edge_blur) if image else 0
             rc = self.lib.cab200_raster_batch(
                 cnt, _lib.as_i32p(gid), _lib.as_i32p(self.g_ncell), _lib.as_i64p(coff),
                 limg.data_ptr(), lmsk.data_ptr(), h, w, self.F, self.frames.data_ptr(),
                 float(threshold), 1 if quirk else 0,
-                img.data_ptr() if img is not None else None,
+                img.data_ptr() if (img is not None and not mode) else None,
                 act.data_ptr() if act is not None else None,
                 ins.data_ptr() if ins is not None else None,
                 nact.data_ptr(), self._scratch.data_ptr() + sim_scr,
                 self.lib.cab200_raster_scratch_bytes(cnt), _stream_ptr(self.device))
             _lib.check(rc, "cab200_raster_batch")
+            if mode:
+                edges, dilated, alpha = self.edge_maps(blur_kernel_size, blur_type)
+                rc = self.lib.cab200_raster_edges_batch(
+                    cnt, _lib.as_i32p(gid), _lib.as_i32p(self.g_ncell), _lib.as_i64p(coff),
+                    limg.data_ptr(), edges.data_ptr(), dilated.data_ptr(), alpha.data_ptr(), h, w, self.F,
+                    self.frames.data_ptr(),
+                    mode, int(blur_kernel_size), blur_code(blur_type), img.data_ptr(),
+                    self._scratch.data_ptr() + sim_scr, self.lib.cab200_raster_scratch_bytes(cnt),
+                    _stream_ptr(self.device))
+                _lib.check(rc, "cab200_raster_edges_batch")
         return res
 
     # -- K3 ------------------------------------------------------------------------------------

@@ -234,39 +234,47 @@ class Pouch:
 
     # ---- images and masks ------------------------------------------------------------------------
     def _raster(self, time_step: int, threshold: float, image: bool, instance: bool, active: bool,
-                quirk: bool = True) -> Dict[str, np.ndarray]:
+                quirk: bool = True, **edge) -> Dict[str, np.ndarray]:
         self._ensure_steps([time_step])
         ens = self._ens
         fi = ens.frame_index(time_step)
         # one frame: rasterise through a 1-frame view of the ensemble
         sub = _SingleFrame(ens, fi)
         return sub.rasterize(image=image, instance=instance, active=active, threshold=threshold,
-                             quirk=quirk)
+                             quirk=quirk, **edge)
 
     def generate_image(self, time_step: int, output_path: Optional[str] = None,
                        with_border: bool = False, colormap: str = "gray", edge_blur: bool = False,
                        blur_kernel_size: int = 3, blur_type: str = "mean") -> np.ndarray:
         """(H, W, 2) uint8 gray + alpha image of step ``time_step`` (reference
-        ``core/pouch.py:374-492``).  The default branch is computed on the GPU (K2); the optional
-        ``edge_blur`` / ``with_border`` branches post-process that image on the host with the same
-        OpenCV calls the reference makes (``:456-481``)."""
+        ``core/pouch.py:374-492``).  The default branch is K2 (``cab200_raster_batch``); the optional
+        ``edge_blur`` / ``with_border`` branches (``:456-481``) are K2b (``cab200_raster_edges_batch``)
+        over the static outline / blend-weight maps of K0c."""
         if time_step < 0 or time_step >= self.T:
             raise ValueError(f"Time step must be between 0 and {self.T-1}, got {time_step}")
         try:
+            edge = dict(with_border=bool(with_border), edge_blur=bool(edge_blur),
+                        blur_kernel_size=int(blur_kernel_size), blur_type=blur_type)
             if not self._simulated:
-                img = self._blank_image()
+                img = self._blank_image(**edge)
             else:
-                img = self._raster(time_step, 0.1, True, False, False)["image"]
-            if with_border or edge_blur:
-                img = self._edge_effects(img, with_border, edge_blur, blur_kernel_size, blur_type)
+                img = self._raster(time_step, 0.1, True, False, False, **edge)["image"]
             if output_path is not None:
                 self._save_image(img, output_path)
             return img
         except Exception as e:  # noqa: BLE001 - same wrapping as the reference (:491-492)
             raise RuntimeError(f"Error generating image: {str(e)}")
 
-    def _blank_image(self) -> np.ndarray:
-        limg, _ = build_label_maps(self._geometry, self.output_size, self._dev())
+    def _blank_image(self, with_border=False, edge_blur=False, blur_kernel_size=3, blur_type="mean") -> np.ndarray:
+        """``generate_image`` before ``simulate()``: the reference's ``disc_dynamics`` is all zeros then, so
+        every cell is painted gray 0 / alpha 255; the edge branches go through K2b on a zero frame."""
+        dev = self._dev()
+        if with_border or edge_blur:
+            return _raster_one(self._geometry, self.output_size, dev, torch.zeros((4, self.n_cells), dtype=torch.float64,
+                                                                                  device=dev),
+                               0.1, True, True, False, False, with_border, edge_blur, blur_kernel_size,
+                               blur_type)["image"]
+        limg, _ = build_label_maps(self._geometry, self.output_size, dev)
         alpha = (_u16_numpy(limg) > 0).astype(np.uint8) * 255
         return np.stack([np.zeros_like(alpha), alpha], axis=-1)
 
@@ -276,33 +284,6 @@ class Pouch:
             k[size // 2, :] = 1.0 / size
             return k
         return np.ones((size, size), np.float32) / (size * size)
-
-    def _edge_effects(self, img, with_border, edge_blur, blur_kernel_size, blur_type) -> np.ndarray:
-        import cv2
-        width, height = self.output_size
-        offs, pts = self._geometry.scaled_polygons(self.output_size)
-        polys = [pts[offs[i]:offs[i + 1]].reshape((-1, 1, 2)) for i in range(self.n_cells)]
-        edges = np.zeros((height, width), dtype=np.uint8)
-        for poly in polys:
-            cv2.polylines(edges, [poly], True, 255, 1)
-        img = img.copy()
-        if edge_blur:
-            kernel = self._create_blur_kernel(blur_kernel_size, blur_type)
-            blurred = cv2.filter2D(edges, -1, kernel)
-            dilated = cv2.dilate(blurred, np.ones((3, 3), np.uint8), iterations=1)
-            blend = dilated / 255.0
-            if not with_border:
-                img_blurred = cv2.filter2D(img, -1, kernel)
-                m2 = np.stack([blend, blend], axis=-1)
-                img = (img * (1 - m2) + img_blurred * m2).astype(np.uint8)
-            else:
-                img[:, :, 0] = np.where(edges > 0, img[:, :, 0] // 2, img[:, :, 0])
-        if with_border and not edge_blur:
-            gray = np.ascontiguousarray(img[:, :, 0])
-            for poly in polys:
-                cv2.polylines(gray, [poly], True, 0, 1)
-            img[:, :, 0] = gray
-        return img
 
     def _save_image(self, img: np.ndarray, output_path: str) -> None:
         from .io import save_gray_alpha_png
@@ -352,47 +333,63 @@ class Pouch:
                 f"  Sim ID: {self.sim_number}")
 
 
+def _raster_one(geometry, output_size, dev, frame: torch.Tensor, threshold: float, quirk: bool,
+                image: bool, instance: bool, active: bool, with_border: bool = False, edge_blur: bool = False,
+                blur_kernel_size: int = 3, blur_type: str = "mean") -> Dict[str, np.ndarray]:
+    """K2 (and K2b for the edge branches) over ONE frame ``frame`` = contiguous ``[4][n]`` float64 on ``dev``."""
+    from .ensemble import _stream_ptr, blur_code, build_edge_maps, edge_mode
+    lib = _lib.load()
+    w, h = output_size
+    limg, lmsk = build_label_maps(geometry, output_size, dev)
+    n = geometry.n_cells
+    out: Dict[str, np.ndarray] = {}
+    mode = edge_mode(with_border, edge_blur) if image else 0
+    with torch.cuda.device(dev):
+        img = torch.empty((h, w, 2), dtype=torch.uint8, device=dev) if image else None
+        ins = torch.empty((h, w), dtype=torch.int16, device=dev) if instance else None
+        act = torch.empty((h, w), dtype=torch.int32, device=dev) if active else None
+        nact = torch.empty(1, dtype=torch.int32, device=dev)
+        scr_bytes = int(lib.cab200_raster_scratch_bytes(1))
+        scratch = torch.empty(scr_bytes + 16, dtype=torch.uint8, device=dev)
+        gid = np.zeros(1, dtype=np.int32)
+        ncell = np.array([n], dtype=np.int32)
+        coff = np.array([0, n], dtype=np.int64)
+        rc = lib.cab200_raster_batch(
+            1, _lib.as_i32p(gid), _lib.as_i32p(ncell), _lib.as_i64p(coff),
+            limg.data_ptr(), lmsk.data_ptr(), h, w, 1, frame.data_ptr(), float(threshold),
+            1 if quirk else 0,
+            img.data_ptr() if (img is not None and not mode) else None,
+            act.data_ptr() if act is not None else None,
+            ins.data_ptr() if ins is not None else None,
+            nact.data_ptr(), scratch.data_ptr(), scr_bytes, _stream_ptr(dev))
+        _lib.check(rc, "cab200_raster_batch")
+        if mode:
+            edges, dilated, alpha = build_edge_maps(geometry, output_size, dev, blur_kernel_size, blur_type)
+            rc = lib.cab200_raster_edges_batch(
+                1, _lib.as_i32p(gid), _lib.as_i32p(ncell), _lib.as_i64p(coff),
+                limg.data_ptr(), edges.data_ptr(), dilated.data_ptr(), alpha.data_ptr(), h, w, 1, frame.data_ptr(),
+                mode, int(blur_kernel_size), blur_code(blur_type), img.data_ptr(),
+                scratch.data_ptr(), scr_bytes, _stream_ptr(dev))
+            _lib.check(rc, "cab200_raster_edges_batch")
+        if img is not None:
+            out["image"] = img.cpu().numpy()
+        if ins is not None:
+            out["instance"] = ins.cpu().numpy().view(np.uint16)
+        if act is not None:
+            out["active"] = act.cpu().numpy()
+        out["n_active"] = int(nact.cpu().item())
+    return out
+
+
 class _SingleFrame:
-    """Rasterises one captured frame of a 1-pouch ensemble (K2 with n_frames = 1)."""
+    """Rasterises one captured frame of a 1-pouch ensemble (K2 / K2b with n_frames = 1)."""
 
     def __init__(self, ens: Ensemble, fi: int):
         self.ens, self.fi = ens, fi
 
-    def rasterize(self, image: bool, instance: bool, active: bool, threshold: float, quirk: bool
-                  ) -> Dict[str, np.ndarray]:
+    def rasterize(self, image: bool, instance: bool, active: bool, threshold: float, quirk: bool,
+                  **edge) -> Dict[str, np.ndarray]:
         ens = self.ens
-        lib = ens.lib
-        w, h = ens.output_size
-        limg, lmsk = ens.label_maps()
-        n = int(ens.g_ncell[0])
-        dev = ens.device
-        # a contiguous [1][4][n] block for this frame
-        frame = ens.frames_of(0)[self.fi].contiguous()
-        out: Dict[str, np.ndarray] = {}
-        with torch.cuda.device(dev):
-            img = torch.empty((h, w, 2), dtype=torch.uint8, device=dev) if image else None
-            ins = torch.empty((h, w), dtype=torch.int16, device=dev) if instance else None
-            act = torch.empty((h, w), dtype=torch.int32, device=dev) if active else None
-            nact = torch.empty(1, dtype=torch.int32, device=dev)
-            scratch = torch.empty(int(lib.cab200_raster_scratch_bytes(1)) + 16, dtype=torch.uint8, device=dev)
-            gid = np.zeros(1, dtype=np.int32)
-            coff = np.array([0, n], dtype=np.int64)
-            from .ensemble import _stream_ptr
-            rc = lib.cab200_raster_batch(
-                1, _lib.as_i32p(gid), _lib.as_i32p(ens.g_ncell), _lib.as_i64p(coff),
-                limg.data_ptr(), lmsk.data_ptr(), h, w, 1, frame.data_ptr(), float(threshold),
-                1 if quirk else 0,
-                img.data_ptr() if img is not None else None,
-                act.data_ptr() if act is not None else None,
-                ins.data_ptr() if ins is not None else None,
-                nact.data_ptr(), scratch.data_ptr(), lib.cab200_raster_scratch_bytes(1),
-                _stream_ptr(dev))
-            _lib.check(rc, "cab200_raster_batch")
-            if img is not None:
-                out["image"] = img.cpu().numpy()
-            if ins is not None:
-                out["instance"] = ins.cpu().numpy().view(np.uint16)
-            if act is not None:
-                out["active"] = act.cpu().numpy()
-            out["n_active"] = int(nact.cpu().item())
-        return out
+        frame = ens.frames_of(0)[self.fi].contiguous()      # a contiguous [4][n] block for this frame
+        return _raster_one(ens.geometries[0], ens.output_size, ens.device, frame, threshold, quirk,
+                           image, instance, active, **edge)
