@@ -375,22 +375,37 @@ def run_gpu(args) -> None:
         wave_ld = int(plan_cost[2])
         wave_st = ((n_cells + 31) // 32) * 4 * (int(lay[2]) + 1)
         smem_clk = (wave_ld + wave_st) * (T_STEPS - 1)
-        roofline = {"kernel": "integrate_kernel (K1)", "bound": "fp64", "achieved": achieved_tf, "peak": peak.value,
-                    "unit": "TFLOP/s", "frac": achieved_tf / peak.value, "traffic": None,
-                    "algorithmic_flops_per_cell_step": flops_per_cell_step,
-                    "peak_source": "cab200_peak_fp64 (independent DFMA chains on every SM), measured in this run; "
-                                   "MEASURED_PEAKS.json has no FP64 entry",
-                    "fp64_pipe_instr_per_cell_step": 89.6,
-                    "fp64_pipe_frac_est": achieved_tf * (2.0 * 89.6 / flops_per_cell_step) / peak.value,
-                    "fp64_pipe_note": "an IEEE divide is ~9 FP64-pipe instructions, so 69.3 algorithmic flops are "
-                                      "89.6 pipe instructions per cell-step (ncu instruction counts, profiles/); "
-                                      "fp64_pipe_frac_est = pipe instructions/s over the measured DFMA issue rate; "
-                                      "ncu's own sm__pipe_fp64_cycles_active is in profiles/r1_k1_v3_immaddr_ncu.txt"}
-        roofline_smem = {"kernel": "integrate_kernel (K1)", "bound": "shared-memory wavefronts",
-                         "wavefronts_per_step_planned": wave_ld + wave_st,
-                         "frac": smem_clk / (k1_ms * 1e-3 * sm_clock_hz),
-                         "note": "1 wavefront/clk/SM peak; planned = host planner's count (loads) + stores; "
-                                 "K1 is co-bound by this pipe and the FP64 pipe"}
+        roofline_fp64 = {"kernel": "integrate_kernel (K1)", "bound": "fp64", "achieved": achieved_tf, "peak": peak.value,
+                         "unit": "TFLOP/s", "frac": achieved_tf / peak.value,
+                         "algorithmic_flops_per_cell_step": flops_per_cell_step,
+                         "peak_source": "cab200_peak_fp64 (independent DFMA chains on every SM), measured in this run; "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "fp64_pipe_instr_per_cell_step": 89.6,
+                         "fp64_pipe_frac_est": achieved_tf * (2.0 * 89.6 / flops_per_cell_step) / peak.value,
+                         "fp64_pipe_note": "an IEEE divide is ~9 FP64-pipe instructions, so 69.3 algorithmic flops are "
+                                           "89.6 pipe instructions per cell-step (ncu instruction counts, profiles/); "
+                                           "fp64_pipe_frac_est = pipe instructions/s over the measured DFMA issue rate; "
+                                           "ncu's own sm__pipe_fp64_cycles_active is in profiles/r1_k1_v3_immaddr_ncu.txt"}
+        # the limiting roofline of K1: the shared-memory pipe (ncu: 88 % of peak wavefronts vs 75 % FP64 pipe).
+        # Algorithmic bytes per cell-step: gather (c, p) of every row entry + publish own (c, p) = 16*nnz/n + 16
+        # (no index or weight reads: entry addresses live in registers, unit weights are skipped) -- DESIGN.md K1.
+        smem_bytes_per_cell_step = 16.0 * nnz / n_cells + 16.0
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        smem_peak_gbs = n_sm * 128.0 * sm_clock_hz / 1e9
+        smem_achieved_gbs = smem_bytes_per_cell_step * work_per_gpu / (k1_ms * 1e-3) / 1e9
+        roofline = {"kernel": "integrate_kernel (K1)", "bound": "smem", "achieved": smem_achieved_gbs,
+                    "peak": smem_peak_gbs, "unit": "GB/s", "frac": smem_achieved_gbs / smem_peak_gbs, "traffic": None,
+                    "algorithmic_bytes_per_cell_step": smem_bytes_per_cell_step,
+                    "peak_source": "128 B/clk/SM shared-memory crossbar (B300_MICROARCH.md, LDS/STS) x SM count x the SM "
+                                   "clock sampled during the timed region; K1 never touches HBM except for the frames "
+                                   "(0.16 B per cell-step), so MEASURED_PEAKS.json's HBM figure does not bound it",
+                    "wavefronts_per_step_planned": wave_ld + wave_st,
+                    "pipe_frac_wavefronts": smem_clk / (k1_ms * 1e-3 * sm_clock_hz),
+                    "note": "frac counts algorithmic bytes only; pipe_frac_wavefronts is the hardware view (1 wavefront = "
+                            "128 B per clk per SM; planned load wavefronts from the host planner's cost model + stores, "
+                            "within 3 % of ncu's l1tex__data_pipe_lsu_wavefronts_mem_shared) -- the gap between the two is "
+                            "bank conflicts, the second value copy and the diagonal entries; traffic = ncu wavefronts x "
+                            "128 B per launch; K1 is co-bound by the FP64 pipe (roofline_fp64)"}
         roofline_k2 = {"kernel": "raster_kernel (K2)", "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9,
                        "peak": hbm_peak, "unit": "GB/s", "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak,
                        "traffic": None, "peak_source": hbm_src,
@@ -398,7 +413,8 @@ def run_gpu(args) -> None:
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             tr = json.load(open(prof))
-            roofline["traffic"] = tr.get("k1_dram_bytes_per_launch")
+            roofline["traffic"] = tr.get("k1_smem_wavefront_bytes_per_launch")
+            roofline_fp64["dram_traffic"] = tr.get("k1_dram_bytes_per_launch")
             roofline_k2["traffic"] = tr.get("k2_dram_bytes_per_launch")
         cores = os.cpu_count() or 1
         cpu = cpu_port_throughput(max(cores, 8), cores) if not args.no_cpu_baseline else None
@@ -409,7 +425,7 @@ def run_gpu(args) -> None:
             "config": workload_config(world, P),
             "pouch_sims_per_hour": P * world / (ms_per_step * 1e-3) * 3600.0,
             "k1_ms": k1_ms, "k2_ms": k2_ms,
-            "roofline": roofline, "roofline_smem": roofline_smem, "roofline_k2": roofline_k2,
+            "roofline": roofline, "roofline_fp64": roofline_fp64, "roofline_k2": roofline_k2,
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "cpu_baseline_reference_style": (cpu_reference_style_throughput() if cpu else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"],
