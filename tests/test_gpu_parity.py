@@ -577,3 +577,34 @@ def test_every_step_capture_through_slot_order_staging(env, size, count, cluster
     if prec == 64:
         want = _oracle_frames(env["O"], specs[0], T, list(range(T)))
         assert np.array_equal(want, a.frames_of(0).cpu().numpy())
+
+
+def test_config3_head_against_reference_fixture(env, golden_dir):
+    """The bench workload's first 8 pouches (make_specs(8, "medium") = BASELINE config 3's enumeration) and a
+    large pouch on the GPU against what the unmodified reference computed for them
+    (tests/golden/traj_config3_head.npz): identical host draws, trajectories within the north-star tolerance,
+    K2's active-cell count equal in every one of the 90 sampled frames."""
+    E = env["E"]
+    z = np.load(os.path.join(golden_dir, "traj_config3_head.npz"))
+    specs = E.make_specs(8, size="medium")
+    for i, s in enumerate(specs):
+        assert np.array_equal(s.vplc, z[f"vplc_{i}"]) and np.array_equal(s.r0, z[f"r0_{i}"])
+    sampled, steps = z["sampled"].tolist(), z["steps"].tolist()
+    allsteps = sorted(set(sampled + steps))
+    ens = E.Ensemble(specs, frame_steps=allsteps, device=env["dev"], output_size=(128, 128))
+    ens.simulate()
+    assert not ens.check_status().any()
+    nact = ens.rasterize(image=False, instance=True)["n_active"].cpu().numpy()
+    for i in range(8):
+        fr = ens.frames_of(i).cpu().numpy()
+        got = fr[[allsteps.index(t) for t in steps]]
+        assert _max_rel(got, z[f"frames_{i}"]) < RTOL, (i, _max_rel(got, z[f"frames_{i}"]))
+        assert np.array_equal(nact[i, [allsteps.index(t) for t in sampled]], z[f"n_active_{i}"]), i
+    from calcium_b200.parameters import SimulationParameters as SP
+    prm = SP("Intercellular waves").generate_random_params(seed=2)
+    spec = E.PouchSpec.draw(prm, size="large", sim_number=2)
+    assert np.array_equal(spec.vplc, z["large_vplc"]) and np.array_equal(spec.r0, z["large_r0"])
+    ens = E.Ensemble([spec], frame_steps=z["large_steps"].tolist(), device=env["dev"])
+    assert ens.g_cluster.tolist() == [4]                     # a large pouch runs as a 4-CTA cluster
+    ens.simulate()
+    assert _max_rel(ens.frames_of(0).cpu().numpy(), z["large_frames"]) < RTOL
