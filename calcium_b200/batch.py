@@ -61,7 +61,8 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                               generate_labels=False, image_size="512x512", jpeg_quality=90,
                               save_pouch=False, dataset_split="train", *, geometry_dir=None,
                               device=None, write_files=True, keep_arrays=False,
-                              max_chunk_bytes=4 << 30, writer_threads=8, generate_prompts=True):
+                              max_chunk_bytes=4 << 30, writer_threads=8, generate_prompts=True,
+                              prompt_threads=8):
     """Generate a batch of simulations with images and instance masks (see module docstring).
 
     Extra keyword-only arguments: ``geometry_dir``, ``device``, ``write_files`` (False: compute only),
@@ -169,23 +170,42 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 del out
             prompt_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             if steps and generate_masks and generate_prompts:
+                # Pouches are independent here: the reference's frame loop continues the generator its Pouch
+                # seeded (core/pouch.py:317), so every pouch gets a private legacy generator restored to the state
+                # its own draws left behind -- same values as the reference's sequential loop -- and the pouches
+                # run on a thread pool (numpy's shuffle / ufuncs and the K4 calls release the GIL).
                 from .prompts import PromptTables, frame_prompts, save_prompts
                 lmsk = ens.label_maps()[1]
                 tables: Dict[int, Any] = {}
-                for li, d in enumerate(part):
+                for li in range(len(part)):
                     g = int(ens.geom_id[li])
                     if g not in tables:
                         tables[g] = PromptTables(lmsk[g], int(ens.g_ncell[g]))
-                    ca_all = ens.frames_of(li)[:, 0, :].cpu().numpy()
-                    np.random.set_state(d["rng_state"])
-                    for fi in range(len(steps)):
-                        if not (ca_all[fi] > 0.1).any():          # no active cell: nothing is written (:318-319)
-                            continue
-                        pos, neg = frame_prompts(tables[g], ca_all[fi])
-                        ppath = os.path.join(prompt_dir, names[li][fi] + ".json")
-                        prompt_files[li].append(ppath)
-                        if write_files:
-                            save_prompts(pos, ppath, neg)
+                ca_host = [ens.frames_of(li)[:, 0, :].cpu().numpy() for li in range(len(part))]
+
+                def pouch_prompts(li: int):
+                    d = part[li]
+                    rs = np.random.RandomState()
+                    rs.set_state(d["rng_state"])
+                    tab, ca_all, files = tables[int(ens.geom_id[li])], ca_host[li], []
+                    with torch.cuda.device(ens.device):
+                        for fi in range(len(steps)):
+                            if not (ca_all[fi] > 0.1).any():          # no active cell: nothing is written (:318-319)
+                                continue
+                            pos, neg = frame_prompts(tab, ca_all[fi], rng=rs)
+                            ppath = os.path.join(prompt_dir, names[li][fi] + ".json")
+                            files.append(ppath)
+                            if write_files:
+                                save_prompts(pos, ppath, neg)
+                    return files, rs.get_state()
+
+                last_state = None
+                with cf.ThreadPoolExecutor(max_workers=max(1, prompt_threads)) as pp:
+                    for li, (files, state) in enumerate(pp.map(pouch_prompts, range(len(part)))):
+                        prompt_files[li] = files
+                        last_state = state
+                if last_state is not None:
+                    np.random.set_state(last_state)                  # where the reference's loop would leave it
             for li, d in enumerate(part):
                 if img is not None:
                     for fi, t in enumerate(steps):

@@ -23,6 +23,7 @@ so with the same generator state the prompts are identical to the reference's, v
 """
 from __future__ import annotations
 
+import ctypes
 import json
 import os
 from typing import Dict, List, Optional, Tuple
@@ -88,7 +89,9 @@ class PromptTables:
         self.n = int(n_cells)
         lab = label_mask.cpu().numpy().view(np.uint16).astype(np.int64)
         self.labels_host = lab
+        self.labels_u16 = label_mask.cpu().numpy().view(np.uint16).copy()
         self.H, self.W = lab.shape
+        self._empty: Dict[float, Tuple[np.ndarray, np.ndarray]] = {}
         d2 = edt_squared(label_mask)[0].cpu().numpy()
         flat = lab.ravel()
         order = np.argsort(flat, kind="stable")                       # groups pixels by label, row-major inside
@@ -106,90 +109,184 @@ class PromptTables:
                 self.cand_off[c + 1] = self.cand_off[c] + len(keep)
             else:
                 self.cand_off[c + 1] = self.cand_off[c]
+        self.empty_frame_candidates(5.0)
         self.cand_y = np.concatenate(cy) if cy else np.zeros(0, np.int64)
         self.cand_x = np.concatenate(cx) if cx else np.zeros(0, np.int64)
         self.cand_d = np.concatenate(cd) if cd else np.zeros(0, np.float64)
 
 
-def _frame_transforms(tables: PromptTables, lut: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-    """The two frame-dependent transforms on the device: squared distance to the nearest pixel whose
-    (id == 1) / (id > 0) class differs."""
-    luts = np.stack([(lut == 1), (lut > 0)]).astype(np.uint16).view(np.int16)
+def _empty_frame_candidates(self, min_distance: float) -> Tuple[np.ndarray, np.ndarray]:
+    """Negative-prompt candidates of a frame without any labelled pixel: row-major flat indices of the pixels
+    with sqrt((y + 1)^2 + x^2) >= min_distance, and the squared distances of all pixels (flat)."""
+    got = self._empty.get(min_distance)
+    if got is None:
+        yy, xx = np.mgrid[0:self.H, 0:self.W]
+        d2 = ((yy + 1) ** 2 + xx ** 2).astype(np.int64)
+        dist = np.sqrt(d2.astype(np.float64))
+        got = (np.flatnonzero(dist >= min_distance), d2.ravel())
+        self._empty[min_distance] = got
+    return got
+
+
+PromptTables.empty_frame_candidates = _empty_frame_candidates
+
+
+def _frame_transforms(tables: PromptTables, lut: np.ndarray, background: bool = True
+                      ) -> Tuple[Optional[np.ndarray], np.ndarray]:
+    """The frame-dependent transforms on the device (one K4 call): squared distance to the nearest pixel
+    whose (id > 0) class differs and -- only when the id mismatch made a background instance -- the same for
+    the class (id == 1).  Returns ``(d2_background_instance or None, d2_negative)``."""
+    rows = [(lut == 1), (lut > 0)] if background else [(lut > 0)]
+    luts = np.stack(rows).astype(np.uint16).view(np.int16)
     d = edt_squared(tables.label_mask, torch.from_numpy(luts).to(tables.label_mask.device))
     both = d.cpu().numpy()
-    return both[0], both[1]
+    return (both[0], both[1]) if background else (None, both[0])
+
+
+def legacy_choice(rng, n: int, k: int) -> np.ndarray:
+    """``rng.choice(n, k, replace=False)`` of a legacy ``np.random.RandomState`` -- same indices, same generator
+    state afterwards -- through ``cab200_legacy_choice`` (numpy's own algorithm as one loop outside the
+    interpreter lock; numpy itself takes 2-5 ms for the ~10^5 draws of one frame and serialises the threads)."""
+    if n < 4096:
+        return rng.choice(n, k, replace=False)
+    name, key, pos, has_gauss, cached = rng.get_state()
+    if name != "MT19937":
+        return rng.choice(n, k, replace=False)
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    cpos = ctypes.c_int32(int(pos))
+    out = np.empty(k, dtype=np.int64)
+    _lib.check(_lib.load().cab200_legacy_choice(key.ctypes.data, ctypes.byref(cpos), int(n), int(k), out.ctypes.data),
+               "cab200_legacy_choice")
+    rng.set_state((name, key, int(cpos.value), has_gauss, cached))
+    return out
+
+
+def global_rng():
+    """The legacy global generator behind ``np.random.randint`` / ``np.random.choice`` (what the reference
+    draws from); pass a private ``np.random.RandomState`` to ``frame_prompts`` to leave it alone."""
+    return np.random.mtrand._rand
 
 
 def frame_prompts(tables: PromptTables, ca: np.ndarray, threshold: float = 0.1, quirk: bool = True,
-                  num_negative: int = 5, min_distance_from_cells: int = 5, min_cell_area: int = 10
-                  ) -> Tuple[Dict[int, Dict], List[Dict]]:
+                  num_negative: int = 5, min_distance_from_cells: int = 5, min_cell_area: int = 10,
+                  rng=None) -> Tuple[Dict[int, Dict], List[Dict]]:
     """``(generate_point_prompts_from_mask(instance_mask), generate_negative_prompts(instance_mask, 5))``
     for the frame whose calcium values are ``ca`` -- the dicts of ``utils/sam2_data_generator.py:124-129``
-    and ``:170-174`` -- consuming the global numpy generator exactly like those two calls."""
-    n = tables.n
+    and ``:170-174`` -- consuming the generator ``rng`` (default: the global legacy numpy generator) exactly
+    like those two calls: one ``randint`` per instance in ascending id order (drawn as one array call per
+    run of single-cell instances, which yields the same values and leaves the same state as the scalar
+    calls), then one ``choice(n, k, replace=False)``."""
+    rng = global_rng() if rng is None else rng
     lut = instance_lut(ca, threshold, quirk)
-    ids = np.unique(lut)
-    ids = ids[ids != 0]
-    prompts: Dict[int, Dict] = {}
-    # which label values carry each id: all ids but the mismatch's background id belong to one cell
-    cell_of = {}
-    for v in np.nonzero(lut[1:])[0]:
-        cell_of.setdefault(int(lut[v + 1]), []).append(int(v))
     background_id = int(lut[0]) if lut[0] else None                    # id given to every zero pixel (cell 0 active)
-    need_maps = background_id is not None or num_negative > 0
+    labelled = (lut > 0)[tables.labels_u16]                            # instance_mask > 0
+    any_labelled = bool(labelled.any())
     d2_bg = d2_neg = None
-    inst = None
-    if need_maps:
-        d2_bg, d2_neg = _frame_transforms(tables, lut)
-        inst = lut[tables.labels_host]
-    for iid in ids.tolist():
-        if iid == background_id:
-            b = inst == iid
-            area = int(b.sum())
-            if area < min_cell_area:
-                continue
-            dist = np.where(b, np.sqrt(d2_bg.astype(np.float64)), 0.0)
-            if dist.max() == 0:
-                continue
-            thr = np.percentile(dist[dist > 0], 80)
-            ys, xs = np.where(dist >= thr)
-            idx = np.random.randint(len(ys))
-            y, x, conf = int(ys[idx]), int(xs[idx]), float(dist[ys[idx], xs[idx]])
-        else:
-            (c,) = cell_of[iid]
-            area = int(tables.area[c])
-            if area < min_cell_area:
-                continue
-            o, cnt = int(tables.cand_off[c]), int(tables.cand_off[c + 1] - tables.cand_off[c])
-            idx = int(np.random.randint(cnt))
-            y, x, conf = int(tables.cand_y[o + idx]), int(tables.cand_x[o + idx]), float(tables.cand_d[o + idx])
-        prompts[int(iid)] = {"point": [x, y], "label": 1, "area": area, "confidence": conf}
+    if background_id is not None or (num_negative > 0 and any_labelled):
+        d2_bg, d2_neg = _frame_transforms(tables, lut, background_id is not None)
 
+    # ---- positive prompts: single-cell instances come from the static tables ---------------------------
+    cells = np.nonzero(lut[1:])[0]                                     # cells whose label value carries an id
+    cid = lut[cells + 1].astype(np.int64)
+    order = np.argsort(cid, kind="stable")
+    cells, cid = cells[order], cid[order]
+    if background_id is not None:
+        keep = cid != background_id                                     # (cannot happen: that id is the background's)
+        cells, cid = cells[keep], cid[keep]
+    big = tables.area[cells] >= min_cell_area
+    cells, cid = cells[big], cid[big]
+    off = tables.cand_off[cells]
+    cnt = tables.cand_off[cells + 1] - off
+    prompts: Dict[int, Dict] = {}
+
+    def draw_cells(lo: int, hi: int) -> None:
+        if hi <= lo:
+            return
+        pick = off[lo:hi] + rng.randint(0, cnt[lo:hi])
+        for iid, x, y, a, c in zip(cid[lo:hi].tolist(), tables.cand_x[pick].tolist(), tables.cand_y[pick].tolist(),
+                                   tables.area[cells[lo:hi]].tolist(), tables.cand_d[pick].tolist()):
+            prompts[iid] = {"point": [x, y], "label": 1, "area": a, "confidence": c}
+
+    if background_id is None:
+        draw_cells(0, len(cid))
+    else:
+        split = int(np.searchsorted(cid, background_id))
+        draw_cells(0, split)
+        inst_is_bg = (lut == background_id)[tables.labels_u16]
+        area = int(inst_is_bg.sum())
+        if area >= min_cell_area:
+            dist = np.where(inst_is_bg, np.sqrt(d2_bg.astype(np.float64)), 0.0)
+            if dist.max() != 0:
+                thr = np.percentile(dist[dist > 0], 80)
+                ys, xs = np.where(dist >= thr)
+                idx = rng.randint(len(ys))
+                prompts[background_id] = {"point": [int(xs[idx]), int(ys[idx])], "label": 1, "area": area,
+                                          "confidence": float(dist[ys[idx], xs[idx]])}
+        draw_cells(split, len(cid))
+
+    # ---- negative prompts -----------------------------------------------------------------------------
     negatives: List[Dict] = []
     if num_negative > 0:
-        cells = inst > 0
-        if cells.any():
-            dist = np.where(cells, 0.0, np.sqrt(d2_neg.astype(np.float64)))
-        else:
+        md = float(min_distance_from_cells)
+        if not any_labelled:
             # no labelled pixel at all: scipy's distance_transform_edt of an array without a zero element
             # returns the distance to the point (-1, 0) (observed with scipy 1.7 - 1.18); the reference
-            # samples its negatives from that map (utils/sam2_data_generator.py:152-159)
-            yy, xx = np.mgrid[0:tables.H, 0:tables.W]
-            dist = np.sqrt(((yy + 1) ** 2 + xx ** 2).astype(np.float64))
-        ys, xs = np.where(dist >= min_distance_from_cells)
-        if len(ys) > 0:
-            k = min(num_negative, len(ys))
-            for idx in np.random.choice(len(ys), k, replace=False):
-                y, x = ys[idx], xs[idx]
-                negatives.append({"point": [int(x), int(y)], "label": 0, "confidence": float(dist[y, x])})
+            # samples its negatives from that map (utils/sam2_data_generator.py:152-159).  Static per size.
+            flat, d2 = tables.empty_frame_candidates(md)
+        elif md >= 1.0 and md.is_integer():
+            # sqrt(d2) >= md  <=>  d2 >= md^2 for integers; labelled pixels have distance 0 < md
+            flat = np.flatnonzero(~labelled & (d2_neg >= int(md) ** 2))
+            d2 = d2_neg.ravel()
+        else:
+            dist = np.where(labelled, 0.0, np.sqrt(d2_neg.astype(np.float64)))
+            flat = np.flatnonzero(dist >= md)
+            d2 = np.where(labelled, 0, d2_neg).ravel()
+        if len(flat) > 0:
+            k = min(num_negative, len(flat))
+            for idx in legacy_choice(rng, len(flat), k):
+                px = int(flat[idx])
+                negatives.append({"point": [px % tables.W, px // tables.W], "label": 0,
+                                  "confidence": float(np.sqrt(np.float64(d2[px])))})
     return prompts, negatives
+
+
+def _fmt_point(pt, ind: str) -> str:
+    return f"[\n{ind}  {pt[0]},\n{ind}  {pt[1]}\n{ind}]"
+
+
+def dumps_prompts(prompts: Dict, negative_prompts: Optional[List] = None) -> str:
+    """The text ``json.dump(data, f, indent=2)`` writes for the reference's prompt file
+    (``utils/sam2_data_generator.py:228-238``), formatted directly: the pure-Python encoder ``indent`` switches
+    ``json`` to costs more than computing the prompts (1 400 instances per frame of a fluttering pouch)."""
+    neg = negative_prompts or []
+    fr = float.__repr__
+    if prompts:
+        body = ",\n".join(
+            f'    "{k}": {{\n      "point": {_fmt_point(v["point"], "      ")},\n      "label": {v["label"]},\n'
+            f'      "area": {v["area"]},\n      "confidence": {fr(v["confidence"])}\n    }}'
+            for k, v in prompts.items())
+        pos = "{\n" + body + "\n  }"
+    else:
+        pos = "{}"
+    if neg:
+        body = ",\n".join(
+            f'    {{\n      "point": {_fmt_point(v["point"], "      ")},\n      "label": {v["label"]},\n'
+            f'      "confidence": {fr(v["confidence"])}\n    }}' for v in neg)
+        ng = "[\n" + body + "\n  ]"
+    else:
+        ng = "[]"
+    return (f'{{\n  "positive_prompts": {pos},\n  "negative_prompts": {ng},\n  "num_cells": {len(prompts)},\n'
+            f'  "version": "1.0"\n}}')
 
 
 def save_prompts(prompts: Dict, output_path: str, negative_prompts: Optional[List] = None) -> str:
     """Same file as the reference's ``save_prompts`` (``utils/sam2_data_generator.py:210-240``)."""
     os.makedirs(os.path.dirname(output_path), exist_ok=True)
-    data = {"positive_prompts": prompts, "negative_prompts": negative_prompts or [],
-            "num_cells": len(prompts), "version": "1.0"}
+    try:
+        text = dumps_prompts(prompts, negative_prompts)
+    except (KeyError, TypeError, IndexError):      # not the dicts frame_prompts builds: the generic encoder
+        text = json.dumps({"positive_prompts": prompts, "negative_prompts": negative_prompts or [],
+                           "num_cells": len(prompts), "version": "1.0"}, indent=2)
     with open(output_path, "w") as f:
-        json.dump(data, f, indent=2)
+        f.write(text)
     return output_path

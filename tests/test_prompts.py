@@ -110,3 +110,96 @@ def test_gpu_prompts_match_the_reference(cuda_device, gold, t, thr):
     pos, neg = frame_prompts(tables, ca, threshold=thr, quirk=True)
     assert pos == _norm(g["positive"])
     assert neg == g["negative"]
+
+
+def test_prompt_file_text_is_json_dump_indent2():
+    """save_prompts formats the file directly; the text must be what json.dump(..., indent=2) writes."""
+    from calcium_b200.prompts import dumps_prompts
+    rng = np.random.RandomState(0)
+    for _ in range(100):
+        n, m = rng.randint(0, 30), rng.randint(0, 6)
+        pos = {int(i): {"point": [int(rng.randint(512)), int(rng.randint(512))], "label": 1, "area": int(rng.randint(10, 9999)),
+                        "confidence": float(np.sqrt(np.float64(rng.randint(1, 400))))}
+               for i in sorted(rng.choice(2000, n, replace=False))}
+        neg = [{"point": [int(rng.randint(512)), int(rng.randint(512))], "label": 0,
+                "confidence": float(np.sqrt(np.float64(rng.randint(25, 90000))))} for _ in range(m)]
+        want = json.dumps({"positive_prompts": pos, "negative_prompts": neg, "num_cells": len(pos), "version": "1.0"}, indent=2)
+        assert dumps_prompts(pos, neg) == want
+        assert json.loads(dumps_prompts(pos, neg))["num_cells"] == n
+
+
+def test_vector_randint_is_the_scalar_sequence():
+    """frame_prompts draws a run of single-cell instances with one array call; the legacy generator must give
+    the values of the reference's scalar calls and end in the same state."""
+    rng = np.random.RandomState(5)
+    for trial in range(50):
+        cnts = rng.randint(1, 400, rng.randint(1, 1500))
+        np.random.seed(trial)
+        a = np.array([np.random.randint(c) for c in cnts])
+        sa = np.random.get_state()
+        rs = np.random.RandomState(trial)
+        b = rs.randint(0, cnts)
+        sb = rs.get_state()
+        assert np.array_equal(a, b) and sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+
+
+@pytest.mark.gpu
+def test_gpu_prompts_match_the_oracle_on_medium_frames(cuda_device):
+    """frame_prompts (static tables + K4 + array draws, private generator) against the oracle's restatement of
+    the reference functions (scipy distance transforms on the instance mask, global generator) on frames of
+    medium pouches of all four sim types -- including frames whose id mismatch leaves no labelled pixel at all
+    and frames with the background instance."""
+    from calcium_b200 import build
+    build.build()
+    from calcium_b200 import ensemble as E
+    from calcium_b200.prompts import PromptTables, frame_prompts, instance_lut
+    from oracle import prompts_oracle as PO
+    specs = E.make_specs(4, size="medium")
+    steps = [0, 4000, 9000, 17999]
+    ens = E.Ensemble(specs, frame_steps=steps, output_size=(256, 256), device=cuda_device)
+    ens.simulate()
+    lmsk = ens.label_maps()[1][0]
+    cm = lmsk.cpu().numpy().view(np.uint16)
+    tables = PromptTables(lmsk, specs[0].geometry.n_cells)
+    seen_empty = seen_bg = 0
+    for i in range(4):
+        ca_all = ens.frames_of(i)[:, 0, :].cpu().numpy()
+        for f in range(len(steps)):
+            for thr in (0.1, 0.0):
+                if not (ca_all[f] > thr).any():
+                    continue
+                lut = instance_lut(ca_all[f], thr, True)
+                inst = lut[cm]
+                seen_empty += int(not (inst > 0).any())
+                seen_bg += int(lut[0] != 0)
+                np.random.seed(100 * i + f)
+                want = (PO.point_prompts(inst), PO.negative_prompts(inst, 5))
+                end = np.random.get_state()
+                rs = np.random.RandomState(100 * i + f)
+                got = frame_prompts(tables, ca_all[f], threshold=thr, rng=rs)
+                assert got[0] == want[0] and list(got[0]) == list(want[0]), (i, f, thr)
+                assert got[1] == want[1], (i, f, thr)
+                st = rs.get_state()
+                assert st[2] == end[2] and np.array_equal(st[1], end[1])       # generator left in the same state
+    assert seen_empty > 0 and seen_bg > 0
+
+
+@pytest.mark.gpu
+def test_batch_prompts_do_not_depend_on_the_thread_count(cuda_device, tmp_path):
+    from calcium_b200 import generate_simulation_batch
+    import random
+    outs = []
+    for k, threads in enumerate((1, 6)):
+        random.seed(3)
+        d = tmp_path / f"run{k}"
+        res = generate_simulation_batch(5, str(d), pouch_sizes=["xsmall", "small"], time_steps=[0, 6000, 12000],
+                                        image_size="128x128", prompt_threads=threads)
+        files = {}
+        pdir = d / "prompts" / "train"
+        for name in sorted(os.listdir(pdir)):
+            key = "_".join(name.split("_")[:-1])            # drop the run id
+            files[key] = open(pdir / name).read()
+        outs.append((files, [s["prompt_count"] for s in res["simulations"]], np.random.get_state()[1].copy()))
+    assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 0
+    assert outs[0][1] == outs[1][1]
+    assert np.array_equal(outs[0][2], outs[1][2])
