@@ -54,6 +54,21 @@ def _parse_image_size(image_size) -> tuple:
     return tuple(image_size)
 
 
+def _resolve_devices(device, devices) -> List[Any]:
+    """``devices``: None (the single ``device``), "all" (every visible CUDA device) or a list of indices /
+    ``torch.device`` objects."""
+    if devices is None:
+        return [device]
+    if isinstance(devices, str):
+        if devices != "all":
+            raise ValueError("devices must be None, 'all' or a list of CUDA devices")
+        return [torch.device("cuda", i) for i in range(torch.cuda.device_count())]
+    out = [torch.device("cuda", d) if isinstance(d, int) else torch.device(d) for d in devices]
+    if not out:
+        raise ValueError("devices is empty")
+    return out
+
+
 def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim_types=None,
                               time_steps=None, defect_configs=None, progress_callback=None,
                               memory_threshold=70, create_stats=True, edge_blur=False,
@@ -62,7 +77,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                               save_pouch=False, dataset_split="train", *, geometry_dir=None,
                               device=None, write_files=True, keep_arrays=False,
                               max_chunk_bytes=4 << 30, writer_threads=8, generate_prompts=True,
-                              prompt_threads=8):
+                              prompt_threads=8, devices=None):
     """Generate a batch of simulations with images and instance masks (see module docstring).
 
     Extra keyword-only arguments: ``geometry_dir``, ``device``, ``write_files`` (False: compute only),
@@ -70,7 +85,10 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     memory budget for one chunk's raster outputs), ``writer_threads``, ``generate_prompts`` (with
     ``generate_masks``: the per-frame prompt JSON of ``process_batch_for_sam2``,
     ``utils/sam2_data_generator.py:325-341`` -- K4 distance transforms + the reference's own draws from
-    the global numpy generator, continued from the state the pouch's own draws left it in).
+    the global numpy generator, continued from the state the pouch's own draws left it in),
+    ``prompt_threads``, ``devices`` (None: the one ``device``; "all" or a list: the pouches are sharded over
+    those GPUs -- independent pouches, longest-processing-time-first, one host thread per device, no
+    collective; the files and the returned dict do not depend on the sharding).
     """
     os.makedirs(output_dir, exist_ok=True)
     if pouch_sizes is None:
@@ -125,7 +143,11 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             fh.write(data)
         return path
 
-    try:
+    mappings_by_sim: Dict[int, List[tuple]] = {}
+    final_states: Dict[int, Any] = {}
+
+    def run_on_device(device, drawn):
+        """The chunk loop for the pouches assigned to one GPU (all of them when there is one device)."""
         for c0 in range(0, len(drawn), chunk):
             part = drawn[c0:c0 + chunk]
             ens = Ensemble([d["spec"] for d in part], output_size=output_size, T=T,
@@ -150,7 +172,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                             if mb is not None:     # no active cell -> no mask (sam2_data_generator.py:318-319)
                                 mpath = os.path.join(mask_dir, base + ".npz")
                                 mask_files[li].append(mpath)
-                                mappings.append((os.path.basename(ipath), os.path.basename(mpath)))
+                                mappings_by_sim.setdefault(part[li]["sim_idx"], []).append((os.path.basename(ipath), os.path.basename(mpath)))
                                 if pool is not None:
                                     pending.append(pool.submit(_write_bytes, mpath, bytes(mb)))
                 ens.run_files_to_host(chunk_pouches=min(len(part), 37), image=True, mask=bool(generate_masks),
@@ -192,11 +214,14 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         for fi in range(len(steps)):
                             if not (ca_all[fi] > 0.1).any():          # no active cell: nothing is written (:318-319)
                                 continue
-                            pos, neg = frame_prompts(tab, ca_all[fi], rng=rs)
-                            ppath = os.path.join(prompt_dir, names[li][fi] + ".json")
-                            files.append(ppath)
-                            if write_files:
-                                save_prompts(pos, ppath, neg)
+                            try:
+                                pos, neg = frame_prompts(tab, ca_all[fi], rng=rs)
+                                ppath = os.path.join(prompt_dir, names[li][fi] + ".json")
+                                if write_files:
+                                    save_prompts(pos, ppath, neg)
+                                files.append(ppath)
+                            except Exception as e:  # noqa: BLE001 - a failing frame is reported and skipped (main.py:342-351)
+                                print(f"Error processing time step {steps[fi]} for simulation {d['sim_idx']}: {str(e)}")
                     return files, rs.get_state()
 
                 last_state = None
@@ -205,7 +230,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         prompt_files[li] = files
                         last_state = state
                 if last_state is not None:
-                    np.random.set_state(last_state)                  # where the reference's loop would leave it
+                    final_states[part[-1]["sim_idx"]] = last_state
             for li, d in enumerate(part):
                 if img is not None:
                     for fi, t in enumerate(steps):
@@ -217,7 +242,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         if generate_masks and nact[li, fi] > 0:      # no active cell -> no mask (sam2_data_generator.py:318-319)
                             mpath = os.path.join(mask_dir, base + ".npz")
                             mask_files[li].append(mpath)
-                            mappings.append((os.path.basename(ipath), os.path.basename(mpath)))
+                            mappings_by_sim.setdefault(part[li]["sim_idx"], []).append((os.path.basename(ipath), os.path.basename(mpath)))
                             if pool is not None:
                                 pending.append(pool.submit(cio.save_instance_mask, ins[li, fi], mpath))
                 if keep_arrays:
@@ -239,6 +264,25 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     "image_count": len(image_files[li]), "image_dir": img_dir, "mask_dir": mask_dir,
                     "mask_count": len(mask_files[li]), "prompt_count": len(prompt_files[li]), "pouch": pouch_obj})
             del ens
+
+    # ---- shard over the GPUs of the box: independent pouches, no exchange; longest-
+    # processing-time-first over n_cells * T, one host thread per device
+    dev_list = _resolve_devices(device, devices)
+    try:
+        if len(dev_list) <= 1:
+            run_on_device(dev_list[0] if dev_list else device, drawn)
+        else:
+            from .parallel import lpt_partition
+            parts = lpt_partition([float(d["spec"].geometry.n_cells) * T for d in drawn], len(dev_list))
+            with cf.ThreadPoolExecutor(max_workers=len(dev_list)) as dpool:
+                futs = [dpool.submit(run_on_device, dev_list[r], [drawn[i] for i in parts[r]])
+                        for r in range(len(dev_list)) if parts[r]]
+                for f in futs:
+                    f.result()
+            results["simulations"].sort(key=lambda s_: s_["simulation_id"])
+        if final_states:
+            np.random.set_state(final_states[max(final_states)])      # where the reference's loop would leave it
+        mappings = [m for k in sorted(mappings_by_sim) for m in mappings_by_sim[k]]
     finally:
         if pool is not None:
             for f in pending:
@@ -341,14 +385,14 @@ class BatchGenerationController:
         cfg["defect_config"] = bp.get("defect_config", None)
         cfg["dataset_split"] = bp.get("dataset_split", "train")
         cfg["memory_threshold"] = 60 if ("large" in cfg["pouch_sizes"] or "xlarge" in cfg["pouch_sizes"]) else 70
-        for k in ("geometry_dir", "device", "write_files", "keep_arrays"):
+        for k in ("geometry_dir", "device", "devices", "write_files", "keep_arrays"):
             if k in bp:
                 cfg[k] = bp[k]
         return cfg
 
     def _call(self, config, output_dir, n, progress_callback, save_pouch):
         dc = config.get("defect_config")
-        extra = {k: config[k] for k in ("geometry_dir", "device", "write_files", "keep_arrays") if k in config}
+        extra = {k: config[k] for k in ("geometry_dir", "device", "devices", "write_files", "keep_arrays") if k in config}
         return generate_simulation_batch(
             num_simulations=n, output_dir=output_dir, pouch_sizes=config["pouch_sizes"],
             sim_types=config["sim_types"], time_steps=config["time_steps"],

@@ -245,9 +245,21 @@ __global__ void __launch_bounds__(ET, 3) raster_edges_kernel(const EdgeArgs a)
             const int yy = KS ? reflect_once(y0 + tr - an, H) : reflect101(y0 + tr - an, H);
             const uint16_t *src = limg + (size_t)yy * W;
             float *dst = tilebuf + tr * stride;
-            for (int tc = lane; tc < tw; tc += 32) {
+            // labels come from L2: four independent loads in flight per lane before the first LUT look-up
+            int tc = lane;
+            for (; tc + 96 < tw; tc += 128) {
+                uint32_t l[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int xx = KS ? reflect_once(tc + 32 * u - an, W) : reflect101(tc + 32 * u - an, W);
+                    l[u] = __ldg(src + xx);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dst[tc + 32 * u] = l[u] ? (float)gray_lut[l[u]] : 0.0f;
+            }
+            for (; tc < tw; tc += 32) {
                 const int xx = KS ? reflect_once(tc - an, W) : reflect101(tc - an, W);
-                const uint32_t l = src[xx];
+                const uint32_t l = __ldg(src + xx);
                 dst[tc] = l ? (float)gray_lut[l] : 0.0f;
             }
         }
@@ -257,10 +269,13 @@ __global__ void __launch_bounds__(ET, 3) raster_edges_kernel(const EdgeArgs a)
             const int gw = W >> 2;
             for (int ry = warp; ry < rows; ry += ET / 32) {
                 const size_t rowpx = (size_t)(y0 + ry) * W;
+                const uint32_t *drow = reinterpret_cast<const uint32_t *>(dil + rowpx);
+                const uint32_t *arow = reinterpret_cast<const uint32_t *>(alpha + rowpx);
+                uint32_t d4n = lane < gw ? __ldg(drow + lane) : 0u, a4n = lane < gw ? __ldg(arow + lane) : 0u;
                 for (int xg = lane; xg < gw; xg += 32) {
                     const int x = xg * 4;
-                    const uint32_t d4 = __ldg(reinterpret_cast<const uint32_t *>(dil + rowpx) + xg);
-                    const uint32_t a4 = __ldg(reinterpret_cast<const uint32_t *>(alpha + rowpx) + xg);
+                    const uint32_t d4 = d4n, a4 = a4n;          // the next group's weights are in flight during this one
+                    if (xg + 32 < gw) { d4n = __ldg(drow + xg + 32); a4n = __ldg(arow + xg + 32); }
                     float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                     float c[4];
                     const int ib = d4 ? (MOTION ? KSc / 2 : 0) : KSc / 2, ie = d4 ? (MOTION ? KSc / 2 + 1 : KSc) : KSc / 2 + 1;

@@ -608,3 +608,31 @@ def test_config3_head_against_reference_fixture(env, golden_dir):
     assert ens.g_cluster.tolist() == [4]                     # a large pouch runs as a 4-CTA cluster
     ens.simulate()
     assert _max_rel(ens.frames_of(0).cpu().numpy(), z["large_frames"]) < RTOL
+
+
+def test_batch_sharded_over_two_gpus_equals_one(env, tmp_path):
+    """generate_simulation_batch(devices=[0, 1]) (independent pouches per GPU, no
+    collective): same files, same result dict and the same generator state as the one-GPU run."""
+    import random
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from calcium_b200 import generate_simulation_batch
+    outs = []
+    for k, devs in enumerate((None, [0, 1])):
+        random.seed(11)
+        d = tmp_path / f"run{k}"
+        res = generate_simulation_batch(7, str(d), pouch_sizes=["xsmall", "small", "medium"], time_steps=[0, 6000, 12000],
+                                        image_size="128x128", devices=devs)
+        files = {}
+        for sub in ("images", "masks", "prompts"):
+            for name in sorted(os.listdir(d / sub / "train")):
+                key = sub + "/" + "_".join(name.split("_")[:-1])          # drop the run id
+                files[key] = open(d / sub / "train" / name, "rb").read()
+        sims = [(s["simulation_id"], s["pouch_size"], s["image_count"], s["mask_count"], s["prompt_count"])
+                for s in res["simulations"]]
+        outs.append((files, sims, np.random.get_state()[1].copy(), res["stats"]))
+    assert outs[0][1] == outs[1][1] and [s[0] for s in outs[1][1]] == list(range(7))
+    assert outs[0][0].keys() == outs[1][0].keys() and len(outs[0][0]) > 0
+    assert all(outs[0][0][k] == outs[1][0][k] for k in outs[0][0])
+    assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
