@@ -125,6 +125,27 @@ def test_raster_edges_batch_matches_oracle(env):
 
 
 @pytest.mark.gpu
+def test_raster_edges_odd_width_takes_the_generic_path(env):
+    """A width that is not a multiple of 4 (and kernels wider than the fast path's 3/5/7/9) runs the
+    one-pixel-per-thread kernel: same bytes as the oracle."""
+    E = env["E"]
+    osz = (75, 50)
+    specs = E.make_specs(2, size="xsmall", first_seed=6)
+    steps = [0, 999]
+    ens = E.Ensemble(specs, T=1000, frame_steps=steps, device=env["dev"], output_size=osz)
+    ens.simulate()
+    img0 = ens.rasterize(image=True, instance=False)["image"].cpu().numpy()
+    _, polys = _polys("xsmall", osz)
+    for wb, eb, ks, bt in [(False, True, 3, "mean"), (False, True, 5, "motion"), (False, True, 10, "mean"),
+                           (False, True, 4, "motion"), (True, True, 3, "mean"), (True, False, 3, "mean")]:
+        got = ens.rasterize(image=True, instance=False, with_border=wb, edge_blur=eb, blur_kernel_size=ks,
+                            blur_type=bt)["image"].cpu().numpy()
+        for i in range(2):
+            for f in range(2):
+                assert np.array_equal(got[i, f], EO.edge_effects_oracle(img0[i, f], polys, osz, wb, eb, ks, bt)), (wb, eb, ks, bt)
+
+
+@pytest.mark.gpu
 def test_raster_edges_full_size_and_cv2(env):
     """512x512 medium frames (BASELINE config 3's image size): K2b == the reference's literal cv2 / numpy
     sequence (core/pouch.py:455-467) applied to K2's image."""

@@ -275,3 +275,14 @@ def test_create_instance_mask_helper(oracle):
         act = sorted(rng.choice(40, rng.randint(0, 15), replace=False).tolist())
         assert np.array_equal(create_instance_mask_from_cells(m, act), oracle.instance_mask_oracle(m, act))
     assert np.array_equal(create_instance_mask_from_cells(m), m.astype(np.uint16))
+
+
+def test_batch_device_list_resolution():
+    import torch
+    from calcium_b200.batch import _resolve_devices
+    assert _resolve_devices("cuda:1", None) == ["cuda:1"]
+    assert _resolve_devices(None, [0, "cuda:3"]) == [torch.device("cuda", 0), torch.device("cuda", 3)]
+    with pytest.raises(ValueError):
+        _resolve_devices(None, [])
+    with pytest.raises(ValueError):
+        _resolve_devices(None, "both")

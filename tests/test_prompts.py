@@ -203,3 +203,31 @@ def test_batch_prompts_do_not_depend_on_the_thread_count(cuda_device, tmp_path):
     assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 0
     assert outs[0][1] == outs[1][1]
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_legacy_choice_is_numpys_choice():
+    """cab200_legacy_choice (host code, no GPU): the indices AND the generator state numpy's own
+    RandomState.choice(n, k, replace=False) produces, for many sizes, states (incl. a cached gaussian) and k."""
+    from calcium_b200 import build
+    build.build()
+    from calcium_b200.prompts import legacy_choice
+    sizes = [4096, 5000, 65535, 65536, 65537, 100000, 131071, 131072, 262143, 262144]
+    for trial in range(40):
+        n = sizes[trial % len(sizes)]
+        k = [5, 1, 3, 17][trial % 4]
+        a, b = np.random.RandomState(trial), np.random.RandomState(trial)
+        pre = (trial * 37) % 700
+        a.random_sample(pre); b.random_sample(pre)
+        if trial % 5 == 0:
+            a.normal(); b.normal()
+        assert np.array_equal(a.choice(n, k, replace=False), legacy_choice(b, n, k)), (trial, n, k)
+        sa, sb = a.get_state(), b.get_state()
+        assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1]) and sa[3] == sb[3] and sa[4] == sb[4]
+        assert np.array_equal(a.randint(0, 1000, 10), b.randint(0, 1000, 10))
+    # the global generator (what the reference draws from) goes through the same path
+    from calcium_b200.prompts import global_rng
+    np.random.seed(9)
+    want = np.random.choice(200000, 5, replace=False)
+    w2 = np.random.randint(1000)
+    np.random.seed(9)
+    assert np.array_equal(legacy_choice(global_rng(), 200000, 5), want) and np.random.randint(1000) == w2
