@@ -77,7 +77,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                               save_pouch=False, dataset_split="train", *, geometry_dir=None,
                               device=None, write_files=True, keep_arrays=False,
                               max_chunk_bytes=4 << 30, writer_threads=8, generate_prompts=True,
-                              prompt_threads=8, devices=None):
+                              prompt_threads=None, devices=None):
     """Generate a batch of simulations with images and instance masks (see module docstring).
 
     Extra keyword-only arguments: ``geometry_dir``, ``device``, ``write_files`` (False: compute only),
@@ -225,7 +225,8 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     return files, rs.get_state()
 
                 last_state = None
-                with cf.ThreadPoolExecutor(max_workers=max(1, prompt_threads)) as pp:
+                n_pt = prompt_threads if prompt_threads else min(32, max(8, os.cpu_count() or 8))
+                with cf.ThreadPoolExecutor(max_workers=max(1, n_pt)) as pp:
                     for li, (files, state) in enumerate(pp.map(pouch_prompts, range(len(part)))):
                         prompt_files[li] = files
                         last_state = state

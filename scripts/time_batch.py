@@ -26,3 +26,5 @@ run("compute only (no files, no prompts) again", write_files=False, generate_pro
 run("files, no prompts", write_files=True, generate_prompts=False)
 run("files + prompts (default)", write_files=True, generate_prompts=True)
 run("edge_blur motion5: files, no prompts", write_files=True, generate_prompts=False, edge_blur=True, blur_kernel_size=5, blur_type="motion")
+for th in (4, 16, 32):
+    run(f"files + prompts, prompt_threads={th}", write_files=True, generate_prompts=True, prompt_threads=th)
