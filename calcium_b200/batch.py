@@ -8,8 +8,8 @@ same ``random.choice`` / ``np.random`` call sequence -- and then pushed through 
 K1 integrates a whole chunk in one launch, K2 rasterises every sampled frame, results stream back
 through pinned buffers to a pool of writer threads.
 
-Out of scope here: the stochastic defect pipeline (``defect_configs`` is
-accepted and ignored, images are the clean frames), prompt generation and label JSON.
+Out of scope here: the stochastic defect pipeline
+(``defect_configs`` is accepted and ignored, images are the clean frames) and label JSON.
 """
 from __future__ import annotations
 
