@@ -2,7 +2,8 @@
 
 Public surface (same names as the reference's Python API for this path):
   ``Pouch``, ``SimulationParameters``, ``GeometryLoader``, ``generate_simulation_batch``,
-  ``BatchGenerationController``, ``create_instance_mask_from_cells``; plus the batched
+  ``BatchGenerationController``, ``create_instance_mask_from_cells``, ``apply_all_defects`` (deterministic
+  defects only); plus the batched
   ``Ensemble`` / ``PouchSpec`` / ``make_specs`` driver the batch path is built on.
 
 Importing the package does not need a GPU; every compute call does (there is no CPU fallback) and
@@ -13,7 +14,7 @@ from .parameters import SimulationParameters  # noqa: F401
 
 __all__ = ["Pouch", "SimulationParameters", "GeometryLoader", "generate_simulation_batch",
            "BatchGenerationController", "Ensemble", "PouchSpec", "make_specs",
-           "create_instance_mask_from_cells", "get_geometry"]
+           "create_instance_mask_from_cells", "get_geometry", "apply_all_defects"]
 
 
 def __getattr__(name):
@@ -30,4 +31,7 @@ def __getattr__(name):
     if name == "create_instance_mask_from_cells":
         from .masks import create_instance_mask_from_cells
         return create_instance_mask_from_cells
+    if name == "apply_all_defects":
+        from .defects import apply_all_defects
+        return apply_all_defects
     raise AttributeError(f"module 'calcium_b200' has no attribute {name!r}")

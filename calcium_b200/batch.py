@@ -8,8 +8,10 @@ same ``random.choice`` / ``np.random`` call sequence -- and then pushed through 
 K1 integrates a whole chunk in one launch, K2 rasterises every sampled frame, results stream back
 through pinned buffers to a pool of writer threads.
 
-Out of scope here: the stochastic defect pipeline
-(``defect_configs`` is accepted and ignored, images are the clean frames) and label JSON.
+Defects: the deterministic ones of a caller-supplied ``defect_configs`` entry are
+applied on the GPU (K5, ``calcium_b200/defects.py``); stochastic ones and the two that raise in the reference itself
+are reported and skipped, and without ``defect_configs`` the frames stay clean (the reference would draw a random
+configuration per frame from the unseeded generator, ``main.py:273-277``).  Label JSON is out of scope.
 """
 from __future__ import annotations
 
@@ -25,6 +27,7 @@ import numpy as np
 import torch
 
 from . import io as cio
+from .defects import apply_defects, plan as defect_plan, unsupported_defects
 from .ensemble import DEFAULT_FRAME_STEPS, Ensemble, PouchSpec
 from .parameters import SimulationParameters
 
@@ -144,6 +147,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
         return path
 
     mappings_by_sim: Dict[int, List[tuple]] = {}
+    warned_defects: List[bool] = []
     final_states: Dict[int, Any] = {}
 
     def run_on_device(device, drawn):
@@ -156,7 +160,10 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             image_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             mask_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             img = ins = nact = None
-            if steps and not keep_arrays and not edge_blur:
+            cfgs = [(defect_configs[d["sim_idx"]] if (defect_configs is not None and d["sim_idx"] < len(defect_configs)) else None)
+                    for d in part]
+            with_defects = any(defect_plan(c, output_size) for c in cfgs)
+            if steps and not keep_arrays and not edge_blur and not with_defects:
                 # K1 -> K3: every frame arrives on the host as the finished .png / .npz byte string
                 # (cab200_encode_batch); writing a file is a plain write of those bytes.
                 def consumer(ch):
@@ -185,6 +192,15 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 # frames are not flat-shaded any more, so they take the raw-array path and the host PNG writer
                 out = ens.rasterize(image=True, instance=bool(generate_masks), edge_blur=bool(edge_blur),
                                     blur_kernel_size=int(blur_kernel_size), blur_type=blur_type) if steps else {}
+                if steps and with_defects:
+                    # K5: the deterministic defects of each pouch's configuration (main.py:289-293), in place
+                    for li, c in enumerate(cfgs):
+                        skipped = unsupported_defects(c)
+                        if skipped and not warned_defects:
+                            print("Defects not applied on the GPU path (stochastic, or raising in the reference itself): "
+                                  + ", ".join(skipped))
+                            warned_defects.append(True)
+                        apply_defects(out["image"][li], c, output_size)
                 ens.synchronize()
                 img = out["image"].cpu().numpy() if steps else None
                 ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and generate_masks) else None
