@@ -141,10 +141,11 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     per_pouch_bytes = max(1, len(steps)) * h * w * (2 + (2 if generate_masks else 0))
     chunk = max(1, int(max_chunk_bytes // per_pouch_bytes))
 
-    def _write_bytes(path: str, data: bytes) -> str:
-        with open(path, "wb") as fh:
-            fh.write(data)
-        return path
+    def _write_many(items) -> int:
+        for path, data in items:
+            with open(path, "wb") as fh:
+                fh.write(data)
+        return len(items)
 
     mappings_by_sim: Dict[int, List[tuple]] = {}
     warned_defects: List[bool] = []
@@ -169,19 +170,22 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 def consumer(ch):
                     for i in range(ch.hi - ch.lo):
                         li = ch.lo + i
+                        todo = []                           # one writer task per pouch: (path, bytes) of its frames
                         for fi in range(len(steps)):
                             base = names[li][fi]
                             ipath = os.path.join(img_dir, base + ".png")
                             image_files[li].append(ipath)
                             if pool is not None:
-                                pending.append(pool.submit(_write_bytes, ipath, bytes(ch.file(i, fi, 0))))
+                                todo.append((ipath, bytes(ch.file(i, fi, 0))))
                             mb = ch.file(i, fi, 1) if generate_masks else None
                             if mb is not None:     # no active cell -> no mask (sam2_data_generator.py:318-319)
                                 mpath = os.path.join(mask_dir, base + ".npz")
                                 mask_files[li].append(mpath)
                                 mappings_by_sim.setdefault(part[li]["sim_idx"], []).append((os.path.basename(ipath), os.path.basename(mpath)))
                                 if pool is not None:
-                                    pending.append(pool.submit(_write_bytes, mpath, bytes(mb)))
+                                    todo.append((mpath, bytes(mb)))
+                        if todo:
+                            pending.append(pool.submit(_write_many, todo))
                 ens.run_files_to_host(chunk_pouches=min(len(part), 37), image=True, mask=bool(generate_masks),
                                       consumer=consumer)
                 status = ens.check_status()

@@ -111,11 +111,28 @@ def vignette_map(output_size: Tuple[int, int], strength: float) -> np.ndarray:
     return np.ascontiguousarray(1 - strength * np.clip(r, 0, 1) ** 2)
 
 
+_PLAN_KEYS = ("background_fluorescence", "non_uniform_background", "background_intensity", "vignetting",
+              "vignetting_strength", "dynamic_range_compression", "gamma", "quantization", "bit_depth",
+              "adjust_brightness_contrast", "brightness", "contrast")
+_PLAN_CACHE: Dict[Any, List[Tuple[int, Optional[np.ndarray]]]] = {}
+
+
 def plan(config: Optional[Dict[str, Any]], output_size: Tuple[int, int]) -> List[Tuple[int, Optional[np.ndarray]]]:
     """The passes of ``apply_all_defects`` for the supported defects of ``config``, in the reference's order:
-    ``(kind, table or float64 map)``."""
+    ``(kind, table or float64 map)``.  Cached per (configuration, output size): a batch usually carries one
+    configuration for all its pouches."""
     if not config:
         return []
+    key = (tuple((k, repr(config.get(k))) for k in _PLAN_KEYS), int(output_size[0]), int(output_size[1]))
+    hit = _PLAN_CACHE.get(key)
+    if hit is None:
+        if len(_PLAN_CACHE) > 64:
+            _PLAN_CACHE.clear()
+        hit = _PLAN_CACHE[key] = _build_plan(config, output_size)
+    return hit
+
+
+def _build_plan(config: Dict[str, Any], output_size: Tuple[int, int]) -> List[Tuple[int, Optional[np.ndarray]]]:
     ops: List[Tuple[int, Optional[np.ndarray]]] = []
     if config.get("background_fluorescence", False) and not config.get("non_uniform_background", True):
         ops.append((_lib.DEFECT_LUT_MAX, table_background(config.get("background_intensity", 0.1))))
