@@ -111,4 +111,4 @@ def test_batch_path_applies_deterministic_defects(cuda_device, tmp_path):
             png = cv2.imread(os.path.join(str(tmp_path), "images", "train", name), cv2.IMREAD_UNCHANGED)
             want = DO.apply_supported_defects(clean[i, f], cfg) if i == 0 else clean[i, f]
             assert np.array_equal(png[..., 0], want[..., 0].astype(np.uint16) * 4), (i, t)
-            assert np.array_equal(png[..., 1], want[..., 1].astype(np.uint16) * 257), (i, t)
+            assert np.array_equal(png[..., -1], want[..., 1].astype(np.uint16) * 257), (i, t)
