@@ -12,6 +12,7 @@
 // numpy itself).
 #include <stdint.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -54,15 +55,11 @@ struct Mt {
 
 }  // namespace
 
-// See include/cab200.h.
-extern "C" int cab200_legacy_choice(uint32_t *mt_key, int32_t *mt_pos, int64_t n, int32_t k, int64_t *out)
+namespace {
+
+// permutation(n)[:k] on the generator mt: numpy's _shuffle_raw + random_interval (see the file header)
+void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
 {
-    using cab200::set_error;
-    if (!mt_key || !mt_pos || !out || n < 1 || k < 0 || k > n || n > 0x7fffffffLL || *mt_pos < 0 || *mt_pos > MT_N) {
-        set_error("cab200_legacy_choice: bad argument");
-        return CAB200_EINVAL;
-    }
-    Mt mt{mt_key, *mt_pos};
     std::vector<int32_t> a((size_t)n);
     for (int64_t i = 0; i < n; ++i) a[(size_t)i] = (int32_t)i;
     for (int64_t i = n - 1; i >= 1; --i) {
@@ -76,6 +73,60 @@ extern "C" int cab200_legacy_choice(uint32_t *mt_key, int32_t *mt_pos, int64_t n
         a[(size_t)i] = t;
     }
     for (int32_t q = 0; q < k; ++q) out[q] = a[(size_t)q];
+}
+
+}  // namespace
+
+// See include/cab200.h.
+extern "C" int cab200_legacy_choice(uint32_t *mt_key, int32_t *mt_pos, int64_t n, int32_t k, int64_t *out)
+{
+    using cab200::set_error;
+    if (!mt_key || !mt_pos || !out || n < 1 || k < 0 || k > n || n > 0x7fffffffLL || *mt_pos < 0 || *mt_pos > MT_N) {
+        set_error("cab200_legacy_choice: bad argument");
+        return CAB200_EINVAL;
+    }
+    Mt mt{mt_key, *mt_pos};
+    choice_first_k(mt, n, k, out);
     *mt_pos = mt.pos;
+    return CAB200_OK;
+}
+
+// See include/cab200.h.
+extern "C" int cab200_sample_background(const uint16_t *labels, const uint8_t *labelled_lut, int32_t n_lut,
+                                        const int32_t *d2, int64_t npix, int32_t min_d2, uint32_t *mt_key,
+                                        int32_t *mt_pos, int32_t k, int64_t *px_out, int64_t *count_out)
+{
+    using cab200::set_error;
+    if (!labels || !labelled_lut || !d2 || !mt_key || !mt_pos || !px_out || !count_out || npix < 1 ||
+        npix > 0x7fffffffLL || k < 0 || n_lut < 1 || *mt_pos < 0 || *mt_pos > MT_N) {
+        set_error("cab200_sample_background: bad argument");
+        return CAB200_EINVAL;
+    }
+    // candidates, row-major: pixels of no instance at least sqrt(min_d2) away from every instance (np.where order)
+    int64_t count = 0;
+    for (int64_t p = 0; p < npix; ++p) {
+        const uint32_t l = labels[p];
+        if (l >= (uint32_t)n_lut) { set_error("cab200_sample_background: label outside the table"); return CAB200_EINVAL; }
+        count += (!labelled_lut[l] && d2[p] >= min_d2) ? 1 : 0;
+    }
+    *count_out = count;
+    if (count == 0 || k == 0) return CAB200_OK;
+    const int32_t kk = (int32_t)std::min<int64_t>(k, count);
+    std::vector<int64_t> rank((size_t)kk);
+    Mt mt{mt_key, *mt_pos};
+    choice_first_k(mt, count, kk, rank.data());
+    *mt_pos = mt.pos;
+    // rank -> pixel: one more pass, visiting the wanted ranks in ascending order
+    std::vector<int32_t> order((size_t)kk);
+    for (int32_t q = 0; q < kk; ++q) order[(size_t)q] = q;
+    std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return rank[(size_t)x] < rank[(size_t)y]; });
+    int64_t seen = 0;
+    int32_t next = 0;
+    for (int64_t p = 0; p < npix && next < kk; ++p) {
+        if (!labelled_lut[labels[p]] && d2[p] >= min_d2) {
+            while (next < kk && rank[(size_t)order[(size_t)next]] == seen) px_out[order[(size_t)next++]] = p;
+            ++seen;
+        }
+    }
     return CAB200_OK;
 }

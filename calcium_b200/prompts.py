@@ -90,6 +90,7 @@ class PromptTables:
         lab = label_mask.cpu().numpy().view(np.uint16).astype(np.int64)
         self.labels_host = lab
         self.labels_u16 = label_mask.cpu().numpy().view(np.uint16).copy()
+        self.present_labels = np.unique(self.labels_u16).astype(np.int64)      # label values that own a pixel
         self.H, self.W = lab.shape
         self._empty: Dict[float, Tuple[np.ndarray, np.ndarray]] = {}
         d2 = edt_squared(label_mask)[0].cpu().numpy()
@@ -161,6 +162,31 @@ def legacy_choice(rng, n: int, k: int) -> np.ndarray:
     return out
 
 
+def sample_background(rng, labels_u16: np.ndarray, labelled_lut: np.ndarray, d2: np.ndarray, min_d2: int, k: int
+                      ) -> Tuple[np.ndarray, int]:
+    """Candidate selection + draw of ``generate_negative_prompts`` (``utils/sam2_data_generator.py:152-166``) in
+    one call outside the interpreter lock (``cab200_sample_background``): flat pixel indices of the drawn
+    candidates (draw order) and the candidate count; ``rng`` ends in the state ``rng.choice`` would leave."""
+    name, key, pos, has_gauss, cached = rng.get_state()
+    if name != "MT19937":
+        raise ValueError("legacy MT19937 generator expected")
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    cpos = ctypes.c_int32(int(pos))
+    out = np.empty(max(k, 1), dtype=np.int64)
+    count = ctypes.c_int64(0)
+    lut8 = np.ascontiguousarray(labelled_lut, dtype=np.uint8)
+    d2c = np.ascontiguousarray(d2, dtype=np.int32)
+    lab = np.ascontiguousarray(labels_u16, dtype=np.uint16)
+    _lib.check(_lib.load().cab200_sample_background(lab.ctypes.data, lut8.ctypes.data, int(lut8.size), d2c.ctypes.data,
+                                                    int(lab.size), int(min_d2), key.ctypes.data, ctypes.byref(cpos),
+                                                    int(k), out.ctypes.data, ctypes.byref(count)),
+               "cab200_sample_background")
+    n = int(count.value)
+    if n > 0 and k > 0:
+        rng.set_state((name, key, int(cpos.value), has_gauss, cached))
+    return out[:min(k, n)], n
+
+
 def global_rng():
     """The legacy global generator behind ``np.random.randint`` / ``np.random.choice`` (what the reference
     draws from); pass a private ``np.random.RandomState`` to ``frame_prompts`` to leave it alone."""
@@ -179,8 +205,8 @@ def frame_prompts(tables: PromptTables, ca: np.ndarray, threshold: float = 0.1, 
     rng = global_rng() if rng is None else rng
     lut = instance_lut(ca, threshold, quirk)
     background_id = int(lut[0]) if lut[0] else None                    # id given to every zero pixel (cell 0 active)
-    labelled = (lut > 0)[tables.labels_u16]                            # instance_mask > 0
-    any_labelled = bool(labelled.any())
+    pos_lut = lut > 0
+    any_labelled = bool(pos_lut[tables.present_labels].any())          # (instance_mask > 0).any()
     d2_bg = d2_neg = None
     if background_id is not None or (num_negative > 0 and any_labelled):
         d2_bg, d2_neg = _frame_transforms(tables, lut, background_id is not None)
@@ -234,10 +260,16 @@ def frame_prompts(tables: PromptTables, ca: np.ndarray, threshold: float = 0.1, 
             # samples its negatives from that map (utils/sam2_data_generator.py:152-159).  Static per size.
             flat, d2 = tables.empty_frame_candidates(md)
         elif md >= 1.0 and md.is_integer():
-            # sqrt(d2) >= md  <=>  d2 >= md^2 for integers; labelled pixels have distance 0 < md
-            flat = np.flatnonzero(~labelled & (d2_neg >= int(md) ** 2))
+            # sqrt(d2) >= md  <=>  d2 >= md^2 for integers; labelled pixels have distance 0 < md.  Selection and
+            # draw in one pass outside the interpreter lock
+            picked, _ = sample_background(rng, tables.labels_u16, pos_lut, d2_neg, int(md) ** 2, num_negative)
             d2 = d2_neg.ravel()
+            for px in picked.tolist():
+                negatives.append({"point": [px % tables.W, px // tables.W], "label": 0,
+                                  "confidence": float(np.sqrt(np.float64(d2[px])))})
+            flat = ()
         else:
+            labelled = pos_lut[tables.labels_u16]
             dist = np.where(labelled, 0.0, np.sqrt(d2_neg.astype(np.float64)))
             flat = np.flatnonzero(dist >= md)
             d2 = np.where(labelled, 0, d2_neg).ravel()

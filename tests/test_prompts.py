@@ -231,3 +231,29 @@ def test_legacy_choice_is_numpys_choice():
     w2 = np.random.randint(1000)
     np.random.seed(9)
     assert np.array_equal(legacy_choice(global_rng(), 200000, 5), want) and np.random.randint(1000) == w2
+
+
+def test_sample_background_is_the_numpy_selection_and_draw():
+    """cab200_sample_background (host code): candidate count, drawn pixels and generator state of
+    flatnonzero(~labelled & (d2 >= 25)) + RandomState.choice(n, k, replace=False)."""
+    from calcium_b200 import build
+    build.build()
+    from calcium_b200.prompts import sample_background
+    R = np.random.RandomState(0)
+    for trial in range(40):
+        H, W = [(64, 80), (512, 512), (200, 333), (16, 16)][trial % 4]
+        n = R.randint(5, 1500)
+        labels = R.randint(0, n + 1, (H, W)).astype(np.uint16)
+        lutpos = R.rand(n + 1) < [0.0, 0.02, 0.5, 1.0][trial % 4]
+        if trial % 4 != 3:
+            lutpos[0] = False
+        d2 = R.randint(0, 60, (H, W)).astype(np.int32)
+        k = [5, 1, 7, 5][trial % 4]
+        a, b = np.random.RandomState(trial), np.random.RandomState(trial)
+        a.random_sample(trial * 13 % 650); b.random_sample(trial * 13 % 650)
+        flat = np.flatnonzero(~lutpos[labels] & (d2 >= 25))
+        want = flat[a.choice(len(flat), min(k, len(flat)), replace=False)] if len(flat) else np.zeros(0, np.int64)
+        got, cnt = sample_background(b, labels, lutpos, d2, 25, k)
+        assert cnt == len(flat) and np.array_equal(got, want), trial
+        sa, sb = a.get_state(), b.get_state()
+        assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1]), trial
