@@ -257,3 +257,54 @@ def test_sample_background_is_the_numpy_selection_and_draw():
         assert cnt == len(flat) and np.array_equal(got, want), trial
         sa, sb = a.get_state(), b.get_state()
         assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1]), trial
+
+
+def _scipy_edt_squared(label_map, class_luts=None):
+    """Stand-in for K4 on the CPU (tests only): exact squared distance to the nearest pixel of a different class."""
+    import torch
+    from scipy.ndimage import distance_transform_edt
+    lab = label_map.cpu().numpy().view(np.uint16)
+    maps = [lab] if class_luts is None else [class_luts.cpu().numpy().view(np.uint16)[i][lab] for i in range(class_luts.shape[0])]
+    out = []
+    for cls in maps:
+        d2 = np.zeros(cls.shape, dtype=np.int64)
+        for v in np.unique(cls):
+            b = cls == v
+            if b.all():
+                d2[b] = 2 ** 30                      # no pixel of another class (K4 writes "far"; never selected)
+                continue
+            ys, xs = np.nonzero(b)
+            y0, y1, x0, x1 = max(ys.min() - 1, 0), min(ys.max() + 2, cls.shape[0]), max(xs.min() - 1, 0), min(xs.max() + 2, cls.shape[1])
+            sub = b[y0:y1, x0:x1]
+            if sub.all():                            # the class touches every border of its box: use the full image
+                sub, y0, x0 = b, 0, 0
+            d = distance_transform_edt(sub)
+            full = np.rint(d * d).astype(np.int64)
+            d2[y0:y0 + sub.shape[0], x0:x0 + sub.shape[1]][sub] = full[sub]
+        out.append(d2.astype(np.int32))
+    return torch.from_numpy(np.stack(out))
+
+
+@pytest.mark.parametrize("t,thr", CASES)
+def test_frame_prompts_host_logic_on_cpu(gold, monkeypatch, t, thr):
+    """The host side of the prompt path (static tables, array draws, the lock-free selection + draw, generator
+    state) against the reference's recorded prompts, with scipy standing in for the K4 kernel."""
+    import torch
+    from calcium_b200 import build
+    build.build()
+    from calcium_b200 import prompts as P
+    monkeypatch.setattr(P, "edt_squared", _scipy_edt_squared)
+    z, j = gold
+    g = j[f"{t}_{thr}"]
+    lmsk = torch.from_numpy(z["cells_mask"].astype(np.uint16).view(np.int16))
+    tables = P.PromptTables(lmsk, int(z["ca"].shape[1]))
+    ca = z["ca"][list(z["t"]).index(t)]
+    np.random.seed(g["seed"])
+    pos, neg = P.frame_prompts(tables, ca, threshold=thr, quirk=True)
+    assert pos == _norm(g["positive"])
+    assert neg == g["negative"]
+    rs = np.random.RandomState(g["seed"])
+    pos2, neg2 = P.frame_prompts(tables, ca, threshold=thr, quirk=True, rng=rs)
+    assert pos2 == pos and neg2 == neg
+    end = np.random.get_state()
+    assert rs.get_state()[2] == end[2] and np.array_equal(rs.get_state()[1], end[1])
