@@ -164,6 +164,12 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             cfgs = [(defect_configs[d["sim_idx"]] if (defect_configs is not None and d["sim_idx"] < len(defect_configs)) else None)
                     for d in part]
             with_defects = any(defect_plan(c, output_size) for c in cfgs)
+            for c in cfgs:
+                skipped = unsupported_defects(c)
+                if skipped and not warned_defects:
+                    print("Defects not applied on the GPU path (stochastic, or raising in the reference itself): "
+                          + ", ".join(skipped))
+                    warned_defects.append(True)
             if steps and not keep_arrays and not edge_blur and not with_defects:
                 # K1 -> K3: every frame arrives on the host as the finished .png / .npz byte string
                 # (cab200_encode_batch); writing a file is a plain write of those bytes.
@@ -199,11 +205,6 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 if steps and with_defects:
                     # K5: the deterministic defects of each pouch's configuration (main.py:289-293), in place
                     for li, c in enumerate(cfgs):
-                        skipped = unsupported_defects(c)
-                        if skipped and not warned_defects:
-                            print("Defects not applied on the GPU path (stochastic, or raising in the reference itself): "
-                                  + ", ".join(skipped))
-                            warned_defects.append(True)
                         apply_defects(out["image"][li], c, output_size)
                 ens.synchronize()
                 img = out["image"].cpu().numpy() if steps else None
