@@ -1,6 +1,6 @@
 """Wall-clock of the public batch entry point (generate_simulation_batch) for N medium pouches, with and
 without prompts / file writing: where the host time goes once the GPU part takes milliseconds."""
-import os, sys, time, tempfile, shutil, io, contextlib
+import os, sys, time, tempfile, shutil, io, contextlib, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from calcium_b200 import generate_simulation_batch
@@ -9,6 +9,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 37
 def run(label, **kw):
     d = tempfile.mkdtemp(prefix="cab_batch_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
+        random.seed(1)                         # the batch draws sizes / sim types from the stdlib generator
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):
             res = generate_simulation_batch(N, d, pouch_sizes=["medium"], **kw)
