@@ -26,6 +26,7 @@ from __future__ import annotations
 import ctypes
 import json
 import os
+import threading
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -38,23 +39,42 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def edt_squared(label_map: torch.Tensor, class_luts: Optional[torch.Tensor] = None) -> torch.Tensor:
+def edt_squared(label_map: torch.Tensor, class_luts: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K4: int32 ``[n_maps, H, W]`` squared distance to the nearest pixel of a different class.
     ``label_map``: uint16-as-int16 ``[H, W]`` device tensor; ``class_luts``: int16 ``[n_maps, L]``
-    (class per label value) or ``None`` (class = label)."""
+    (class per label value) or ``None`` (class = label).  ``out`` / ``scratch``: optional preallocated buffers."""
     lib = _lib.load()
     dev = label_map.device
     h, w = int(label_map.shape[0]), int(label_map.shape[1])
     n_maps = 1 if class_luts is None else int(class_luts.shape[0])
     with torch.cuda.device(dev):
-        out = torch.empty((n_maps, h, w), dtype=torch.int32, device=dev)
         nb = int(lib.cab200_edt_scratch_bytes(n_maps, h, w))
-        scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty((n_maps, h, w), dtype=torch.int32, device=dev)
+        if scratch is None or scratch.numel() < nb:
+            scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
         rc = lib.cab200_edt_classes(label_map.data_ptr(), class_luts.data_ptr() if class_luts is not None else None,
                                     int(class_luts.shape[1]) if class_luts is not None else 0, n_maps, h, w,
                                     out.data_ptr(), scratch.data_ptr(), nb, _stream_ptr(dev))
         _lib.check(rc, "cab200_edt_classes")
     return out
+
+
+class _Workspace:
+    """Per-thread buffers of the frame-dependent transforms (device maps + scratch + class tables, pinned host
+    copy): allocating them per frame cost more than the kernel."""
+
+    def __init__(self, tables: "PromptTables"):
+        dev = tables.label_mask.device
+        lib = _lib.load()
+        h, w = tables.H, tables.W
+        with torch.cuda.device(dev):
+            self.out = torch.empty((2, h, w), dtype=torch.int32, device=dev)
+            self.scratch = torch.empty(max(int(lib.cab200_edt_scratch_bytes(2, h, w)), 16), dtype=torch.uint8, device=dev)
+            self.luts = torch.empty((2, tables.n + 1), dtype=torch.int16, device=dev)
+        self.host = torch.empty((2, h, w), dtype=torch.int32, pin_memory=True)
+        self.host_luts = torch.empty((2, tables.n + 1), dtype=torch.int16, pin_memory=True)
 
 
 def instance_lut(ca: np.ndarray, threshold: float = 0.1, quirk: bool = True) -> np.ndarray:
@@ -93,6 +113,7 @@ class PromptTables:
         self.present_labels = np.unique(self.labels_u16).astype(np.int64)      # label values that own a pixel
         self.H, self.W = lab.shape
         self._empty: Dict[float, Tuple[np.ndarray, np.ndarray]] = {}
+        self._tls = threading.local()                                  # per-thread K4 workspace
         d2 = edt_squared(label_mask)[0].cpu().numpy()
         flat = lab.ravel()
         order = np.argsort(flat, kind="stable")                       # groups pixels by label, row-major inside
@@ -136,11 +157,25 @@ def _frame_transforms(tables: PromptTables, lut: np.ndarray, background: bool = 
                       ) -> Tuple[Optional[np.ndarray], np.ndarray]:
     """The frame-dependent transforms on the device (one K4 call): squared distance to the nearest pixel
     whose (id > 0) class differs and -- only when the id mismatch made a background instance -- the same for
-    the class (id == 1).  Returns ``(d2_background_instance or None, d2_negative)``."""
-    rows = [(lut == 1), (lut > 0)] if background else [(lut > 0)]
-    luts = np.stack(rows).astype(np.uint16).view(np.int16)
-    d = edt_squared(tables.label_mask, torch.from_numpy(luts).to(tables.label_mask.device))
-    both = d.cpu().numpy()
+    the class (id == 1).  Returns ``(d2_background_instance or None, d2_negative)`` as views of this thread's
+    pinned buffer (valid until the thread's next call)."""
+    ws = getattr(tables._tls, "ws", None)
+    if ws is None:
+        ws = tables._tls.ws = _Workspace(tables)
+    k = 2 if background else 1
+    hl = ws.host_luts.numpy()
+    if background:
+        hl[0] = lut == 1
+        hl[1] = lut > 0
+    else:
+        hl[0] = lut > 0
+    dev = tables.label_mask.device
+    with torch.cuda.device(dev):
+        ws.luts[:k].copy_(ws.host_luts[:k], non_blocking=True)
+        d = edt_squared(tables.label_mask, ws.luts[:k], out=ws.out[:k], scratch=ws.scratch)
+        ws.host[:k].copy_(d, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    both = ws.host.numpy()
     return (both[0], both[1]) if background else (None, both[0])
 
 

@@ -294,6 +294,13 @@ def test_frame_prompts_host_logic_on_cpu(gold, monkeypatch, t, thr):
     build.build()
     from calcium_b200 import prompts as P
     monkeypatch.setattr(P, "edt_squared", _scipy_edt_squared)
+
+    def cpu_transforms(tables, lut, background=True):          # _frame_transforms without the device workspace
+        rows = [(lut == 1), (lut > 0)] if background else [(lut > 0)]
+        luts = torch.from_numpy(np.stack(rows).astype(np.uint16).view(np.int16))
+        both = _scipy_edt_squared(tables.label_mask, luts).numpy()
+        return (both[0], both[1]) if background else (None, both[0])
+    monkeypatch.setattr(P, "_frame_transforms", cpu_transforms)
     z, j = gold
     g = j[f"{t}_{thr}"]
     lmsk = torch.from_numpy(z["cells_mask"].astype(np.uint16).view(np.int16))
