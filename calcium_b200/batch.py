@@ -217,13 +217,14 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 # seeded (core/pouch.py:317), so every pouch gets a private legacy generator restored to the state
                 # its own draws left behind -- same values as the reference's sequential loop -- and the pouches
                 # run on a thread pool (numpy's shuffle / ufuncs and the K4 calls release the GIL).
-                from .prompts import PromptTables, frame_prompts, save_prompts
+                from .prompts import PromptTables, frame_prompts
                 lmsk = ens.label_maps()[1]
                 tables: Dict[int, Any] = {}
                 for li in range(len(part)):
                     g = int(ens.geom_id[li])
                     if g not in tables:
                         tables[g] = PromptTables(lmsk[g], int(ens.g_ncell[g]))
+                        tables[g].candidate_entries()                 # built before the threads start
                 ca_host = [ens.frames_of(li)[:, 0, :].cpu().numpy() for li in range(len(part))]
 
                 def pouch_prompts(li: int):
@@ -236,10 +237,11 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                             if not (ca_all[fi] > 0.1).any():          # no active cell: nothing is written (:318-319)
                                 continue
                             try:
-                                pos, neg = frame_prompts(tab, ca_all[fi], rng=rs)
+                                text, _ = frame_prompts(tab, ca_all[fi], rng=rs, as_text=True)
                                 ppath = os.path.join(prompt_dir, names[li][fi] + ".json")
                                 if write_files:
-                                    save_prompts(pos, ppath, neg)
+                                    with open(ppath, "w") as fh:        # the text save_prompts writes (prompts.py)
+                                        fh.write(text)
                                 files.append(ppath)
                             except Exception as e:  # noqa: BLE001 - a failing frame is reported and skipped (main.py:342-351)
                                 print(f"Error processing time step {steps[fi]} for simulation {d['sim_idx']}: {str(e)}")

@@ -153,6 +153,21 @@ def _empty_frame_candidates(self, min_distance: float) -> Tuple[np.ndarray, np.n
 PromptTables.empty_frame_candidates = _empty_frame_candidates
 
 
+def _candidate_entries(self) -> List[str]:
+    """The prompt-file entry of a single-cell instance for every candidate pixel (static: the pixel fixes point,
+    area and confidence), built on first use."""
+    got = getattr(self, "_cand_text", None)
+    if got is None:
+        area_of = np.repeat(self.area, np.diff(self.cand_off))
+        got = [_positive_entry({"point": [x, y], "label": 1, "area": a, "confidence": d})
+               for x, y, a, d in zip(self.cand_x.tolist(), self.cand_y.tolist(), area_of.tolist(), self.cand_d.tolist())]
+        self._cand_text = got
+    return got
+
+
+PromptTables.candidate_entries = _candidate_entries
+
+
 def _frame_transforms(tables: PromptTables, lut: np.ndarray, background: bool = True
                       ) -> Tuple[Optional[np.ndarray], np.ndarray]:
     """The frame-dependent transforms on the device (one K4 call): squared distance to the nearest pixel
@@ -230,13 +245,18 @@ def global_rng():
 
 def frame_prompts(tables: PromptTables, ca: np.ndarray, threshold: float = 0.1, quirk: bool = True,
                   num_negative: int = 5, min_distance_from_cells: int = 5, min_cell_area: int = 10,
-                  rng=None) -> Tuple[Dict[int, Dict], List[Dict]]:
+                  rng=None, as_text: bool = False):
     """``(generate_point_prompts_from_mask(instance_mask), generate_negative_prompts(instance_mask, 5))``
     for the frame whose calcium values are ``ca`` -- the dicts of ``utils/sam2_data_generator.py:124-129``
     and ``:170-174`` -- consuming the generator ``rng`` (default: the global legacy numpy generator) exactly
     like those two calls: one ``randint`` per instance in ascending id order (drawn as one array call per
     run of single-cell instances, which yields the same values and leaves the same state as the scalar
-    calls), then one ``choice(n, k, replace=False)``."""
+    calls), then one ``choice(n, k, replace=False)``.
+
+    ``as_text=True`` returns the prompt file's text (what ``save_prompts`` writes, byte for byte) instead of the
+    two structures: the entry of a single-cell instance depends on the drawn candidate pixel only, so it is a
+    precomputed string and a frame with 1 400 instances costs 1 400 list look-ups instead of 1 400 dicts plus
+    their JSON encoding."""
     rng = global_rng() if rng is None else rng
     lut = instance_lut(ca, threshold, quirk)
     background_id = int(lut[0]) if lut[0] else None                    # id given to every zero pixel (cell 0 active)
@@ -259,11 +279,16 @@ def frame_prompts(tables: PromptTables, ca: np.ndarray, threshold: float = 0.1, 
     off = tables.cand_off[cells]
     cnt = tables.cand_off[cells + 1] - off
     prompts: Dict[int, Dict] = {}
+    entries: List[str] = []                                            # as_text: the positive entries, in id order
+    cand_text = tables.candidate_entries() if as_text else None
 
     def draw_cells(lo: int, hi: int) -> None:
         if hi <= lo:
             return
         pick = off[lo:hi] + rng.randint(0, cnt[lo:hi])
+        if as_text:
+            entries.extend(f'    "{iid}": {cand_text[k]}' for iid, k in zip(cid[lo:hi].tolist(), pick.tolist()))
+            return
         for iid, x, y, a, c in zip(cid[lo:hi].tolist(), tables.cand_x[pick].tolist(), tables.cand_y[pick].tolist(),
                                    tables.area[cells[lo:hi]].tolist(), tables.cand_d[pick].tolist()):
             prompts[iid] = {"point": [x, y], "label": 1, "area": a, "confidence": c}
@@ -281,8 +306,12 @@ def frame_prompts(tables: PromptTables, ca: np.ndarray, threshold: float = 0.1, 
                 thr = np.percentile(dist[dist > 0], 80)
                 ys, xs = np.where(dist >= thr)
                 idx = rng.randint(len(ys))
-                prompts[background_id] = {"point": [int(xs[idx]), int(ys[idx])], "label": 1, "area": area,
-                                          "confidence": float(dist[ys[idx], xs[idx]])}
+                bg = {"point": [int(xs[idx]), int(ys[idx])], "label": 1, "area": area,
+                      "confidence": float(dist[ys[idx], xs[idx]])}
+                if as_text:
+                    entries.append(f'    "{background_id}": {_positive_entry(bg)}')
+                else:
+                    prompts[background_id] = bg
         draw_cells(split, len(cid))
 
     # ---- negative prompts -----------------------------------------------------------------------------
@@ -314,6 +343,8 @@ def frame_prompts(tables: PromptTables, ca: np.ndarray, threshold: float = 0.1, 
                 px = int(flat[idx])
                 negatives.append({"point": [px % tables.W, px // tables.W], "label": 0,
                                   "confidence": float(np.sqrt(np.float64(d2[px])))})
+    if as_text:
+        return _assemble(entries, negatives), len(entries)
     return prompts, negatives
 
 
@@ -321,20 +352,15 @@ def _fmt_point(pt, ind: str) -> str:
     return f"[\n{ind}  {pt[0]},\n{ind}  {pt[1]}\n{ind}]"
 
 
-def dumps_prompts(prompts: Dict, negative_prompts: Optional[List] = None) -> str:
-    """The text ``json.dump(data, f, indent=2)`` writes for the reference's prompt file
-    (``utils/sam2_data_generator.py:228-238``), formatted directly: the pure-Python encoder ``indent`` switches
-    ``json`` to costs more than computing the prompts (1 400 instances per frame of a fluttering pouch)."""
-    neg = negative_prompts or []
+def _positive_entry(v: Dict) -> str:
+    return (f'{{\n      "point": {_fmt_point(v["point"], "      ")},\n      "label": {v["label"]},\n'
+            f'      "area": {v["area"]},\n      "confidence": {float.__repr__(v["confidence"])}\n    }}')
+
+
+def _assemble(entries: List[str], neg: List[Dict]) -> str:
+    """The file text from the positive entries (already formatted, in id order) and the negative prompts."""
     fr = float.__repr__
-    if prompts:
-        body = ",\n".join(
-            f'    "{k}": {{\n      "point": {_fmt_point(v["point"], "      ")},\n      "label": {v["label"]},\n'
-            f'      "area": {v["area"]},\n      "confidence": {fr(v["confidence"])}\n    }}'
-            for k, v in prompts.items())
-        pos = "{\n" + body + "\n  }"
-    else:
-        pos = "{}"
+    pos = "{\n" + ",\n".join(entries) + "\n  }" if entries else "{}"
     if neg:
         body = ",\n".join(
             f'    {{\n      "point": {_fmt_point(v["point"], "      ")},\n      "label": {v["label"]},\n'
@@ -342,8 +368,15 @@ def dumps_prompts(prompts: Dict, negative_prompts: Optional[List] = None) -> str
         ng = "[\n" + body + "\n  ]"
     else:
         ng = "[]"
-    return (f'{{\n  "positive_prompts": {pos},\n  "negative_prompts": {ng},\n  "num_cells": {len(prompts)},\n'
+    return (f'{{\n  "positive_prompts": {pos},\n  "negative_prompts": {ng},\n  "num_cells": {len(entries)},\n'
             f'  "version": "1.0"\n}}')
+
+
+def dumps_prompts(prompts: Dict, negative_prompts: Optional[List] = None) -> str:
+    """The text ``json.dump(data, f, indent=2)`` writes for the reference's prompt file
+    (``utils/sam2_data_generator.py:228-238``), formatted directly: the pure-Python encoder ``indent`` switches
+    ``json`` to costs more than computing the prompts (1 400 instances per frame of a fluttering pouch)."""
+    return _assemble([f'    "{k}": {_positive_entry(v)}' for k, v in prompts.items()], negative_prompts or [])
 
 
 def save_prompts(prompts: Dict, output_path: str, negative_prompts: Optional[List] = None) -> str:

@@ -152,7 +152,7 @@ def test_gpu_prompts_match_the_oracle_on_medium_frames(cuda_device):
     from calcium_b200 import build
     build.build()
     from calcium_b200 import ensemble as E
-    from calcium_b200.prompts import PromptTables, frame_prompts, instance_lut
+    from calcium_b200.prompts import PromptTables, dumps_prompts, frame_prompts, instance_lut
     from oracle import prompts_oracle as PO
     specs = E.make_specs(4, size="medium")
     steps = [0, 4000, 9000, 17999]
@@ -181,6 +181,9 @@ def test_gpu_prompts_match_the_oracle_on_medium_frames(cuda_device):
                 assert got[1] == want[1], (i, f, thr)
                 st = rs.get_state()
                 assert st[2] == end[2] and np.array_equal(st[1], end[1])       # generator left in the same state
+                rt = np.random.RandomState(100 * i + f)
+                text, n_pos = frame_prompts(tables, ca_all[f], threshold=thr, rng=rt, as_text=True)
+                assert text == dumps_prompts(got[0], got[1]) and n_pos == len(got[0])
     assert seen_empty > 0 and seen_bg > 0
 
 
@@ -313,5 +316,11 @@ def test_frame_prompts_host_logic_on_cpu(gold, monkeypatch, t, thr):
     rs = np.random.RandomState(g["seed"])
     pos2, neg2 = P.frame_prompts(tables, ca, threshold=thr, quirk=True, rng=rs)
     assert pos2 == pos and neg2 == neg
+    # the text route of the batch path: the file save_prompts / json.dump(indent=2) would write, byte for byte
+    rt = np.random.RandomState(g["seed"])
+    text, n_pos = P.frame_prompts(tables, ca, threshold=thr, quirk=True, rng=rt, as_text=True)
+    want = json.dumps({"positive_prompts": pos, "negative_prompts": neg, "num_cells": len(pos), "version": "1.0"}, indent=2)
+    assert text == want and n_pos == len(pos)
+    assert rt.get_state()[2] == rs.get_state()[2] and np.array_equal(rt.get_state()[1], rs.get_state()[1])
     end = np.random.get_state()
     assert rs.get_state()[2] == end[2] and np.array_equal(rs.get_state()[1], end[1])
