@@ -28,7 +28,7 @@ import torch
 
 from . import io as cio
 from .defects import apply_defects, plan as defect_plan, unsupported_defects
-from .ensemble import DEFAULT_FRAME_STEPS, Ensemble, PouchSpec
+from .ensemble import DEFAULT_FRAME_STEPS, Ensemble, PouchSpec, build_label_maps
 from .parameters import SimulationParameters
 
 DEFAULT_SIZES = ["xsmall", "small", "medium", "large"]
@@ -217,13 +217,14 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 # seeded (core/pouch.py:317), so every pouch gets a private legacy generator restored to the state
                 # its own draws left behind -- same values as the reference's sequential loop -- and the pouches
                 # run on a thread pool (numpy's shuffle / ufuncs and the K4 calls release the GIL).
-                from .prompts import PromptTables, frame_prompts
-                lmsk = ens.label_maps()[1]
+                from .prompts import frame_prompts, prompt_tables
                 tables: Dict[int, Any] = {}
                 for li in range(len(part)):
                     g = int(ens.geom_id[li])
                     if g not in tables:
-                        tables[g] = PromptTables(lmsk[g], int(ens.g_ncell[g]))
+                        # the per-geometry label map is cached for the life of the process, so are its tables
+                        tables[g] = prompt_tables(build_label_maps(ens.geometries[g], output_size, ens.device)[1],
+                                                  int(ens.g_ncell[g]))
                         tables[g].candidate_entries()                 # built before the threads start
                 ca_host = [ens.frames_of(li)[:, 0, :].cpu().numpy() for li in range(len(part))]
 

@@ -27,7 +27,7 @@ import ctypes
 import json
 import os
 import threading
-from typing import Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -113,7 +113,8 @@ class PromptTables:
         self.present_labels = np.unique(self.labels_u16).astype(np.int64)      # label values that own a pixel
         self.H, self.W = lab.shape
         self._empty: Dict[float, Tuple[np.ndarray, np.ndarray]] = {}
-        self._tls = threading.local()                                  # per-thread K4 workspace
+        self._pool: List[_Workspace] = []                              # free K4 workspaces (pinned memory is
+        self._pool_lock = threading.Lock()                             # expensive to allocate: 17 ms each)
         d2 = edt_squared(label_mask)[0].cpu().numpy()
         flat = lab.ravel()
         order = np.argsort(flat, kind="stable")                       # groups pixels by label, row-major inside
@@ -168,15 +169,48 @@ def _candidate_entries(self) -> List[str]:
 PromptTables.candidate_entries = _candidate_entries
 
 
-def _frame_transforms(tables: PromptTables, lut: np.ndarray, background: bool = True
+def _acquire_workspace(self) -> "_Workspace":
+    with self._pool_lock:
+        if self._pool:
+            return self._pool.pop()
+    return _Workspace(self)
+
+
+def _release_workspace(self, ws: "_Workspace") -> None:
+    with self._pool_lock:
+        self._pool.append(ws)
+
+
+PromptTables.acquire_workspace = _acquire_workspace
+PromptTables.release_workspace = _release_workspace
+
+_TABLES: Dict[Any, PromptTables] = {}
+_TABLES_LOCK = threading.Lock()
+
+
+def prompt_tables(label_mask: torch.Tensor, n_cells: int) -> PromptTables:
+    """Process-wide cache of :class:`PromptTables` per label map (the label maps themselves are cached per
+    geometry, output size and device, so their address identifies them)."""
+    key = (label_mask.data_ptr(), str(label_mask.device), tuple(label_mask.shape), int(n_cells))
+    with _TABLES_LOCK:
+        t = _TABLES.get(key)
+        if t is None:
+            if len(_TABLES) > 16:
+                _TABLES.clear()
+            t = _TABLES[key] = PromptTables(label_mask, n_cells)
+        return t
+
+
+def _frame_transforms(tables: PromptTables, lut: np.ndarray, background: bool = True, held: Optional[list] = None
                       ) -> Tuple[Optional[np.ndarray], np.ndarray]:
     """The frame-dependent transforms on the device (one K4 call): squared distance to the nearest pixel
     whose (id > 0) class differs and -- only when the id mismatch made a background instance -- the same for
-    the class (id == 1).  Returns ``(d2_background_instance or None, d2_negative)`` as views of this thread's
-    pinned buffer (valid until the thread's next call)."""
-    ws = getattr(tables._tls, "ws", None)
-    if ws is None:
-        ws = tables._tls.ws = _Workspace(tables)
+    the class (id == 1).  Returns ``(d2_background_instance or None, d2_negative)`` as views of a pooled
+    workspace's pinned buffer; the workspace is appended to ``held`` and goes back to the pool when the caller is
+    done with the views (without ``held`` it is simply not reused)."""
+    ws = tables.acquire_workspace()
+    if held is not None:
+        held.append(ws)
     k = 2 if background else 1
     hl = ws.host_luts.numpy()
     if background:
@@ -263,8 +297,19 @@ def frame_prompts(tables: PromptTables, ca: np.ndarray, threshold: float = 0.1, 
     pos_lut = lut > 0
     any_labelled = bool(pos_lut[tables.present_labels].any())          # (instance_mask > 0).any()
     d2_bg = d2_neg = None
-    if background_id is not None or (num_negative > 0 and any_labelled):
-        d2_bg, d2_neg = _frame_transforms(tables, lut, background_id is not None)
+    held: list = []                                                     # workspaces whose pinned views are in use
+    try:
+        if background_id is not None or (num_negative > 0 and any_labelled):
+            d2_bg, d2_neg = _frame_transforms(tables, lut, background_id is not None, held)
+        return _frame_prompts_body(tables, lut, background_id, pos_lut, any_labelled, d2_bg, d2_neg, num_negative,
+                                   min_distance_from_cells, min_cell_area, rng, as_text)
+    finally:
+        for ws in held:
+            tables.release_workspace(ws)
+
+
+def _frame_prompts_body(tables, lut, background_id, pos_lut, any_labelled, d2_bg, d2_neg, num_negative,
+                        min_distance_from_cells, min_cell_area, rng, as_text):
 
     # ---- positive prompts: single-cell instances come from the static tables ---------------------------
     cells = np.nonzero(lut[1:])[0]                                     # cells whose label value carries an id

@@ -298,7 +298,7 @@ def test_frame_prompts_host_logic_on_cpu(gold, monkeypatch, t, thr):
     from calcium_b200 import prompts as P
     monkeypatch.setattr(P, "edt_squared", _scipy_edt_squared)
 
-    def cpu_transforms(tables, lut, background=True):          # _frame_transforms without the device workspace
+    def cpu_transforms(tables, lut, background=True, held=None):   # _frame_transforms without the device workspace
         rows = [(lut == 1), (lut > 0)] if background else [(lut > 0)]
         luts = torch.from_numpy(np.stack(rows).astype(np.uint16).view(np.int16))
         both = _scipy_edt_squared(tables.label_mask, luts).numpy()
