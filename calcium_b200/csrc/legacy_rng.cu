@@ -60,7 +60,10 @@ namespace {
 // permutation(n)[:k] on the generator mt: numpy's _shuffle_raw + random_interval (see the file header)
 void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
 {
-    std::vector<int32_t> a((size_t)n);
+    // one scratch array per host thread, kept between calls: a fresh 1 MB vector per frame means an mmap / munmap
+    // pair per call, and with 32 prompt threads those serialise on the process's address-space lock
+    thread_local std::vector<int32_t> a;
+    a.resize((size_t)n);
     for (int64_t i = 0; i < n; ++i) a[(size_t)i] = (int32_t)i;
     for (int64_t i = n - 1; i >= 1; --i) {
         // random_interval(i): smallest bit mask >= i, rejection on masked 32-bit outputs (i <= 0xffffffff here)
