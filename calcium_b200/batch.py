@@ -79,7 +79,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                               generate_labels=False, image_size="512x512", jpeg_quality=90,
                               save_pouch=False, dataset_split="train", *, geometry_dir=None,
                               device=None, write_files=True, keep_arrays=False,
-                              max_chunk_bytes=4 << 30, writer_threads=8, generate_prompts=True,
+                              max_chunk_bytes=4 << 30, writer_threads=None, generate_prompts=True,
                               prompt_threads=None, devices=None):
     """Generate a batch of simulations with images and instance masks (see module docstring).
 
@@ -133,7 +133,8 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
 
     arrays: Dict[int, Dict[str, Any]] = {}
     mappings: List[tuple] = []
-    pool = cf.ThreadPoolExecutor(max_workers=max(1, writer_threads)) if write_files else None
+    n_wt = writer_threads if writer_threads else min(32, max(8, os.cpu_count() or 8))
+    pool = cf.ThreadPoolExecutor(max_workers=max(1, n_wt)) if write_files else None
     pending: List[cf.Future] = []
     T = int(3600 / 0.2)
     steps = sorted({int(t) for t in time_steps if 0 <= int(t) < T})
@@ -160,7 +161,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             names = {li: [f"{d['name']}_t{t:05d}_{batch_run_id}" for t in steps] for li, d in enumerate(part)}
             image_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             mask_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
-            img = ins = nact = None
+            img = ins = nact = masks_k3 = None
             cfgs = [(defect_configs[d["sim_idx"]] if (defect_configs is not None and d["sim_idx"] < len(defect_configs)) else None)
                     for d in part]
             with_defects = any(defect_plan(c, output_size) for c in cfgs)
@@ -200,15 +201,23 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 status = ens.check_status()
                 # edge_blur (main.py:281-287): K2b blends the blurred frame in along the cell outlines; these
                 # frames are not flat-shaded any more, so they take the raw-array path and the host PNG writer
-                out = ens.rasterize(image=True, instance=bool(generate_masks), edge_blur=bool(edge_blur),
-                                    blur_kernel_size=int(blur_kernel_size), blur_type=blur_type) if steps else {}
+                # the instance masks are not touched by blur or defects: unless the caller wants the arrays, they
+                # still arrive as finished .npz files from K3 (mask stream only)
+                if steps and generate_masks and not keep_arrays:
+                    from . import _lib as _clib
+                    m_arena, m_off, m_size, m_flags = ens.encoded_files(ens.encode(image=False, mask=True))
+                    if not np.any(m_flags[:, :, 1] & _clib.ENC_STAGE_FULL):
+                        masks_k3 = (m_arena, m_off[:, :, 1], m_size[:, :, 1])
+                out = ens.rasterize(image=True, instance=bool(generate_masks) and masks_k3 is None,
+                                    edge_blur=bool(edge_blur), blur_kernel_size=int(blur_kernel_size),
+                                    blur_type=blur_type) if steps else {}
                 if steps and with_defects:
                     # K5: the deterministic defects of each pouch's configuration (main.py:289-293), in place
                     for li, c in enumerate(cfgs):
                         apply_defects(out["image"][li], c, output_size)
                 ens.synchronize()
                 img = out["image"].cpu().numpy() if steps else None
-                ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and generate_masks) else None
+                ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and "instance" in out) else None
                 nact = out["n_active"].cpu().numpy() if steps else None
                 del out
             prompt_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
@@ -268,7 +277,10 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                             mpath = os.path.join(mask_dir, base + ".npz")
                             mask_files[li].append(mpath)
                             mappings_by_sim.setdefault(part[li]["sim_idx"], []).append((os.path.basename(ipath), os.path.basename(mpath)))
-                            if pool is not None:
+                            if pool is not None and masks_k3 is not None:
+                                o_, n_ = int(masks_k3[1][li, fi]), int(masks_k3[2][li, fi])
+                                pending.append(pool.submit(_write_many, [(mpath, masks_k3[0][o_:o_ + n_].tobytes())]))
+                            elif pool is not None:
                                 pending.append(pool.submit(cio.save_instance_mask, ins[li, fi], mpath))
                 if keep_arrays:
                     arrays[d["sim_idx"]] = {

@@ -196,14 +196,25 @@ def test_batch_path_applies_edge_blur(env, tmp_path):
     from calcium_b200 import generate_simulation_batch
     res = generate_simulation_batch(2, str(tmp_path), pouch_sizes=["xsmall"], sim_types=["Intercellular waves"],
                                     time_steps=[0, 9000], edge_blur=True, blur_kernel_size=5, blur_type="motion",
-                                    image_size="160x120", generate_masks=False)
+                                    image_size="160x120", generate_masks=True, generate_prompts=False)
     assert len(res["simulations"]) == 2 and all(s["image_count"] == 2 for s in res["simulations"])
     E = env["E"]
     specs = [E.PouchSpec.draw(res["simulations"][i]["parameters"], size="xsmall", sim_number=i) for i in range(2)]
     ens = E.Ensemble(specs, frame_steps=[0, 9000], device=env["dev"], output_size=(160, 120))
     ens.simulate()
-    want = ens.rasterize(image=True, instance=False, edge_blur=True, blur_kernel_size=5,
-                         blur_type="motion")["image"].cpu().numpy()
+    res_k2 = ens.rasterize(image=True, instance=True, edge_blur=True, blur_kernel_size=5, blur_type="motion")
+    want = res_k2["image"].cpu().numpy()
+    want_ins = res_k2["instance"].cpu().numpy().view(np.uint16)
+    n_act = res_k2["n_active"].cpu().numpy()
+    mdir = os.path.join(str(tmp_path), "masks", "train")
+    mfiles = sorted(os.listdir(mdir))
+    assert len(mfiles) == int((n_act > 0).sum()) == sum(s["mask_count"] for s in res["simulations"])
+    for i in range(2):
+        for f, t in enumerate((0, 9000)):
+            hit = [x for x in mfiles if f"_{i}_t{t:05d}_" in x]
+            assert len(hit) == int(n_act[i, f] > 0)
+            if hit:            # the masks are not blurred: finished .npz files from K3's mask stream
+                assert np.array_equal(np.load(os.path.join(mdir, hit[0]))["mask"], want_ins[i, f])
     files = sorted(os.listdir(os.path.join(str(tmp_path), "images", "train")))
     assert len(files) == 4
     for i in range(2):
