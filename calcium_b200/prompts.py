@@ -343,16 +343,21 @@ def _frame_prompts_body(tables, lut, background_id, pos_lut, any_labelled, d2_bg
     else:
         split = int(np.searchsorted(cid, background_id))
         draw_cells(0, split)
-        inst_is_bg = (lut == background_id)[tables.labels_u16]
-        area = int(inst_is_bg.sum())
+        # the reference's dist = distance_transform_edt(instance == id) is 0 outside the instance, so its
+        # percentile / candidate selection only ever sees the instance's own pixels: work on those (row-major,
+        # the order np.where gives), same values, a fraction of the traffic
+        flat_bg = np.flatnonzero((lut == background_id)[tables.labels_u16])
+        area = int(flat_bg.size)
         if area >= min_cell_area:
-            dist = np.where(inst_is_bg, np.sqrt(d2_bg.astype(np.float64)), 0.0)
-            if dist.max() != 0:
-                thr = np.percentile(dist[dist > 0], 80)
-                ys, xs = np.where(dist >= thr)
-                idx = rng.randint(len(ys))
-                bg = {"point": [int(xs[idx]), int(ys[idx])], "label": 1, "area": area,
-                      "confidence": float(dist[ys[idx], xs[idx]])}
+            dist = np.sqrt(d2_bg.ravel()[flat_bg].astype(np.float64))
+            positive = dist[dist > 0]
+            if positive.size:                                            # dist_transform.max() != 0
+                thr = np.percentile(positive, 80)
+                cand = np.flatnonzero(dist >= thr)                      # thr > 0: pixels outside never qualify
+                idx = rng.randint(len(cand))
+                px = int(flat_bg[cand[idx]])
+                bg = {"point": [px % tables.W, px // tables.W], "label": 1, "area": area,
+                      "confidence": float(dist[cand[idx]])}
                 if as_text:
                     entries.append(f'    "{background_id}": {_positive_entry(bg)}')
                 else:
