@@ -102,26 +102,142 @@ def cpu_reference_style_throughput() -> dict:
                       f"(numba={'yes' if RS.HAVE_NUMBA else 'no'}, scipy CSR, strided (n,4,T) history), {dt:.1f} s"}
 
 
+# ---- the real reference (oracle/_ref: byte-for-byte copy made by oracle/make_ref.py) on the host cores ----
+
+def _ref_worker_init(gdir: str) -> None:
+    """Pool initializer: import the reference with the shims, warm numba's JIT on a short horizon."""
+    global _REF
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("NUMBA_NUM_THREADS", "1")
+    from oracle import reference_shims as R
+    ns = R.load_reference()
+    _REF = (ns, gdir)
+    _ref_pouch_job((0, 400, 0))
+
+
+def _ref_pouch_job(arg):
+    """One pouch the way reference main.py:241-328 runs it (sleeps and file I/O excluded): Pouch(...),
+    simulate(), then per sampled step generate_image / get_active_cells / get_cell_masks(active_only) /
+    create_instance_mask_from_cells.  Returns (cells * steps, seconds simulate, seconds frames)."""
+    i, T, n_frames = arg
+    ns, gdir = _REF
+    types = ns.SimulationParameters.get_available_sim_types()
+    prm = ns.SimulationParameters(types[i % len(types)]).generate_random_params(seed=i)
+    pouch = ns.Pouch(params=prm, size=SIZE, sim_number=i, geometry_dir=gdir, output_size=OUTPUT_SIZE)
+    if T != pouch.T:                       # horizon override for the warm-up only (SURVEY.md section 7)
+        pouch.T = T
+        pouch.disc_dynamics = np.zeros((pouch.n_cells, 4, T))
+    t0 = time.perf_counter()
+    pouch.simulate()
+    t1 = time.perf_counter()
+    steps = list(range(0, pouch.T, 200))[:n_frames]
+    for t in steps:
+        pouch.generate_image(t)
+        act = pouch.get_active_cells(t)
+        if len(act):
+            ns.create_instance_mask_from_cells(pouch.get_cell_masks(active_only=True, time_step=t), act)
+    t2 = time.perf_counter()
+    return pouch.n_cells * (pouch.T - 1), t1 - t0, t2 - t1
+
+
+class ReferencePool:
+    """The unmodified reference, one pouch per host process (the reference itself is single-process:
+    main.py:149 computes max_cores and never uses it)."""
+
+    def __init__(self, procs: int):
+        import multiprocessing as mp
+        from oracle import reference_shims as R
+        if not R.reference_available():
+            raise RuntimeError("oracle/_ref is absent (python -m oracle.make_ref in the build container)")
+        gdir = R.synthetic_geometry_dir(("xsmall", "small", "medium"))
+        self.procs = procs
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_ref_worker_init, initargs=(gdir,))
+        self.pool.map(_ref_pouch_job, [(0, 400, 0)] * procs)            # every worker imported + JIT-warmed
+
+    def step(self, n_pouches: int, first_seed: int = 0, T: int = T_STEPS, n_frames: int = 90) -> dict:
+        t0 = time.perf_counter()
+        res = self.pool.map(_ref_pouch_job, [(first_seed + i, T, n_frames) for i in range(n_pouches)], chunksize=1)
+        dt = time.perf_counter() - t0
+        return {"work": sum(r[0] for r in res), "seconds": dt, "sim_s": sum(r[1] for r in res),
+                "frames_s": sum(r[2] for r in res)}
+
+    def close(self):
+        self.pool.terminate()
+
+
+def cpu_reference_throughput(procs: int, n_pouches: int) -> dict:
+    """cpu_baseline of the GPU arm: the real reference on `procs` processes, one bounded sample."""
+    pool = ReferencePool(procs)
+    try:
+        r = pool.step(n_pouches)
+    finally:
+        pool.close()
+    return {"value": r["work"] / r["seconds"], "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": f"{n_pouches} medium pouches (full T, 90 frames: generate_image + active / instance masks) through the "
+                      f"unmodified reference (oracle/_ref, numba JIT warm, D_p shim), one pouch per process on {procs} "
+                      f"processes, {r['seconds']:.1f} s wall ({r['sim_s'] / n_pouches:.1f} s simulate + "
+                      f"{r['frames_s'] / n_pouches:.1f} s frames per pouch); sleeps and file I/O of main.py excluded",
+            "seconds": r["seconds"]}
+
+
 def run_reference_arm(args) -> None:
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores.  Every one of
+    the K timed steps (and W warm-up steps) is one bounded sample of the workload: `cores` pouches, one per process,
+    full T, all 90 frames, through the unmodified reference when oracle/_ref travelled with the tree
+    (kind=reference); else 148 pouches through the oracle's C port on all host threads (kind=port).  ms_per_step is
+    the measured time of such a step, value = the cell-timesteps of the timed steps / their total time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = max(cores, 8)
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):       # each step: a bounded sample of the workload
-        vals.append(cpu_port_throughput(n, cores))
-    best = max(vals, key=lambda d: d["value"])
-    line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["seconds"] * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, args.pouches_per_gpu),
-            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "cpu_baseline_reference_style": cpu_reference_style_throughput(),
-            "note": "the reference is pure Python (numpy/scipy/numba) and cannot travel to the GPU box; this arm times "
-                    "the oracle's C port of the same algorithm on all host cores (kind=port)"}
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.gpus, args.pouches_per_gpu), "gpu_launches": 0}
+    kind, err = "port", None
+    if not args.port_only:
+        try:
+            pool = ReferencePool(cores)
+            kind = "reference"
+        except Exception as e:  # noqa: BLE001 - no oracle/_ref on this box, or numba/cv2 missing: the C port
+            err = f"{type(e).__name__}: {e}"
+    if kind == "reference":
+        try:
+            per_step = cores
+            for w in range(args.warmup):
+                pool.step(per_step, first_seed=1000 + w * per_step, T=2000, n_frames=4)      # short-horizon warm-up
+            work = secs = sim_s = fr_s = 0.0
+            for k in range(args.steps):
+                r = pool.step(per_step, first_seed=k * per_step)
+                work += r["work"]; secs += r["seconds"]; sim_s += r["sim_s"]; fr_s += r["frames_s"]
+        finally:
+            pool.close()
+        n_p = per_step * args.steps
+        value = work / secs
+        sample = (f"each step = {per_step} of the workload's {args.pouches_per_gpu * args.gpus} medium pouches (full T, 90 "
+                  f"frames: generate_image + active / instance masks) through the unmodified reference (oracle/_ref, numba "
+                  f"JIT warm), one pouch per process on {cores} processes; {args.steps} steps in {secs:.1f} s "
+                  f"({sim_s / n_p:.1f} s simulate + {fr_s / n_p:.1f} s frames per pouch and core); warm-up steps use "
+                  f"T=2000; main.py's sleeps and file I/O excluded")
+        line["cpu_baseline_port"] = {k: v for k, v in cpu_port_throughput(max(cores, 8), cores, min_seconds=4.0).items()
+                                     if k != "seconds"}
+    else:
+        per_step = args.pouches_per_gpu
+        for w in range(args.warmup):
+            cpu_port_throughput(max(cores, 8), cores, min_seconds=0.0)
+        work = secs = 0.0
+        from calcium_b200.geometry import get_geometry
+        n_cells = get_geometry(SIZE).n_cells
+        for k in range(args.steps):
+            r = cpu_port_throughput(per_step, cores, first_seed=k * per_step, min_seconds=0.0)
+            work += per_step * n_cells * (T_STEPS - 1); secs += r["seconds"]
+        value = work / secs
+        sample = (f"each step = {per_step} of the workload's {args.pouches_per_gpu * args.gpus} medium pouches (full T, 90 "
+                  f"frames rasterised) through oracle/csrc/oracle.c (gcc -O3 -march=native, strict IEEE) on {cores} host "
+                  f"threads; {args.steps} steps in {secs:.1f} s" + (f"; reference unavailable: {err}" if err else ""))
+    line.update({"value": value, "ms_per_step": secs / args.steps * 1e3,
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "cpu_baseline_reference_style": cpu_reference_style_throughput()})
     print(json.dumps(line), flush=True)
 
 
@@ -343,12 +459,31 @@ def run_gpu(args) -> None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return {"h2d_bytes": h2d // e2e_steps, "d2h_bytes": d2h // e2e_steps}, ms.item()
 
+    # Multi-GPU: the device->host path of the box is a shared, lopsided resource.  relay.setup measures it with
+    # every rank copying at once and, if a trial on this box says it pays, routes the chunks of the slow-path
+    # ranks over NVLink through a fast-path partner GPU (calcium_b200/relay.py).  No collective on the data path.
+    relay_ep = None
+    if world > 1 and not args.no_relay:
+        from calcium_b200 import relay
+        relay_ep = relay.setup(rank, world, dev, ens.files_chunk_capacity(chunk))
+        ens.set_relay(relay_ep)
     # steps are pipelined: the copy-out of a step's last chunks overlaps the next step's integration
     moved, e2e_ms_v = timed_e2e(lambda: ens.run_files_to_host(chunk_pouches=chunk, wait=False), ens.flush_files)
     e2e_value = work_per_gpu * world / (e2e_ms_v * 1e-3)
+    relay_info = None
+    if relay_ep is not None:
+        relay_info = dict(relay_ep.info)
+        fwd = torch.tensor([float(relay_ep.forwarded_bytes)], dtype=torch.float64, device=dev)
+        dist.all_reduce(fwd)
+        relay_info["bytes_forwarded_per_step_all_ranks"] = int(fwd.item() / (e2e_steps + 1))
+        barrier()
+        ens.set_relay(None)
+        relay_ep.close()
     if hasattr(ens, "_fring"):
         del ens._fring
     # (b) the same with raw arrays (images + instance masks uncompressed): PCIe bound
+    e2e_files_steps = e2e_steps
+    e2e_steps = min(e2e_steps, 2)
     moved_raw, e2e_raw_ms = timed_e2e(lambda: ens.run_to_host(chunk_pouches=args.e2e_chunk))
     e2e_raw_value = work_per_gpu * world / (e2e_raw_ms * 1e-3)
 
@@ -369,11 +504,11 @@ def run_gpu(args) -> None:
         plan = slot_plan(ens.geometries[0], True, 64).copy()
         lay = np.zeros(4, dtype=np.int64)
         lib.cab200_sim_layout(n_cells, 1, 64, _lib.as_i64p(lay))
-        lib.cab200_plan_slots(n_cells, _lib.as_i32p(rowptr), _lib.as_i32p(col), int(lay[2]), int(lay[1]), 0, 1, 1,
+        lib.cab200_plan_slots(n_cells, _lib.as_i32p(rowptr), _lib.as_i32p(col), int(lay[2]), 1, int(lay[1]), 0, 1, 1,
                               plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(plan_cost))
         sm_clock_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
         wave_ld = int(plan_cost[2])
-        wave_st = ((n_cells + 31) // 32) * 4 * (int(lay[2]) + 1)
+        wave_st = ((n_cells + 31) // 32) * 4 * int(lay[2])      # value entry + second copy; the diagonal is added from registers
         smem_clk = (wave_ld + wave_st) * (T_STEPS - 1)
         roofline_fp64 = {"kernel": "integrate_kernel (K1)", "bound": "fp64", "achieved": achieved_tf, "peak": peak.value,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak.value,
@@ -391,21 +526,28 @@ def run_gpu(args) -> None:
         # (no index or weight reads: entry addresses live in registers, unit weights are skipped) -- DESIGN.md K1.
         smem_bytes_per_cell_step = 16.0 * nnz / n_cells + 16.0
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-        smem_peak_gbs = n_sm * 128.0 * sm_clock_hz / 1e9
+        lds = np.zeros(3)
+        _lib.check(lib.cab200_peak_smem(0, 20000, lds.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), None), "cab200_peak_smem")
+        sts = np.zeros(3)
+        _lib.check(lib.cab200_peak_smem(6, 20000, sts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), None), "cab200_peak_smem")
+        smem_peak_gbs = float(lds[1])                      # measured: conflict-free LDS.128 from 16 warps on every SM
         smem_achieved_gbs = smem_bytes_per_cell_step * work_per_gpu / (k1_ms * 1e-3) / 1e9
         roofline = {"kernel": "integrate_kernel (K1)", "bound": "smem", "achieved": smem_achieved_gbs,
                     "peak": smem_peak_gbs, "unit": "GB/s", "frac": smem_achieved_gbs / smem_peak_gbs, "traffic": None,
                     "algorithmic_bytes_per_cell_step": smem_bytes_per_cell_step,
-                    "peak_source": "128 B/clk/SM shared-memory crossbar (B300_MICROARCH.md, LDS/STS) x SM count x the SM "
-                                   "clock sampled during the timed region; K1 never touches HBM except for the frames "
-                                   "(0.16 B per cell-step), so MEASURED_PEAKS.json's HBM figure does not bound it",
+                    "peak_source": "measured in this run: cab200_peak_smem mode 0 (conflict-free LDS.128, 16 warps per SM, "
+                                   "every SM; %.1f B/clk/SM; conflict-free STS.128 reaches %.1f B/clk/SM) -- "
+                                   "MEASURED_PEAKS.json has no shared-memory entry, and K1 never touches HBM except for "
+                                   "the frames (0.16 B per cell-step)" % (lds[0], sts[0]),
+                    "peak_nominal": n_sm * 128.0 * sm_clock_hz / 1e9,
                     "wavefronts_per_step_planned": wave_ld + wave_st,
                     "pipe_frac_wavefronts": smem_clk / (k1_ms * 1e-3 * sm_clock_hz),
                     "note": "frac counts algorithmic bytes only; pipe_frac_wavefronts is the hardware view (1 wavefront = "
                             "128 B per clk per SM; planned load wavefronts from the host planner's cost model + stores, "
                             "within 3 % of ncu's l1tex__data_pipe_lsu_wavefronts_mem_shared) -- the gap between the two is "
-                            "bank conflicts, the second value copy and the diagonal entries; traffic = ncu wavefronts x "
-                            "128 B per launch; K1 is co-bound by the FP64 pipe (roofline_fp64)"}
+                            "bank conflicts, padding positions and the second value copy (the diagonal term is added "
+                            "from registers since round 2); traffic = ncu wavefronts x 128 B per launch; K1 is co-bound by "
+                            "the FP64 pipe (roofline_fp64)"}
         roofline_k2 = {"kernel": "raster_kernel (K2)", "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9,
                        "peak": hbm_peak, "unit": "GB/s", "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak,
                        "traffic": None, "peak_source": hbm_src,
@@ -417,7 +559,15 @@ def run_gpu(args) -> None:
             roofline_fp64["dram_traffic"] = tr.get("k1_dram_bytes_per_launch")
             roofline_k2["traffic"] = tr.get("k2_dram_bytes_per_launch")
         cores = os.cpu_count() or 1
-        cpu = cpu_port_throughput(max(cores, 8), cores) if not args.no_cpu_baseline else None
+        cpu = cpu_port = None
+        if not args.no_cpu_baseline:
+            cpu_port = cpu_port_throughput(max(cores, 8), cores, min_seconds=5.0)
+            cpu = cpu_port
+            if not args.port_only:
+                try:                                       # the unmodified reference, if oracle/_ref travelled with the tree
+                    cpu = cpu_reference_throughput(cores, cores)
+                except Exception as e:  # noqa: BLE001
+                    cpu_port["sample"] += f"; reference unavailable here: {type(e).__name__}: {e}"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -427,13 +577,17 @@ def run_gpu(args) -> None:
             "k1_ms": k1_ms, "k2_ms": k2_ms,
             "roofline": roofline, "roofline_fp64": roofline_fp64, "roofline_k2": roofline_k2,
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+            "cpu_baseline_port": ({k: cpu_port[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                                  if (cpu_port and cpu is not cpu_port) else None),
             "cpu_baseline_reference_style": (cpu_reference_style_throughput() if cpu else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"],
-                    "d2h_bytes_per_step": moved["d2h_bytes"], "ms_per_step": e2e_ms_v, "steps": e2e_steps,
+                    "d2h_bytes_per_step": moved["d2h_bytes"], "ms_per_step": e2e_ms_v, "steps": e2e_files_steps,
                     "path": "Ensemble.run_files_to_host (what generate_simulation_batch runs): pinned host inputs -> K1 -> "
                             "K3 (rasterise + DEFLATE-encode on the device) -> every frame's finished .png (16-bit gray+alpha) "
-                            "and .npz (instance mask) + the sampled float64 calcium state copied to pinned host memory; "
-                            "decoding the files gives bit for bit the arrays of e2e_raw_arrays"},
+                            "and .npz (instance mask) in pinned host memory (round 2: the float64 calcium state is no longer "
+                            "shipped by default -- the batch path never read it); decoding the files gives bit for bit the "
+                            "arrays of e2e_raw_arrays",
+                    "relay": relay_info},
             "e2e_raw_arrays": {"value": e2e_raw_value, "unit": UNIT, "h2d_bytes_per_step": moved_raw["h2d_bytes"],
                                "d2h_bytes_per_step": moved_raw["d2h_bytes"], "ms_per_step": e2e_raw_ms,
                                "path": "Ensemble.run_to_host: K1 -> K2 -> frames + uncompressed images + instance "
@@ -458,6 +612,8 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunk", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-relay", action="store_true", help="multi-GPU e2e: always copy device->host directly")
+    ap.add_argument("--port-only", action="store_true", help="reference arm / cpu_baseline: the oracle's C port even if oracle/_ref exists")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcalcium_b200.so")
+# CALCIUM_B200_LIB: an alternative build of the same library (kernel experiments, scripts/k1_variants.py)
+LIB_PATH = os.environ.get("CALCIUM_B200_LIB") or os.path.join(HERE, "libcalcium_b200.so")
 
 FP64_STRICT = 64
 FP32 = 32
@@ -27,13 +28,16 @@ DEFECT_MAX_ONLY, DEFECT_LUT_MAX, DEFECT_LUT_FLAG, DEFECT_MUL = 0, 1, 2, 3
 
 #: every symbol include/cab200.h declares (tests check the library exports all of them)
 EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
-           "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_frames_tmp_bytes", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_sim_layout",
+           "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_frames_tmp_bytes", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_k1_legacy_rows", "cab200_sim_layout",
            "cab200_cluster_layout", "cab200_plan_cluster",
            "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
            "cab200_edge_maps", "cab200_raster_edges_batch", "cab200_legacy_choice", "cab200_sample_background", "cab200_defect_pass",
            "cab200_encode_tables_bytes", "cab200_encode_tables", "cab200_encode_scratch_bytes", "cab200_encode_batch",
            "cab200_encode_geometry_bytes", "cab200_encode_geometry", "cab200_publish_to_host", "cab200_edt_scratch_bytes", "cab200_edt_classes",
-           "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_selftest_division"]
+           "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_peak_smem", "cab200_selftest_division",
+           "cab200_relay_alloc", "cab200_relay_free", "cab200_relay_open", "cab200_relay_close", "cab200_ipc_event_create",
+           "cab200_ipc_event_open", "cab200_event_create", "cab200_event_record", "cab200_event_synchronize",
+           "cab200_event_destroy", "cab200_stream_wait_event", "cab200_copy_async"]
 
 
 class Cab200Error(RuntimeError):
@@ -70,7 +74,9 @@ def load() -> ctypes.CDLL:
     lib.cab200_sim_frames_tmp_bytes.restype = c_size_t
     lib.cab200_sim_frames_tmp_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
     lib.cab200_plan_slots.restype = c_int
-    lib.cab200_plan_slots.argtypes = [c_int, i32p, i32p, c_int, c_int, ctypes.c_longlong,
+    lib.cab200_k1_legacy_rows.restype = c_int
+    lib.cab200_k1_legacy_rows.argtypes = [c_int, i32p, i32p]
+    lib.cab200_plan_slots.argtypes = [c_int, i32p, i32p, c_int, c_int, c_int, ctypes.c_longlong,
                                       ctypes.c_ulonglong, c_int, POINTER(ctypes.c_uint16), i64p]
     lib.cab200_cluster_layout.restype = c_int
     lib.cab200_cluster_layout.argtypes = [c_int, c_int, c_int, i64p]
@@ -132,6 +138,24 @@ def load() -> ctypes.CDLL:
     lib.cab200_peak_fp64.argtypes = [c_int, f64p, c_void_p]
     lib.cab200_peak_hbm_write.restype = c_int
     lib.cab200_peak_hbm_write.argtypes = [c_void_p, c_size_t, c_int, f64p, c_void_p]
+    vpp = POINTER(c_void_p)
+    lib.cab200_relay_alloc.argtypes = [c_size_t, vpp, c_void_p]
+    lib.cab200_relay_free.argtypes = [c_void_p]
+    lib.cab200_relay_open.argtypes = [c_void_p, vpp]
+    lib.cab200_relay_close.argtypes = [c_void_p]
+    lib.cab200_ipc_event_create.argtypes = [vpp, c_void_p]
+    lib.cab200_ipc_event_open.argtypes = [c_void_p, vpp]
+    lib.cab200_event_create.argtypes = [vpp]
+    lib.cab200_event_record.argtypes = [c_void_p, c_void_p]
+    lib.cab200_event_synchronize.argtypes = [c_void_p]
+    lib.cab200_event_destroy.argtypes = [c_void_p]
+    lib.cab200_stream_wait_event.argtypes = [c_void_p, c_void_p]
+    lib.cab200_copy_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
+    for _n in ("relay_alloc", "relay_free", "relay_open", "relay_close", "ipc_event_create", "ipc_event_open", "event_create",
+               "event_record", "event_synchronize", "event_destroy", "stream_wait_event", "copy_async"):
+        getattr(lib, "cab200_" + _n).restype = c_int
+    lib.cab200_peak_smem.restype = c_int
+    lib.cab200_peak_smem.argtypes = [c_int, c_int, f64p, c_void_p]
     lib.cab200_selftest_division.restype = c_int
     lib.cab200_selftest_division.argtypes = [ctypes.c_longlong, c_int, ctypes.c_ulonglong,
                                              POINTER(ctypes.c_ulonglong), c_void_p]

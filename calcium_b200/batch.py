@@ -21,6 +21,7 @@ import gc
 import json
 import os
 import random
+import threading
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -55,6 +56,28 @@ def _parse_image_size(image_size) -> tuple:
             print(f"Failed to parse image size '{image_size}', using default 512x512")
             return (512, 512)
     return tuple(image_size)
+
+
+_RUN_ID_LOCK = threading.Lock()
+_LAST_RUN_ID: List[datetime.datetime] = []
+
+
+def _unique_run_id(img_dir: str) -> str:
+    """The reference stamps a batch's files with ``%Y%m%d%H%M%S`` (``main.py:174``) and never produces two
+    batches within one second (it sleeps seconds per simulation); here batches finish in milliseconds, and a
+    second batch with the same stamp would overwrite the first one's files (same sim names, same stamp).
+    Same format, but strictly increasing within the process and never a stamp already present in ``img_dir``."""
+    with _RUN_ID_LOCK:
+        t = datetime.datetime.now().replace(microsecond=0)
+        if _LAST_RUN_ID and t <= _LAST_RUN_ID[0]:
+            t = _LAST_RUN_ID[0] + datetime.timedelta(seconds=1)
+        existing = set()
+        if os.path.isdir(img_dir):
+            existing = {f.rsplit("_", 1)[-1][:-4] for f in os.listdir(img_dir) if f.endswith(".png")}
+        while t.strftime("%Y%m%d%H%M%S") in existing:
+            t += datetime.timedelta(seconds=1)
+        _LAST_RUN_ID[:] = [t]
+        return t.strftime("%Y%m%d%H%M%S")
 
 
 def _resolve_devices(device, devices) -> List[Any]:
@@ -101,8 +124,8 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     if time_steps is None:
         time_steps = list(DEFAULT_FRAME_STEPS)
     batch_dir = output_dir
-    batch_run_id = datetime.datetime.now().strftime("%Y%m%d%H%M%S")
     img_dir = os.path.join(batch_dir, "images", dataset_split)
+    batch_run_id = _unique_run_id(img_dir)
     mask_dir = os.path.join(batch_dir, "masks", dataset_split)
     prompt_dir = os.path.join(batch_dir, "prompts", dataset_split)
     for d in (img_dir, mask_dir, prompt_dir):
@@ -328,6 +351,9 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
 
     try:
         if mappings and write_files:
+            # every pair present in the directory (earlier batches included), like the reference's scan
+            on_disk = cio.scan_image_mask_pairs(batch_dir, dataset_split)
+            mappings = sorted(set(on_disk) | set(mappings))
             results["image_mask_csv"] = cio.save_csv_mapping(mappings, batch_dir, "train.csv")
             print(f"Created CSV mapping: {results['image_mask_csv']}")
         else:

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcalcium_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
 SOURCES = ["integrate_f64.cu", "integrate_cl64.cu", "integrate_f32.cu", "integrate_cl32.cu", "integrate.cu",
-           "api.cu", "raster.cu", "edges.cu", "legacy_rng.cu", "defects.cu", "encode.cu", "edt.cu", "plan.cu"]
+           "api.cu", "microbench.cu", "relay.cu", "raster.cu", "edges.cu", "legacy_rng.cu", "defects.cu", "encode.cu", "edt.cu", "plan.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -45,6 +45,30 @@ def _compile(src: str, verbose: bool) -> str:
     if verbose:
         sys.stderr.write(res.stderr)
     return obj
+
+
+def build_variant(name: str, defines: List[str]) -> str:
+    """An experimental build of the whole library with extra -D flags -> calcium_b200/_variants/lib<name>.so
+    (selected at run time with CALCIUM_B200_LIB; see scripts/k1_variants.py)."""
+    vdir = os.path.join(HERE, "_variants")
+    odir = os.path.join(vdir, "_obj_" + name)
+    os.makedirs(odir, exist_ok=True)
+    out = os.path.join(vdir, f"lib{name}.so")
+
+    def comp(src: str) -> str:
+        obj = os.path.join(odir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(comp, SOURCES))
+    res = subprocess.run([_nvcc()] + ARCH + ["-shared", "-o", out] + objs, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return out
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -82,14 +82,17 @@ extern "C" int cab200_selftest_division(long long n_pairs, int exp_range, unsign
     }
     unsigned long long *d = nullptr;
     CAB_CUDA(cudaMalloc(&d, sizeof(*d)));
-    CAB_CUDA(cudaMemsetAsync(d, 0, sizeof(*d), stream));
     const int blocks = 148 * 8, threads = 256;
     const int per_thread = (int)((n_pairs + (long long)blocks * threads - 1) / ((long long)blocks * threads));
-    divtest_kernel<<<blocks, threads, 0, stream>>>(seed, per_thread, exp_range, d);
-    CAB_CUDA(cudaGetLastError());
-    CAB_CUDA(cudaMemcpyAsync(mismatches_out, d, sizeof(*d), cudaMemcpyDeviceToHost, stream));
-    CAB_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(d);
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(*d), stream);
+    if (e == cudaSuccess) {
+        divtest_kernel<<<blocks, threads, 0, stream>>>(seed, per_thread, exp_range, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mismatches_out, d, sizeof(*d), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);                                   // on every path
+    if (e != cudaSuccess) { set_error("cab200_selftest_division: %s", cudaGetErrorString(e)); return CAB200_ECUDA; }
     return CAB200_OK;
 }
 

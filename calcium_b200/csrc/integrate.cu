@@ -34,7 +34,7 @@ int sim_copies(int n, bool unit, size_t elem2, int nslot)
 {
     if (!unit) return 1;
     const int np = (n + 31) & ~31;
-    return integrate_smem_bytes(np, nslot, elem2, 2) <= 227 * 1024 ? 2 : 1;
+    return integrate_smem_bytes(np, nslot, elem2, 2, true) <= 227 * 1024 ? 2 : 1;
 }
 
 // frames_tmp (slot order, see integrate.cuh) -> frames_out (original cell order).  One CTA per
@@ -97,7 +97,7 @@ extern "C" int cab200_sim_layout(int n, int unit, int precision, int64_t out[4])
     const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
     const int copies = sim_copies(n, unit != 0, elem2, threads * cpt);
     out[0] = threads; out[1] = cpt; out[2] = copies;
-    out[3] = (int64_t)integrate_smem_bytes((n + 31) & ~31, threads * cpt, elem2, copies);
+    out[3] = (int64_t)integrate_smem_bytes((n + 31) & ~31, threads * cpt, elem2, copies, unit != 0);
     return CAB200_OK;
 }
 
@@ -112,9 +112,9 @@ extern "C" int cab200_cluster_layout(int n, int n_cta, int precision, int64_t ou
     cluster_shape((n + n_cta - 1) / n_cta, &threads, &cpt);
     if (!threads) { set_error("cab200_cluster_layout: %d cells exceed %d CTAs x 1536", n, n_cta); return CAB200_ESIZE; }
     const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
-    const int copies = integrate_smem_bytes(0, threads * cpt, elem2, 2, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
+    const int copies = integrate_smem_bytes(0, threads * cpt, elem2, 2, true, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
     out[0] = threads; out[1] = cpt; out[2] = copies;
-    out[3] = (int64_t)integrate_smem_bytes(0, threads * cpt, elem2, copies, CAB_HMAX);
+    out[3] = (int64_t)integrate_smem_bytes(0, threads * cpt, elem2, copies, true, CAB_HMAX);
     return CAB200_OK;
 }
 
@@ -232,12 +232,12 @@ extern "C" int cab200_sim_batch(
             cluster_shape((n + ncta - 1) / ncta, &cth, &ccpt);
             if (!cth) { set_error("cab200_sim_batch: geometry %d: %d cells exceed %d CTAs x 1536", g, n, ncta); return CAB200_ESIZE; }
             const size_t el2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
-            const int ccopies = integrate_smem_bytes(0, cth * ccpt, el2, 2, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
-            const int cep = (max_row_c + 1) / 2;
+            const int ccopies = integrate_smem_bytes(0, cth * ccpt, el2, 2, true, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
+            const int cep = k1_ep(max_row_c);
             KernelFn cfn = (precision == CAB200_FP64_STRICT) ? pick_cluster_kernel_f64(cth, ccpt, ncta, cep, ccopies)
                                                              : pick_cluster_kernel_f32(cth, ccpt, ncta, cep, ccopies);
             if (!cfn) { set_error("cab200_sim_batch: no cluster kernel for %dx%d x%d", cth, ccpt, ncta); return CAB200_EINVAL; }
-            const size_t csmem = integrate_smem_bytes(0, cth * ccpt, el2, ccopies, CAB_HMAX);
+            const size_t csmem = integrate_smem_bytes(0, cth * ccpt, el2, ccopies, true, CAB_HMAX);
             CAB_CUDA(cudaFuncSetAttribute((const void *)cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
             SimArgs ca;
             ca.pouch_list = d_list + g_begin[g];
@@ -251,7 +251,7 @@ extern "C" int cab200_sim_batch(
             ca.T = T; ca.n_frames = n_frames; ca.frame_steps = d_frame_steps;
             ca.frames_out = frames_out; ca.status_out = status_out;
             const size_t tmp_need = (size_t)count * n_frames * 4 * ((size_t)ncta * cth * ccpt) * (el2 / 2);
-            ca.frames_tmp = (frames_tmp && n_frames > 0 && tmp_need <= frames_tmp_bytes) ? frames_tmp : nullptr;
+            ca.frames_tmp = (frames_tmp && n_frames > 0 && tmp_need <= frames_tmp_bytes && count <= 65535) ? frames_tmp : nullptr;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(count * ncta), 1, 1);
             cfg.blockDim = dim3((unsigned)cth, 1, 1);
@@ -289,7 +289,7 @@ extern "C" int cab200_sim_batch(
             set_error("cab200_sim_batch: geometry %d: longest CSR row %d outside [0,16]", g, max_row);
             return CAB200_ESIZE;
         }
-        const int ep = (max_row + 1) / 2;   // 0 and 1..10 use the 5-pair variant
+        const int ep = k1_ep(max_row);      // rows of up to 10 entries use the 5-pair variant
         const bool unit = g_unit[g] != 0;
         const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
         const int np = (n + 31) & ~31;
@@ -297,7 +297,7 @@ extern "C" int cab200_sim_batch(
         KernelFn fn = (precision == CAB200_FP64_STRICT) ? pick_kernel_f64(threads, cpt, ep, unit, copies)
                                                         : pick_kernel_f32(threads, cpt, ep, unit, copies);
         if (!fn) { set_error("cab200_sim_batch: no kernel for shape %dx%d", threads, cpt); return CAB200_EINVAL; }
-        const size_t smem = integrate_smem_bytes(np, threads * cpt, elem2, copies);
+        const size_t smem = integrate_smem_bytes(np, threads * cpt, elem2, copies, unit);
         if (smem > 227 * 1024) {
             set_error("cab200_sim_batch: geometry %d needs %zu bytes of shared memory (> 227 KB)", g, smem);
             return CAB200_ESIZE;

@@ -4,30 +4,34 @@
 // scipy CSR products per step (:346-347) for a whole ensemble in one launch.
 //
 // Data placement for one pouch (n cells), fixed for all T steps:
-//   shared   two buffers (step parity) of ENT = (COPIES+1)*NP+1 entries, one entry = the pair (c, p):
+//   shared   two buffers (step parity) of COPIES*NP + LEG + 1 entries, one entry = the pair (c, p):
 //              [0, NP)            value entries   (c_i, p_i) at index slot_i
 //              [NP, 2NP)          (COPIES == 2) a second copy of the values at NP + (slot_i ^ 4),
 //                                 i.e. in the bank group 4 away: every gather may read either copy,
 //                                 which the host planner uses to dodge bank conflicts
-//              [COPIES*NP, +NP)   diagonal entries (L_ii*c_i, L_ii*p_i)
-//              [(COPIES+1)*NP]    the zero entry (+0, +0), never written after the prologue
-//            Step t reads buffer t&1 and writes buffer (t+1)&1: ONE __syncthreads() per step.
-//   regs     per owned cell: c, p, s, r, V_PLC, L_ii and the row's entry indices (16-bit, packed in
-//            pairs; time-invariant), plus the pouch's parameters (uniform registers).
+//              [COPIES*NP, +LEG)  (UNIT) diagonal entries (L_ii*c_i, L_ii*p_i) of the few "legacy" cells
+//                                 whose row does not fit the register-diagonal layout (k1_layout.cuh)
+//              [COPIES*NP+LEG]    the zero entry (+0, +0), never written after the prologue
+//            Step t reads buffer t&1 and writes buffer (t+1)&1: one split barrier per step.
+//   regs     per owned cell: c, p, s, r, V_PLC, L_ii and the shared addresses of the row's entries
+//            (time-invariant), plus the pouch's parameters (uniform registers).
 //   HBM      only the captured frames, [F][4][n] in original cell order.
 //
-// A Laplacian row is then a branch-free gather: sum = +0; for each stored entry in ascending column
-// order sum += entry -- off-diagonal entries index the neighbour's value entry (1.0*x == x exactly
-// for the adjacency-minus-degree Laplacian), the diagonal entry indexes the cell's own diagonal
-// entry, and rows shorter than the warp's longest row are padded with the zero entry.  Because the
-// sum starts from +0.0 it can never be -0.0, so adding the +0.0 padding is an exact no-op and the
-// result is bit-identical to scipy's csr_matvec followed by the reference's `D * (...)`.
+// A Laplacian row is then a branch-free gather: sum = +0; for each stored entry in CSR order
+// sum += entry -- off-diagonal entries index the neighbour's value entry (1.0*x == x exactly for the
+// adjacency-minus-degree Laplacian), the diagonal term L_ii*(c_i, p_i) is computed from the owner's
+// registers and added at its place in the order (between positions EP-1 and EP of the unrolled
+// sequence, see k1_layout.cuh: no shared-memory store or load for it), and unused positions read the
+// zero entry.  Because the sum starts from +0.0 it can never be -0.0, so adding the +0.0 padding is an
+// exact no-op and the result is bit-identical to scipy's csr_matvec followed by the reference's
+// `D * (...)`.
 //
 // Cell -> thread ownership is static.  Cells are ranked by CSR row length (descending, stable) and
 // dealt to slots `k*THREADS + tid`, so the 32 cells a warp handles together have (almost) equal
 // row length and the padding costs next to nothing.
 #pragma once
 #include "common.cuh"
+#include "k1_layout.cuh"
 
 namespace cab200 {
 
@@ -53,16 +57,26 @@ struct SimArgs {
     int32_t *status_out;
 };
 
-// Shared-memory bytes K1 needs for a pouch padded to `np` slots.
-static inline size_t integrate_buf_stride(int np, int nslot, size_t elem2, int copies, int hmax = 0)
+// Shared-memory bytes K1 needs for a pouch padded to `np` slots.  Entries per step-parity buffer:
+// `copies` value regions, the legacy diagonal entries (unit Laplacian only), the zero entry, the halo.
+static inline size_t integrate_buf_entries(int nr, int copies, bool unit, int hmax)
 {
-    const size_t fixed = ((((size_t)copies + 1) * nslot + 1 + hmax) * elem2 + 127) & ~(size_t)127;
-    if (2 * fixed + 2 * (size_t)nslot + 64 <= 227 * 1024) return fixed;          // == BufGeom::STRIDE
-    return ((((size_t)copies + 1) * np + 1) * elem2 + 127) & ~(size_t)127;        // runtime stride
+    return (size_t)copies * nr + (unit ? CAB_LEGMAX : 0) + 1 + hmax;
 }
-static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2, int copies, int hmax = 0)
+// persistent tables behind the two buffers: orig_of[NSLOT] u16; unit: lrank_of[NSLOT] u16 + dco[LEGMAX]
+static inline size_t integrate_tail_bytes(int nslot, size_t elem2, bool unit)
 {
-    return 2 * integrate_buf_stride(np, nslot, elem2, copies, hmax) + 2 * (size_t)nslot + 64;   // + orig_of[NSLOT]
+    return 2 * (size_t)nslot + (unit ? 2 * (size_t)nslot + CAB_LEGMAX * (elem2 / 2) : 0) + 64;
+}
+static inline size_t integrate_buf_stride(int np, int nslot, size_t elem2, int copies, bool unit, int hmax = 0)
+{
+    const size_t fixed = (integrate_buf_entries(nslot, copies, unit, hmax) * elem2 + 127) & ~(size_t)127;
+    if (2 * fixed + integrate_tail_bytes(nslot, elem2, unit) <= 227 * 1024) return fixed;     // == BufGeom::STRIDE
+    return (integrate_buf_entries(np, copies, unit, hmax) * elem2 + 127) & ~(size_t)127;       // runtime stride
+}
+static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2, int copies, bool unit, int hmax = 0)
+{
+    return 2 * integrate_buf_stride(np, nslot, elem2, copies, unit, hmax) + integrate_tail_bytes(nslot, elem2, unit);
 }
 
 // One Euler step for one cell, reference source order (core/pouch.py:77-102), every operation
@@ -199,11 +213,13 @@ template <> struct Smem2<float> {
 // Entries per region and bytes between the two step-parity buffers.  When both buffers fit with
 // NSLOT-sized regions the stride is a compile-time constant (CSTRIDE): parity becomes an immediate
 // and slots beyond n own real (unused) entries, so nothing in the step loop is predicated on them.
-template <typename R, int NSLOT, int COPIES, int HMAX = 0>
+template <typename R, int NSLOT, int COPIES, bool UNIT, int HMAX = 0>
 struct BufGeom {
     static constexpr size_t ESZ = 2 * sizeof(R);
-    static constexpr size_t STRIDE = ((((size_t)(COPIES + 1) * NSLOT + 1 + HMAX) * ESZ) + 127) & ~(size_t)127;
-    static constexpr bool CSTRIDE = 2 * STRIDE + 2 * (size_t)NSLOT + 64 <= 227 * 1024;
+    static constexpr int LEG = UNIT ? CAB_LEGMAX : 0;
+    static constexpr size_t STRIDE = ((((size_t)COPIES * NSLOT + LEG + 1 + HMAX) * ESZ) + 127) & ~(size_t)127;
+    static constexpr size_t TAIL = 2 * (size_t)NSLOT + (UNIT ? 2 * (size_t)NSLOT + CAB_LEGMAX * sizeof(R) : 0) + 64;
+    static constexpr bool CSTRIDE = 2 * STRIDE + TAIL <= 227 * 1024;
 };
 
 // Halo entries a cluster CTA can hold (values of other CTAs' cells that its rows read).
@@ -232,7 +248,9 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     constexpr int NSLOT = THREADS * CPT;
     constexpr int EMAX = 2 * EP;
     constexpr int HMAX = (NCTA > 1) ? CAB_HMAX : 0;
-    typedef BufGeom<R, NSLOT, COPIES, HMAX> G;
+    constexpr int LEG = UNIT ? CAB_LEGMAX : 0;
+    constexpr int DPAIR = (EP & 1) ? EP - 1 : EP - 2;     // k1_diag_pair(EP)
+    typedef BufGeom<R, NSLOT, COPIES, UNIT, HMAX> G;
     static_assert(NCTA == 1 || (G::CSTRIDE && UNIT), "cluster kernels need the compile-time layout");
     constexpr bool CSTRIDE = G::CSTRIDE;
     constexpr uint32_t ESZ = (uint32_t)G::ESZ;
@@ -240,16 +258,21 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int n = a.n, np = a.np;
-    const int npr = CSTRIDE ? NSLOT : np;                 // entries per region
+    const int npr = CSTRIDE ? NSLOT : np;                 // entries per value region
     const uint32_t stride = CSTRIDE ? (uint32_t)G::STRIDE
-                                    : (uint32_t)(((((size_t)(COPIES + 1) * np + 1) * ESZ) + 127) & ~(size_t)127);
+                                    : (uint32_t)(((((size_t)COPIES * np + LEG + 1) * ESZ) + 127) & ~(size_t)127);
     R2 *buf1 = reinterpret_cast<R2 *>(smem_raw + stride);
     uint16_t *orig_of = reinterpret_cast<uint16_t *>(smem_raw + 2 * (size_t)stride);   // [NSLOT]
+    uint16_t *lrank_of = orig_of + NSLOT;                 // [NSLOT] (UNIT) legacy rank of the slot's cell, 0xffff = none
+    R *dco = reinterpret_cast<R *>(lrank_of + NSLOT);     // [LEG]   (UNIT) L_ii of the legacy cells
     // prologue scratch aliases buffer 1 (initialised after the scratch is dead)
     unsigned char *scr = reinterpret_cast<unsigned char *>(buf1);
     uint8_t *rlen = scr;                                                           // [n]
     uint16_t *slot_of = reinterpret_cast<uint16_t *>(scr + np);                    // [n]
     uint16_t *copy_sel = slot_of + np;                                             // [n]
+    uint8_t *part_of = reinterpret_cast<uint8_t *>(copy_sel + np);                 // [n] (clusters)
+    int8_t *rdg = reinterpret_cast<int8_t *>(part_of + np);                        // [n] diagonal index in the row, -1, -2
+    uint16_t *lrank = reinterpret_cast<uint16_t *>(rdg + np);                      // [n] rank among the legacy cells
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -258,16 +281,31 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     const uint32_t rank = (NCTA > 1) ? cluster_ctarank() : 0u;
     int bad = 0;
 
-    // ---- prologue 1: row lengths -------------------------------------------------------------
+    // ---- prologue 1: row lengths, where the diagonal sits, which rows take the legacy layout ----
     for (int i = tid; i < n; i += THREADS) {
-        int len = a.rowptr[i + 1] - a.rowptr[i];
+        const int rb = a.rowptr[i];
+        int len = a.rowptr[i + 1] - rb;
         if (len > EMAX || len < 0) { bad = 1; len = 0; }
         rlen[i] = (uint8_t)len;
+        int nd = 0, di = -1;
+        for (int j = 0; j < len; ++j)
+            if (a.colidx[rb + j] == i) { ++nd; di = j; }
+        rdg[i] = (int8_t)(nd == 0 ? -1 : (nd == 1 ? di : -2));
     }
-    for (int s = tid; s < NSLOT; s += THREADS) orig_of[s] = 0xffff;
+    for (int s = tid; s < NSLOT; s += THREADS) { orig_of[s] = 0xffff; if (UNIT) lrank_of[s] = 0xffff; }
     __syncthreads();
+    if (UNIT && warp == 0) {       // legacy cells ranked in cell order (deterministic; the planner does the same)
+        int running = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool lg = i < n && k1_row(true, EP, rlen[i], rdg[i]).legacy;
+            const unsigned m = __ballot_sync(0xffffffffu, lg);
+            if (i < n) lrank[i] = lg ? (uint16_t)(running + __popc(m & ((1u << lane) - 1u))) : (uint16_t)0xffff;
+            running += __popc(m);
+        }
+        if (running > LEG) bad = 1;
+    }
     // ---- prologue 2: cell -> slot.  Host plan if given, else stable rank by (length desc, id asc) --
-    uint8_t *part_of = reinterpret_cast<uint8_t *>(copy_sel + np);                 // [n] (clusters)
     if (NCTA > 1) {
         // cluster plan: this CTA owns the cells of part `rank`; slot_of is the slot inside the part
         for (int i = tid; i < n; i += THREADS) {
@@ -326,38 +364,51 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     }
 
     // ---- prologue 4: private per-cell state ------------------------------------------------------
-    // Slot of (warp w, group k, lane l) = (w*CPT + k)*32 + l: the CPT*32 cells a warp owns are
-    // consecutive in the length-sorted order, so ONE warp-uniform trip count W serves all of them.
-    // Rows are right-aligned in EMAX positions: positions [start, start+len) hold the row's entries
-    // in CSR order (start = EMAX-W rounded down to even), everything else points at the zero entry;
-    // the step loop enters a fully unrolled position sequence at `start` through one jump.
-    // ent[k][pos] is the 32-bit shared address of the entry inside buffer 0; buffer 1 is +stride.
+    // Slot of (warp w, group k, lane l) = (w*CPT + k)*32 + l: the host planner deals cells with similar
+    // row shapes to the same warp, so ONE warp-uniform position range [start, end) serves all CPT*32
+    // cells of a warp.  k1_row (k1_layout.cuh) places a row's entries among the EMAX positions: entries
+    // before the diagonal right-aligned below EP, the others left-aligned from EP; the diagonal itself
+    // is added from registers inside the pair DPAIR.  Everything else points at the zero entry; the
+    // step loop enters the fully unrolled position sequence at `start` through one jump and leaves it
+    // at `end`.  ent[k][pos] is the 32-bit shared address of the entry inside buffer 0; buffer 1 is
+    // +stride.
     const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t zero_addr = sb0 + (uint32_t)((COPIES + 1) * npr) * ESZ;
+    const uint32_t leg_addr = sb0 + (uint32_t)(COPIES * npr) * ESZ;          // legacy diagonal entries
+    const uint32_t zero_addr = leg_addr + (uint32_t)LEG * ESZ;
+    const uint32_t halo_addr = zero_addr + ESZ;
     R c[CPT], p[CPT], s[CPT], r[CPT], vplc[CPT], dcoef[CPT];
     uint32_t ent[CPT][EMAX];
     uint32_t own[CPT];              // shared address (buffer 0) of the cell's own value entry
     int rowbeg[CPT], len[CPT];
     bool live[CPT];
-    int mylen = 0;
+    K1Row row[CPT];
+    int min_first = EMAX, max_last = 0;
+    bool any_legacy = false;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int slot = (warp * CPT + k) * 32 + lane;
         const int cell = (int)orig_of[slot];          // 0xffff: no cell in this slot
         live[k] = (cell != 0xffff);
         own[k] = sb0 + (uint32_t)slot * ESZ;
+#ifdef CAB_X_OWN_OPAQUE     // experiment: keep the address in a register instead of re-deriving it from %tid
+        if (k == 0) asm volatile("mov.u32 %0, %0;" : "+r"(own[0]));
+        else own[k] = own[0] + (uint32_t)(k * 32) * ESZ;
+#endif
         rowbeg[k] = 0; len[k] = 0;
         c[k] = p[k] = s[k] = r[k] = vplc[k] = dcoef[k] = (R)0;
+        row[k] = k1_row(UNIT, EP, 0, -1);
         if (live[k]) {
             len[k] = rlen[cell];
             rowbeg[k] = a.rowptr[cell];
+            row[k] = k1_row(UNIT, EP, len[k], rdg[cell]);
             c[k] = (R)a.c0[coff + cell];
             p[k] = (R)a.p0[coff + cell];
             r[k] = (R)a.r0[coff + cell];
             vplc[k] = (R)a.vplc[coff + cell];
+            if (len[k] > 0) { min_first = min(min_first, row[k].first); max_last = max(max_last, row[k].last); }
+            if (UNIT && row[k].legacy) { any_legacy = true; lrank_of[slot] = lrank[cell]; }
         }
         s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                          // core/pouch.py:322
-        mylen = max(mylen, len[k]);
     }
     // cluster: halo lists (sorted global cell ids per part) follow the three per-cell arrays
     const uint16_t *hcount = a.slot_plan + 3 * (size_t)n;
@@ -374,33 +425,44 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         }
         return -1;
     };
-    const int W = __reduce_max_sync(0xffffffffu, mylen);
-    const int start = (EMAX - W) & ~1;          // even: positions are processed in pairs
+    int start, end;
+    k1_warp_range(UNIT, EP, __reduce_min_sync(0xffffffffu, min_first), __reduce_max_sync(0xffffffffu, max_last),
+                  &start, &end);
+#ifdef CAB_X_NO_LEGACY      // experiment (timing only, wrong results for legacy cells)
+    const bool wleg = false && __any_sync(0xffffffffu, any_legacy);
+#else
+    const bool wleg = UNIT && __any_sync(0xffffffffu, any_legacy);     // this warp owns legacy cells
+#endif
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int slot = (warp * CPT + k) * 32 + lane;
         const int cell = live[k] ? (int)orig_of[slot] : 0;
         const uint32_t sel = live[k] ? (uint32_t)copy_sel[cell] : 0u;
+        const uint32_t lrk = (UNIT && live[k] && row[k].legacy) ? (uint32_t)lrank[cell] : 0u;
+        if (UNIT && live[k] && !row[k].legacy && row[k].skip)                 // register diagonal: its weight
+            dcoef[k] = (R)a.vals[rowbeg[k] + row[k].split];
 #pragma unroll
         for (int pos = 0; pos < EMAX; ++pos) {
-            const int e = pos - start;
+            const int e = live[k] ? k1_entry_at(row[k], EP, pos) : -1;
             uint32_t o = zero_addr;
-            if (live[k] && e >= 0 && e < len[k]) {
+            if (e >= 0 && e < len[k]) {
                 const int col = a.colidx[rowbeg[k] + e];
                 if (col < 0 || col >= n) bad = 1;
                 else if (NCTA > 1 && part_of[col] != rank) {
                     const int h = halo_find((int)rank, col);        // another CTA's cell: local halo entry
                     if (h < 0 || h >= HMAX || a.vals[rowbeg[k] + e] != 1.0) bad = 1;
-                    else o = sb0 + (uint32_t)((COPIES + 1) * npr + 1 + h) * ESZ;
+                    else o = halo_addr + (uint32_t)h * ESZ;
                 } else {
                     uint32_t j = slot_of[col];
                     if (COPIES == 2 && ((sel >> e) & 1u)) j = (uint32_t)npr + (j ^ 4u);
+                    o = sb0 + j * ESZ;
                     if (UNIT) {
                         const double w = a.vals[rowbeg[k] + e];
-                        if (col == cell) { dcoef[k] = (R)w; j = (uint32_t)(COPIES * npr + slot); }
-                        else if (w != 1.0) bad = 1;
+                        if (col == cell) {                           // only legacy rows gather their diagonal
+                            if (lrk < (uint32_t)LEG) { dco[lrk] = (R)w; o = leg_addr + lrk * ESZ; }
+                            else bad = 1;
+                        } else if (w != 1.0) bad = 1;
                     }
-                    o = sb0 + j * ESZ;
                 }
             }
             ent[k][pos] = o;
@@ -420,7 +482,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
                 const int h = halo_find((int)q2, cell);
                 if (h >= HMAX) bad = 1;
                 else if (h >= 0)
-                    push[k][d] = mapa_shared(sb0 + (uint32_t)((COPIES + 1) * npr + 1 + h) * ESZ, q2);
+                    push[k][d] = mapa_shared(halo_addr + (uint32_t)h * ESZ, q2);
             }
         }
     }
@@ -444,14 +506,12 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     for (int d = 0; d < (NCTA > 1 ? NCTA - 1 : 1); ++d)
         bar_peer[d] = (NCTA > 1) ? mapa_shared(bar_addr, (rank + 1 + d) % NCTA) : bar_addr;
     const uint32_t copyb_off = (uint32_t)npr * ESZ;                 // second value copy (multiple of 128 B)
-    const uint32_t diag_off = (uint32_t)(COPIES * npr) * ESZ;       // diagonal entries
-    // Publishes a cell's new (c, p): value entry, second copy in the bank group 4 away, diagonal
-    // term.  IMM selects the step-parity buffer at compile time (CSTRIDE) -- else roff does.
+    // Publishes a cell's new (c, p): value entry and second copy in the bank group 4 away.  IMM selects
+    // the step-parity buffer at compile time (CSTRIDE) -- else roff does.
 #define CAB_PUBLISH(IMM, ROFF, K, CV, PV, ASYNC_BAR)                                               \
     if (CSTRIDE || live[K]) {                                                                     \
         M::template st<IMM>(own[K] + (ROFF), (CV), (PV));                                         \
         if (COPIES == 2) M::template st<IMM>(((own[K] + copyb_off) ^ (4u * ESZ)) + (ROFF), (CV), (PV)); \
-        if (UNIT) M::template st<IMM>(own[K] + diag_off + (ROFF), S::mul(dcoef[K], (CV)), S::mul(dcoef[K], (PV))); \
         if (NCTA > 1) {                                                                           \
             _Pragma("unroll") for (int d_ = 0; d_ < NCTA - 1; ++d_)                               \
                 if (push[K][d_]) {                                                                \
@@ -460,8 +520,21 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
                 }                                                                                 \
         }                                                                                         \
     }
+    // A legacy cell's diagonal entry is read by nobody but its owner (in the owner's next gather), so it
+    // needs no barrier: it is rewritten AFTER the arrival, off the step's critical path.
+#define CAB_PUBLISH_LEGACY(IMM, ROFF)                                                             \
+    if (wleg) {                                                                                   \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
+            const uint32_t lr_ = lrank_of[(warp * CPT + k) * 32 + lane];                          \
+            if (lr_ != 0xffffu) {                                                                 \
+                const R dc_ = dco[lr_];                                                           \
+                M::template st<IMM>(leg_addr + lr_ * ESZ + (ROFF), S::mul(dc_, c[k]), S::mul(dc_, p[k])); \
+            }                                                                                     \
+        }                                                                                         \
+    }
 #pragma unroll
     for (int k = 0; k < CPT; ++k) { CAB_PUBLISH(0, 0u, k, c[k], p[k], -1) }
+    CAB_PUBLISH_LEGACY(0, 0u)
     __syncthreads();
     if (NCTA > 1) cluster_sync_all();    // initial values, halo entries included, are in place
     const uint32_t halo_bytes = (NCTA > 1) ? (uint32_t)hcount[rank] * ESZ : 0u;   // pushed to this CTA per step
@@ -527,8 +600,31 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     if (lane == 0) mbar_arrive(&step_bar[0]);   // state(0) was published (and pushed) before the barriers above
     unsigned parity = 0;
 
+#ifdef CAB_X_NO_EXIT
+#define CAB_EXIT_CHECK(P0)
+#else
+#define CAB_EXIT_CHECK(P0) if (end <= (P0) + 2) break;
+#endif
+// The register diagonal of every owned cell: L_ii * (c_i, p_i), each product rounded like the stored
+// diagonal entry of round 1 was (dcoef is 0 for legacy cells and empty slots: +-0 never changes a sum
+// that cannot be -0).
+#ifdef CAB_X_DIAG_EARLY
+#define CAB_DIAG_ADD                                                                              \
+    _Pragma("unroll") for (int k = 0; k < CPT; ++k) { sc[k] = S::add(sc[k], dgc[k]); sp[k] = S::add(sp[k], dgp[k]); }
+#define CAB_DIAG_PREP                                                                             \
+    R dgc[CPT], dgp[CPT];                                                                         \
+    _Pragma("unroll") for (int k = 0; k < CPT; ++k) { dgc[k] = S::mul(dcoef[k], c[k]); dgp[k] = S::mul(dcoef[k], p[k]); }
+#else
+#define CAB_DIAG_ADD                                                                              \
+    _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                             \
+        sc[k] = S::add(sc[k], S::mul(dcoef[k], c[k])); sp[k] = S::add(sp[k], S::mul(dcoef[k], p[k])); \
+    }
+#define CAB_DIAG_PREP
+#endif
+
 // One pair of row positions for every owned cell: all loads of the pair first (2*CPT independent
-// 16-byte loads in flight per thread), then the additions in position order.
+// 16-byte loads in flight per thread), then the additions in position order.  The pair DPAIR also
+// carries the register diagonal at its place in the order.
 #define CAB_GATHER_PAIR(IMM, ROFF, P0)                                                            \
     {                                                                                             \
         R2 va[CPT], vb[CPT];                                                                      \
@@ -536,28 +632,36 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             va[k] = M::template ld<IMM>(ent[k][(P0)] + (ROFF));                                   \
             vb[k] = M::template ld<IMM>(ent[k][(P0) + 1] + (ROFF));                               \
         }                                                                                         \
-        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
-            if (UNIT) {                                                                           \
+        if (UNIT) {                                                                               \
+            _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                     \
                 sc[k] = S::add(sc[k], va[k].x); sp[k] = S::add(sp[k], va[k].y);                   \
+            }                                                                                     \
+            if ((P0) == DPAIR && (EP & 1)) { CAB_DIAG_ADD }                                       \
+            _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                     \
                 sc[k] = S::add(sc[k], vb[k].x); sp[k] = S::add(sp[k], vb[k].y);                   \
-            } else {                                                                              \
-                const int e0 = (P0) - start;                                                      \
+            }                                                                                     \
+            if ((P0) == DPAIR && !(EP & 1)) { CAB_DIAG_ADD }                                      \
+        } else {                                                                                  \
+            _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                     \
+                const int e0 = (P0) - row[k].lo_base;                                             \
                 const R w0 = (e0 >= 0 && e0 < len[k]) ? (R)__ldg(a.vals + rowbeg[k] + e0) : (R)0;  \
                 const R w1 = (e0 + 1 >= 0 && e0 + 1 < len[k]) ? (R)__ldg(a.vals + rowbeg[k] + e0 + 1) : (R)0; \
                 sc[k] = S::add(sc[k], S::mul(w0, va[k].x)); sp[k] = S::add(sp[k], S::mul(w0, va[k].y)); \
                 sc[k] = S::add(sc[k], S::mul(w1, vb[k].x)); sp[k] = S::add(sp[k], S::mul(w1, vb[k].y)); \
             }                                                                                     \
         }                                                                                         \
+        CAB_EXIT_CHECK(P0)                                                                        \
     }
 
 // One time step reading the buffer at +CUR and writing the one at +NXT (immediates when CSTRIDE).
 #define CAB_STEP(CUR_IMM, NXT_IMM, CUR_R, NXT_R, CUR_BAR, NXT_BAR)                                \
     {                                                                                             \
+        CAB_DIAG_PREP                                                                             \
         mbar_wait(&step_bar[CUR_BAR], parity);                                                    \
         if (NCTA == 1 || (CUR_BAR) == 1) parity ^= 1u;   /* a cluster uses each barrier every 2nd step */ \
         R sc[CPT], sp[CPT];                                                                       \
         _Pragma("unroll") for (int k = 0; k < CPT; ++k) { sc[k] = (R)0; sp[k] = (R)0; }           \
-        switch (start) { /* warp-uniform entry point; every later position follows */             \
+        switch (start) { /* warp-uniform entry point; later positions follow until `end` */       \
             case 0: CAB_GATHER_PAIR(CUR_IMM, CUR_R, 0)                                            \
             case 2: CAB_GATHER_PAIR(CUR_IMM, CUR_R, 2)                                            \
             case 4: CAB_GATHER_PAIR(CUR_IMM, CUR_R, 4)                                            \
@@ -579,6 +683,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         /* one arrival per warp: __syncwarp orders the other lanes' stores before lane 0's release */ \
         __syncwarp();                                                                             \
         if (lane == 0) arrive_step(NXT_BAR);                                                      \
+        CAB_PUBLISH_LEGACY(NXT_IMM, NXT_R)                                                        \
         /* own-state work for the next step, overlapping the other warps' gathers */              \
         _Pragma("unroll") for (int k = 0; k < CPT; ++k)                                           \
             s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                      /* :95 */          \
@@ -607,6 +712,10 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     }
 #undef CAB_STEP
 #undef CAB_GATHER_PAIR
+#undef CAB_DIAG_ADD
+#undef CAB_DIAG_PREP
+#undef CAB_EXIT_CHECK
+#undef CAB_PUBLISH_LEGACY
 #undef CAB_PUBLISH
 }
 

@@ -31,39 +31,55 @@
 #include <vector>
 
 #include "common.cuh"
+#include "k1_layout.cuh"
 
 namespace cab200 {
 
 namespace {
 
 // One CTA's planning problem: nloc local cells; row entries are local cell ids (>= 0), or -1-h for
-// halo entry h.  The cell's own id marks the diagonal.
+// halo entry h.  The cell's own id marks the diagonal.  Rows are laid out among the 2*ep gather
+// positions by k1_row (k1_layout.cuh) -- the same rule the kernel applies.
 struct Problem {
-    int n, np, copies, cpt;
+    int n, np, copies, cpt, ep;
+    bool unit;
     std::vector<int> rowptr, ecol;
+    std::vector<int> lrank;                   // legacy rank of a cell (index of its shared-memory diagonal entry)
+    std::vector<K1Row> row;
     std::vector<int> slot_of, cell_of;        // cell_of[slot] = cell or -1
     std::vector<std::vector<int>> refs;       // refs[c] = local cells whose row contains c (incl. c)
-    std::vector<int> wlen;                    // per warp (32*cpt slots): longest row, rounded to even
+    std::vector<int> wstart, wend;            // per warp (32*cpt slots): the position range it runs
     int n_groups;
 
     inline int rowlen(int c) const { return rowptr[c + 1] - rowptr[c]; }
 
-    // Wavefronts of phase group g at entry position e; if sel_out, also reports which lanes should
-    // read copy B (bit l of *sel_out).
-    inline int phase_cost(int g, int e, unsigned *sel_out) const
+    void compute_rows()
     {
-        const int zero_idx = (copies + 1) * np;
+        row.resize(n);
+        for (int c = 0; c < n; ++c) {
+            int nd = 0, di = -1;
+            for (int j = rowptr[c]; j < rowptr[c + 1]; ++j)
+                if (ecol[j] == c) { ++nd; di = j - rowptr[c]; }
+            row[c] = k1_row(unit, ep, rowlen(c), nd == 0 ? -1 : (nd == 1 ? di : -2));
+        }
+    }
+
+    // Wavefronts of phase group g at gather position pos; if sel_out, also reports which lanes should
+    // read copy B (bit l of *sel_out).
+    inline int phase_cost(int g, int pos, unsigned *sel_out) const
+    {
+        const int zero_idx = copies * np + (unit ? CAB_LEGMAX : 0);
         int a_idx[8], b_idx[8];     // candidate entry indices (b = -1: no choice)
         for (int l = 0; l < 8; ++l) {
             const int c = cell_of[g * 8 + l];
             a_idx[l] = zero_idx;
             b_idx[l] = -1;
             if (c < 0) continue;
-            const int rb = rowptr[c];
-            if (e >= rowlen(c)) continue;
-            const int cc = ecol[rb + e];
+            const int e = k1_entry_at(row[c], ep, pos);
+            if (e < 0 || e >= rowlen(c)) continue;
+            const int cc = ecol[rowptr[c] + e];
             if (cc < 0) { a_idx[l] = zero_idx + 1 + (-1 - cc); continue; }       // halo entry
-            if (cc == c) { a_idx[l] = copies * np + slot_of[c]; continue; }      // diagonal entry
+            if (cc == c && unit) { a_idx[l] = copies * np + lrank[c]; continue; } // legacy diagonal entry
             a_idx[l] = slot_of[cc];
             if (copies == 2) b_idx[l] = np + (slot_of[cc] ^ 4);
         }
@@ -108,9 +124,9 @@ struct Problem {
 
     int group_cost(int g) const
     {
-        const int wl = wlen[(g * 8) / (32 * cpt)];
+        const int w = (g * 8) / (32 * cpt);
         int cost = 0;
-        for (int e = 0; e < wl; ++e) cost += phase_cost(g, e, nullptr);
+        for (int pos = wstart[w]; pos < wend[w]; ++pos) cost += phase_cost(g, pos, nullptr);
         return cost;
     }
 
@@ -121,17 +137,24 @@ struct Problem {
         return c;
     }
 
-    // a warp owns 32*cpt consecutive slots and runs one trip count for all of them: its longest
-    // row, rounded up to even (the kernel walks row positions in pairs)
-    void compute_wlen()
+    // a warp owns 32*cpt consecutive slots and runs one position range for all of them (k1_warp_range)
+    void compute_wrange()
     {
         const int per = 32 * cpt, nw = (np + per - 1) / per;
-        wlen.assign(nw, 0);
+        wstart.assign(nw, 0); wend.assign(nw, 0);
         for (int w = 0; w < nw; ++w) {
-            for (int s = w * per; s < std::min(np, (w + 1) * per); ++s)
-                if (cell_of[s] >= 0) wlen[w] = std::max(wlen[w], rowlen(cell_of[s]));
-            wlen[w] = (wlen[w] + 1) & ~1;
+            int mf = 2 * ep, ml = 0;
+            for (int s = w * per; s < std::min(np, (w + 1) * per); ++s) {
+                const int c = cell_of[s];
+                if (c >= 0 && rowlen(c) > 0) { mf = std::min(mf, row[c].first); ml = std::max(ml, row[c].last); }
+            }
+            k1_warp_range(unit, ep, mf, ml, &wstart[w], &wend[w]);
         }
+    }
+
+    inline bool fits(int c, int w) const
+    {
+        return rowlen(c) == 0 || (row[c].first >= wstart[w] && row[c].last <= wend[w]);
     }
 
     // order: cell at each slot (a permutation of 0..n-1)
@@ -142,17 +165,17 @@ struct Problem {
         slot_of.assign(n, 0);
         cell_of.assign(np, -1);
         for (int s = 0; s < n; ++s) { slot_of[order[s]] = s; cell_of[s] = order[s]; }
-        compute_wlen();
+        compute_wrange();
         refs.assign(n, {});
         for (int i = 0; i < n; ++i)
             for (int j = rowptr[i]; j < rowptr[i + 1]; ++j)
                 if (ecol[j] >= 0) refs[ecol[j]].push_back(i);
     }
 
-    long long gather_instructions() const
+    long long gather_instructions() const      // warp-wide loads per step
     {
         long long rows = 0;
-        for (int g = 0; g < n_groups; g += 4) rows += wlen[(g * 8) / (32 * cpt)];
+        for (int g = 0; g < n_groups; g += 4) { const int w = (g * 8) / (32 * cpt); rows += wend[w] - wstart[w]; }
         return rows;
     }
 };
@@ -169,17 +192,11 @@ struct Rng {
     double unit() { return (next() >> 11) * (1.0 / 9007199254740992.0); }
 };
 
-// Simulated annealing over swaps inside row-length classes.  Returns the final cost.
+// Simulated annealing over swaps of two cells that each fit the other's warp (its position range
+// covers the row), so no warp's range ever grows.  Returns the final cost.
 long long anneal(Problem &P, long long iters, uint64_t seed, long long *cost0_out)
 {
-    const int n = P.n;
-    std::vector<std::vector<int>> class_slots(32);
-    std::vector<int> class_of(n);
-    for (int s = 0; s < n; ++s) {
-        const int len = std::min(31, P.rowlen(P.cell_of[s]));
-        class_of[s] = len;
-        class_slots[len].push_back(s);
-    }
+    const int n = P.n, per = 32 * P.cpt;
     long long cost = P.total_cost();
     if (cost0_out) *cost0_out = cost;
     Rng rng{seed ? seed : 0x5EEDull};
@@ -187,13 +204,14 @@ long long anneal(Problem &P, long long iters, uint64_t seed, long long *cost0_ou
     // CALCIUM_B200_PLAN_T0: start temperature (default 0.8); a low value polishes an existing plan (use_input)
     const char *t0_env = getenv("CALCIUM_B200_PLAN_T0");
     const double t_start = (t0_env && atof(t0_env) > 0.0) ? atof(t0_env) : 0.8, t_end = 0.02;
+    if (n < 2) return cost;
     for (long long it = 0; it < iters; ++it) {
         const int sa = (int)(rng.next() % (uint64_t)n);
-        const std::vector<int> &cls = class_slots[class_of[sa]];
-        if (cls.size() < 2) continue;
-        const int sb = cls[rng.next() % cls.size()];
+        const int sb = (int)(rng.next() % (uint64_t)n);
         if (sb == sa) continue;
         const int a = P.cell_of[sa], b = P.cell_of[sb];
+        const int wa = sa / per, wb = sb / per;
+        if (wa != wb && !(P.fits(a, wb) && P.fits(b, wa))) continue;
         touched.clear();
         for (int r : P.refs[a]) touched.push_back(P.slot_of[r] / 8);
         for (int r : P.refs[b]) touched.push_back(P.slot_of[r] / 8);
@@ -223,12 +241,15 @@ void emit_sel(const Problem &P, std::vector<uint16_t> &sel)
     sel.assign(P.n, 0);
     if (P.copies != 2) return;
     for (int g = 0; g < P.n_groups; ++g) {
-        const int wl = P.wlen[(g * 8) / (32 * P.cpt)];
-        for (int e = 0; e < wl; ++e) {
+        const int w = (g * 8) / (32 * P.cpt);
+        for (int pos = P.wstart[w]; pos < P.wend[w]; ++pos) {
             unsigned m = 0;
-            P.phase_cost(g, e, &m);
+            P.phase_cost(g, pos, &m);
             for (int l = 0; l < 8; ++l)
-                if ((m >> l) & 1u) sel[P.cell_of[g * 8 + l]] |= (uint16_t)(1u << e);
+                if ((m >> l) & 1u) {
+                    const int c = P.cell_of[g * 8 + l];
+                    sel[c] |= (uint16_t)(1u << k1_entry_at(P.row[c], P.ep, pos));     // bit e: row entry e reads copy B
+                }
         }
     }
 }
@@ -246,12 +267,51 @@ int check_csr(int n, const int32_t *rowptr, const int32_t *colidx, const char *w
     return CAB200_OK;
 }
 
-std::vector<int> length_sorted_order(const Problem &P)
+// Start order: cells with the same (even-rounded) position range next to each other, so that a warp's
+// range is as tight as its cells allow.  Three sort keys are tried; the one with the fewest warp-wide
+// loads per step wins.
+std::vector<int> shape_sorted_order(Problem &P)
 {
-    std::vector<int> order(P.n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return P.rowlen(a) > P.rowlen(b); });
-    return order;
+    std::vector<int> best;
+    long long best_rows = -1;
+    for (int variant = 0; variant < 3; ++variant) {
+        std::vector<int> order(P.n);
+        std::iota(order.begin(), order.end(), 0);
+        auto fr = [&](int c) { return P.rowlen(c) ? (P.row[c].first & ~1) : 2 * P.ep; };
+        auto lr = [&](int c) { return P.rowlen(c) ? ((P.row[c].last + 1) & ~1) : 0; };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const int fa = fr(a), fb = fr(b), la = lr(a), lb = lr(b);
+            if (variant == 0) return fa != fb ? fa < fb : la > lb;
+            if (variant == 1) return la != lb ? la > lb : fa < fb;
+            return (la - fa) != (lb - fb) ? (la - fa) > (lb - fb) : fa < fb;
+        });
+        P.set_order(order);
+        const long long rows = P.gather_instructions();
+        if (best_rows < 0 || rows < best_rows) { best_rows = rows; best = order; }
+    }
+    return best;
+}
+
+// legacy ranks in cell order (what the kernel's prologue computes)
+int legacy_ranks(int n, const int32_t *rowptr, const int32_t *colidx, bool unit, int ep, std::vector<int> &lrank)
+{
+    lrank.assign(n, -1);
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        int nd = 0, di = -1;
+        const int len = rowptr[i + 1] - rowptr[i];
+        for (int j = 0; j < len; ++j)
+            if (colidx[rowptr[i] + j] == i) { ++nd; di = j; }
+        if (unit && k1_row(true, ep, len, nd == 0 ? -1 : (nd == 1 ? di : -2)).legacy) lrank[i] = cnt++;
+    }
+    return cnt;
+}
+
+int max_row_of(int n, const int32_t *rowptr)
+{
+    int m = 0;
+    for (int i = 0; i < n; ++i) m = std::max(m, rowptr[i + 1] - rowptr[i]);
+    return m;
 }
 
 }  // namespace
@@ -260,7 +320,7 @@ std::vector<int> length_sorted_order(const Problem &P)
 using namespace cab200;
 
 // See include/cab200.h.
-extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *colidx, int copies,
+extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *colidx, int copies, int unit,
                                  int cells_per_thread, long long iters, unsigned long long seed,
                                  int use_input, uint16_t *plan_out, int64_t *cost_out)
 {
@@ -272,9 +332,15 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
     if (int rc = check_csr(n, rowptr, colidx, "cab200_plan_slots")) return rc;
     Problem P;
     P.n = n; P.copies = copies; P.cpt = cells_per_thread;
+    P.unit = unit != 0; P.ep = k1_ep(max_row_of(n, rowptr));
     P.rowptr.assign(rowptr, rowptr + n + 1);
     P.ecol.assign(colidx, colidx + rowptr[n]);
-    std::vector<int> order = length_sorted_order(P);
+    if (legacy_ranks(n, rowptr, colidx, P.unit, P.ep, P.lrank) > CAB_LEGMAX) {
+        set_error("cab200_plan_slots: more than %d rows need the legacy layout; declare the geometry non-unit", CAB_LEGMAX);
+        return CAB200_ESIZE;
+    }
+    P.compute_rows();
+    std::vector<int> order = shape_sorted_order(P);
     if (use_input) {
         std::vector<char> seen(n, 0);
         for (int i = 0; i < n; ++i) {
@@ -298,6 +364,14 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
 }
 
 // See include/cab200.h.
+extern "C" int cab200_k1_legacy_rows(int n, const int32_t *rowptr, const int32_t *colidx)
+{
+    if (n <= 0 || !rowptr || !colidx) { set_error("cab200_k1_legacy_rows: bad argument"); return CAB200_EINVAL; }
+    std::vector<int> lrank;
+    return legacy_ranks(n, rowptr, colidx, true, k1_ep(max_row_of(n, rowptr)), lrank);
+}
+
+// See include/cab200.h.
 extern "C" long long cab200_plan_cluster(int n, const int32_t *rowptr, const int32_t *colidx, int n_cta,
                                          int copies, int cells_per_thread, long long iters,
                                          unsigned long long seed, uint16_t *plan_out,
@@ -309,6 +383,12 @@ extern "C" long long cab200_plan_cluster(int n, const int32_t *rowptr, const int
         return CAB200_EINVAL;
     }
     if (int rc = check_csr(n, rowptr, colidx, "cab200_plan_cluster")) return rc;
+    const int ep = k1_ep(max_row_of(n, rowptr));        // clusters run the unit-weight kernel only
+    std::vector<int> glrank;
+    if (legacy_ranks(n, rowptr, colidx, true, ep, glrank) > CAB_LEGMAX) {
+        set_error("cab200_plan_cluster: more than %d rows need the legacy layout", CAB_LEGMAX);
+        return CAB200_ESIZE;
+    }
     // ---- 1. breadth-first order from a pseudo-peripheral cell; parts = equal contiguous chunks ----
     auto bfs = [&](int src, std::vector<int> &order) {
         std::vector<char> seen(n, 0);
@@ -350,7 +430,9 @@ extern "C" long long cab200_plan_cluster(int n, const int32_t *rowptr, const int
         halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
         Problem P;
         P.n = (int)cells.size(); P.copies = copies; P.cpt = cells_per_thread;
+        P.unit = true; P.ep = ep;
         P.rowptr.assign(1, 0);
+        for (int c : cells) P.lrank.push_back(glrank[c]);
         for (int c : cells) {
             for (int j = rowptr[c]; j < rowptr[c + 1]; ++j) {
                 const int cc = colidx[j];
@@ -360,7 +442,8 @@ extern "C" long long cab200_plan_cluster(int n, const int32_t *rowptr, const int
             P.rowptr.push_back((int)P.ecol.size());
         }
         if (P.n == 0) { set_error("cab200_plan_cluster: empty part"); return CAB200_EINVAL; }
-        P.set_order(length_sorted_order(P));
+        P.compute_rows();
+        P.set_order(shape_sorted_order(P));
         long long cost0 = 0;
         c1 += anneal(P, iters / n_cta, seed + 977 * (q + 1), &cost0);
         c0 += cost0;

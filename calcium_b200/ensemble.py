@@ -102,6 +102,12 @@ class _DeviceGeometry:
         offdiag &= rows != col
         self.unit = bool(np.all(val[offdiag] == 1.0))
         self.nnz = len(col)
+        if self.unit and self.n and self.nnz:
+            # the unit-weight kernel keeps at most 256 rows whose diagonal cannot be added from registers
+            # (csrc/k1_layout.cuh); geometries with more run the general-weight kernel (1.0 * x == x exactly)
+            legacy = int(_lib.load().cab200_k1_legacy_rows(self.n, _lib.as_i32p(rowptr), _lib.as_i32p(col)))
+            if legacy < 0 or legacy > 256:
+                self.unit = False
         if self.nnz == 0:        # a graph without any entry still needs non-null device pointers
             col, val = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.float64)
         self.rowptr = torch.from_numpy(rowptr).to(device)
@@ -160,8 +166,8 @@ def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool, n_cta: int = 
     rowptr, col, _ = geo.csr
     h = hashlib.sha1()
     h.update(rowptr.tobytes()); h.update(col.tobytes())
-    h.update(f"copies={copies}:cpt={cpt}:v3".encode() if n_cta == 1
-             else f"copies={copies}:cpt={cpt}:ncta={n_cta}:v1".encode())
+    h.update(f"copies={copies}:cpt={cpt}:v4-diagreg".encode() if n_cta == 1          # v4: register-diagonal row layout
+             else f"copies={copies}:cpt={cpt}:ncta={n_cta}:v2-diagreg".encode())
     name = f"plan_{h.hexdigest()[:16]}.npy"
     if tracked:
         return os.path.join(_PLANS_DIR, name)
@@ -197,7 +203,7 @@ def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = 
     n_it = PLAN_ITERS if iters is None else iters
     if n_cta == 1:
         plan = np.zeros(2 * n, dtype=np.uint16)
-        _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, cpt, n_it, 1, 0,
+        _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 1 if unit else 0, cpt, n_it, 1, 0,
                                          plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None),
                    "cab200_plan_slots")
     else:
@@ -223,8 +229,18 @@ _DEV_GEO: Dict[Tuple[int, int], _DeviceGeometry] = {}
 _DEV_GEO_LOCK = threading.Lock()
 
 
+def resolve_device(device) -> torch.device:
+    """``torch.device`` with an explicit index (``torch.device("cuda")`` means the CURRENT device, which is not
+    necessarily device 0: caches keyed on the index must not mix the two up)."""
+    d = torch.device(device) if device is not None else torch.device("cuda")
+    if d.type == "cuda" and d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
 def device_geometry(geo: Geometry, device: torch.device) -> _DeviceGeometry:
-    key = (id(geo), device.index or 0)
+    device = resolve_device(device)
+    key = (id(geo), device.index)
     with _DEV_GEO_LOCK:
         dg = _DEV_GEO.get(key)
         if dg is None:
@@ -340,8 +356,7 @@ class Ensemble:
         if not torch.cuda.is_available():
             raise RuntimeError("calcium_b200 needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
-        self.device = torch.device(device) if device is not None else torch.device(
-            "cuda", torch.cuda.current_device())
+        self.device = resolve_device(device)
         self.specs = list(specs)
         self.P = len(self.specs)
         self.T = int(T)
@@ -725,7 +740,7 @@ class Ensemble:
     def run_files_to_host(self, chunk_pouches: int = 37, image: bool = True, mask: bool = True,
                            consumer=None, threshold: float = 0.1, quirk: bool = True,
                            arena_bytes_per_pixel: float = 0.5, wait: bool = True,
-                           stage_bytes: int = 0, frames: str = "ca") -> Dict[str, int]:
+                           stage_bytes: int = 0, frames: str = "none") -> Dict[str, int]:
         """The whole hot path with HOST buffers on both sides, in the form the reference's batch path
         stores its results: pinned host inputs -> device, K1, then K3 chunk by chunk -- every sampled
         frame as a finished ``.png`` and ``.npz`` byte string -- copied into pinned host memory together
@@ -735,15 +750,17 @@ class Ensemble:
         ``wait=False`` the last chunks are left in flight (their copy-out then overlaps whatever the
         caller queues next, e.g. the next ensemble's integration); :meth:`flush_files` completes them.
         ``frames``: which part of the sampled float64 state also goes to the host (``_fring["h_frames"]``):
-        ``"ca"`` -- the calcium state ``[P, F, n]``, what labels and prompts are computed from (default;
-        ensembles of one pouch size, otherwise like ``"all"``), ``"all"`` -- c, p, s, r as laid out on the
-        device, ``"none"``.  Returns the byte counts moved (with ``wait=False``: of the copies queued
-        during this call)."""
+        ``"none"`` (default: the files are the product; the batch path fetches the calcium state of a chunk
+        itself when it generates prompts), ``"ca"`` -- the calcium state ``[P, F, n]`` (ensembles of one
+        pouch size, otherwise like ``"all"``), ``"all"`` -- c, p, s, r as laid out on the device.
+        With :meth:`set_relay` (multi-GPU, one process per GPU) chunks of a rank whose host path is slow
+        travel over NVLink through a partner GPU.  Returns the byte counts moved (with ``wait=False``: of
+        the copies queued during this call)."""
         dev = self.device
         w, h = self.output_size
         cur = torch.cuda.current_stream(dev)
         cp = max(1, min(chunk_pouches, self.P))
-        cap = (int(cp * self.F * h * w * arena_bytes_per_pixel) + (1 << 20) + 15) // 16 * 16
+        cap = self.files_chunk_capacity(cp, arena_bytes_per_pixel)
         uniform = len(set(int(x) for x in self.g_ncell[self.geom_id])) == 1
         if frames == "ca" and not uniform:
             frames = "all"
@@ -782,16 +799,26 @@ class Ensemble:
                 raise _lib.Cab200Error(f"encode arena too small: {used} > {cap} bytes "
                                        f"(raise arena_bytes_per_pixel above {arena_bytes_per_pixel})")
             e["used"] = used
-            with torch.cuda.stream(cs):
-                if used:
-                    slot["h_arena"][:used].copy_(slot["dev"]["arena"][:used], non_blocking=True)
+            relay = getattr(self, "_relay", None)
+            consumer_ = e["consumer"][0]
+            if relay is not None and relay.active and relay.role == "sender" and consumer_ is None and used:
+                # slow host path: the chunk goes over NVLink into the partner GPU's staging ring, which
+                # forwards it to pinned host memory (calcium_b200/relay.py); acknowledged in finish()
+                e["ticket"] = relay.send(slot["dev"]["arena"].data_ptr(), used, cs)
                 slot["data"].record(cs)
+            else:
+                with torch.cuda.stream(cs):
+                    if used:
+                        slot["h_arena"][:used].copy_(slot["dev"]["arena"][:used], non_blocking=True)
+                    slot["data"].record(cs)
             d2h += used
             copying.append(e)
 
         def finish(e):
             slot = e["slot"]
             slot["data"].synchronize()
+            if "ticket" in e:
+                self._relay.wait_ack(e.pop("ticket"))      # the partner has landed the chunk in host memory
             consumer, threshold, quirk = e["consumer"]
             if consumer is not None:
                 n = e["hi"] - e["lo"]
@@ -852,6 +879,16 @@ class Ensemble:
             if wait:
                 self.flush_files()
         return {"h2d_bytes": self.h2d_bytes, "d2h_bytes": d2h}
+
+    def files_chunk_capacity(self, chunk_pouches: int = 37, arena_bytes_per_pixel: float = 0.5) -> int:
+        """Arena bytes :meth:`run_files_to_host` reserves per chunk (the relay ring's slot size)."""
+        w, h = self.output_size
+        cp = max(1, min(chunk_pouches, self.P))
+        return (int(cp * self.F * h * w * arena_bytes_per_pixel) + (1 << 20) + 15) // 16 * 16
+
+    def set_relay(self, endpoint) -> None:
+        """Attach a :class:`calcium_b200.relay.Endpoint` (or None) for the chunk copy-out."""
+        self._relay = endpoint
 
     def flush_files(self) -> int:
         """Completes every chunk :meth:`run_files_to_host` left in flight (copy-out finished, consumer

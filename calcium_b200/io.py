@@ -64,3 +64,17 @@ def save_csv_mapping(mappings: List[Tuple[str, str]], output_path: str, filename
         wr.writerow(["ImageId", "MaskId"])
         wr.writerows(mappings)
     return file_path
+
+
+def scan_image_mask_pairs(batch_dir: str, split: str = "train") -> List[Tuple[str, str]]:
+    """``(image, mask)`` basenames of every ``images/<split>/X.png`` that has a ``masks/<split>/X.npz`` --
+    what the reference intends its CSV generator to find by scanning the dataset directory
+    (``utils/generate_csv.py:32-55``; its own glob never matches the current layout).  Scanning
+    instead of remembering makes the mapping cover every batch written into the same directory."""
+    img_dir = os.path.join(batch_dir, "images", split)
+    mask_dir = os.path.join(batch_dir, "masks", split)
+    if not (os.path.isdir(img_dir) and os.path.isdir(mask_dir)):
+        return []
+    masks = {os.path.splitext(f)[0] for f in os.listdir(mask_dir) if f.endswith(".npz")}
+    return [(f, os.path.splitext(f)[0] + ".npz") for f in sorted(os.listdir(img_dir))
+            if f.endswith(".png") and os.path.splitext(f)[0] in masks]

@@ -74,8 +74,16 @@ class FrameStore:
             ts = list(range(*tk.indices(self._pouch.T)))
         else:
             ts = [int(t) for t in np.asarray(tk).ravel()]
-        self._pouch._ensure_steps(ts)
-        block = np.stack([self._frame(t) for t in ts], axis=-1)   # (4, n, len)
+        T = self._pouch.T
+        ts = [t + T if t < 0 else t for t in ts]
+        for t in ts:
+            if not 0 <= t < T:
+                raise IndexError(f"index {t} is out of bounds for axis 2 with size {T}")
+        missing = [t for t in ts if t not in self._host]
+        if missing:                                               # one capture pass + ONE device->host copy
+            for t, f in zip(missing, self._pouch._fetch_frames(missing)):
+                self._host[t] = f
+        block = np.stack([self._host[t] for t in ts], axis=-1)    # (4, n, len)
         return np.transpose(block, (1, 0, 2))[cells, state]
 
     def materialize(self) -> np.ndarray:
@@ -185,6 +193,10 @@ class Pouch:
             if not torch.cuda.is_available():
                 raise RuntimeError("calcium_b200 needs a CUDA device (no CPU fallback)")
             self._device = torch.device("cuda", torch.cuda.current_device())
+        elif self._device.type == "cuda" and self._device.index is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("calcium_b200 needs a CUDA device (no CPU fallback)")
+            self._device = torch.device("cuda", torch.cuda.current_device())     # "cuda" = the current device
         return self._device
 
     def _run(self) -> None:
@@ -221,7 +233,20 @@ class Pouch:
             self._steps = sorted(set(self._steps) | set(missing))
 
     def _steps_set(self):
-        return set(self._steps)
+        cached = getattr(self, "_steps_cache", None)
+        if cached is None or cached[0] is not self._steps:
+            cached = (self._steps, set(self._steps))
+            self._steps_cache = cached
+        return cached[1]
+
+    def _fetch_frames(self, ts: Sequence[int]) -> np.ndarray:
+        """(len(ts), 4, n) host copy of the states at steps ``ts``: the steps are captured in one pass and
+        fetched with one device->host copy."""
+        if not self._simulated:
+            return np.zeros((len(ts), 4, self.n_cells))
+        self._ensure_steps(ts)
+        idx = torch.as_tensor([self._ens.frame_index(t) for t in ts], dtype=torch.long, device=self._ens.device)
+        return self._ens.frames_of(0).index_select(0, idx).cpu().numpy()
 
     def _fetch_frame(self, t: int) -> np.ndarray:
         """(4, n) host copy of the state at step t."""

@@ -20,7 +20,18 @@ import sys
 import tempfile
 import types
 
-REFERENCE_ROOT = os.environ.get("CALCIUM_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """The mounted reference in the build container; on the GPU box the byte-for-byte copy that
+    ``oracle/make_ref.py`` leaves under ``oracle/_ref`` (git-ignored, shipped with the tree)."""
+    env = os.environ.get("CALCIUM_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/core/pouch.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

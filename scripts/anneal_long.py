@@ -15,7 +15,7 @@ lib = _lib.load()
 plan = slot_plan(g, True, 64).copy() if polish else np.zeros(2 * n, dtype=np.uint16)
 cost = np.zeros(4, dtype=np.int64)
 t = time.time()
-_lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, cpt, iters, seed, 1 if polish else 0,
+_lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 1, cpt, iters, seed, 1 if polish else 0,
                                  plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(cost)), "plan")
 out = f"/tmp/plan_{size}_{seed}{'_p' if polish else ''}.npy"
 np.save(out, plan)

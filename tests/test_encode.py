@@ -336,7 +336,9 @@ def test_files_pipeline_delivers_every_frame_to_the_host(env, stage_bytes, wait)
             assert b is None
         else:
             assert np.array_equal(np.load(io.BytesIO(b))["mask"], inst[i, f])
-    ca_host = ens._fring["h_frames"].numpy()            # default frames="ca": the calcium state [P, F, n]
+    assert ens._fring["h_frames"] is None               # default frames="none": the files are the product
+    ens.run_files_to_host(chunk_pouches=5, frames="ca")
+    ca_host = ens._fring["h_frames"].numpy()            # frames="ca": the calcium state [P, F, n]
     dev_frames = ens.frames.cpu().numpy().reshape(ens.P, ens.F, 4, -1)
     assert np.array_equal(ca_host, dev_frames[:, :, 0, :])
     ens.run_files_to_host(chunk_pouches=5, frames="all")

@@ -84,15 +84,18 @@ def test_layout_and_planner(lib):
     for copies in (1, 2):
         plan = np.zeros(2 * n, dtype=np.uint16)
         cost = np.zeros(4, dtype=np.int64)
-        rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 2, 20000, 7, 0,
+        rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 1, 2, 20000, 7, 0,
                                    plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(cost))
         assert rc == 0
         assert sorted(plan[:n].tolist()) == list(range(n)), "slot_of must be a permutation"
         assert cost[1] == cost[2] <= cost[0]
         lens = np.diff(rowptr)
-        order = np.argsort(plan[:n])
-        assert np.all(np.diff(lens[order]) <= 0), "cells stay sorted by row length"
         assert np.all(plan[n:] < (1 << lens.max())) and (copies == 2 or not plan[n:].any())
+        # cost[3] = warp-wide gather loads per step: never below the off-diagonal entries / 32 (the
+        # diagonal is added from registers), and the shape-sorted start keeps the padding below 45 %
+        offdiag = int(lens.sum()) - n
+        assert offdiag / 32 <= cost[3] <= 1.45 * offdiag / 32 + 2, (cost[3], offdiag / 32)
+    assert lib.cab200_k1_legacy_rows(n, _lib.as_i32p(rowptr), _lib.as_i32p(col)) <= 8
 
 
 def test_cluster_planner(lib):

@@ -23,7 +23,7 @@ def test_lpt_partition_is_a_partition_and_balanced(sizes, world):
 
 @settings(max_examples=25, deadline=None)
 @given(st.integers(3, 120), st.integers(0, 2 ** 31 - 1), st.sampled_from([1, 2]), st.sampled_from([1, 2, 3, 4]))
-def test_planner_returns_permutation_that_keeps_length_classes(n, seed, copies, cpt):
+def test_planner_returns_permutation_with_valid_copy_masks(n, seed, copies, cpt):
     from calcium_b200 import _lib, build
     build.build()
     lib = _lib.load()
@@ -40,13 +40,13 @@ def test_planner_returns_permutation_that_keeps_length_classes(n, seed, copies, 
     col = cols.astype(np.int32)
     plan = np.zeros(2 * n, dtype=np.uint16)
     cost = np.zeros(4, dtype=np.int64)
-    rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, cpt, 3000, seed + 1, 0,
+    rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 1, cpt, 3000, seed + 1, 0,
                                plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(cost))
     assert rc == 0
     assert sorted(plan[:n].tolist()) == list(range(n))
     lens = np.diff(rowptr)
-    assert np.all(np.diff(lens[np.argsort(plan[:n])]) <= 0)
     assert cost[1] == cost[2] <= cost[0]
+    assert cost[3] * 32 >= int(lens.sum()) - n               # every off-diagonal entry is gathered somewhere
     if copies == 1:
         assert not plan[n:].any()
     else:
