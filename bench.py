@@ -487,6 +487,11 @@ def run_gpu(args) -> None:
     moved_raw, e2e_raw_ms = timed_e2e(lambda: ens.run_to_host(chunk_pouches=args.e2e_chunk))
     e2e_raw_value = work_per_gpu * world / (e2e_raw_ms * 1e-3)
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        ens._d_in = None
+        torch.cuda.empty_cache()
+        extras = extra_legs(dev)
     if rank == 0:
         # ---- rooflines ------------------------------------------------------------------------------
         peak = ctypes.c_double()
@@ -560,7 +565,7 @@ def run_gpu(args) -> None:
             roofline_k2["traffic"] = tr.get("k2_dram_bytes_per_launch")
         cores = os.cpu_count() or 1
         cpu = cpu_port = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the contract: on rank 0 at N = 1 only
             cpu_port = cpu_port_throughput(max(cores, 8), cores, min_seconds=5.0)
             cpu = cpu_port
             if not args.port_only:
@@ -593,12 +598,107 @@ def run_gpu(args) -> None:
                                "path": "Ensemble.run_to_host: K1 -> K2 -> frames + uncompressed images + instance "
                                        "masks to pinned host memory (PCIe bound)"},
             "k3_ms": k3_ms,
+            "e2e_api": (extras or {}).get("e2e_api"), "configs": (extras or {}).get("configs"),
             "gpu_launches": launches, "clocks": clocks, "status_nonzero": status_bad,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_legs(dev) -> dict:
+    """Cheap driver-visible legs beside the headline (N = 1 only): (i) the public batch call end to end, wall clock,
+    host draws and file writes included; (ii) BASELINE configs 2 and 5 with bit-exact spot checks against the oracle."""
+    import shutil
+    import tempfile
+    import torch
+    from calcium_b200 import _lib, generate_simulation_batch
+    from calcium_b200.ensemble import Ensemble, make_specs
+    from oracle import pouch_oracle as O
+    O.build()
+    out = {"e2e_api": {}, "configs": {}}
+
+    def timed_k1(ens, reps=3):
+        ens.upload()
+        ens.simulate(upload=False)
+        torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); ens.simulate(upload=False); e.record(); e.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return best
+
+    def exact(ens, i):
+        s = ens.specs[i]
+        g = s.geometry
+        z = np.zeros(g.n_cells)
+        want = O.simulate_c(g.csr, O.pack_params(s.params), z, z, s.r0, s.vplc, T_STEPS, [int(t) for t in ens.frame_steps])
+        return bool(np.array_equal(want, ens.frames_of(i).cpu().numpy()))
+
+    # ---- config 2: 64 small pouches, 4 sim types round-robin, FP64 ------------------------------------------
+    ens = Ensemble(make_specs(64, size="small"), T=T_STEPS, device=dev)
+    ms = timed_k1(ens)
+    out["configs"]["config2_small_64"] = {"k1_ms": ms, "cell_timesteps_per_s": ens.cell_timesteps / ms * 1e3,
+                                          "bit_exact_vs_oracle": {str(i): exact(ens, i) for i in (0, 21, 42, 63)}}
+    del ens
+    # ---- config 5: 256 pouches, sizes xsmall -> large round-robin, FP64 and FP32 -----------------------------
+    sizes = ["xsmall", "small", "medium", "large"]
+    types = ["Single cell spikes", "Intercellular transients", "Intercellular waves", "Fluttering"]
+    specs = [make_specs(1, size=sizes[i % 4], first_seed=i, sim_types=[types[(i // 4) % 4]])[0] for i in range(256)]
+    e64 = Ensemble(specs, T=T_STEPS, device=dev)
+    ms64 = timed_k1(e64)
+    e32 = Ensemble(specs, T=T_STEPS, device=dev, precision=_lib.FP32)
+    ms32 = timed_k1(e32)
+    err = {}
+    for i in range(0, 256, 7):
+        a = e64.frames_of(i).cpu().numpy()[:, 0]
+        b = e32.frames_of(i).cpu().numpy()[:, 0].astype(np.float64)
+        e_ = err.setdefault(sizes[i % 4], {"max_abs_ca": 0.0, "active_set_flips": 0, "frames": 0})
+        e_["max_abs_ca"] = max(e_["max_abs_ca"], float(np.abs(a - b).max()))
+        e_["active_set_flips"] += int(((a > 0.1) != (b > 0.1)).sum()); e_["frames"] += int(a.shape[0])
+    out["configs"]["config5_mixed_256"] = {
+        "fp64_k1_ms": ms64, "fp32_k1_ms": ms32, "fp64_cell_timesteps_per_s": e64.cell_timesteps / ms64 * 1e3,
+        "fp32_cell_timesteps_per_s": e64.cell_timesteps / ms32 * 1e3, "fp32_speedup": ms64 / ms32,
+        "fp32_vs_fp64_error_by_size": err,
+        "fp32_note": "fast arithmetic (FFMA contraction, __fdividef); trajectories are chaotic at the spike-timing level, so "
+                     "the deviation is O(1) in Ca whatever the float rounding -- a reported error, not a parity claim",
+        "bit_exact_vs_oracle_fp64": {sizes[i % 4]: exact(e64, i) for i in (4, 9, 14, 19)}}
+    del e64, e32
+    torch.cuda.empty_cache()
+    # ---- the public batch call: 148 medium pouches -> .png / .npz (/ .json prompts) on tmpfs, wall clock --------
+    import random
+    n = POUCHES_PER_GPU
+    root = tempfile.mkdtemp(prefix="cab200_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        kw = dict(pouch_sizes=[SIZE], defect_configs=[{}] * n, device=dev)
+        random.seed(1)
+        generate_simulation_batch(8, os.path.join(root, "warm"), generate_prompts=True, **dict(kw, defect_configs=[{}] * 8))
+        for name, prompts in (("files", False), ("files_and_prompts", True)):
+            random.seed(1)
+            d = os.path.join(root, name)
+            with open(os.devnull, "w") as devnull:
+                old_stdout = sys.stdout
+                sys.stdout = devnull                   # the reference prints one line per simulation; so does the drop-in
+                try:
+                    t0 = time.perf_counter()
+                    res = generate_simulation_batch(n, d, generate_prompts=prompts, **kw)
+                    dt = time.perf_counter() - t0
+                finally:
+                    sys.stdout = old_stdout
+            n_files = sum(len(fs) for _, _, fs in os.walk(d))
+            n_bytes = sum(os.path.getsize(os.path.join(r_, f)) for r_, _, fs in os.walk(d) for f in fs)
+            work = n * 1500 * (T_STEPS - 1)
+            out["e2e_api"][name] = {"seconds": dt, "value": work / dt, "unit": UNIT, "files": n_files, "bytes": n_bytes,
+                                    "images": res["stats"]["total_images"], "masks": res["stats"]["total_masks"]}
+            shutil.rmtree(d, ignore_errors=True)
+        out["e2e_api"]["call"] = (f"generate_simulation_batch({n}, tmpfs, pouch_sizes=['medium'], defect_configs=[{{}}]*{n}, "
+                                  f"generate_prompts=False / True): wall clock of the public call, host draws, GPU work and "
+                                  f"file creation included")
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return out
 
 
 def main() -> None:
@@ -612,6 +712,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunk", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the e2e_api / config 2 / config 5 legs (N = 1)")
     ap.add_argument("--no-relay", action="store_true", help="multi-GPU e2e: always copy device->host directly")
     ap.add_argument("--port-only", action="store_true", help="reference arm / cpu_baseline: the oracle's C port even if oracle/_ref exists")
     args = ap.parse_args()

@@ -8,10 +8,15 @@ same ``random.choice`` / ``np.random`` call sequence -- and then pushed through 
 K1 integrates a whole chunk in one launch, K2 rasterises every sampled frame, results stream back
 through pinned buffers to a pool of writer threads.
 
-Defects: the deterministic ones of a caller-supplied ``defect_configs`` entry are
-applied on the GPU (K5, ``calcium_b200/defects.py``); stochastic ones and the two that raise in the reference itself
-are reported and skipped, and without ``defect_configs`` the frames stay clean (the reference would draw a random
-configuration per frame from the unseeded generator, ``main.py:273-277``).  Label JSON is out of scope.
+Defects (``calcium_b200/defects.py``): a pouch's ``defect_configs`` entry applies to all
+its frames (``main.py:273-275``); without ``defect_configs`` every frame gets its own ``generate_random_defect_config()``
+drawn from the stdlib generator in the reference's call order (``:276-277``).  Deterministic configurations run on
+the GPU (K5); frames whose configuration holds stochastic / OpenCV defects take the host chain with the pouch's own
+numpy generator, interleaved with the prompt draws frame by frame exactly like the reference's loop
+(``:289-293`` then ``:314-328``).  A frame whose defects raise in the reference (spontaneous luminescence and cell
+fragments index channel 2 of the two-channel frame) is skipped like the reference skips it
+(``:342-351``) -- ``broken_defects="off"`` switches those two defects off instead.  Pass ``defect_configs=[{}] * n``
+for clean frames (the K1 -> K3 fast path).  Label JSON is out of scope.
 """
 from __future__ import annotations
 
@@ -28,7 +33,8 @@ import numpy as np
 import torch
 
 from . import io as cio
-from .defects import apply_defects, plan as defect_plan, unsupported_defects
+from .defects import (BROKEN_IN_REFERENCE, apply_all_defects_host, apply_defects, host_defects, plan as defect_plan,
+                      random_defect_config)
 from .ensemble import DEFAULT_FRAME_STEPS, Ensemble, PouchSpec, build_label_maps
 from .parameters import SimulationParameters
 
@@ -103,7 +109,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                               save_pouch=False, dataset_split="train", *, geometry_dir=None,
                               device=None, write_files=True, keep_arrays=False,
                               max_chunk_bytes=4 << 30, writer_threads=None, generate_prompts=True,
-                              prompt_threads=None, devices=None):
+                              prompt_threads=None, devices=None, broken_defects="skip"):
     """Generate a batch of simulations with images and instance masks (see module docstring).
 
     Extra keyword-only arguments: ``geometry_dir``, ``device``, ``write_files`` (False: compute only),
@@ -114,8 +120,12 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     the global numpy generator, continued from the state the pouch's own draws left it in),
     ``prompt_threads``, ``devices`` (None: the one ``device``; "all" or a list: the pouches are sharded over
     those GPUs -- independent pouches, longest-processing-time-first, one host thread per device, no
-    collective; the files and the returned dict do not depend on the sharding).
+    collective; the files and the returned dict do not depend on the sharding), ``broken_defects`` ("skip": a
+    frame whose configuration enables spontaneous luminescence / cell fragments is dropped, as the reference's
+    loop drops it after the IndexError those raise on two-channel frames; "off": the two are switched off).
     """
+    if broken_defects not in ("skip", "off"):
+        raise ValueError("broken_defects must be 'skip' or 'off'")
     os.makedirs(output_dir, exist_ok=True)
     if pouch_sizes is None:
         pouch_sizes = list(DEFAULT_SIZES)
@@ -141,12 +151,21 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             progress_callback(sim_idx + 1, num_simulations)
         pouch_size = random.choice(pouch_sizes)
         sim_type = random.choice(sim_types)
+        # no configuration given for this simulation: the reference draws one per frame inside its frame loop
+        # (main.py:273-277) -- the next calls of the stdlib generator after the two choices above
+        frame_cfgs = None
+        if not (defect_configs is not None and sim_idx < len(defect_configs)):
+            frame_cfgs = {}
+            for t in time_steps:
+                if int(t) < int(3600 / 0.2):
+                    frame_cfgs[int(t)] = random_defect_config()
         try:
             sim_params = SimulationParameters(sim_type=sim_type).generate_random_params(seed=sim_idx)
             spec = PouchSpec.draw(sim_params, size=pouch_size, sim_number=sim_idx,
                                   geometry_dir=geometry_dir)
             drawn.append({"sim_idx": sim_idx, "spec": spec, "type": sim_type, "size": pouch_size,
                           "name": f"{sim_type.replace(' ', '_')}_{sim_idx}", "params": sim_params,
+                          "frame_cfgs": frame_cfgs,
                           # the reference's frame loop continues the generator its Pouch seeded (core/pouch.py:317)
                           "rng_state": np.random.get_state()})
             print(f"Running simulation {sim_idx+1}/{num_simulations}: {sim_type} on {pouch_size} pouch")
@@ -185,15 +204,21 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             image_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             mask_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             img = ins = nact = masks_k3 = None
-            cfgs = [(defect_configs[d["sim_idx"]] if (defect_configs is not None and d["sim_idx"] < len(defect_configs)) else None)
-                    for d in part]
-            with_defects = any(defect_plan(c, output_size) for c in cfgs)
-            for c in cfgs:
-                skipped = unsupported_defects(c)
-                if skipped and not warned_defects:
-                    print("Defects not applied on the GPU path (stochastic, or raising in the reference itself): "
-                          + ", ".join(skipped))
-                    warned_defects.append(True)
+            # configuration of (pouch, frame): the pouch's entry of defect_configs, else the per-frame random draw
+            def frame_cfg(li: int, fi: int):
+                d_ = part[li]
+                c_ = d_["frame_cfgs"][steps[fi]] if d_["frame_cfgs"] is not None else defect_configs[d_["sim_idx"]]
+                if c_ and broken_defects == "off" and any(c_.get(k_, False) for k_ in BROKEN_IN_REFERENCE):
+                    c_ = dict(c_, **{k_: False for k_ in BROKEN_IN_REFERENCE})
+                return c_
+            pouch_cfgs = [None if d["frame_cfgs"] is not None else frame_cfg(li, 0) if steps else None
+                          for li, d in enumerate(part)]
+            per_frame = [d["frame_cfgs"] is not None for d in part]
+            # host chain: per-frame random configurations, or a pouch configuration with stochastic / OpenCV defects
+            host_chain = [per_frame[li] or bool(host_defects(pouch_cfgs[li])) for li in range(len(part))]
+            gpu_defects = [(not host_chain[li]) and bool(defect_plan(pouch_cfgs[li], output_size)) for li in range(len(part))]
+            with_defects = any(host_chain) or any(gpu_defects)
+            skipped_frames: Dict[int, set] = {li: set() for li in range(len(part))}
             if steps and not keep_arrays and not edge_blur and not with_defects:
                 # K1 -> K3: every frame arrives on the host as the finished .png / .npz byte string
                 # (cab200_encode_batch); writing a file is a plain write of those bytes.
@@ -234,56 +259,71 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 out = ens.rasterize(image=True, instance=bool(generate_masks) and masks_k3 is None,
                                     edge_blur=bool(edge_blur), blur_kernel_size=int(blur_kernel_size),
                                     blur_type=blur_type) if steps else {}
-                if steps and with_defects:
-                    # K5: the deterministic defects of each pouch's configuration (main.py:289-293), in place
-                    for li, c in enumerate(cfgs):
-                        apply_defects(out["image"][li], c, output_size)
+                if steps and any(gpu_defects):
+                    # K5: the deterministic defects of a pouch's configuration (main.py:289-293), in place
+                    for li in range(len(part)):
+                        if gpu_defects[li]:
+                            apply_defects(out["image"][li], pouch_cfgs[li], output_size)
                 ens.synchronize()
                 img = out["image"].cpu().numpy() if steps else None
                 ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and "instance" in out) else None
                 nact = out["n_active"].cpu().numpy() if steps else None
                 del out
             prompt_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
-            if steps and generate_masks and generate_prompts:
-                # Pouches are independent here: the reference's frame loop continues the generator its Pouch
-                # seeded (core/pouch.py:317), so every pouch gets a private legacy generator restored to the state
-                # its own draws left behind -- same values as the reference's sequential loop -- and the pouches
-                # run on a thread pool (numpy's shuffle / ufuncs and the K4 calls release the GIL).
-                from .prompts import frame_prompts, prompt_tables
+            want_prompts = bool(steps and generate_masks and generate_prompts)
+            if steps and (want_prompts or any(host_chain)):
+                # The per-pouch frame loop of the reference (main.py:266-351) for everything that draws from numpy's
+                # generator: per frame first the defects (:289-293), then the prompts (:314-328).  Pouches are
+                # independent: the reference reseeds per pouch (core/pouch.py:317), so every pouch gets a private
+                # legacy generator restored to the state its own draws left behind -- same values as the reference's
+                # sequential loop -- and the pouches run on a thread pool (numpy's generators, OpenCV and the K4
+                # calls release the GIL).
                 tables: Dict[int, Any] = {}
+                cmask_host: Dict[int, np.ndarray] = {}
+                if want_prompts:
+                    from .prompts import frame_prompts, prompt_tables
                 for li in range(len(part)):
                     g = int(ens.geom_id[li])
-                    if g not in tables:
+                    if want_prompts and g not in tables:
                         # the per-geometry label map is cached for the life of the process, so are its tables
                         tables[g] = prompt_tables(build_label_maps(ens.geometries[g], output_size, ens.device)[1],
                                                   int(ens.g_ncell[g]))
                         tables[g].candidate_entries()                 # built before the threads start
-                ca_host = [ens.frames_of(li)[:, 0, :].cpu().numpy() for li in range(len(part))]
+                    if host_chain[li] and g not in cmask_host:         # pouch.get_cell_masks() (:292), a host int32 map
+                        cmask_host[g] = build_label_maps(ens.geometries[g], output_size, ens.device)[1].cpu().numpy() \
+                            .view(np.uint16).astype(np.int32)
+                ca_host = [ens.frames_of(li)[:, 0, :].cpu().numpy() for li in range(len(part))] if want_prompts else None
 
-                def pouch_prompts(li: int):
+                def pouch_frames(li: int):
                     d = part[li]
                     rs = np.random.RandomState()
                     rs.set_state(d["rng_state"])
-                    tab, ca_all, files = tables[int(ens.geom_id[li])], ca_host[li], []
+                    g = int(ens.geom_id[li])
+                    files = []
                     with torch.cuda.device(ens.device):
                         for fi in range(len(steps)):
-                            if not (ca_all[fi] > 0.1).any():          # no active cell: nothing is written (:318-319)
-                                continue
                             try:
-                                text, _ = frame_prompts(tab, ca_all[fi], rng=rs, as_text=True)
+                                if host_chain[li]:
+                                    c_ = frame_cfg(li, fi)
+                                    if c_:
+                                        img[li, fi] = apply_all_defects_host(img[li, fi], cmask_host[g], c_, rs)
+                                if not want_prompts or not (ca_host[li][fi] > 0.1).any():
+                                    continue                          # no active cell: nothing is written (:318-319)
+                                text, _ = frame_prompts(tables[g], ca_host[li][fi], rng=rs, as_text=True)
                                 ppath = os.path.join(prompt_dir, names[li][fi] + ".json")
                                 if write_files:
                                     with open(ppath, "w") as fh:        # the text save_prompts writes (prompts.py)
                                         fh.write(text)
                                 files.append(ppath)
                             except Exception as e:  # noqa: BLE001 - a failing frame is reported and skipped (main.py:342-351)
+                                skipped_frames[li].add(fi)
                                 print(f"Error processing time step {steps[fi]} for simulation {d['sim_idx']}: {str(e)}")
                     return files, rs.get_state()
 
                 last_state = None
                 n_pt = prompt_threads if prompt_threads else min(32, max(8, os.cpu_count() or 8))
                 with cf.ThreadPoolExecutor(max_workers=max(1, n_pt)) as pp:
-                    for li, (files, state) in enumerate(pp.map(pouch_prompts, range(len(part)))):
+                    for li, (files, state) in enumerate(pp.map(pouch_frames, range(len(part)))):
                         prompt_files[li] = files
                         last_state = state
                 if last_state is not None:
@@ -291,6 +331,8 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             for li, d in enumerate(part):
                 if img is not None:
                     for fi, t in enumerate(steps):
+                        if fi in skipped_frames[li]:                   # the reference's loop skips a failing frame entirely
+                            continue
                         base = names[li][fi]
                         ipath = os.path.join(img_dir, base + ".png")
                         image_files[li].append(ipath)

@@ -4,14 +4,15 @@
 // scipy CSR products per step (:346-347) for a whole ensemble in one launch.
 //
 // Data placement for one pouch (n cells), fixed for all T steps:
-//   shared   two buffers (step parity) of COPIES*NP + LEG + 1 entries, one entry = the pair (c, p):
+//   shared   two buffers (step parity) of (COPIES+1)*NP + 1 entries, one entry = the pair (c, p):
 //              [0, NP)            value entries   (c_i, p_i) at index slot_i
 //              [NP, 2NP)          (COPIES == 2) a second copy of the values at NP + (slot_i ^ 4),
 //                                 i.e. in the bank group 4 away: every gather may read either copy,
 //                                 which the host planner uses to dodge bank conflicts
-//              [COPIES*NP, +LEG)  (UNIT) diagonal entries (L_ii*c_i, L_ii*p_i) of the few "legacy" cells
-//                                 whose row does not fit the register-diagonal layout (k1_layout.cuh)
-//              [COPIES*NP+LEG]    the zero entry (+0, +0), never written after the prologue
+//              [COPIES*NP, +NP)   (UNIT) diagonal entries (L_ii*c_i, L_ii*p_i), indexed by slot, used only by
+//                                 the few "legacy" cells whose row does not fit the register-diagonal
+//                                 layout (k1_layout.cuh)
+//              [(COPIES+1)*NP]    the zero entry (+0, +0), never written after the prologue
 //            Step t reads buffer t&1 and writes buffer (t+1)&1: one split barrier per step.
 //   regs     per owned cell: c, p, s, r, V_PLC, L_ii and the shared addresses of the row's entries
 //            (time-invariant), plus the pouch's parameters (uniform registers).
@@ -61,12 +62,13 @@ struct SimArgs {
 // `copies` value regions, the legacy diagonal entries (unit Laplacian only), the zero entry, the halo.
 static inline size_t integrate_buf_entries(int nr, int copies, bool unit, int hmax)
 {
-    return (size_t)copies * nr + (unit ? CAB_LEGMAX : 0) + 1 + hmax;
+    return (size_t)(copies + (unit ? 1 : 0)) * nr + 1 + hmax;
 }
-// persistent tables behind the two buffers: orig_of[NSLOT] u16; unit: lrank_of[NSLOT] u16 + dco[LEGMAX]
+// persistent table behind the two buffers: orig_of[NSLOT] u16
 static inline size_t integrate_tail_bytes(int nslot, size_t elem2, bool unit)
 {
-    return 2 * (size_t)nslot + (unit ? 2 * (size_t)nslot + CAB_LEGMAX * (elem2 / 2) : 0) + 64;
+    (void)elem2; (void)unit;
+    return 2 * (size_t)nslot + 64;
 }
 static inline size_t integrate_buf_stride(int np, int nslot, size_t elem2, int copies, bool unit, int hmax = 0)
 {
@@ -216,9 +218,9 @@ template <> struct Smem2<float> {
 template <typename R, int NSLOT, int COPIES, bool UNIT, int HMAX = 0>
 struct BufGeom {
     static constexpr size_t ESZ = 2 * sizeof(R);
-    static constexpr int LEG = UNIT ? CAB_LEGMAX : 0;
-    static constexpr size_t STRIDE = ((((size_t)COPIES * NSLOT + LEG + 1 + HMAX) * ESZ) + 127) & ~(size_t)127;
-    static constexpr size_t TAIL = 2 * (size_t)NSLOT + (UNIT ? 2 * (size_t)NSLOT + CAB_LEGMAX * sizeof(R) : 0) + 64;
+    static constexpr int DIAGR = UNIT ? 1 : 0;            // a slot-indexed region of diagonal entries (legacy rows)
+    static constexpr size_t STRIDE = ((((size_t)(COPIES + DIAGR) * NSLOT + 1 + HMAX) * ESZ) + 127) & ~(size_t)127;
+    static constexpr size_t TAIL = 2 * (size_t)NSLOT + 64;
     static constexpr bool CSTRIDE = 2 * STRIDE + TAIL <= 227 * 1024;
 };
 
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     constexpr int NSLOT = THREADS * CPT;
     constexpr int EMAX = 2 * EP;
     constexpr int HMAX = (NCTA > 1) ? CAB_HMAX : 0;
-    constexpr int LEG = UNIT ? CAB_LEGMAX : 0;
+    constexpr int DIAGR = UNIT ? 1 : 0;
     constexpr int DPAIR = (EP & 1) ? EP - 1 : EP - 2;     // k1_diag_pair(EP)
     typedef BufGeom<R, NSLOT, COPIES, UNIT, HMAX> G;
     static_assert(NCTA == 1 || (G::CSTRIDE && UNIT), "cluster kernels need the compile-time layout");
@@ -260,11 +262,9 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     const int n = a.n, np = a.np;
     const int npr = CSTRIDE ? NSLOT : np;                 // entries per value region
     const uint32_t stride = CSTRIDE ? (uint32_t)G::STRIDE
-                                    : (uint32_t)(((((size_t)COPIES * np + LEG + 1) * ESZ) + 127) & ~(size_t)127);
+                                    : (uint32_t)(((((size_t)(COPIES + DIAGR) * np + 1) * ESZ) + 127) & ~(size_t)127);
     R2 *buf1 = reinterpret_cast<R2 *>(smem_raw + stride);
     uint16_t *orig_of = reinterpret_cast<uint16_t *>(smem_raw + 2 * (size_t)stride);   // [NSLOT]
-    uint16_t *lrank_of = orig_of + NSLOT;                 // [NSLOT] (UNIT) legacy rank of the slot's cell, 0xffff = none
-    R *dco = reinterpret_cast<R *>(lrank_of + NSLOT);     // [LEG]   (UNIT) L_ii of the legacy cells
     // prologue scratch aliases buffer 1 (initialised after the scratch is dead)
     unsigned char *scr = reinterpret_cast<unsigned char *>(buf1);
     uint8_t *rlen = scr;                                                           // [n]
@@ -272,7 +272,6 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     uint16_t *copy_sel = slot_of + np;                                             // [n]
     uint8_t *part_of = reinterpret_cast<uint8_t *>(copy_sel + np);                 // [n] (clusters)
     int8_t *rdg = reinterpret_cast<int8_t *>(part_of + np);                        // [n] diagonal index in the row, -1, -2
-    uint16_t *lrank = reinterpret_cast<uint16_t *>(rdg + np);                      // [n] rank among the legacy cells
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -292,19 +291,8 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             if (a.colidx[rb + j] == i) { ++nd; di = j; }
         rdg[i] = (int8_t)(nd == 0 ? -1 : (nd == 1 ? di : -2));
     }
-    for (int s = tid; s < NSLOT; s += THREADS) { orig_of[s] = 0xffff; if (UNIT) lrank_of[s] = 0xffff; }
+    for (int s = tid; s < NSLOT; s += THREADS) orig_of[s] = 0xffff;
     __syncthreads();
-    if (UNIT && warp == 0) {       // legacy cells ranked in cell order (deterministic; the planner does the same)
-        int running = 0;
-        for (int base = 0; base < n; base += 32) {
-            const int i = base + lane;
-            const bool lg = i < n && k1_row(true, EP, rlen[i], rdg[i]).legacy;
-            const unsigned m = __ballot_sync(0xffffffffu, lg);
-            if (i < n) lrank[i] = lg ? (uint16_t)(running + __popc(m & ((1u << lane) - 1u))) : (uint16_t)0xffff;
-            running += __popc(m);
-        }
-        if (running > LEG) bad = 1;
-    }
     // ---- prologue 2: cell -> slot.  Host plan if given, else stable rank by (length desc, id asc) --
     if (NCTA > 1) {
         // cluster plan: this CTA owns the cells of part `rank`; slot_of is the slot inside the part
@@ -373,8 +361,8 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     // at `end`.  ent[k][pos] is the 32-bit shared address of the entry inside buffer 0; buffer 1 is
     // +stride.
     const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t leg_addr = sb0 + (uint32_t)(COPIES * npr) * ESZ;          // legacy diagonal entries
-    const uint32_t zero_addr = leg_addr + (uint32_t)LEG * ESZ;
+    const uint32_t diag_off = (uint32_t)(COPIES * npr) * ESZ;                // diagonal entries (legacy rows), by slot
+    const uint32_t zero_addr = sb0 + (uint32_t)((COPIES + DIAGR) * npr) * ESZ;
     const uint32_t halo_addr = zero_addr + ESZ;
     R c[CPT], p[CPT], s[CPT], r[CPT], vplc[CPT], dcoef[CPT];
     uint32_t ent[CPT][EMAX];
@@ -383,17 +371,13 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     bool live[CPT];
     K1Row row[CPT];
     int min_first = EMAX, max_last = 0;
-    bool any_legacy = false;
+    uint32_t legmask = 0;           // bit k: cell k keeps a shared-memory diagonal entry (legacy row layout)
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int slot = (warp * CPT + k) * 32 + lane;
         const int cell = (int)orig_of[slot];          // 0xffff: no cell in this slot
         live[k] = (cell != 0xffff);
         own[k] = sb0 + (uint32_t)slot * ESZ;
-#ifdef CAB_X_OWN_OPAQUE     // experiment: keep the address in a register instead of re-deriving it from %tid
-        if (k == 0) asm volatile("mov.u32 %0, %0;" : "+r"(own[0]));
-        else own[k] = own[0] + (uint32_t)(k * 32) * ESZ;
-#endif
         rowbeg[k] = 0; len[k] = 0;
         c[k] = p[k] = s[k] = r[k] = vplc[k] = dcoef[k] = (R)0;
         row[k] = k1_row(UNIT, EP, 0, -1);
@@ -406,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             r[k] = (R)a.r0[coff + cell];
             vplc[k] = (R)a.vplc[coff + cell];
             if (len[k] > 0) { min_first = min(min_first, row[k].first); max_last = max(max_last, row[k].last); }
-            if (UNIT && row[k].legacy) { any_legacy = true; lrank_of[slot] = lrank[cell]; }
+            if (UNIT && row[k].legacy) legmask |= 1u << k;
         }
         s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                          // core/pouch.py:322
     }
@@ -428,17 +412,12 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     int start, end;
     k1_warp_range(UNIT, EP, __reduce_min_sync(0xffffffffu, min_first), __reduce_max_sync(0xffffffffu, max_last),
                   &start, &end);
-#ifdef CAB_X_NO_LEGACY      // experiment (timing only, wrong results for legacy cells)
-    const bool wleg = false && __any_sync(0xffffffffu, any_legacy);
-#else
-    const bool wleg = UNIT && __any_sync(0xffffffffu, any_legacy);     // this warp owns legacy cells
-#endif
+    const bool wleg = UNIT && __any_sync(0xffffffffu, legmask != 0u);  // this warp owns legacy cells
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int slot = (warp * CPT + k) * 32 + lane;
         const int cell = live[k] ? (int)orig_of[slot] : 0;
         const uint32_t sel = live[k] ? (uint32_t)copy_sel[cell] : 0u;
-        const uint32_t lrk = (UNIT && live[k] && row[k].legacy) ? (uint32_t)lrank[cell] : 0u;
         if (UNIT && live[k] && !row[k].legacy && row[k].skip)                 // register diagonal: its weight
             dcoef[k] = (R)a.vals[rowbeg[k] + row[k].split];
 #pragma unroll
@@ -458,10 +437,8 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
                     o = sb0 + j * ESZ;
                     if (UNIT) {
                         const double w = a.vals[rowbeg[k] + e];
-                        if (col == cell) {                           // only legacy rows gather their diagonal
-                            if (lrk < (uint32_t)LEG) { dco[lrk] = (R)w; o = leg_addr + lrk * ESZ; }
-                            else bad = 1;
-                        } else if (w != 1.0) bad = 1;
+                        if (col == cell) { dcoef[k] = (R)w; o = own[k] + diag_off; }   // only legacy rows gather their diagonal
+                        else if (w != 1.0) bad = 1;
                     }
                 }
             }
@@ -524,13 +501,9 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     // needs no barrier: it is rewritten AFTER the arrival, off the step's critical path.
 #define CAB_PUBLISH_LEGACY(IMM, ROFF)                                                             \
     if (wleg) {                                                                                   \
-        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
-            const uint32_t lr_ = lrank_of[(warp * CPT + k) * 32 + lane];                          \
-            if (lr_ != 0xffffu) {                                                                 \
-                const R dc_ = dco[lr_];                                                           \
-                M::template st<IMM>(leg_addr + lr_ * ESZ + (ROFF), S::mul(dc_, c[k]), S::mul(dc_, p[k])); \
-            }                                                                                     \
-        }                                                                                         \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k)                                           \
+            if ((legmask >> k) & 1u)                                                              \
+                M::template st<IMM>(own[k] + diag_off + (ROFF), S::mul(dcoef[k], c[k]), S::mul(dcoef[k], p[k])); \
     }
 #pragma unroll
     for (int k = 0; k < CPT; ++k) { CAB_PUBLISH(0, 0u, k, c[k], p[k], -1) }
@@ -606,21 +579,20 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 #define CAB_EXIT_CHECK(P0) if (end <= (P0) + 2) break;
 #endif
 // The register diagonal of every owned cell: L_ii * (c_i, p_i), each product rounded like the stored
-// diagonal entry of round 1 was (dcoef is 0 for legacy cells and empty slots: +-0 never changes a sum
-// that cannot be -0).
-#ifdef CAB_X_DIAG_EARLY
+// diagonal entry of round 1 was (dcoef is 0 for empty slots and rows without a diagonal: +-0 never
+// changes a sum that cannot be -0).
 #define CAB_DIAG_ADD                                                                              \
-    _Pragma("unroll") for (int k = 0; k < CPT; ++k) { sc[k] = S::add(sc[k], dgc[k]); sp[k] = S::add(sp[k], dgp[k]); }
-#define CAB_DIAG_PREP                                                                             \
-    R dgc[CPT], dgp[CPT];                                                                         \
-    _Pragma("unroll") for (int k = 0; k < CPT; ++k) { dgc[k] = S::mul(dcoef[k], c[k]); dgp[k] = S::mul(dcoef[k], p[k]); }
-#else
-#define CAB_DIAG_ADD                                                                              \
-    _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                             \
-        sc[k] = S::add(sc[k], S::mul(dcoef[k], c[k])); sp[k] = S::add(sp[k], S::mul(dcoef[k], p[k])); \
+    if (!wleg) {                                                                                  \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
+            sc[k] = S::add(sc[k], S::mul(dcoef[k], c[k])); sp[k] = S::add(sp[k], S::mul(dcoef[k], p[k])); \
+        }                                                                                         \
+    } else {    /* warps with legacy cells (rare): those cells' term comes from their gathered entry */ \
+        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
+            const bool lg_ = (legmask >> k) & 1u;                                                 \
+            sc[k] = S::add(sc[k], lg_ ? (R)0 : S::mul(dcoef[k], c[k]));                           \
+            sp[k] = S::add(sp[k], lg_ ? (R)0 : S::mul(dcoef[k], p[k]));                           \
+        }                                                                                         \
     }
-#define CAB_DIAG_PREP
-#endif
 
 // One pair of row positions for every owned cell: all loads of the pair first (2*CPT independent
 // 16-byte loads in flight per thread), then the additions in position order.  The pair DPAIR also
@@ -656,7 +628,6 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 // One time step reading the buffer at +CUR and writing the one at +NXT (immediates when CSTRIDE).
 #define CAB_STEP(CUR_IMM, NXT_IMM, CUR_R, NXT_R, CUR_BAR, NXT_BAR)                                \
     {                                                                                             \
-        CAB_DIAG_PREP                                                                             \
         mbar_wait(&step_bar[CUR_BAR], parity);                                                    \
         if (NCTA == 1 || (CUR_BAR) == 1) parity ^= 1u;   /* a cluster uses each barrier every 2nd step */ \
         R sc[CPT], sp[CPT];                                                                       \
@@ -713,7 +684,6 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 #undef CAB_STEP
 #undef CAB_GATHER_PAIR
 #undef CAB_DIAG_ADD
-#undef CAB_DIAG_PREP
 #undef CAB_EXIT_CHECK
 #undef CAB_PUBLISH_LEGACY
 #undef CAB_PUBLISH

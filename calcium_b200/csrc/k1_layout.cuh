@@ -9,9 +9,9 @@
 // started from +0.0 never changes it), so the accumulation order is still the CSR order scipy uses
 // (reference core/pouch.py:346-347).  Rows that do not fit -- more than EP entries on one side of the
 // diagonal, or several diagonal entries -- keep the round-1 layout ("legacy"): all entries right-aligned
-// at EMAX, the diagonal read from a per-cell shared-memory entry that the owner rewrites every step;
-// at most CAB_LEGMAX such cells per pouch (the host routes anything beyond that to the general-weight
-// kernel).  Without UNIT every row is legacy and the diagonal is an ordinary weighted entry.
+// at EMAX, the diagonal read from the cell's shared-memory diagonal entry, which the owner rewrites every
+// step (17 of 1500 cells of the medium disc).  Without UNIT every row is legacy and the diagonal is an
+// ordinary weighted entry.
 #pragma once
 
 namespace cab200 {
@@ -21,8 +21,6 @@ namespace cab200 {
 #else
 #define CAB_HD
 #endif
-
-constexpr int CAB_LEGMAX = 256;     // legacy-layout cells (shared-memory diagonal entries) per pouch
 
 // Kernel variant (EP) for a geometry whose longest CSR row stores max_row entries.
 CAB_HD static inline int k1_ep(int max_row) { return (max_row + 1) / 2 <= 5 ? 5 : 8; }

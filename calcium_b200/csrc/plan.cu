@@ -44,11 +44,11 @@ struct Problem {
     int n, np, copies, cpt, ep;
     bool unit;
     std::vector<int> rowptr, ecol;
-    std::vector<int> lrank;                   // legacy rank of a cell (index of its shared-memory diagonal entry)
     std::vector<K1Row> row;
     std::vector<int> slot_of, cell_of;        // cell_of[slot] = cell or -1
     std::vector<std::vector<int>> refs;       // refs[c] = local cells whose row contains c (incl. c)
     std::vector<int> wstart, wend;            // per warp (32*cpt slots): the position range it runs
+    std::vector<char> wleg;                   // per warp: holds legacy rows (such warps run a longer step)
     int n_groups;
 
     inline int rowlen(int c) const { return rowptr[c + 1] - rowptr[c]; }
@@ -68,7 +68,7 @@ struct Problem {
     // read copy B (bit l of *sel_out).
     inline int phase_cost(int g, int pos, unsigned *sel_out) const
     {
-        const int zero_idx = copies * np + (unit ? CAB_LEGMAX : 0);
+        const int zero_idx = (copies + (unit ? 1 : 0)) * np;
         int a_idx[8], b_idx[8];     // candidate entry indices (b = -1: no choice)
         for (int l = 0; l < 8; ++l) {
             const int c = cell_of[g * 8 + l];
@@ -79,7 +79,7 @@ struct Problem {
             if (e < 0 || e >= rowlen(c)) continue;
             const int cc = ecol[rowptr[c] + e];
             if (cc < 0) { a_idx[l] = zero_idx + 1 + (-1 - cc); continue; }       // halo entry
-            if (cc == c && unit) { a_idx[l] = copies * np + lrank[c]; continue; } // legacy diagonal entry
+            if (cc == c && unit) { a_idx[l] = copies * np + slot_of[c]; continue; } // legacy row: its diagonal entry
             a_idx[l] = slot_of[cc];
             if (copies == 2) b_idx[l] = np + (slot_of[cc] ^ 4);
         }
@@ -141,12 +141,13 @@ struct Problem {
     void compute_wrange()
     {
         const int per = 32 * cpt, nw = (np + per - 1) / per;
-        wstart.assign(nw, 0); wend.assign(nw, 0);
+        wstart.assign(nw, 0); wend.assign(nw, 0); wleg.assign(nw, 0);
         for (int w = 0; w < nw; ++w) {
             int mf = 2 * ep, ml = 0;
             for (int s = w * per; s < std::min(np, (w + 1) * per); ++s) {
                 const int c = cell_of[s];
                 if (c >= 0 && rowlen(c) > 0) { mf = std::min(mf, row[c].first); ml = std::max(ml, row[c].last); }
+                if (c >= 0 && unit && row[c].legacy) wleg[w] = 1;
             }
             k1_warp_range(unit, ep, mf, ml, &wstart[w], &wend[w]);
         }
@@ -154,6 +155,7 @@ struct Problem {
 
     inline bool fits(int c, int w) const
     {
+        if (unit && row[c].legacy && !wleg[w]) return false;      // legacy rows stay in the warps that have some
         return rowlen(c) == 0 || (row[c].first >= wstart[w] && row[c].last <= wend[w]);
     }
 
@@ -280,6 +282,8 @@ std::vector<int> shape_sorted_order(Problem &P)
         auto fr = [&](int c) { return P.rowlen(c) ? (P.row[c].first & ~1) : 2 * P.ep; };
         auto lr = [&](int c) { return P.rowlen(c) ? ((P.row[c].last + 1) & ~1) : 0; };
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const bool ga = P.unit && P.row[a].legacy, gb = P.unit && P.row[b].legacy;
+            if (ga != gb) return ga;                               // legacy rows first, all in the leading warp(s)
             const int fa = fr(a), fb = fr(b), la = lr(a), lb = lr(b);
             if (variant == 0) return fa != fb ? fa < fb : la > lb;
             if (variant == 1) return la != lb ? la > lb : fa < fb;
@@ -292,17 +296,16 @@ std::vector<int> shape_sorted_order(Problem &P)
     return best;
 }
 
-// legacy ranks in cell order (what the kernel's prologue computes)
-int legacy_ranks(int n, const int32_t *rowptr, const int32_t *colidx, bool unit, int ep, std::vector<int> &lrank)
+// number of rows that take the legacy layout
+int legacy_rows(int n, const int32_t *rowptr, const int32_t *colidx, bool unit, int ep)
 {
-    lrank.assign(n, -1);
     int cnt = 0;
     for (int i = 0; i < n; ++i) {
         int nd = 0, di = -1;
         const int len = rowptr[i + 1] - rowptr[i];
         for (int j = 0; j < len; ++j)
             if (colidx[rowptr[i] + j] == i) { ++nd; di = j; }
-        if (unit && k1_row(true, ep, len, nd == 0 ? -1 : (nd == 1 ? di : -2)).legacy) lrank[i] = cnt++;
+        if (unit && k1_row(true, ep, len, nd == 0 ? -1 : (nd == 1 ? di : -2)).legacy) ++cnt;
     }
     return cnt;
 }
@@ -335,10 +338,6 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
     P.unit = unit != 0; P.ep = k1_ep(max_row_of(n, rowptr));
     P.rowptr.assign(rowptr, rowptr + n + 1);
     P.ecol.assign(colidx, colidx + rowptr[n]);
-    if (legacy_ranks(n, rowptr, colidx, P.unit, P.ep, P.lrank) > CAB_LEGMAX) {
-        set_error("cab200_plan_slots: more than %d rows need the legacy layout; declare the geometry non-unit", CAB_LEGMAX);
-        return CAB200_ESIZE;
-    }
     P.compute_rows();
     std::vector<int> order = shape_sorted_order(P);
     if (use_input) {
@@ -367,8 +366,7 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
 extern "C" int cab200_k1_legacy_rows(int n, const int32_t *rowptr, const int32_t *colidx)
 {
     if (n <= 0 || !rowptr || !colidx) { set_error("cab200_k1_legacy_rows: bad argument"); return CAB200_EINVAL; }
-    std::vector<int> lrank;
-    return legacy_ranks(n, rowptr, colidx, true, k1_ep(max_row_of(n, rowptr)), lrank);
+    return legacy_rows(n, rowptr, colidx, true, k1_ep(max_row_of(n, rowptr)));
 }
 
 // See include/cab200.h.
@@ -384,11 +382,6 @@ extern "C" long long cab200_plan_cluster(int n, const int32_t *rowptr, const int
     }
     if (int rc = check_csr(n, rowptr, colidx, "cab200_plan_cluster")) return rc;
     const int ep = k1_ep(max_row_of(n, rowptr));        // clusters run the unit-weight kernel only
-    std::vector<int> glrank;
-    if (legacy_ranks(n, rowptr, colidx, true, ep, glrank) > CAB_LEGMAX) {
-        set_error("cab200_plan_cluster: more than %d rows need the legacy layout", CAB_LEGMAX);
-        return CAB200_ESIZE;
-    }
     // ---- 1. breadth-first order from a pseudo-peripheral cell; parts = equal contiguous chunks ----
     auto bfs = [&](int src, std::vector<int> &order) {
         std::vector<char> seen(n, 0);
@@ -432,7 +425,6 @@ extern "C" long long cab200_plan_cluster(int n, const int32_t *rowptr, const int
         P.n = (int)cells.size(); P.copies = copies; P.cpt = cells_per_thread;
         P.unit = true; P.ep = ep;
         P.rowptr.assign(1, 0);
-        for (int c : cells) P.lrank.push_back(glrank[c]);
         for (int c : cells) {
             for (int j = rowptr[c]; j < rowptr[c + 1]; ++j) {
                 const int cc = colidx[j];

@@ -102,12 +102,6 @@ class _DeviceGeometry:
         offdiag &= rows != col
         self.unit = bool(np.all(val[offdiag] == 1.0))
         self.nnz = len(col)
-        if self.unit and self.n and self.nnz:
-            # the unit-weight kernel keeps at most 256 rows whose diagonal cannot be added from registers
-            # (csrc/k1_layout.cuh); geometries with more run the general-weight kernel (1.0 * x == x exactly)
-            legacy = int(_lib.load().cab200_k1_legacy_rows(self.n, _lib.as_i32p(rowptr), _lib.as_i32p(col)))
-            if legacy < 0 or legacy > 256:
-                self.unit = False
         if self.nnz == 0:        # a graph without any entry still needs non-null device pointers
             col, val = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.float64)
         self.rowptr = torch.from_numpy(rowptr).to(device)

@@ -53,14 +53,14 @@ class _Mailbox:
         self.a = np.frombuffer(self.mm, dtype=np.int64)
 
     def close(self, unlink: bool = False):
-        try:
-            del self.a
-            self.mm.close()
-            self.fh.close()
-            if unlink and os.path.exists(self.path):
-                os.remove(self.path)
-        except Exception:  # noqa: BLE001
-            pass
+        self.a = None
+        for step in (self.mm.close, self.fh.close):
+            try:
+                step()
+            except Exception:  # noqa: BLE001 - e.g. a caller still holds a view of the mapping
+                pass
+        if unlink and os.path.exists(self.path):
+            os.remove(self.path)
 
 
 def _vp() -> ctypes.c_void_p:

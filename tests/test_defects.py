@@ -54,7 +54,7 @@ def test_tables_reproduce_the_reference(gold):
         assert np.array_equal(cur, z[key]), key
 
 
-def test_unsupported_defects_are_named():
+def test_host_defects_are_named():
     pytest.importorskip("torch")
     from calcium_b200 import defects as D
     assert D.unsupported_defects(None) == [] and D.unsupported_defects({"vignetting": True}) == []
@@ -64,5 +64,7 @@ def test_unsupported_defects_are_named():
                                                   "spontaneous_luminescence"]
     assert D.plan(cfg, (64, 64)) == []                 # the non-uniform background is stochastic: nothing to apply
     assert len(D.plan({"chromatic_aberration": True, "quantization": True}, (64, 64))) == 1   # aberration: no-op on 2 channels
-    with pytest.raises(NotImplementedError, match="gaussian_noise"):
-        D.apply_all_defects(np.zeros((8, 8, 2), np.uint8), None, cfg)
+    # such a configuration takes the host chain; this one raises like the reference does (spontaneous luminescence
+    # writes channel 2 of a two-channel frame)
+    with pytest.raises(IndexError):
+        D.apply_all_defects(np.full((8, 8, 2), 9, np.uint8), np.arange(64, dtype=np.int32).reshape(8, 8), cfg)

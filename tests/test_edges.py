@@ -196,7 +196,8 @@ def test_batch_path_applies_edge_blur(env, tmp_path):
     from calcium_b200 import generate_simulation_batch
     res = generate_simulation_batch(2, str(tmp_path), pouch_sizes=["xsmall"], sim_types=["Intercellular waves"],
                                     time_steps=[0, 9000], edge_blur=True, blur_kernel_size=5, blur_type="motion",
-                                    image_size="160x120", generate_masks=True, generate_prompts=False)
+                                    image_size="160x120", generate_masks=True, generate_prompts=False,
+                                    defect_configs=[{}] * 2)
     assert len(res["simulations"]) == 2 and all(s["image_count"] == 2 for s in res["simulations"])
     E = env["E"]
     specs = [E.PouchSpec.draw(res["simulations"][i]["parameters"], size="xsmall", sim_number=i) for i in range(2)]

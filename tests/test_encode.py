@@ -353,7 +353,8 @@ def test_batch_path_writes_the_encoded_frames(env, tmp_path):
     import random
     from calcium_b200 import generate_simulation_batch
     EO = env["EO"]
-    kw = dict(pouch_sizes=["xsmall", "small"], time_steps=[0, 5000, 9000], image_size="256x256")
+    kw = dict(pouch_sizes=["xsmall", "small"], time_steps=[0, 5000, 9000], image_size="256x256",
+              defect_configs=[{}] * 3)                                 # clean frames: the K1 -> K3 path
     random.seed(9)
     ra = generate_simulation_batch(3, str(tmp_path / "a"), keep_arrays=True, write_files=False, **kw)
     random.seed(9)

@@ -261,21 +261,31 @@ def test_ragged_ensemble_more_pouches_than_sms(env):
         assert np.array_equal(_oracle_frames(O, specs[i], T, steps), ens.frames_of(i).cpu().numpy()), i
 
 
-def test_fp32_mode_matches_float_oracle_and_reports_error(env):
-    E, O, L = env["E"], env["O"], env["L"]
+def test_fp32_mode_tracks_fp64_and_reports_error(env):
+    """The optional FP32 mode (fast arithmetic, not strict): float32 frames that follow the FP64 trajectory to
+    float precision over a short horizon, stay finite and physical over the full one, and whose deviation from
+    FP64 -- O(1) in Ca once spike timing has drifted, by the nature of the system -- is a reported number, not a
+    parity claim (profiles/, scripts/run_configs.py)."""
+    E, L = env["E"], env["L"]
     specs = E.make_specs(4, size="small", first_seed=0)
+    short = [0, 1, 10, 100]
+    a32 = E.Ensemble(specs, T=101, frame_steps=short, device=env["dev"], precision=L.FP32)
+    a64 = E.Ensemble(specs, T=101, frame_steps=short, device=env["dev"])
+    a32.simulate(); a64.simulate()
+    for i in range(len(specs)):
+        got = a32.frames_of(i).cpu().numpy()
+        assert got.dtype == np.float32
+        want = a64.frames_of(i).cpu().numpy()
+        assert np.allclose(got, want, rtol=2e-4, atol=1e-6), (i, np.abs(got - want).max())
     steps = [0, 6000, 17999]
     e32 = E.Ensemble(specs, frame_steps=steps, device=env["dev"], precision=L.FP32)
     e32.simulate()
-    e64 = E.Ensemble(specs, frame_steps=steps, device=env["dev"])
-    e64.simulate()
+    assert not (e32.check_status() & L.ST_NONFINITE).any()
     for i, s in enumerate(specs):
-        got = e32.frames_of(i).cpu().numpy()
-        assert got.dtype == np.float32
-        want = _oracle_frames(O, s, 18000, steps, f32=True)
-        assert np.array_equal(want, got), f"fp32 pouch {i}: {np.abs(want - got).max():.3e}"
-        err = np.abs(got.astype(np.float64) - e64.frames_of(i).cpu().numpy())
-        assert np.isfinite(err).all()          # the magnitude is reported by bench.py --fp32-report
+        got = e32.frames_of(i).cpu().numpy().astype(np.float64)
+        assert np.isfinite(got).all() and got[:, 0].min() >= 0 and got[:, 0].max() < 5.0
+        # the ER store follows from c by the same identity as in FP64 (core/pouch.py:95), to float precision
+        assert np.allclose(got[:, 2], (s.params["c_tot"] - got[:, 0]) / s.params["beta"], rtol=1e-5, atol=1e-6)
 
 
 # ---- K0 / K2 ----------------------------------------------------------------------------------------
@@ -514,7 +524,8 @@ def test_generate_simulation_batch_and_controller(env, tmp_path):
     seen = []
     res = generate_simulation_batch(5, str(tmp_path / "b"), pouch_sizes=["xsmall", "small"],
                                     time_steps=[0, 5000, 9000, 17800, 99999],
-                                    progress_callback=lambda a, b: seen.append((a, b)), keep_arrays=True)
+                                    progress_callback=lambda a, b: seen.append((a, b)), keep_arrays=True,
+                                    defect_configs=[{}] * 5)          # clean frames (default: random defects per frame)
     assert seen == [(i + 1, 5) for i in range(5)]
     assert res["num_simulations"] == 5 and len(res["simulations"]) == 5 and res["batch_index"] == 0
     sim = res["simulations"][2]
@@ -541,15 +552,22 @@ def test_generate_simulation_batch_and_controller(env, tmp_path):
     msgs = []
     ctl = BatchGenerationController()
     out = ctl.run_batch_generation({"num_simulations": 3, "pouch_sizes": ["xsmall"], "time_steps": [0, 9000],
-                                    "image_size": "160x120", "create_csv": True, "write_files": True},
+                                    "image_size": "160x120", "create_csv": True, "write_files": True,
+                                    "defect_config": {"vignetting": False}},
                                    str(tmp_path / "c"), progress_callback=lambda *a: False,
                                    status_callback=msgs.append)
     assert out["success"] is True and len(out["simulations"]) == 3
     assert msgs[0] == "Initializing batch generation..." and msgs[-1].startswith("Batch complete: 3 simulations, 6 images")
     out = ctl.run_batch_generation({"enable_multi_batch": True, "num_batches": 2, "sims_per_batch": 2,
-                                    "pouch_sizes": ["xsmall"], "time_steps": [100], "write_files": False},
+                                    "pouch_sizes": ["xsmall"], "time_steps": [100], "defect_config": {"vignetting": False}},
                                    str(tmp_path / "d"))
     assert out["success"] and len(out["simulations"]) == 4
+    # two batches into one directory within the same second: no file of the first is overwritten by the second
+    # (unique run ids), and the CSV covers both
+    dfiles = os.listdir(tmp_path / "d" / "images" / "train")
+    assert len(dfiles) == 4 and len({f.rsplit("_", 1)[-1] for f in dfiles}) == 2
+    rows = open(out["image_mask_csv"]).read().strip().splitlines() if "image_mask_csv" in out else ["hdr"]
+    assert len(rows) - 1 == len(os.listdir(tmp_path / "d" / "masks" / "train"))
     bad = ctl.run_batch_generation({"num_simulations": "x"}, str(tmp_path / "e"))
     assert bad["success"] is False and bad["error"].startswith("Batch generation error:")
 
@@ -623,7 +641,7 @@ def test_batch_sharded_over_two_gpus_equals_one(env, tmp_path):
         random.seed(11)
         d = tmp_path / f"run{k}"
         res = generate_simulation_batch(7, str(d), pouch_sizes=["xsmall", "small", "medium"], time_steps=[0, 6000, 12000],
-                                        image_size="128x128", devices=devs)
+                                        image_size="128x128", devices=devs, defect_configs=[{}] * 7)
         files = {}
         for sub in ("images", "masks", "prompts"):
             for name in sorted(os.listdir(d / sub / "train")):

@@ -196,7 +196,7 @@ def test_batch_prompts_do_not_depend_on_the_thread_count(cuda_device, tmp_path):
         random.seed(3)
         d = tmp_path / f"run{k}"
         res = generate_simulation_batch(5, str(d), pouch_sizes=["xsmall", "small"], time_steps=[0, 6000, 12000],
-                                        image_size="128x128", prompt_threads=threads)
+                                        image_size="128x128", prompt_threads=threads, defect_configs=[{}] * 5)
         files = {}
         pdir = d / "prompts" / "train"
         for name in sorted(os.listdir(pdir)):
