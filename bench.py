@@ -671,22 +671,18 @@ def extra_legs(dev) -> dict:
     import random
     n = POUCHES_PER_GPU
     root = tempfile.mkdtemp(prefix="cab200_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    old_stdout = sys.stdout
     try:
         kw = dict(pouch_sizes=[SIZE], defect_configs=[{}] * n, device=dev)
+        sys.stdout = sys.stderr                        # the reference prints one line per simulation; so does the drop-in
         random.seed(1)
         generate_simulation_batch(8, os.path.join(root, "warm"), generate_prompts=True, **dict(kw, defect_configs=[{}] * 8))
         for name, prompts in (("files", False), ("files_and_prompts", True)):
             random.seed(1)
             d = os.path.join(root, name)
-            with open(os.devnull, "w") as devnull:
-                old_stdout = sys.stdout
-                sys.stdout = devnull                   # the reference prints one line per simulation; so does the drop-in
-                try:
-                    t0 = time.perf_counter()
-                    res = generate_simulation_batch(n, d, generate_prompts=prompts, **kw)
-                    dt = time.perf_counter() - t0
-                finally:
-                    sys.stdout = old_stdout
+            t0 = time.perf_counter()
+            res = generate_simulation_batch(n, d, generate_prompts=prompts, **kw)
+            dt = time.perf_counter() - t0
             n_files = sum(len(fs) for _, _, fs in os.walk(d))
             n_bytes = sum(os.path.getsize(os.path.join(r_, f)) for r_, _, fs in os.walk(d) for f in fs)
             work = n * 1500 * (T_STEPS - 1)
@@ -697,6 +693,7 @@ def extra_legs(dev) -> dict:
                                   f"generate_prompts=False / True): wall clock of the public call, host draws, GPU work and "
                                   f"file creation included")
     finally:
+        sys.stdout = old_stdout
         shutil.rmtree(root, ignore_errors=True)
     return out
 

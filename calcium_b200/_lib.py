@@ -37,7 +37,7 @@ EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
            "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_peak_smem", "cab200_selftest_division",
            "cab200_relay_alloc", "cab200_relay_free", "cab200_relay_open", "cab200_relay_close", "cab200_ipc_event_create",
            "cab200_ipc_event_open", "cab200_event_create", "cab200_event_record", "cab200_event_synchronize",
-           "cab200_event_destroy", "cab200_stream_wait_event", "cab200_copy_async"]
+           "cab200_event_destroy", "cab200_stream_wait_event", "cab200_copy_async", "cab200_write_files"]
 
 
 class Cab200Error(RuntimeError):
@@ -154,6 +154,8 @@ def load() -> ctypes.CDLL:
     for _n in ("relay_alloc", "relay_free", "relay_open", "relay_close", "ipc_event_create", "ipc_event_open", "event_create",
                "event_record", "event_synchronize", "event_destroy", "stream_wait_event", "copy_async"):
         getattr(lib, "cab200_" + _n).restype = c_int
+    lib.cab200_write_files.restype = c_int
+    lib.cab200_write_files.argtypes = [c_int64, c_void_p, i64p, c_void_p, i64p, i64p, c_int, i64p]
     lib.cab200_peak_smem.restype = c_int
     lib.cab200_peak_smem.argtypes = [c_int, c_int, f64p, c_void_p]
     lib.cab200_selftest_division.restype = c_int

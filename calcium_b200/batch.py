@@ -140,6 +140,8 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     prompt_dir = os.path.join(batch_dir, "prompts", dataset_split)
     for d in (img_dir, mask_dir, prompt_dir):
         os.makedirs(d, exist_ok=True)
+    with os.scandir(mask_dir) as it_:
+        earlier_batches = any(True for _ in it_)            # an earlier batch already wrote into this directory
     results: Dict[str, Any] = {"simulations": [], "output_dir": batch_dir,
                                "num_simulations": num_simulations, "batch_index": 0}
     output_size = _parse_image_size(image_size)
@@ -147,8 +149,6 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     # ---- host: draw every pouch (same RNG call order as the reference loop, main.py:202-249) ----
     drawn: List[Dict[str, Any]] = []
     for sim_idx in range(num_simulations):
-        if progress_callback:
-            progress_callback(sim_idx + 1, num_simulations)
         pouch_size = random.choice(pouch_sizes)
         sim_type = random.choice(sim_types)
         # no configuration given for this simulation: the reference draws one per frame inside its frame loop
@@ -194,13 +194,39 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     warned_defects: List[bool] = []
     final_states: Dict[int, Any] = {}
 
+    def is_clean(d) -> bool:
+        """No defect of any kind for this pouch: its frames stay flat-shaded and take the K1 -> K3 path."""
+        if d["frame_cfgs"] is not None:
+            return False
+        c_ = defect_configs[d["sim_idx"]]
+        return not c_ or not (host_defects(c_) or defect_plan(c_, output_size))
+
+    done_count = [0]
+    done_lock = threading.Lock()
+
+    def report_done(n_done: int) -> None:
+        """``progress_callback(current, total)`` as simulations complete (the reference calls it as each simulation
+        of its sequential loop starts, ``main.py:212-213``; its return value is ignored there too)."""
+        if not progress_callback:
+            return
+        with done_lock:
+            for _ in range(n_done):
+                done_count[0] += 1
+                progress_callback(done_count[0], num_simulations)
+
     def run_on_device(device, drawn):
         """The chunk loop for the pouches assigned to one GPU (all of them when there is one device)."""
-        for c0 in range(0, len(drawn), chunk):
-            part = drawn[c0:c0 + chunk]
+        # The raw-array routes (edge_blur, defects, keep_arrays) are chunked by the device memory their uncompressed
+        # frames take; the K1 -> K3 route keeps no frame on the device, so one ensemble -- one K1 launch filling
+        # every SM -- covers up to 1184 clean pouches.
+        fast = bool(steps) and not keep_arrays and not edge_blur and all(is_clean(d) for d in drawn)
+        dchunk = 1184 if fast else chunk
+        for c0 in range(0, len(drawn), dchunk):
+            part = drawn[c0:c0 + dchunk]
             ens = Ensemble([d["spec"] for d in part], output_size=output_size, T=T,
                            frame_steps=steps, device=device)
-            names = {li: [f"{d['name']}_t{t:05d}_{batch_run_id}" for t in steps] for li, d in enumerate(part)}
+            tsfx = [f"_t{t:05d}_{batch_run_id}" for t in steps]
+            names = {li: [d["name"] + x for x in tsfx] for li, d in enumerate(part)}
             image_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             mask_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             img = ins = nact = masks_k3 = None
@@ -219,28 +245,34 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             gpu_defects = [(not host_chain[li]) and bool(defect_plan(pouch_cfgs[li], output_size)) for li in range(len(part))]
             with_defects = any(host_chain) or any(gpu_defects)
             skipped_frames: Dict[int, set] = {li: set() for li in range(len(part))}
-            if steps and not keep_arrays and not edge_blur and not with_defects:
+            took_k3 = bool(steps and not keep_arrays and not edge_blur and not with_defects)
+            if took_k3:
                 # K1 -> K3: every frame arrives on the host as the finished .png / .npz byte string
                 # (cab200_encode_batch); writing a file is a plain write of those bytes.
                 def consumer(ch):
-                    for i in range(ch.hi - ch.lo):
-                        li = ch.lo + i
-                        todo = []                           # one writer task per pouch: (path, bytes) of its frames
-                        for fi in range(len(steps)):
-                            base = names[li][fi]
-                            ipath = os.path.join(img_dir, base + ".png")
-                            image_files[li].append(ipath)
-                            if pool is not None:
-                                todo.append((ipath, bytes(ch.file(i, fi, 0))))
-                            mb = ch.file(i, fi, 1) if generate_masks else None
-                            if mb is not None:     # no active cell -> no mask (sam2_data_generator.py:318-319)
-                                mpath = os.path.join(mask_dir, base + ".npz")
-                                mask_files[li].append(mpath)
-                                mappings_by_sim.setdefault(part[li]["sim_idx"], []).append((os.path.basename(ipath), os.path.basename(mpath)))
-                                if pool is not None:
-                                    todo.append((mpath, bytes(mb)))
-                        if todo:
-                            pending.append(pool.submit(_write_many, todo))
+                    ipaths = [[os.path.join(img_dir, b + ".png") for b in names[li]] for li in range(ch.lo, ch.hi)]
+                    mpaths = [[os.path.join(mask_dir, b + ".npz") for b in names[li]] for li in range(ch.lo, ch.hi)] \
+                        if generate_masks else None
+                    for i, li in enumerate(range(ch.lo, ch.hi)):
+                        image_files[li] = ipaths[i]
+                        if generate_masks:     # no active cell -> no mask (sam2_data_generator.py:318-319)
+                            has = ch.n_active[i] > 0
+                            mask_files[li] = [p_ for p_, h_ in zip(mpaths[i], has) if h_]
+                            sid = part[li]["sim_idx"]
+                            mappings_by_sim.setdefault(sid, []).extend(
+                                (os.path.basename(a_), os.path.basename(b_)) for a_, b_, h_ in zip(ipaths[i], mpaths[i], has) if h_)
+                    n_done = ch.hi - ch.lo
+                    if pool is None:
+                        report_done(n_done)
+                        return None
+                    # the chunk's files go to disk straight from the pinned arena on native writer threads
+                    # (cab200_write_files); the ring slot is held until they are done
+                    def write_chunk():
+                        ch.write_files(ipaths, mpaths, threads=n_wt)
+                        report_done(n_done)
+                    fut = pool.submit(write_chunk)
+                    pending.append(fut)
+                    return fut
                 ens.run_files_to_host(chunk_pouches=min(len(part), 37), image=True, mask=bool(generate_masks),
                                       consumer=consumer)
                 status = ens.check_status()
@@ -365,6 +397,9 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     "simulation_type": d["type"], "pouch_size": d["size"], "parameters": d["params"],
                     "image_count": len(image_files[li]), "image_dir": img_dir, "mask_dir": mask_dir,
                     "mask_count": len(mask_files[li]), "prompt_count": len(prompt_files[li]), "pouch": pouch_obj})
+            if not took_k3:
+                report_done(len(part))
+            ens.release_files_ring()
             del ens
 
     # ---- shard over the GPUs of the box: independent pouches, no exchange; longest-
@@ -394,8 +429,9 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     try:
         if mappings and write_files:
             # every pair present in the directory (earlier batches included), like the reference's scan
-            on_disk = cio.scan_image_mask_pairs(batch_dir, dataset_split)
-            mappings = sorted(set(on_disk) | set(mappings))
+            if earlier_batches:
+                on_disk = cio.scan_image_mask_pairs(batch_dir, dataset_split)
+                mappings = sorted(set(on_disk) | set(mappings))
             results["image_mask_csv"] = cio.save_csv_mapping(mappings, batch_dir, "train.csv")
             print(f"Created CSV mapping: {results['image_mask_csv']}")
         else:

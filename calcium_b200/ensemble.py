@@ -733,14 +733,17 @@ class Ensemble:
 
     def run_files_to_host(self, chunk_pouches: int = 37, image: bool = True, mask: bool = True,
                            consumer=None, threshold: float = 0.1, quirk: bool = True,
-                           arena_bytes_per_pixel: float = 0.5, wait: bool = True,
+                           arena_bytes_per_pixel: float = 0.25, wait: bool = True,
                            stage_bytes: int = 0, frames: str = "none") -> Dict[str, int]:
         """The whole hot path with HOST buffers on both sides, in the form the reference's batch path
         stores its results: pinned host inputs -> device, K1, then K3 chunk by chunk -- every sampled
         frame as a finished ``.png`` and ``.npz`` byte string -- copied into pinned host memory together
         with the float64 frames and the per-frame records.  Four ring slots: while K3 encodes chunk k,
         the host learns the size of chunk k-1 (a 16-byte read) and queues its copy-out on a second
-        stream.  ``consumer(chunk: EncodedChunk)`` is called once a chunk has landed.  With
+        stream.  ``consumer(chunk: EncodedChunk)`` is called once a chunk has landed; if it returns an object
+        with a ``result()`` method (a future of a writer thread that still reads the chunk), the chunk's host
+        buffer is not reused before that has returned.  A chunk that outgrows its arena slot (about 0.16 bytes
+        per pixel are typical, 0.25 reserved) is encoded again into an arena of the size it asked for.  With
         ``wait=False`` the last chunks are left in flight (their copy-out then overlaps whatever the
         caller queues next, e.g. the next ensemble's integration); :meth:`flush_files` completes them.
         ``frames``: which part of the sampled float64 state also goes to the host (``_fring["h_frames"]``):
@@ -764,20 +767,28 @@ class Ensemble:
         st = getattr(self, "_fring", None)
         if st is None or st["key"] != key:
             self.flush_files()
-            st = {"key": key, "cs": torch.cuda.Stream(device=dev), "fs": torch.cuda.Stream(device=dev),
-                  "slots": [], "launched": [], "copying": [],
+            self.release_files_ring()
+            # pinned rings are expensive to allocate (~0.3 s per GB) and identical from one ensemble of a batch to
+            # the next: a process-wide cache keyed by device and shape hands them on (release_files_ring)
+            pool_key = (dev.index, cp, cap, self.F)
+            with _RING_LOCK:
+                slots = _RING_CACHE.pop(pool_key, None)
+            if slots is None:
+                slots = []
+                for _ in range(4):
+                    slots.append({
+                        "dev": {}, "h_arena": torch.empty(cap, dtype=torch.uint8, pin_memory=True),
+                        "h_rec": torch.empty((cp, self.F, 2, 2), dtype=torch.int64, pin_memory=True),
+                        "h_cur": torch.empty(2, dtype=torch.int64, pin_memory=True),
+                        "h_nact": torch.empty((cp * self.F + 3) // 4 * 4, dtype=torch.int32, pin_memory=True),
+                        "meta": torch.cuda.Event(), "data": torch.cuda.Event(), "busy": None})
+            st = {"key": key, "pool_key": pool_key, "cs": torch.cuda.Stream(device=dev), "fs": torch.cuda.Stream(device=dev),
+                  "slots": slots, "launched": [], "copying": [],
                   "frames_done": torch.cuda.Event(),
                   "h_frames": (torch.empty(max(self.frame_elems, 1), dtype=torch.float64, pin_memory=True)
                                if frames == "all" else
                                torch.empty((self.P, self.F, int(self.g_ncell[0])), dtype=torch.float64, pin_memory=True)
                                if frames == "ca" else None)}
-            for _ in range(4):
-                st["slots"].append({
-                    "dev": {}, "h_arena": torch.empty(cap, dtype=torch.uint8, pin_memory=True),
-                    "h_rec": torch.empty((cp, self.F, 2, 2), dtype=torch.int64, pin_memory=True),
-                    "h_cur": torch.empty(2, dtype=torch.int64, pin_memory=True),
-                    "h_nact": torch.empty((cp * self.F + 3) // 4 * 4, dtype=torch.int32, pin_memory=True),
-                    "meta": torch.cuda.Event(), "data": torch.cuda.Event(), "busy": None})
             self._fring = st
         cs = st["cs"]
         d2h = 0
@@ -788,10 +799,26 @@ class Ensemble:
             nonlocal d2h
             slot = e["slot"]
             slot["meta"].synchronize()
+            w_ = slot.pop("writer", None)
+            if w_ is not None:
+                w_.result()                      # a writer thread still read this slot's previous chunk
             used = int(slot["h_cur"][0])
             if used > cap:
-                raise _lib.Cab200Error(f"encode arena too small: {used} > {cap} bytes "
-                                       f"(raise arena_bytes_per_pixel above {arena_bytes_per_pixel})")
+                # the chunk outgrew its arena slot: encode it again into an arena of the size it asked for
+                # (synchronous and rare; the files of a flat-shaded frame take ~0.16 bytes per pixel)
+                consumer_, threshold_, quirk_ = e["consumer"]
+                big = self.encode(image=image, mask=mask, pouches=(e["lo"], e["hi"]), threshold=threshold_, quirk=quirk_,
+                                  out={}, arena_bytes=used + (1 << 20), stage_bytes=stage_bytes)
+                torch.cuda.current_stream(dev).synchronize()
+                used = int(big["cursor"].item())
+                n_ = e["hi"] - e["lo"]
+                slot["h_rec"][:n_].copy_(big["records"])
+                slot["h_nact"][: n_ * self.F].copy_(big["n_active"].reshape(-1))
+                e["big_arena"] = big["arena"][:used].cpu()
+                e["used"] = used
+                d2h += used
+                copying.append(e)
+                return
             e["used"] = used
             relay = getattr(self, "_relay", None)
             consumer_ = e["consumer"][0]
@@ -816,9 +843,13 @@ class Ensemble:
             consumer, threshold, quirk = e["consumer"]
             if consumer is not None:
                 n = e["hi"] - e["lo"]
-                consumer(EncodedChunk(self, e["lo"], e["hi"], slot["h_arena"][: e["used"]].numpy(),
-                                      slot["h_rec"][:n].numpy(),
-                                      slot["h_nact"][: n * self.F].view(n, self.F).numpy(), threshold, quirk))
+                arena_host = e.pop("big_arena", None)
+                arena_host = slot["h_arena"][: e["used"]] if arena_host is None else arena_host
+                ret = consumer(EncodedChunk(self, e["lo"], e["hi"], arena_host.numpy(),
+                                            slot["h_rec"][:n].numpy(),
+                                            slot["h_nact"][: n * self.F].view(n, self.F).numpy(), threshold, quirk))
+                if ret is not None and hasattr(ret, "result"):
+                    slot["writer"] = ret         # the slot's host buffers stay untouched until it has returned
             slot["busy"] = None
 
         st["queue_copy"], st["finish"] = queue_copy, finish
@@ -874,7 +905,7 @@ class Ensemble:
                 self.flush_files()
         return {"h2d_bytes": self.h2d_bytes, "d2h_bytes": d2h}
 
-    def files_chunk_capacity(self, chunk_pouches: int = 37, arena_bytes_per_pixel: float = 0.5) -> int:
+    def files_chunk_capacity(self, chunk_pouches: int = 37, arena_bytes_per_pixel: float = 0.25) -> int:
         """Arena bytes :meth:`run_files_to_host` reserves per chunk (the relay ring's slot size)."""
         w, h = self.output_size
         cp = max(1, min(chunk_pouches, self.P))
@@ -883,6 +914,22 @@ class Ensemble:
     def set_relay(self, endpoint) -> None:
         """Attach a :class:`calcium_b200.relay.Endpoint` (or None) for the chunk copy-out."""
         self._relay = endpoint
+
+    def release_files_ring(self) -> None:
+        """Hands the pinned ring of :meth:`run_files_to_host` to the process-wide cache (call when done with the
+        ensemble; the next ensemble of the same shape on this device takes it over instead of allocating)."""
+        st = getattr(self, "_fring", None)
+        if st is None:
+            return
+        self.flush_files()
+        for slot in st["slots"]:
+            w_ = slot.pop("writer", None)
+            if w_ is not None:
+                w_.result()
+            slot["busy"] = None
+        with _RING_LOCK:
+            _RING_CACHE.setdefault(st["pool_key"], st["slots"])
+        self._fring = None
 
     def flush_files(self) -> int:
         """Completes every chunk :meth:`run_files_to_host` left in flight (copy-out finished, consumer
@@ -976,6 +1023,10 @@ class Ensemble:
         return {"h2d_bytes": self.h2d_bytes, "d2h_bytes": d2h}
 
 
+_RING_CACHE: Dict[Any, List[Dict[str, Any]]] = {}
+_RING_LOCK = threading.Lock()
+
+
 class EncodedChunk:
     """The files of pouches ``[lo, hi)`` as K3 left them in (pinned) host memory.  Valid until the
     ring slot is reused, i.e. until the consumer callback returns."""
@@ -1001,6 +1052,49 @@ class EncodedChunk:
         if fl & _lib.ENC_STAGE_FULL:
             return self._host_encoded(i, f, kind)
         raise _lib.Cab200Error(f"frame ({self.lo + i}, {f}) kind {kind}: encode flags {fl}")
+
+    def write_files(self, image_paths, mask_paths, threads: int = 16) -> Tuple[List[Tuple[int, int]], int]:
+        """Writes the chunk's files with the native writer pool (``cab200_write_files``), straight from the arena.
+        ``image_paths[i][f]`` / ``mask_paths[i][f]`` (``None`` entries and a ``None`` list are skipped) name the
+        files of chunk-local pouch i, frame f.  Returns the ``(i, f)`` of the masks written and the bytes written."""
+        lib = _lib.load()
+        paths: List[bytes] = []
+        offs: List[int] = []
+        sizes: List[int] = []
+        late: List[Tuple[str, bytes]] = []
+        masks_written: List[Tuple[int, int]] = []
+        n, F = self.flags.shape[0], self.flags.shape[1]
+        for kind, table in ((0, image_paths), (1, mask_paths)):
+            if table is None:
+                continue
+            fl = self.flags[:, :, kind]
+            for i in range(n):
+                row = table[i]
+                for f in range(F):
+                    flag = int(fl[i, f])
+                    if row[f] is None or flag & _lib.ENC_SKIPPED:
+                        continue
+                    if flag & _lib.ENC_OK:
+                        paths.append(row[f].encode())
+                        offs.append(int(self.offset[i, f, kind])); sizes.append(int(self.size[i, f, kind]))
+                    else:
+                        late.append((row[f], bytes(self.file(i, f, kind))))     # staging overflow: host-encoded
+                    if kind == 1:
+                        masks_written.append((i, f))
+        blob = b"\0".join(paths) + b"\0"
+        poff = np.zeros(len(paths), dtype=np.int64)
+        if paths:
+            np.cumsum([len(p) + 1 for p in paths[:-1]], out=poff[1:])
+        o = np.asarray(offs, dtype=np.int64)
+        z = np.asarray(sizes, dtype=np.int64)
+        written = np.zeros(1, dtype=np.int64)
+        arena = np.ascontiguousarray(self.arena)
+        _lib.check(lib.cab200_write_files(len(paths), blob, _lib.as_i64p(poff), arena.ctypes.data, _lib.as_i64p(o),
+                                          _lib.as_i64p(z), int(threads), _lib.as_i64p(written)), "cab200_write_files")
+        for path, data in late:
+            with open(path, "wb") as fh:
+                fh.write(data)
+        return masks_written, int(written[0]) + sum(len(d) for _, d in late)
 
     def _host_encoded(self, i: int, f: int, kind: int) -> bytes:
         """A file that did not fit K3's staging buffer: rasterise the pouch with K2 and encode on the host."""

@@ -79,7 +79,8 @@ class FrameStore:
         for t in ts:
             if not 0 <= t < T:
                 raise IndexError(f"index {t} is out of bounds for axis 2 with size {T}")
-        missing = [t for t in ts if t not in self._host]
+        self._pouch._ensure_steps(ts)                             # may re-run the capture and drop the host copies
+        missing = [t for t in dict.fromkeys(ts) if t not in self._host]
         if missing:                                               # one capture pass + ONE device->host copy
             for t, f in zip(missing, self._pouch._fetch_frames(missing)):
                 self._host[t] = f
