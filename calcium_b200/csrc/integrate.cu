@@ -1,5 +1,6 @@
 // integrate.cu -- host launcher of K1 (see integrate.cuh) behind cab200_sim_batch.
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -59,6 +60,77 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const R *tmp, R *out, co
 
 static std::mutex g_plan_mu;
 static int g_force_nmax = 0, g_force_threads = 0, g_force_cpt = 0;
+
+// Side streams for launches of different geometries inside one cab200_sim_batch call.  A mixed-size ensemble is
+// one persistent kernel launch per geometry; on the caller's stream alone those run back to back, although a small
+// group leaves most SMs idle (8 GPUs x 32 mixed pouches: 52.7 ms as a sequence, the longest group alone ~20 ms).
+// Group 0 stays on the caller's stream, group k > 0 goes to side stream (k-1) mod 3 of the current device, forked
+// and joined with events, so the call remains stream-ordered for the caller.  A few sets per device: host threads
+// that drive the same device concurrently (devices=[0, 0]) must not share events.
+constexpr int CAB_SIDE_STREAMS = 3, CAB_SIDE_SETS = 4, CAB_MAX_DEVICES = 64;
+struct SideStreams {
+    std::atomic<int> busy{0};
+    bool ready = false;
+    cudaStream_t s[CAB_SIDE_STREAMS] = {};
+    cudaEvent_t fork = nullptr, join[CAB_SIDE_STREAMS] = {};
+};
+static SideStreams g_side[CAB_MAX_DEVICES][CAB_SIDE_SETS];
+
+static SideStreams *acquire_side_streams(int device)
+{
+    if (device < 0 || device >= CAB_MAX_DEVICES) return nullptr;
+    for (int k = 0; k < CAB_SIDE_SETS; ++k) {
+        SideStreams &ss = g_side[device][k];
+        int expect = 0;
+        if (!ss.busy.compare_exchange_strong(expect, 1)) continue;
+        if (!ss.ready) {
+            bool ok = cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; ok && i < CAB_SIDE_STREAMS; ++i)
+                ok = cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) { cudaGetLastError(); ss.busy = 0; return nullptr; }
+            ss.ready = true;
+        }
+        return &ss;
+    }
+    return nullptr;                      // every set is in use by another host thread: stay on the caller's stream
+}
+
+// Hands out the stream of the k-th non-empty geometry group and joins the side streams back into the caller's
+// stream when it goes out of scope (error returns included), so the call stays stream-ordered.
+struct GroupStreams {
+    cudaStream_t main;
+    SideStreams *ss = nullptr;
+    bool used[CAB_SIDE_STREAMS] = {};
+    int next = 0;
+    GroupStreams(cudaStream_t main_, int n_groups) : main(main_)
+    {
+        if (n_groups < 2) return;
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+        ss = acquire_side_streams(dev);
+        if (ss && cudaEventRecord(ss->fork, main) != cudaSuccess) { cudaGetLastError(); ss->busy = 0; ss = nullptr; }
+    }
+    bool concurrent() const { return ss != nullptr; }
+    cudaStream_t take()
+    {
+        const int k = next++;
+        if (!ss || k == 0) return main;
+        const int i = (k - 1) % CAB_SIDE_STREAMS;
+        if (!used[i]) {
+            if (cudaStreamWaitEvent(ss->s[i], ss->fork, 0) != cudaSuccess) { cudaGetLastError(); return main; }
+            used[i] = true;
+        }
+        return ss->s[i];
+    }
+    ~GroupStreams()
+    {
+        if (!ss) return;
+        for (int i = 0; i < CAB_SIDE_STREAMS; ++i)
+            if (used[i] && cudaEventRecord(ss->join[i], ss->s[i]) == cudaSuccess) cudaStreamWaitEvent(main, ss->join[i], 0);
+        ss->busy = 0;
+    }
+};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -214,11 +286,25 @@ extern "C" int cab200_sim_batch(
         force_nmax = g_force_nmax; force_threads = g_force_threads; force_cpt = g_force_cpt;
     }
 
-    for (int g = 0; g < n_geom; ++g) {
+    int n_groups = 0;
+    for (int g = 0; g < n_geom; ++g) n_groups += g_begin[g + 1] > g_begin[g];
+    GroupStreams gs(stream, n_groups);          // forks after the metadata copies above, joins on scope exit
+    size_t tmp_cursor = 0;                      // concurrent groups take disjoint pieces of frames_tmp
+
+    // largest pouches first: their CTAs run longest, so they should not start behind the short ones
+    std::vector<int> g_order(n_geom);
+    for (int g = 0; g < n_geom; ++g) g_order[g] = g;
+    std::stable_sort(g_order.begin(), g_order.end(), [&](int a_, int b_) { return g_ncell[a_] > g_ncell[b_]; });
+
+    for (int gi = 0; gi < n_geom; ++gi) {
+        const int g = g_order[gi];
         const int count = g_begin[g + 1] - g_begin[g];
         if (count == 0) continue;
         const int n = g_ncell[g];
         if (n <= 0) { set_error("cab200_sim_batch: geometry %d has no cells", g); return CAB200_EINVAL; }
+        stream = gs.take();
+        unsigned char *const tmp_base = frames_tmp ? (unsigned char *)frames_tmp + tmp_cursor : nullptr;
+        const size_t tmp_avail = frames_tmp ? frames_tmp_bytes - tmp_cursor : 0;
         const int ncta = g_cluster ? g_cluster[g] : 1;
         const int64_t plan_off = (slot_plan && g_plan_off) ? g_plan_off[g] : -1;
         if (ncta > 1) {
@@ -251,7 +337,8 @@ extern "C" int cab200_sim_batch(
             ca.T = T; ca.n_frames = n_frames; ca.frame_steps = d_frame_steps;
             ca.frames_out = frames_out; ca.status_out = status_out;
             const size_t tmp_need = (size_t)count * n_frames * 4 * ((size_t)ncta * cth * ccpt) * (el2 / 2);
-            ca.frames_tmp = (frames_tmp && n_frames > 0 && tmp_need <= frames_tmp_bytes && count <= 65535) ? frames_tmp : nullptr;
+            ca.frames_tmp = (tmp_base && n_frames > 0 && tmp_need <= tmp_avail && count <= 65535) ? tmp_base : nullptr;
+            if (ca.frames_tmp && gs.concurrent()) tmp_cursor += align_up(tmp_need, 256);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(count * ncta), 1, 1);
             cfg.blockDim = dim3((unsigned)cth, 1, 1);
@@ -265,10 +352,10 @@ extern "C" int cab200_sim_batch(
             if (ca.frames_tmp) {
                 const dim3 ug((unsigned)n_frames, (unsigned)count);
                 if (precision == CAB200_FP64_STRICT)
-                    unpermute_kernel<double><<<ug, 256, 0, stream>>>((const double *)frames_tmp, (double *)frames_out, ca.pouch_list,
+                    unpermute_kernel<double><<<ug, 256, 0, stream>>>((const double *)ca.frames_tmp, (double *)frames_out, ca.pouch_list,
                                                                      d_cell_off, ca.slot_plan, n, ncta, cth * ccpt, n_frames);
                 else
-                    unpermute_kernel<float><<<ug, 256, 0, stream>>>((const float *)frames_tmp, (float *)frames_out, ca.pouch_list,
+                    unpermute_kernel<float><<<ug, 256, 0, stream>>>((const float *)ca.frames_tmp, (float *)frames_out, ca.pouch_list,
                                                                     d_cell_off, ca.slot_plan, n, ncta, cth * ccpt, n_frames);
                 CAB_CUDA(cudaGetLastError());
             }
@@ -320,17 +407,18 @@ extern "C" int cab200_sim_batch(
         a.frames_out = frames_out;
         a.status_out = status_out;
         const size_t tmp_need = (size_t)count * n_frames * 4 * (size_t)(threads * cpt) * (elem2 / 2);
-        a.frames_tmp = (frames_tmp && n_frames > 0 && a.slot_plan && tmp_need <= frames_tmp_bytes && count <= 65535)
-                           ? frames_tmp : nullptr;
+        a.frames_tmp = (tmp_base && n_frames > 0 && a.slot_plan && tmp_need <= tmp_avail && count <= 65535)
+                           ? tmp_base : nullptr;
+        if (a.frames_tmp && gs.concurrent()) tmp_cursor += align_up(tmp_need, 256);
         fn<<<count, threads, smem, stream>>>(a);
         CAB_CUDA(cudaGetLastError());
         if (a.frames_tmp) {
             const dim3 ug((unsigned)n_frames, (unsigned)count);
             if (precision == CAB200_FP64_STRICT)
-                unpermute_kernel<double><<<ug, 256, 0, stream>>>((const double *)frames_tmp, (double *)frames_out, a.pouch_list,
+                unpermute_kernel<double><<<ug, 256, 0, stream>>>((const double *)a.frames_tmp, (double *)frames_out, a.pouch_list,
                                                                  d_cell_off, a.slot_plan, n, 1, threads * cpt, n_frames);
             else
-                unpermute_kernel<float><<<ug, 256, 0, stream>>>((const float *)frames_tmp, (float *)frames_out, a.pouch_list,
+                unpermute_kernel<float><<<ug, 256, 0, stream>>>((const float *)a.frames_tmp, (float *)frames_out, a.pouch_list,
                                                                 d_cell_off, a.slot_plan, n, 1, threads * cpt, n_frames);
             CAB_CUDA(cudaGetLastError());
         }

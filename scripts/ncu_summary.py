@@ -14,6 +14,9 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_tensor_op_hmma.sum", "sm__inst_executed_pipe_tensor_op_dmma.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tc.sum", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
@@ -29,7 +32,7 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     print("=" * 100)
-    for k in KEYS:
+    for k in KEYS + sorted(k_ for k_ in d if "tensor" in k_ and k_ not in KEYS):     # every tensor-pipe counter the report holds
         if k in d:
             u = units[hdr.index(k)]
             print(f"{k:88s} {d[k]:>16s} {u}")

@@ -628,6 +628,32 @@ def test_config3_head_against_reference_fixture(env, golden_dir):
     assert _max_rel(ens.frames_of(0).cpu().numpy(), z["large_frames"]) < RTOL
 
 
+def test_batch_sharded_over_two_shards_of_one_gpu_equals_unsharded(env, tmp_path):
+    """The ``devices=[...]`` drop-in sharding (LPT partition, one host thread per shard, results merged) on a
+    one-GPU box: two shards on ``cuda:0`` run through exactly the code the multi-GPU call runs
+    (``run_on_device`` per entry of ``devices``) -- same files, result dict and generator state as unsharded."""
+    import random
+    from calcium_b200 import generate_simulation_batch
+    outs = []
+    for k, devs in enumerate((None, [0, 0])):
+        random.seed(13)
+        d = tmp_path / f"run{k}"
+        res = generate_simulation_batch(7, str(d), pouch_sizes=["xsmall", "small", "medium"], time_steps=[0, 6000, 12000],
+                                        image_size="128x128", devices=devs, defect_configs=[{}] * 7)
+        files = {}
+        for sub in ("images", "masks", "prompts"):
+            for name in sorted(os.listdir(d / sub / "train")):
+                key = sub + "/" + "_".join(name.split("_")[:-1])          # drop the run id
+                files[key] = open(d / sub / "train" / name, "rb").read()
+        sims = [(s["simulation_id"], s["pouch_size"], s["image_count"], s["mask_count"], s["prompt_count"])
+                for s in res["simulations"]]
+        outs.append((files, sims, np.random.get_state()[1].copy(), res["stats"]))
+    assert outs[0][1] == outs[1][1] and [s[0] for s in outs[1][1]] == list(range(7))
+    assert outs[0][0].keys() == outs[1][0].keys() and len(outs[0][0]) > 0
+    assert all(outs[0][0][k] == outs[1][0][k] for k in outs[0][0])
+    assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
+
+
 def test_batch_sharded_over_two_gpus_equals_one(env, tmp_path):
     """generate_simulation_batch(devices=[0, 1]) (independent pouches per GPU, no
     collective): same files, same result dict and the same generator state as the one-GPU run."""
