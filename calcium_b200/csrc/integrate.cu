@@ -175,13 +175,14 @@ extern "C" int cab200_sim_layout(int n, int unit, int precision, int64_t out[4])
 
 extern "C" int cab200_cluster_layout(int n, int n_cta, int precision, int64_t out[4])
 {
-    if (!out || n <= 0 || (n_cta != 2 && n_cta != 4) ||
+    if (!out || n <= 0 || (n_cta != 2 && n_cta != 4 && n_cta != 8) ||
         (precision != CAB200_FP64_STRICT && precision != CAB200_FP32)) {
-        set_error("cab200_cluster_layout: bad argument (cluster sizes 2 and 4 are supported)");
+        set_error("cab200_cluster_layout: bad argument (cluster sizes 2, 4 and 8 are supported)");
         return CAB200_EINVAL;
     }
     int threads = 0, cpt = 0;
     cluster_shape((n + n_cta - 1) / n_cta, &threads, &cpt);
+    if (n_cta == 8 && threads && threads < 512) { threads = 512; cpt = 2; }      // clusters of 8: 512-thread shapes only
     if (!threads) { set_error("cab200_cluster_layout: %d cells exceed %d CTAs x 1536", n, n_cta); return CAB200_ESIZE; }
     const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
     const int copies = integrate_smem_bytes(0, threads * cpt, elem2, 2, true, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
@@ -309,13 +310,14 @@ extern "C" int cab200_sim_batch(
         const int64_t plan_off = (slot_plan && g_plan_off) ? g_plan_off[g] : -1;
         if (ncta > 1) {
             // ---- pouch split over a thread-block cluster ---------------------------------------
-            if (ncta != 2 && ncta != 4) { set_error("cab200_sim_batch: geometry %d: cluster size %d (2 or 4)", g, ncta); return CAB200_EINVAL; }
+            if (ncta != 2 && ncta != 4 && ncta != 8) { set_error("cab200_sim_batch: geometry %d: cluster size %d (2, 4 or 8)", g, ncta); return CAB200_EINVAL; }
             if (plan_off < 0) { set_error("cab200_sim_batch: geometry %d: a cluster needs a cab200_plan_cluster plan", g); return CAB200_EINVAL; }
             if (!g_unit[g]) { set_error("cab200_sim_batch: geometry %d: clusters need the unit-weight Laplacian", g); return CAB200_EINVAL; }
             const int max_row_c = g_max_row[g];
             if (max_row_c > 16 || max_row_c < 0) { set_error("cab200_sim_batch: geometry %d: longest CSR row %d outside [0,16]", g, max_row_c); return CAB200_ESIZE; }
             int cth = 0, ccpt = 0;
             cluster_shape((n + ncta - 1) / ncta, &cth, &ccpt);
+            if (ncta == 8 && cth && cth < 512) { cth = 512; ccpt = 2; }
             if (!cth) { set_error("cab200_sim_batch: geometry %d: %d cells exceed %d CTAs x 1536", g, n, ncta); return CAB200_ESIZE; }
             const size_t el2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
             const int ccopies = integrate_smem_bytes(0, cth * ccpt, el2, 2, true, CAB_HMAX) <= 227 * 1024 ? 2 : 1;

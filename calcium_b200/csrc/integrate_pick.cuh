@@ -18,7 +18,8 @@ static KernelFn pick_cluster_variant(int ep, int copies)
     return integrate_kernel<R, THREADS, CPT, 8, true, 1, 1, NCTA>;
 }
 
-// Cluster kernels exist for three CTA shapes and cluster sizes 2 and 4.
+// Cluster kernels exist for three CTA shapes and cluster sizes 2 and 4, and for the two 512-thread shapes as
+// clusters of 8 (the portable maximum: pouches of up to 8 x 1536 = 12 288 cells, the reference's `xlarge`).
 template <typename R>
 static KernelFn pick_cluster_kernel(int threads, int cpt, int ncta, int ep, int copies)
 {
@@ -31,6 +32,8 @@ static KernelFn pick_cluster_kernel(int threads, int cpt, int ncta, int ep, int 
     CAB_CSHAPE(512, 2)
     CAB_CSHAPE(512, 3)
 #undef CAB_CSHAPE
+    if (ncta == 8 && threads == 512 && cpt == 2) return pick_cluster_variant<R, 512, 2, 8>(ep, copies);
+    if (ncta == 8 && threads == 512 && cpt == 3) return pick_cluster_variant<R, 512, 3, 8>(ep, copies);
     return nullptr;
 }
 

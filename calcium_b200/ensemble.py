@@ -131,6 +131,8 @@ class _DeviceGeometry:
         exchange would only add to that) and stay on one CTA."""
         if not self.unit:
             return 1
+        if self.n > 4 * 1536:
+            return 8                 # up to 8 x 1536 = 12 288 cells (the portable cluster maximum)
         if self.n > 1536:
             return 4
         if self.n > 1024:

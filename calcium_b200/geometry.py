@@ -38,8 +38,9 @@ SYNTHETIC_CELL_COUNTS: Dict[str, int] = {
     "small": 500,
     "medium": 1500,
     "large": 3255,
+    "xlarge": 6500,      # the reference lists the name (core/geometry_loader.py:36) without a size; K1 runs it as a cluster of 8
 }
-_SYNTHETIC_SEEDS = {"xsmall": 1000, "small": 1001, "medium": 1002, "large": 1003}
+_SYNTHETIC_SEEDS = {"xsmall": 1000, "small": 1001, "medium": 1002, "large": 1003, "xlarge": 1004}
 DEFAULT_SIZES = ["xsmall", "small", "medium", "large", "xlarge"]
 
 
