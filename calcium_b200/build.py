@@ -71,6 +71,37 @@ def build_variant(name: str, defines: List[str]) -> str:
     return out
 
 
+K1_CHECK_LIB = os.path.join(HERE, "_variants", "libk1check.so")
+
+
+def build_k1_check(force: bool = False) -> str:
+    """``_variants/libk1check.so``: the library with the FP64 integrator compiled with ``-DCAB_K1_CHECK`` (the step
+    loop's buffer-reuse invariants as run-time checks, see integrate.cuh); every other object is the regular build's.
+    Loaded through ``CALCIUM_B200_LIB`` by ``tests/test_gpu_parity.py::test_k1_protocol_checks``."""
+    build()
+    if not force and os.path.exists(K1_CHECK_LIB) and os.path.getmtime(K1_CHECK_LIB) >= os.path.getmtime(LIB):
+        return K1_CHECK_LIB
+    odir = os.path.join(HERE, "_variants", "_obj_k1check")
+    os.makedirs(odir, exist_ok=True)
+    checked = ["integrate_f64.cu", "integrate_cl64.cu"]
+
+    def comp(src: str) -> str:
+        obj = os.path.join(odir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-DCAB_K1_CHECK", "-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=2) as ex:
+        objs = list(ex.map(comp, checked))
+    objs += [os.path.join(OBJDIR, os.path.splitext(s_)[0] + ".o") for s_ in SOURCES if s_ not in checked]
+    res = subprocess.run([_nvcc()] + ARCH + ["-shared", "-o", K1_CHECK_LIB] + objs, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return K1_CHECK_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB

@@ -175,20 +175,53 @@ extern "C" int cab200_sim_layout(int n, int unit, int precision, int64_t out[4])
 
 extern "C" int cab200_cluster_layout(int n, int n_cta, int precision, int64_t out[4])
 {
-    if (!out || n <= 0 || (n_cta != 2 && n_cta != 4 && n_cta != 8) ||
+    if (!out || n <= 0 || (n_cta != 2 && n_cta != 3 && n_cta != 4 && n_cta != 8) ||
         (precision != CAB200_FP64_STRICT && precision != CAB200_FP32)) {
-        set_error("cab200_cluster_layout: bad argument (cluster sizes 2, 4 and 8 are supported)");
+        set_error("cab200_cluster_layout: bad argument (cluster sizes 2, 3, 4 and 8 are supported)");
         return CAB200_EINVAL;
     }
     int threads = 0, cpt = 0;
     cluster_shape((n + n_cta - 1) / n_cta, &threads, &cpt);
     if (n_cta == 8 && threads && threads < 512) { threads = 512; cpt = 2; }      // clusters of 8: 512-thread shapes only
+    if (n_cta == 3 && threads) { threads = 512; cpt = 3; }                       // clusters of 3: the 512 x 3 shape only
     if (!threads) { set_error("cab200_cluster_layout: %d cells exceed %d CTAs x 1536", n, n_cta); return CAB200_ESIZE; }
     const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
     const int copies = integrate_smem_bytes(0, threads * cpt, elem2, 2, true, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
     out[0] = threads; out[1] = cpt; out[2] = copies;
     out[3] = (int64_t)integrate_smem_bytes(0, threads * cpt, elem2, copies, true, CAB_HMAX);
     return CAB200_OK;
+}
+
+extern "C" int cab200_cluster_capacity(int n, int max_row, int n_cta, int precision)
+{
+    int64_t lay[4];
+    if (int rc = cab200_cluster_layout(n, n_cta, precision, lay)) return rc;
+    if (max_row < 0 || max_row > 16) { set_error("cab200_cluster_capacity: longest CSR row %d outside [0,16]", max_row); return CAB200_ESIZE; }
+    const int ep = k1_ep(max_row);
+    KernelFn fn = (precision == CAB200_FP64_STRICT) ? pick_cluster_kernel_f64((int)lay[0], (int)lay[1], n_cta, ep, (int)lay[2])
+                                                    : pick_cluster_kernel_f32((int)lay[0], (int)lay[1], n_cta, ep, (int)lay[2]);
+    if (!fn) { set_error("cab200_cluster_capacity: no cluster kernel for %dx%d x%d", (int)lay[0], (int)lay[1], n_cta); return CAB200_EINVAL; }
+    if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay[3]) != cudaSuccess) {
+        set_error("cab200_cluster_capacity: %s", cudaGetErrorString(cudaGetLastError()));
+        return CAB200_ECUDA;
+    }
+    int n_sm = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_cta * std::max(1, n_sm / n_cta)), 1, 1);
+    cfg.blockDim = dim3((unsigned)lay[0], 1, 1);
+    cfg.dynamicSmemBytes = (size_t)lay[3];
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)n_cta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, (const void *)fn, &cfg) != cudaSuccess) {
+        set_error("cab200_cluster_capacity: %s", cudaGetErrorString(cudaGetLastError()));
+        return CAB200_ECUDA;
+    }
+    return n_clusters;
 }
 
 extern "C" size_t cab200_sim_frames_tmp_bytes(int n_cells, int n_cta, int unit, int precision, int n_pouch, int n_frames)
@@ -310,7 +343,7 @@ extern "C" int cab200_sim_batch(
         const int64_t plan_off = (slot_plan && g_plan_off) ? g_plan_off[g] : -1;
         if (ncta > 1) {
             // ---- pouch split over a thread-block cluster ---------------------------------------
-            if (ncta != 2 && ncta != 4 && ncta != 8) { set_error("cab200_sim_batch: geometry %d: cluster size %d (2, 4 or 8)", g, ncta); return CAB200_EINVAL; }
+            if (ncta != 2 && ncta != 3 && ncta != 4 && ncta != 8) { set_error("cab200_sim_batch: geometry %d: cluster size %d (2, 3, 4 or 8)", g, ncta); return CAB200_EINVAL; }
             if (plan_off < 0) { set_error("cab200_sim_batch: geometry %d: a cluster needs a cab200_plan_cluster plan", g); return CAB200_EINVAL; }
             if (!g_unit[g]) { set_error("cab200_sim_batch: geometry %d: clusters need the unit-weight Laplacian", g); return CAB200_EINVAL; }
             const int max_row_c = g_max_row[g];
@@ -318,6 +351,7 @@ extern "C" int cab200_sim_batch(
             int cth = 0, ccpt = 0;
             cluster_shape((n + ncta - 1) / ncta, &cth, &ccpt);
             if (ncta == 8 && cth && cth < 512) { cth = 512; ccpt = 2; }
+            if (ncta == 3 && cth) { cth = 512; ccpt = 3; }
             if (!cth) { set_error("cab200_sim_batch: geometry %d: %d cells exceed %d CTAs x 1536", g, n, ncta); return CAB200_ESIZE; }
             const size_t el2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
             const int ccopies = integrate_smem_bytes(0, cth * ccpt, el2, 2, true, CAB_HMAX) <= 227 * 1024 ? 2 : 1;

@@ -464,16 +464,65 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         }
     }
     if (bad) atomicOr(a.status_out + pouch, CAB200_ST_BADGEOM);
+#ifdef CAB_K1_CHECK
+    unsigned chk_adj_local = 0u;           // ranks whose cells sit in this CTA's halo list, i.e. who push to this CTA
+    if (NCTA > 1) {
+        int hbase = 0;
+        for (int qq = 0; qq < (int)rank; ++qq) hbase += hcount[qq];
+        for (int h = tid; h < (int)hcount[rank]; h += THREADS) chk_adj_local |= 1u << part_of[hlists[hbase + h]];
+    }
+#endif
     __syncthreads();   // scratch (inside buffer 1) is dead from here on
     for (uint32_t i = tid; i < 2 * stride / 16; i += THREADS)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
     __shared__ uint64_t step_bar[2];     // clusters alternate between two (see above); else [0] only
+#ifdef CAB_K1_CHECK
+    // Debug build (compute-sanitizer's racecheck is not available on every pool): the buffer-reuse argument of the
+    // step loop as run-time checks.  ann_time[w] = the time warp w is ABOUT to publish (written before its stores and
+    // pushes), pub_time[w] = the time it HAS published (written after them, before its arrival).  A warp that gathers
+    // time t must find every local pub_time >= t (the values are there) and every ann_time <= t + 1 -- locally and in
+    // every peer CTA that pushes halo values to it (nobody has started to overwrite buffer t&1 with time t + 2).
+    // A violation sets CAB200_ST_PROTOCOL in the pouch's status word.
+    __shared__ int ann_time[32], pub_time[32], chk_adj;
+    if (tid < 32) { ann_time[tid] = 0; pub_time[tid] = 0; }
+    if (tid == 0) chk_adj = 0;
+#endif
     if (tid == 0) {
         mbar_init(&step_bar[0], THREADS / 32);         // one arrival per warp
         mbar_init(&step_bar[1], THREADS / 32);
         if (NCTA > 1) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+#ifdef CAB_K1_CHECK
+    if (chk_adj_local) atomicOr(&chk_adj, (int)chk_adj_local);
+    __syncthreads();
+    const unsigned chk_peers = (unsigned)chk_adj & ~(1u << rank);
+    const uint32_t ann_addr = (uint32_t)__cvta_generic_to_shared(&ann_time[0]);
+#define CAB_CHECK_ANNOUNCE(TNEW) if (lane == 0) ((volatile int *)ann_time)[warp] = (TNEW);
+#define CAB_CHECK_PUBLISHED(TNEW) if (lane == 0) ((volatile int *)pub_time)[warp] = (TNEW);
+#define CAB_CHECK_GATHERED(TCUR)                                                                   \
+    {                                                                                             \
+        int viol_ = 0;                                                                            \
+        if (lane < THREADS / 32) {                                                                \
+            const int pv_ = ((volatile int *)pub_time)[lane], av_ = ((volatile int *)ann_time)[lane]; \
+            viol_ |= (pv_ < (TCUR)) || (av_ > (TCUR) + 1);                                        \
+            if (NCTA > 1) {                                                                       \
+                _Pragma("unroll") for (int q_ = 0; q_ < NCTA; ++q_)                               \
+                    if ((chk_peers >> q_) & 1u) {                                                 \
+                        int rv_;                                                                  \
+                        asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(rv_)      \
+                                     : "r"(mapa_shared(ann_addr + 4u * (uint32_t)lane, (uint32_t)q_)) : "memory"); \
+                        viol_ |= rv_ > (TCUR) + 1;                                                \
+                    }                                                                             \
+            }                                                                                     \
+        }                                                                                         \
+        if (viol_) atomicOr(a.status_out + pouch, CAB200_ST_PROTOCOL);                            \
+    }
+#else
+#define CAB_CHECK_ANNOUNCE(TNEW)
+#define CAB_CHECK_PUBLISHED(TNEW)
+#define CAB_CHECK_GATHERED(TCUR)
+#endif
     if (NCTA > 1) cluster_sync_all();    // every CTA's buffers are zeroed and its barrier exists
 
     // cluster: the peers' step barriers (as cluster addresses) that this thread's pushes complete on
@@ -643,6 +692,8 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             case 14: if constexpr (EMAX > 14) CAB_GATHER_PAIR(CUR_IMM, CUR_R, 14 % EMAX)          \
             default: break;                                                                       \
         }                                                                                         \
+        CAB_CHECK_GATHERED(t)                                                                     \
+        CAB_CHECK_ANNOUNCE(t + 1)                                                                 \
         _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
             const R lap_c = S::mul(q.D_c, sc[k]);                              /* :346 */         \
             const R lap_p = S::mul(q.D_p, sp[k]);                              /* :347 */         \
@@ -653,6 +704,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         }                                                                                         \
         /* one arrival per warp: __syncwarp orders the other lanes' stores before lane 0's release */ \
         __syncwarp();                                                                             \
+        CAB_CHECK_PUBLISHED(t + 1)                                                                \
         if (lane == 0) arrive_step(NXT_BAR);                                                      \
         CAB_PUBLISH_LEGACY(NXT_IMM, NXT_R)                                                        \
         /* own-state work for the next step, overlapping the other warps' gathers */              \
@@ -682,6 +734,9 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         cluster_sync_all();
     }
 #undef CAB_STEP
+#undef CAB_CHECK_ANNOUNCE
+#undef CAB_CHECK_PUBLISHED
+#undef CAB_CHECK_GATHERED
 #undef CAB_GATHER_PAIR
 #undef CAB_DIAG_ADD
 #undef CAB_EXIT_CHECK

@@ -32,6 +32,7 @@ static KernelFn pick_cluster_kernel(int threads, int cpt, int ncta, int ep, int 
     CAB_CSHAPE(512, 2)
     CAB_CSHAPE(512, 3)
 #undef CAB_CSHAPE
+    if (ncta == 3 && threads == 512 && cpt == 3) return pick_cluster_variant<R, 512, 3, 3>(ep, copies);   // see cab200_cluster_capacity
     if (ncta == 8 && threads == 512 && cpt == 2) return pick_cluster_variant<R, 512, 2, 8>(ep, copies);
     if (ncta == 8 && threads == 512 && cpt == 3) return pick_cluster_variant<R, 512, 3, 8>(ep, copies);
     return nullptr;

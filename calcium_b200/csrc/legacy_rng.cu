@@ -57,24 +57,123 @@ struct Mt {
 
 namespace {
 
-// permutation(n)[:k] on the generator mt: numpy's _shuffle_raw + random_interval (see the file header)
+// Tempered outputs of the rest of the current state block, produced a block at a time (a plain loop the host
+// compiler vectorises) instead of one output per call; `mt.pos` is advanced as outputs are consumed, so the
+// generator state left behind is exactly what per-call draws would leave.
+struct MtBlock {
+    Mt &mt;
+    uint32_t out[MT_N];
+    int end = 0;                      // outputs out[mt.pos .. end) are ready
+    explicit MtBlock(Mt &m) : mt(m) { fill(); }
+    void fill()
+    {
+        if (mt.pos == MT_N) mt.gen();
+        const uint32_t *key = mt.key;
+        for (int i = mt.pos; i < MT_N; ++i) {
+            uint32_t y = key[i];
+            y ^= (y >> 11);
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= (y >> 18);
+            out[i] = y;
+        }
+        end = MT_N;
+    }
+    inline uint32_t next32()
+    {
+        if (mt.pos == end) fill();
+        return out[mt.pos++];
+    }
+};
+
+// permutation(n)[:k] on the generator mt: numpy's _shuffle_raw + random_interval (see the file header).
+// The shuffle runs i = n-1 .. 1, swap(a[i], a[j_i]); only a[0..k) is wanted.  Instead of swapping inside a
+// megabyte-sized array (random accesses), the draws j_i are stored in generator order and the k wanted positions
+// are traced BACKWARDS through the swaps (i = 1 .. n-1: a position equal to i moves to j_i, one equal to j_i moves
+// to i): where a position ends up is the original index = the value numpy returns.  j_i <= i, so beyond i = k a
+// tracked position can only be hit as j_i -- k compares per draw over a sequential array.
 void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
 {
     // one scratch array per host thread, kept between calls: a fresh 1 MB vector per frame means an mmap / munmap
     // pair per call, and with 32 prompt threads those serialise on the process's address-space lock
+    thread_local std::vector<uint32_t> J;
+    J.resize((size_t)n);
+    MtBlock blk(mt);
+    // random_interval(i): smallest bit mask >= i, rejection on masked 32-bit outputs (i <= 0x7fffffff here).  The
+    // accept / reject outcome is close to a coin flip for i just above a power of two, so the loop is written without
+    // a data-dependent branch: every output is stored at J[i] and i only moves on when the output was accepted.
+    {
+        int64_t i = n - 1;
+        while (i >= 1) {
+            uint32_t mask = (uint32_t)i;
+            mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+            const int64_t lo = std::max<int64_t>(1, (int64_t)(mask >> 1) + 1);     // the mask serves i = lo .. mask
+            while (i >= lo) {
+                if (mt.pos == blk.end) blk.fill();
+                int p = mt.pos;
+                const int e = blk.end;
+                uint32_t *Jp = J.data();
+                while (p < e && i >= lo) {
+                    const uint32_t v = blk.out[p++] & mask;
+                    Jp[i] = v;
+                    i -= (v <= (uint32_t)i) ? 1 : 0;
+                }
+                mt.pos = p;
+            }
+        }
+    }
+    constexpr int KMAX = 32;
+    if (k <= KMAX) {
+        uint32_t pos[KMAX];
+        for (int32_t q = 0; q < k; ++q) pos[q] = (uint32_t)q;
+        const int64_t head = std::min<int64_t>(n, (int64_t)k);
+        for (int64_t i = 1; i < head; ++i) {                 // i < k: a tracked position can also BE i
+            const uint32_t j = J[(size_t)i];
+            for (int32_t q = 0; q < k; ++q) {
+                if (pos[q] == (uint32_t)i) pos[q] = j;
+                else if (pos[q] == j) pos[q] = (uint32_t)i;
+            }
+        }
+        if (k == 5) {                                        // the reference's num_samples
+            uint32_t p0 = pos[0], p1 = pos[1], p2 = pos[2], p3 = pos[3], p4 = pos[4];
+            // a hit is rare (k / i per draw): test 16 draws at a time (a reduction the compiler vectorises) and
+            // walk a chunk one by one only when it holds a hit
+            const uint32_t *Jp = J.data();
+            int64_t i = head;
+            for (; i + 16 <= n; i += 16) {
+                uint32_t hit = 0;
+                for (int e = 0; e < 16; ++e) {
+                    const uint32_t j = Jp[i + e];
+                    hit |= (uint32_t)(j == p0) | (uint32_t)(j == p1) | (uint32_t)(j == p2) | (uint32_t)(j == p3) | (uint32_t)(j == p4);
+                }
+                if (hit) {
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t j = Jp[i + e], ii = (uint32_t)(i + e);
+                        p0 = (j == p0) ? ii : p0; p1 = (j == p1) ? ii : p1; p2 = (j == p2) ? ii : p2;
+                        p3 = (j == p3) ? ii : p3; p4 = (j == p4) ? ii : p4;
+                    }
+                }
+            }
+            for (; i < n; ++i) {
+                const uint32_t j = Jp[i], ii = (uint32_t)i;
+                p0 = (j == p0) ? ii : p0; p1 = (j == p1) ? ii : p1; p2 = (j == p2) ? ii : p2;
+                p3 = (j == p3) ? ii : p3; p4 = (j == p4) ? ii : p4;
+            }
+            pos[0] = p0; pos[1] = p1; pos[2] = p2; pos[3] = p3; pos[4] = p4;
+        } else {
+            for (int64_t i = head; i < n; ++i) {
+                const uint32_t j = J[(size_t)i];
+                for (int32_t q = 0; q < k; ++q) pos[q] = (j == pos[q]) ? (uint32_t)i : pos[q];
+            }
+        }
+        for (int32_t q = 0; q < k; ++q) out[q] = (int64_t)pos[q];
+        return;
+    }
+    // many samples: the shuffle itself, replayed from the stored draws
     thread_local std::vector<int32_t> a;
     a.resize((size_t)n);
     for (int64_t i = 0; i < n; ++i) a[(size_t)i] = (int32_t)i;
-    for (int64_t i = n - 1; i >= 1; --i) {
-        // random_interval(i): smallest bit mask >= i, rejection on masked 32-bit outputs (i <= 0xffffffff here)
-        uint32_t mask = (uint32_t)i;
-        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-        uint32_t v;
-        while ((v = (mt.next32() & mask)) > (uint32_t)i) {}
-        const int32_t t = a[v];
-        a[v] = a[(size_t)i];
-        a[(size_t)i] = t;
-    }
+    for (int64_t i = n - 1; i >= 1; --i) std::swap(a[(size_t)i], a[J[(size_t)i]]);
     for (int32_t q = 0; q < k; ++q) out[q] = a[(size_t)q];
 }
 

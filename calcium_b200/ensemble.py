@@ -110,6 +110,7 @@ class _DeviceGeometry:
         self.label_maps: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.edge_maps: Dict[Tuple[int, int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.plans: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._capacity: Dict[Tuple[int, int], int] = {}
 
     def plan(self, precision: int, n_cta: int = 1) -> torch.Tensor:
         """Device copy of the K1 layout plan (``cab200_plan_slots`` / ``cab200_plan_cluster``) for this
@@ -122,25 +123,45 @@ class _DeviceGeometry:
             self.plans[(precision, n_cta)] = t
         return t
 
+    def capacity(self, n_cta: int, precision: int = _lib.FP64_STRICT) -> int:
+        """Clusters of ``n_cta`` CTAs of this geometry's kernel that are resident at once on the geometry's device
+        (``cab200_cluster_capacity``; <= 0: that cluster size does not apply).  On a 148-SM B200: 74 clusters of 2,
+        45 of 3, 33 of 4, 15 of 8 -- a cluster lives inside one GPC."""
+        key = (n_cta, precision)
+        c = self._capacity.get(key)
+        if c is None:
+            with torch.cuda.device(self.rowptr.device):
+                c = int(_lib.load().cab200_cluster_capacity(self.n, self.max_row, n_cta, precision))
+            self._capacity[key] = c
+        return c
+
     def auto_cluster(self, count: int = 1 << 30, n_sm: int = 148) -> int:
-        """CTAs per pouch when the caller leaves the choice to the library.  Above 1536 cells (what a
-        512-thread CTA holds without spilling) always a cluster of 4.  Medium-sized pouches (> 1024
-        cells) take one CTA each when there are enough of them to fill the machine, and a cluster of 2
-        or 4 when fewer than half / a quarter of the SMs would otherwise be busy -- a lone medium pouch
-        finishes in 13 ms instead of 25.  Smaller pouches are latency bound per step (a cluster's halo
-        exchange would only add to that) and stay on one CTA."""
-        if not self.unit:
+        """CTAs per pouch when the caller leaves the choice to the library: the option with the shortest predicted
+        time for ``count`` pouches of this geometry, time = waves x step time, waves = ceil(count / resident pouches).
+        Step times as measured on B200 (scripts/time_cluster.py): one CTA holds up to 1536 cells without spilling at
+        0.88 ns per cell and step (1.32 us for 1500 cells), beyond that 1.94 ns per cell; a cluster CTA costs 1.4 ns per
+        cell and step plus nothing else (the halo exchange latency sits inside that figure) -- so a lone medium pouch
+        finishes in 13 ms on 4 CTAs instead of 24 ms on one, 148 of them are fastest on one CTA each, and 40 large
+        pouches run faster as clusters of 3 (45 resident) than as clusters of 4 (33 resident, two waves).  Pouches of
+        up to 1024 cells are latency bound per step and stay on one CTA; above 4 x 1536 cells only a cluster of 8
+        fits (up to 12 288 cells)."""
+        if not self.unit or self.n <= 1024:
             return 1
         if self.n > 4 * 1536:
-            return 8                 # up to 8 x 1536 = 12 288 cells (the portable cluster maximum)
-        if self.n > 1536:
-            return 4
-        if self.n > 1024:
-            if 4 * count <= n_sm:
-                return 4
-            if 2 * count <= n_sm:
-                return 2
-        return 1
+            return 8
+        count = max(1, min(int(count), 1 << 20))
+        options = []
+        if self.n <= 4096:
+            per_cell = 0.88e-3 if self.n <= 1536 else 1.94e-3
+            options.append((-(-count // n_sm) * per_cell * self.n, 1))
+        for nc in (2, 3, 4):
+            cells = -(-self.n // nc)
+            if cells > 1536 or (nc == 3 and cells <= 1024):      # clusters of 3 exist for the 512 x 3 shape only
+                continue
+            cap = self.capacity(nc)
+            if cap > 0:
+                options.append((-(-count // cap) * 1.4e-3 * cells, nc))
+        return min(options)[1] if options else 4
 
 
 PLAN_ITERS = int(os.environ.get("CALCIUM_B200_PLAN_ITERS", "300000"))
@@ -516,6 +537,30 @@ class Ensemble:
                 _stream_ptr(self.device))
             _lib.check(rc, "cab200_sim_batch")
         return self.frames
+
+    def continue_from_last_frame(self) -> None:
+        """Makes the state of the last captured frame (it must be step T-1) the initial state of the next
+        ``simulate(upload=False)``: c, p and r are copied on the device into the input block; s is a function of c
+        (``core/pouch.py:95`` and ``:322`` are the same expression), so the continuation is bit-identical to one
+        long run.  This is how horizons whose every-step history exceeds HBM are run: segment by segment, each
+        segment's frames consumed (copied out, rasterised, or overwritten) before the next one lands."""
+        if self.frames is None or self._d_in is None or self.F == 0 or int(self.frame_steps[-1]) != self.T - 1:
+            raise RuntimeError("continue_from_last_frame needs a finished simulate() whose last captured step is T-1")
+        if self.precision != _lib.FP64_STRICT:
+            raise RuntimeError("continue_from_last_frame: FP64 only (FP32 frames are rounded copies of the inputs)")
+        np_, tc = self.P * _lib.NPARAM, self.total_cells
+        with torch.cuda.device(self.device):
+            for g in range(len(self.dgeo)):
+                idx = np.nonzero(self.geom_id == g)[0]
+                n = int(self.g_ncell[g])
+                contiguous = len(idx) > 0 and np.array_equal(idx, np.arange(idx[0], idx[0] + len(idx)))
+                groups = [idx] if contiguous else [np.array([i]) for i in idx]
+                for grp in groups:
+                    a = int(self.cell_off[grp[0]])
+                    cnt = len(grp)
+                    last = self.frames[a * 4 * self.F: (a + cnt * n) * 4 * self.F].view(cnt, self.F, 4, n)[:, -1]
+                    for dst, state in ((0, 0), (1, 1), (2, 3)):           # c0 <- c, p0 <- p, r0 <- r
+                        self._d_in[np_ + dst * tc + a: np_ + dst * tc + a + cnt * n].view(cnt, n).copy_(last[:, state])
 
     def frames_of(self, i: int) -> torch.Tensor:
         """Device view ``[F, 4, n_i]`` of pouch i's captured frames."""

@@ -32,7 +32,7 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     print("=" * 100)
-    for k in KEYS + sorted(k_ for k_ in d if "tensor" in k_ and k_ not in KEYS):     # every tensor-pipe counter the report holds
+    for k in KEYS + sorted(k_ for k_ in d if "tensor" in k_ and k_ not in KEYS and (k_.endswith(".sum") or k_.endswith(".avg.pct_of_peak_sustained_active"))):     # every tensor-pipe counter the report holds
         if k in d:
             u = units[hdr.index(k)]
             print(f"{k:88s} {d[k]:>16s} {u}")

@@ -111,7 +111,8 @@ def test_layout_choices_never_change_results(env):
 
 
 @pytest.mark.parametrize("size,n_cta,count,T", [("xsmall", 2, 3, 4000), ("small", 2, 3, 4000), ("medium", 2, 3, 6000),
-                                                  ("medium", 4, 5, 6000), ("large", 4, 2, 5000)])
+                                                  ("medium", 4, 5, 6000), ("large", 4, 2, 5000),
+                                                  ("large", 3, 2, 3000), ("large", 8, 2, 3000), ("xlarge", 8, 2, 3000)])
 def test_cluster_path_bit_exact(env, size, n_cta, count, T):
     """A pouch split over a thread-block cluster (halo entries pushed through distributed shared
     memory, cluster-wide step barrier) produces the same bits as the oracle."""
@@ -126,6 +127,24 @@ def test_cluster_path_bit_exact(env, size, n_cta, count, T):
         want = _oracle_frames(O, s, T, steps)
         got = ens.frames_of(i).cpu().numpy()
         assert np.array_equal(want, got), f"{size} x{n_cta} [{i}] max abs diff {np.abs(want - got).max():.3e}"
+
+
+def test_xlarge_takes_a_cluster_of_eight(env):
+    """`xlarge` (core/geometry_loader.py:36; 6500 synthetic cells) exceeds 4 x 1536 cells: cluster="auto" runs it
+    on 8 CTAs, next to a large pouch on 4, in one call; a pouch beyond 8 x 1536 cells is refused with the limit."""
+    E, O = env["E"], env["O"]
+    specs = E.make_specs(1, size="xlarge", first_seed=3) + E.make_specs(1, size="large", first_seed=4)
+    T, steps = 2500, [0, 1250, 2499]
+    ens = E.Ensemble(specs, T=T, frame_steps=steps, device=env["dev"])
+    assert sorted(ens.g_cluster.tolist()) == [4, 8]
+    ens.simulate()
+    assert not ens.check_status().any()
+    for i, s in enumerate(specs):
+        assert np.array_equal(_oracle_frames(O, s, T, steps), ens.frames_of(i).cpu().numpy()), i
+    lay = np.zeros(4, dtype=np.int64)
+    lib = env["lib"]
+    assert lib.cab200_cluster_layout(8 * 1536 + 1, 8, 64, env["L"].as_i64p(lay)) != 0
+    assert b"1536" in lib.cab200_last_error()
 
 
 def test_cluster_auto_for_large_and_mixed_ensembles(env):
@@ -680,3 +699,45 @@ def test_batch_sharded_over_two_gpus_equals_one(env, tmp_path):
     assert outs[0][0].keys() == outs[1][0].keys() and len(outs[0][0]) > 0
     assert all(outs[0][0][k] == outs[1][0][k] for k in outs[0][0])
     assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
+
+
+def test_segmented_run_continues_bit_exactly(env):
+    """Ensemble.continue_from_last_frame: two segments of an every-step capture, the second started on the device from
+    the first one's last frame, equal one long run bit for bit (how histories larger than HBM are produced, BASELINE
+    config 4) -- mixed sizes, one of them a cluster."""
+    E = env["E"]
+    specs = E.make_specs(2, size="small", first_seed=11) + E.make_specs(1, size="large", first_seed=12) + \
+        E.make_specs(1, size="small", first_seed=13)
+    T1, T2 = 1201, 801
+    whole = E.Ensemble(specs, T=T1 + T2 - 1, frame_steps=range(T1 + T2 - 1), device=env["dev"])
+    whole.simulate(); whole.synchronize()
+    seg = E.Ensemble(specs, T=T1, frame_steps=range(T1), device=env["dev"])
+    seg.simulate()
+    a = [seg.frames_of(i).cpu().numpy().copy() for i in range(len(specs))]
+    seg.continue_from_last_frame()
+    seg2 = E.Ensemble(specs, T=T2, frame_steps=range(T2), device=env["dev"])
+    seg2.upload(); seg2._d_in.copy_(seg._d_in)
+    seg2.simulate(upload=False); seg2.synchronize()
+    assert not whole.check_status().any() and not seg2.check_status().any()
+    for i in range(len(specs)):
+        w = whole.frames_of(i).cpu().numpy()
+        assert np.array_equal(w[:T1], a[i]), i
+        assert np.array_equal(w[T1 - 1:], seg2.frames_of(i).cpu().numpy()), i
+
+
+def test_k1_protocol_checks(env):
+    """K1 compiled with -DCAB_K1_CHECK (the split-phase barrier's buffer-reuse invariants and the cluster halo
+    protocol as run-time checks, integrate.cuh) on oversubscribed single-CTA and cluster ensembles: no step may see
+    a buffer outside its time window, and the checked build produces the same bits.  Stands in for
+    compute-sanitizer's racecheck, which this GPU pool does not offer."""
+    import json, subprocess, sys
+    from calcium_b200 import build
+    lib = build.build_k1_check()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "k1_check_run.py")], capture_output=True, text=True,
+                         env=dict(os.environ, CALCIUM_B200_LIB=lib), timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out["lib"] == lib and len(out["cases"]) == 6
+    for c in out["cases"]:
+        assert c["status_or"] == 0 and not c["protocol_violation"] and c["bit_exact"], c

@@ -133,7 +133,9 @@ def test_cluster_planner(lib):
             off += hcount[q]
             assert hcount[q] <= 384                                            # CAB_HMAX
         assert hcount.sum() < 0.25 * n                                         # thin boundaries
-    assert lib.cab200_cluster_layout(1500, 3, 64, _lib.as_i64p(lay)) == -1
+    assert lib.cab200_cluster_layout(1500, 5, 64, _lib.as_i64p(lay)) == -1        # sizes 2, 3, 4, 8
+    assert lib.cab200_cluster_layout(3255, 3, 64, _lib.as_i64p(lay)) == 0 and lay[:2].tolist() == [512, 3]
+    assert lib.cab200_cluster_layout(6500, 8, 64, _lib.as_i64p(lay)) == 0 and lay[:2].tolist() == [512, 2]
     assert lib.cab200_cluster_layout(3255, 2, 64, _lib.as_i64p(lay)) == -3      # 1628 cells per CTA > 1536
     assert lib.cab200_cluster_layout(20000, 4, 64, _lib.as_i64p(lay)) == -3
 
@@ -229,14 +231,18 @@ def test_lpt_partition():
 
 
 def test_auto_cluster_policy():
-    """CTAs per pouch under cluster="auto": large always 4; medium by how many there are; small 1."""
+    """CTAs per pouch under cluster="auto": the shortest predicted time given how many clusters of each size are
+    resident at once (B200: 74 / 45 / 33 / 15 clusters of 2 / 3 / 4 / 8)."""
     from types import SimpleNamespace as NS
     from calcium_b200.ensemble import _DeviceGeometry as DG
-    pick = lambda n, count, unit=True: DG.auto_cluster(NS(unit=unit, n=n), count, 148)
-    assert pick(3255, 1) == 4 and pick(3255, 1000) == 4
-    assert pick(1500, 1) == 4 and pick(1500, 37) == 4 and pick(1500, 38) == 2
+    caps = {2: 74, 3: 45, 4: 33, 8: 15}
+    pick = lambda n, count, unit=True: DG.auto_cluster(NS(unit=unit, n=n, capacity=lambda nc: caps[nc]), count, 148)
+    assert pick(3255, 1) == 4 and pick(3255, 33) == 4 and pick(3255, 148) == 4
+    assert pick(3255, 40) == 3 and pick(3255, 45) == 3 and pick(3255, 90) == 3      # 33 resident clusters of 4 would need one more wave
+    assert pick(1500, 1) == 4 and pick(1500, 33) == 4 and pick(1500, 34) == 2
     assert pick(1500, 74) == 2 and pick(1500, 75) == 1 and pick(1500, 148) == 1
     assert pick(500, 1) == 1 and pick(200, 3) == 1
+    assert pick(6500, 1) == 8 and pick(6500, 100) == 8
     assert pick(3255, 1, unit=False) == 1          # general weights: single-CTA kernel only
 
 
