@@ -32,7 +32,7 @@ EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
            "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_frames_tmp_bytes", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_k1_legacy_rows", "cab200_sim_layout",
            "cab200_cluster_layout", "cab200_cluster_capacity", "cab200_plan_cluster",
            "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
-           "cab200_edge_maps", "cab200_raster_edges_batch", "cab200_legacy_choice", "cab200_sample_background", "cab200_defect_pass",
+           "cab200_edge_maps", "cab200_raster_edges_batch", "cab200_legacy_choice", "cab200_sample_background", "cab200_prompts_pouch", "cab200_np_percentile80_sqrt", "cab200_legacy_randint", "cab200_defect_pass",
            "cab200_encode_tables_bytes", "cab200_encode_tables", "cab200_encode_scratch_bytes", "cab200_encode_batch",
            "cab200_encode_geometry_bytes", "cab200_encode_geometry", "cab200_publish_to_host", "cab200_edt_scratch_bytes", "cab200_edt_classes",
            "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_peak_smem", "cab200_selftest_division",
@@ -132,6 +132,14 @@ def load() -> ctypes.CDLL:
         c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cab200_defect_pass.restype = c_int
     lib.cab200_defect_pass.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.cab200_prompts_pouch.restype = c_int
+    lib.cab200_prompts_pouch.argtypes = [c_void_p, c_int, c_void_p, c_double, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.cab200_np_percentile80_sqrt.restype = c_int
+    lib.cab200_np_percentile80_sqrt.argtypes = [c_void_p, c_int64, c_void_p]
+    lib.cab200_legacy_randint.restype = c_int
+    lib.cab200_legacy_randint.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     lib.cab200_sample_background.restype = c_int
     lib.cab200_sample_background.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p,
                                              POINTER(c_int32), c_int32, c_void_p, POINTER(c_int64)]

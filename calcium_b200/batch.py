@@ -313,7 +313,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 tables: Dict[int, Any] = {}
                 cmask_host: Dict[int, np.ndarray] = {}
                 if want_prompts:
-                    from .prompts import frame_prompts, prompt_tables
+                    from .prompts import frame_prompts, pouch_prompts, prompt_tables
                 for li in range(len(part)):
                     g = int(ens.geom_id[li])
                     if want_prompts and g not in tables:
@@ -332,6 +332,13 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     rs.set_state(d["rng_state"])
                     g = int(ens.geom_id[li])
                     files = []
+                    if want_prompts and not host_chain[li]:
+                        # clean frames: nothing but the prompts draws from the pouch's generator, so all its frames go
+                        # through one native call outside the interpreter lock (cab200_prompts_pouch) -- same draws,
+                        # same files, same generator state as the frame loop below
+                        ppaths = [os.path.join(prompt_dir, names[li][fi] + ".json") for fi in range(len(steps))]
+                        nent, _ = pouch_prompts(tables[g], ca_host[li], rs, paths=ppaths if write_files else None)
+                        return [ppaths[fi] for fi in range(len(steps)) if nent[fi] >= 0], rs.get_state()
                     with torch.cuda.device(ens.device):
                         for fi in range(len(steps)):
                             try:

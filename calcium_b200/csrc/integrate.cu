@@ -188,7 +188,7 @@ extern "C" int cab200_cluster_layout(int n, int n_cta, int precision, int64_t ou
     const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
     const int copies = integrate_smem_bytes(0, threads * cpt, elem2, 2, true, CAB_HMAX) <= 227 * 1024 ? 2 : 1;
     out[0] = threads; out[1] = cpt; out[2] = copies;
-    out[3] = (int64_t)integrate_smem_bytes(0, threads * cpt, elem2, copies, true, CAB_HMAX);
+    out[3] = (int64_t)integrate_smem_bytes(0, threads * cpt, elem2, copies, true, CAB_HMAX, n);
     return CAB200_OK;
 }
 
@@ -359,7 +359,7 @@ extern "C" int cab200_sim_batch(
             KernelFn cfn = (precision == CAB200_FP64_STRICT) ? pick_cluster_kernel_f64(cth, ccpt, ncta, cep, ccopies)
                                                              : pick_cluster_kernel_f32(cth, ccpt, ncta, cep, ccopies);
             if (!cfn) { set_error("cab200_sim_batch: no cluster kernel for %dx%d x%d", cth, ccpt, ncta); return CAB200_EINVAL; }
-            const size_t csmem = integrate_smem_bytes(0, cth * ccpt, el2, ccopies, true, CAB_HMAX);
+            const size_t csmem = integrate_smem_bytes(0, cth * ccpt, el2, ccopies, true, CAB_HMAX, n);
             CAB_CUDA(cudaFuncSetAttribute((const void *)cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
             SimArgs ca;
             ca.pouch_list = d_list + g_begin[g];
@@ -413,7 +413,9 @@ extern "C" int cab200_sim_batch(
             return CAB200_ESIZE;
         }
         const int ep = k1_ep(max_row);      // rows of up to 10 entries use the 5-pair variant
-        const bool unit = g_unit[g] != 0;
+        // the unit-weight kernel needs the planner's cell -> slot map (rows with many entries on one side of their
+        // diagonal must share a warp, k1_layout.cuh); without a plan the general-weights kernel runs: same bits, slower
+        const bool unit = g_unit[g] != 0 && plan_off >= 0;
         const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
         const int np = (n + 31) & ~31;
         const int copies = sim_copies(n, unit, elem2, threads * cpt);

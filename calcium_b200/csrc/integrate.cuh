@@ -9,10 +9,7 @@
 //              [NP, 2NP)          (COPIES == 2) a second copy of the values at NP + (slot_i ^ 4),
 //                                 i.e. in the bank group 4 away: every gather may read either copy,
 //                                 which the host planner uses to dodge bank conflicts
-//              [COPIES*NP, +NP)   (UNIT) diagonal entries (L_ii*c_i, L_ii*p_i), indexed by slot, used only by
-//                                 the few "legacy" cells whose row does not fit the register-diagonal
-//                                 layout (k1_layout.cuh)
-//              [(COPIES+1)*NP]    the zero entry (+0, +0), never written after the prologue
+//              [COPIES*NP]        the zero entry (+0, +0), never written after the prologue
 //            Step t reads buffer t&1 and writes buffer (t+1)&1: one split barrier per step.
 //   regs     per owned cell: c, p, s, r, V_PLC, L_ii and the shared addresses of the row's entries
 //            (time-invariant), plus the pouch's parameters (uniform registers).
@@ -21,9 +18,9 @@
 // A Laplacian row is then a branch-free gather: sum = +0; for each stored entry in CSR order
 // sum += entry -- off-diagonal entries index the neighbour's value entry (1.0*x == x exactly for the
 // adjacency-minus-degree Laplacian), the diagonal term L_ii*(c_i, p_i) is computed from the owner's
-// registers and added at its place in the order (between positions EP-1 and EP of the unrolled
-// sequence, see k1_layout.cuh: no shared-memory store or load for it), and unused positions read the
-// zero entry.  Because the sum starts from +0.0 it can never be -0.0, so adding the +0.0 padding is an
+// registers and added at its place in the order (after D positions of the unrolled sequence, D the
+// warp's diagonal point, see k1_layout.cuh: no shared-memory store or load for it), and unused positions
+// read the zero entry.  Because the sum starts from +0.0 it can never be -0.0, so adding the +0.0 padding is an
 // exact no-op and the result is bit-identical to scipy's csr_matvec followed by the reference's
 // `D * (...)`.
 //
@@ -59,10 +56,11 @@ struct SimArgs {
 };
 
 // Shared-memory bytes K1 needs for a pouch padded to `np` slots.  Entries per step-parity buffer:
-// `copies` value regions, the legacy diagonal entries (unit Laplacian only), the zero entry, the halo.
+// `copies` value regions, the zero entry, the halo.
 static inline size_t integrate_buf_entries(int nr, int copies, bool unit, int hmax)
 {
-    return (size_t)(copies + (unit ? 1 : 0)) * nr + 1 + hmax;
+    (void)unit;
+    return (size_t)copies * nr + 1 + hmax;
 }
 // persistent table behind the two buffers: orig_of[NSLOT] u16
 static inline size_t integrate_tail_bytes(int nslot, size_t elem2, bool unit)
@@ -76,9 +74,15 @@ static inline size_t integrate_buf_stride(int np, int nslot, size_t elem2, int c
     if (2 * fixed + integrate_tail_bytes(nslot, elem2, unit) <= 227 * 1024) return fixed;     // == BufGeom::STRIDE
     return (integrate_buf_entries(np, copies, unit, hmax) * elem2 + 127) & ~(size_t)127;       // runtime stride
 }
-static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2, int copies, bool unit, int hmax = 0)
+// The prologue's scratch (7 bytes per cell of the WHOLE pouch: row lengths, slots, copy masks, parts, diagonal
+// indices) lies over the two buffers, which are initialised after it is dead; for a cluster CTA of a big pouch it
+// can be larger than the buffers (n_total = cells of the pouch; 0: not more than the slots, single CTA).
+static inline size_t integrate_scratch_bytes(int n_total) { return ((size_t)7 * ((n_total + 31) & ~31) + 127) & ~(size_t)127; }
+static inline size_t integrate_smem_bytes(int np, int nslot, size_t elem2, int copies, bool unit, int hmax = 0, int n_total = 0)
 {
-    return 2 * integrate_buf_stride(np, nslot, elem2, copies, unit, hmax) + integrate_tail_bytes(nslot, elem2, unit);
+    const size_t bufs = 2 * integrate_buf_stride(np, nslot, elem2, copies, unit, hmax);
+    const size_t scr = integrate_scratch_bytes(n_total);
+    return (bufs > scr ? bufs : scr) + integrate_tail_bytes(nslot, elem2, unit);
 }
 
 // One Euler step for one cell, reference source order (core/pouch.py:77-102), every operation
@@ -218,7 +222,7 @@ template <> struct Smem2<float> {
 template <typename R, int NSLOT, int COPIES, bool UNIT, int HMAX = 0>
 struct BufGeom {
     static constexpr size_t ESZ = 2 * sizeof(R);
-    static constexpr int DIAGR = UNIT ? 1 : 0;            // a slot-indexed region of diagonal entries (legacy rows)
+    static constexpr int DIAGR = 0;                       // (round 1 kept a region of diagonal entries here)
     static constexpr size_t STRIDE = ((((size_t)(COPIES + DIAGR) * NSLOT + 1 + HMAX) * ESZ) + 127) & ~(size_t)127;
     static constexpr size_t TAIL = 2 * (size_t)NSLOT + 64;
     static constexpr bool CSTRIDE = 2 * STRIDE + TAIL <= 227 * 1024;
@@ -250,8 +254,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     constexpr int NSLOT = THREADS * CPT;
     constexpr int EMAX = 2 * EP;
     constexpr int HMAX = (NCTA > 1) ? CAB_HMAX : 0;
-    constexpr int DIAGR = UNIT ? 1 : 0;
-    constexpr int DPAIR = (EP & 1) ? EP - 1 : EP - 2;     // k1_diag_pair(EP)
+    constexpr int DIAGR = 0;
     typedef BufGeom<R, NSLOT, COPIES, UNIT, HMAX> G;
     static_assert(NCTA == 1 || (G::CSTRIDE && UNIT), "cluster kernels need the compile-time layout");
     constexpr bool CSTRIDE = G::CSTRIDE;
@@ -263,10 +266,13 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     const int npr = CSTRIDE ? NSLOT : np;                 // entries per value region
     const uint32_t stride = CSTRIDE ? (uint32_t)G::STRIDE
                                     : (uint32_t)(((((size_t)(COPIES + DIAGR) * np + 1) * ESZ) + 127) & ~(size_t)127);
-    R2 *buf1 = reinterpret_cast<R2 *>(smem_raw + stride);
-    uint16_t *orig_of = reinterpret_cast<uint16_t *>(smem_raw + 2 * (size_t)stride);   // [NSLOT]
-    // prologue scratch aliases buffer 1 (initialised after the scratch is dead)
-    unsigned char *scr = reinterpret_cast<unsigned char *>(buf1);
+    // persistent table behind the buffers (and behind the prologue scratch, which may be the larger of the two in a
+    // cluster CTA: integrate_scratch_bytes)
+    const size_t scr_bytes = (NCTA > 1) ? (((size_t)7 * np + 127) & ~(size_t)127) : 0;
+    const size_t tail_off = 2 * (size_t)stride > scr_bytes ? 2 * (size_t)stride : scr_bytes;
+    uint16_t *orig_of = reinterpret_cast<uint16_t *>(smem_raw + tail_off);   // [NSLOT]
+    // prologue scratch lies over the two buffers (initialised after the scratch is dead)
+    unsigned char *scr = smem_raw;
     uint8_t *rlen = scr;                                                           // [n]
     uint16_t *slot_of = reinterpret_cast<uint16_t *>(scr + np);                    // [n]
     uint16_t *copy_sel = slot_of + np;                                             // [n]
@@ -355,13 +361,12 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     // Slot of (warp w, group k, lane l) = (w*CPT + k)*32 + l: the host planner deals cells with similar
     // row shapes to the same warp, so ONE warp-uniform position range [start, end) serves all CPT*32
     // cells of a warp.  k1_row (k1_layout.cuh) places a row's entries among the EMAX positions: entries
-    // before the diagonal right-aligned below EP, the others left-aligned from EP; the diagonal itself
-    // is added from registers inside the pair DPAIR.  Everything else points at the zero entry; the
+    // before the diagonal right-aligned below the warp's diagonal point D, the others left-aligned from D;
+    // the diagonal itself is added from registers inside the pair `dpair`.  Everything else points at the zero entry; the
     // step loop enters the fully unrolled position sequence at `start` through one jump and leaves it
     // at `end`.  ent[k][pos] is the 32-bit shared address of the entry inside buffer 0; buffer 1 is
     // +stride.
     const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t diag_off = (uint32_t)(COPIES * npr) * ESZ;                // diagonal entries (legacy rows), by slot
     const uint32_t zero_addr = sb0 + (uint32_t)((COPIES + DIAGR) * npr) * ESZ;
     const uint32_t halo_addr = zero_addr + ESZ;
     R c[CPT], p[CPT], s[CPT], r[CPT], vplc[CPT], dcoef[CPT];
@@ -371,7 +376,20 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     bool live[CPT];
     K1Row row[CPT];
     int min_first = EMAX, max_last = 0;
-    uint32_t legmask = 0;           // bit k: cell k keeps a shared-memory diagonal entry (legacy row layout)
+    // the warp's diagonal point (k1_layout.cuh): one D for the CPT*32 cells of the warp, from the largest number of
+    // entries before / after the diagonal among them -- the planner has made sure these go together
+    int max_nb = 0, max_na = 0;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int cell = (int)orig_of[(warp * CPT + k) * 32 + lane];
+        if (cell != 0xffff) {
+            max_nb = max(max_nb, k1_row_nb(rlen[cell], rdg[cell]));
+            max_na = max(max_na, k1_row_na(rlen[cell], rdg[cell]));
+        }
+    }
+    int dpt = UNIT ? k1_warp_diag(EP, __reduce_max_sync(0xffffffffu, max_nb), __reduce_max_sync(0xffffffffu, max_na)) : EP;
+    if (dpt < 0) { bad = 1; dpt = EP; }
+    const int dpair = k1_diag_pair(EP, dpt);          // warp-uniform: the pair of positions that carries the diagonal
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int slot = (warp * CPT + k) * 32 + lane;
@@ -380,17 +398,17 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         own[k] = sb0 + (uint32_t)slot * ESZ;
         rowbeg[k] = 0; len[k] = 0;
         c[k] = p[k] = s[k] = r[k] = vplc[k] = dcoef[k] = (R)0;
-        row[k] = k1_row(UNIT, EP, 0, -1);
+        row[k] = k1_row(UNIT, EP, 0, -1, dpt);
         if (live[k]) {
             len[k] = rlen[cell];
             rowbeg[k] = a.rowptr[cell];
-            row[k] = k1_row(UNIT, EP, len[k], rdg[cell]);
+            row[k] = k1_row(UNIT, EP, len[k], rdg[cell], dpt);
             c[k] = (R)a.c0[coff + cell];
             p[k] = (R)a.p0[coff + cell];
             r[k] = (R)a.r0[coff + cell];
             vplc[k] = (R)a.vplc[coff + cell];
             if (len[k] > 0) { min_first = min(min_first, row[k].first); max_last = max(max_last, row[k].last); }
-            if (UNIT && row[k].legacy) legmask |= 1u << k;
+            if (UNIT && row[k].legacy) bad = 1;       // several diagonal entries: this geometry needs the general kernel
         }
         s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                          // core/pouch.py:322
     }
@@ -411,14 +429,13 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
     };
     int start, end;
     k1_warp_range(UNIT, EP, __reduce_min_sync(0xffffffffu, min_first), __reduce_max_sync(0xffffffffu, max_last),
-                  &start, &end);
-    const bool wleg = UNIT && __any_sync(0xffffffffu, legmask != 0u);  // this warp owns legacy cells
+                  dpt, &start, &end);
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int slot = (warp * CPT + k) * 32 + lane;
         const int cell = live[k] ? (int)orig_of[slot] : 0;
         const uint32_t sel = live[k] ? (uint32_t)copy_sel[cell] : 0u;
-        if (UNIT && live[k] && !row[k].legacy && row[k].skip)                 // register diagonal: its weight
+        if (UNIT && live[k] && row[k].skip)                                   // register diagonal: its weight
             dcoef[k] = (R)a.vals[rowbeg[k] + row[k].split];
 #pragma unroll
         for (int pos = 0; pos < EMAX; ++pos) {
@@ -437,8 +454,7 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
                     o = sb0 + j * ESZ;
                     if (UNIT) {
                         const double w = a.vals[rowbeg[k] + e];
-                        if (col == cell) { dcoef[k] = (R)w; o = own[k] + diag_off; }   // only legacy rows gather their diagonal
-                        else if (w != 1.0) bad = 1;
+                        if (col == cell || w != 1.0) bad = 1;       // the diagonal is never gathered (row[k].skip)
                     }
                 }
             }
@@ -546,17 +562,8 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
                 }                                                                                 \
         }                                                                                         \
     }
-    // A legacy cell's diagonal entry is read by nobody but its owner (in the owner's next gather), so it
-    // needs no barrier: it is rewritten AFTER the arrival, off the step's critical path.
-#define CAB_PUBLISH_LEGACY(IMM, ROFF)                                                             \
-    if (wleg) {                                                                                   \
-        _Pragma("unroll") for (int k = 0; k < CPT; ++k)                                           \
-            if ((legmask >> k) & 1u)                                                              \
-                M::template st<IMM>(own[k] + diag_off + (ROFF), S::mul(dcoef[k], c[k]), S::mul(dcoef[k], p[k])); \
-    }
 #pragma unroll
     for (int k = 0; k < CPT; ++k) { CAB_PUBLISH(0, 0u, k, c[k], p[k], -1) }
-    CAB_PUBLISH_LEGACY(0, 0u)
     __syncthreads();
     if (NCTA > 1) cluster_sync_all();    // initial values, halo entries included, are in place
     const uint32_t halo_bytes = (NCTA > 1) ? (uint32_t)hcount[rank] * ESZ : 0u;   // pushed to this CTA per step
@@ -627,25 +634,17 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 #else
 #define CAB_EXIT_CHECK(P0) if (end <= (P0) + 2) break;
 #endif
-// The register diagonal of every owned cell: L_ii * (c_i, p_i), each product rounded like the stored
-// diagonal entry of round 1 was (dcoef is 0 for empty slots and rows without a diagonal: +-0 never
-// changes a sum that cannot be -0).
+// The register diagonal of every owned cell: L_ii * (c_i, p_i), each product rounded like a stored diagonal
+// entry would be (dcoef is 0 for empty slots and rows without a diagonal: +-0 never changes a sum that cannot
+// be -0).
 #define CAB_DIAG_ADD                                                                              \
-    if (!wleg) {                                                                                  \
-        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
-            sc[k] = S::add(sc[k], S::mul(dcoef[k], c[k])); sp[k] = S::add(sp[k], S::mul(dcoef[k], p[k])); \
-        }                                                                                         \
-    } else {    /* warps with legacy cells (rare): those cells' term comes from their gathered entry */ \
-        _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                         \
-            const bool lg_ = (legmask >> k) & 1u;                                                 \
-            sc[k] = S::add(sc[k], lg_ ? (R)0 : S::mul(dcoef[k], c[k]));                           \
-            sp[k] = S::add(sp[k], lg_ ? (R)0 : S::mul(dcoef[k], p[k]));                           \
-        }                                                                                         \
+    _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                             \
+        sc[k] = S::add(sc[k], S::mul(dcoef[k], c[k])); sp[k] = S::add(sp[k], S::mul(dcoef[k], p[k])); \
     }
 
 // One pair of row positions for every owned cell: all loads of the pair first (2*CPT independent
-// 16-byte loads in flight per thread), then the additions in position order.  The pair DPAIR also
-// carries the register diagonal at its place in the order.
+// 16-byte loads in flight per thread), then the additions in position order.  The warp's pair `dpair` also
+// carries the register diagonal at its place in the order (a warp-uniform test per pair).
 #define CAB_GATHER_PAIR(IMM, ROFF, P0)                                                            \
     {                                                                                             \
         R2 va[CPT], vb[CPT];                                                                      \
@@ -657,11 +656,11 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
             _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                     \
                 sc[k] = S::add(sc[k], va[k].x); sp[k] = S::add(sp[k], va[k].y);                   \
             }                                                                                     \
-            if ((P0) == DPAIR && (EP & 1)) { CAB_DIAG_ADD }                                       \
+            if ((EP & 1) && dpair == (P0)) { CAB_DIAG_ADD }                                       \
             _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                     \
                 sc[k] = S::add(sc[k], vb[k].x); sp[k] = S::add(sp[k], vb[k].y);                   \
             }                                                                                     \
-            if ((P0) == DPAIR && !(EP & 1)) { CAB_DIAG_ADD }                                      \
+            if (!(EP & 1) && dpair == (P0)) { CAB_DIAG_ADD }                                      \
         } else {                                                                                  \
             _Pragma("unroll") for (int k = 0; k < CPT; ++k) {                                     \
                 const int e0 = (P0) - row[k].lo_base;                                             \
@@ -706,7 +705,6 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
         __syncwarp();                                                                             \
         CAB_CHECK_PUBLISHED(t + 1)                                                                \
         if (lane == 0) arrive_step(NXT_BAR);                                                      \
-        CAB_PUBLISH_LEGACY(NXT_IMM, NXT_R)                                                        \
         /* own-state work for the next step, overlapping the other warps' gathers */              \
         _Pragma("unroll") for (int k = 0; k < CPT; ++k)                                           \
             s[k] = S::div(S::sub(q.c_tot, c[k]), q.beta);                      /* :95 */          \
@@ -740,7 +738,6 @@ __global__ void __launch_bounds__(THREADS, MINB) integrate_kernel(const SimArgs 
 #undef CAB_GATHER_PAIR
 #undef CAB_DIAG_ADD
 #undef CAB_EXIT_CHECK
-#undef CAB_PUBLISH_LEGACY
 #undef CAB_PUBLISH
 }
 

@@ -179,6 +179,23 @@ void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
 
 }  // namespace
 
+namespace cab200 {
+// for prompts_host.cu: the same draws on a caller-held state (key[624], pos)
+void legacy_choice_first_k(uint32_t *mt_key, int32_t *mt_pos, int64_t n, int32_t k, int64_t *out)
+{
+    Mt mt{mt_key, *mt_pos};
+    choice_first_k(mt, n, k, out);
+    *mt_pos = mt.pos;
+}
+uint32_t legacy_next32(uint32_t *mt_key, int32_t *mt_pos)
+{
+    Mt mt{mt_key, *mt_pos};
+    const uint32_t v = mt.next32();
+    *mt_pos = mt.pos;
+    return v;
+}
+}  // namespace cab200
+
 // See include/cab200.h.
 extern "C" int cab200_legacy_choice(uint32_t *mt_key, int32_t *mt_pos, int64_t n, int32_t k, int64_t *out)
 {

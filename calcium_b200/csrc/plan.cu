@@ -44,23 +44,31 @@ struct Problem {
     int n, np, copies, cpt, ep;
     bool unit;
     std::vector<int> rowptr, ecol;
-    std::vector<K1Row> row;
+    std::vector<K1Row> row;                   // laid out for the diagonal point of the warp the cell sits in
+    std::vector<int> rdiag;                   // per cell: index of the diagonal inside the row, -1 none, -2 several
     std::vector<int> slot_of, cell_of;        // cell_of[slot] = cell or -1
     std::vector<std::vector<int>> refs;       // refs[c] = local cells whose row contains c (incl. c)
     std::vector<int> wstart, wend;            // per warp (32*cpt slots): the position range it runs
-    std::vector<char> wleg;                   // per warp: holds legacy rows (such warps run a longer step)
+    std::vector<int> wdiag;                   // per warp: its diagonal point D (k1_warp_diag of its cells)
     int n_groups;
+    bool feasible = true;                     // every warp has a diagonal point (set_order)
 
     inline int rowlen(int c) const { return rowptr[c + 1] - rowptr[c]; }
+    inline int nb(int c) const { return k1_row_nb(rowlen(c), rdiag[c]); }
+    inline int na(int c) const { return k1_row_na(rowlen(c), rdiag[c]); }
+    // a row that does not fit the default diagonal point: it pins its warp's D, and stays in that warp
+    inline bool special(int c) const { return unit && (nb(c) > ep || na(c) > ep); }
 
     void compute_rows()
     {
         row.resize(n);
+        rdiag.resize(n);
         for (int c = 0; c < n; ++c) {
             int nd = 0, di = -1;
             for (int j = rowptr[c]; j < rowptr[c + 1]; ++j)
                 if (ecol[j] == c) { ++nd; di = j - rowptr[c]; }
-            row[c] = k1_row(unit, ep, rowlen(c), nd == 0 ? -1 : (nd == 1 ? di : -2));
+            rdiag[c] = nd == 0 ? -1 : (nd == 1 ? di : -2);
+            row[c] = k1_row(unit, ep, rowlen(c), rdiag[c], ep);
         }
     }
 
@@ -68,7 +76,7 @@ struct Problem {
     // read copy B (bit l of *sel_out).
     inline int phase_cost(int g, int pos, unsigned *sel_out) const
     {
-        const int zero_idx = (copies + (unit ? 1 : 0)) * np;
+        const int zero_idx = copies * np;
         int a_idx[8], b_idx[8];     // candidate entry indices (b = -1: no choice)
         for (int l = 0; l < 8; ++l) {
             const int c = cell_of[g * 8 + l];
@@ -79,7 +87,6 @@ struct Problem {
             if (e < 0 || e >= rowlen(c)) continue;
             const int cc = ecol[rowptr[c] + e];
             if (cc < 0) { a_idx[l] = zero_idx + 1 + (-1 - cc); continue; }       // halo entry
-            if (cc == c && unit) { a_idx[l] = copies * np + slot_of[c]; continue; } // legacy row: its diagonal entry
             a_idx[l] = slot_of[cc];
             if (copies == 2) b_idx[l] = np + (slot_of[cc] ^ 4);
         }
@@ -137,27 +144,46 @@ struct Problem {
         return c;
     }
 
-    // a warp owns 32*cpt consecutive slots and runs one position range for all of them (k1_warp_range)
-    void compute_wrange()
+    // a warp owns 32*cpt consecutive slots, has one diagonal point and runs one position range for all of them
+    // (k1_warp_diag, k1_warp_range: the rules the kernel applies).  false: some warp's cells do not go together.
+    bool compute_wrange()
     {
         const int per = 32 * cpt, nw = (np + per - 1) / per;
-        wstart.assign(nw, 0); wend.assign(nw, 0); wleg.assign(nw, 0);
+        wstart.assign(nw, 0); wend.assign(nw, 0); wdiag.assign(nw, ep);
+        bool ok = true;
         for (int w = 0; w < nw; ++w) {
+            int mnb = 0, mna = 0;
+            for (int s = w * per; s < std::min(np, (w + 1) * per); ++s) {
+                const int c = cell_of[s];
+                if (c >= 0) { mnb = std::max(mnb, nb(c)); mna = std::max(mna, na(c)); }
+            }
+            int d = unit ? k1_warp_diag(ep, mnb, mna) : ep;
+            if (d < 0) { ok = false; d = ep; }
+            wdiag[w] = d;
             int mf = 2 * ep, ml = 0;
             for (int s = w * per; s < std::min(np, (w + 1) * per); ++s) {
                 const int c = cell_of[s];
-                if (c >= 0 && rowlen(c) > 0) { mf = std::min(mf, row[c].first); ml = std::max(ml, row[c].last); }
-                if (c >= 0 && unit && row[c].legacy) wleg[w] = 1;
+                if (c < 0) continue;
+                row[c] = k1_row(unit, ep, rowlen(c), rdiag[c], d);
+                if (unit && row[c].legacy) ok = false;            // several diagonal entries: no D fits
+                if (rowlen(c) > 0) { mf = std::min(mf, row[c].first); ml = std::max(ml, row[c].last); }
             }
-            k1_warp_range(unit, ep, mf, ml, &wstart[w], &wend[w]);
+            k1_warp_range(unit, ep, mf, ml, d, &wstart[w], &wend[w]);
         }
+        return ok;
     }
 
-    inline bool fits(int c, int w) const
+    // May cell c (now in warp wc) move to warp w?  Its row, laid out for w's diagonal point, must stay inside w's
+    // position range; rows that pin a warp's diagonal point never leave their warp.
+    inline bool fits(int c, int wc, int w) const
     {
-        if (unit && row[c].legacy && !wleg[w]) return false;      // legacy rows stay in the warps that have some
-        return rowlen(c) == 0 || (row[c].first >= wstart[w] && row[c].last <= wend[w]);
+        if (wc == w) return true;
+        if (special(c)) return false;
+        if (rowlen(c) == 0) return true;
+        const K1Row r = k1_row(unit, ep, rowlen(c), rdiag[c], wdiag[w]);
+        return !(unit && r.legacy) && r.first >= wstart[w] && r.last <= wend[w];
     }
+    inline void relayout(int c, int w) { if (row[c].dpt != wdiag[w]) row[c] = k1_row(unit, ep, rowlen(c), rdiag[c], wdiag[w]); }
 
     // order: cell at each slot (a permutation of 0..n-1)
     void set_order(const std::vector<int> &order)
@@ -167,7 +193,7 @@ struct Problem {
         slot_of.assign(n, 0);
         cell_of.assign(np, -1);
         for (int s = 0; s < n; ++s) { slot_of[order[s]] = s; cell_of[s] = order[s]; }
-        compute_wrange();
+        feasible = compute_wrange();
         refs.assign(n, {});
         for (int i = 0; i < n; ++i)
             for (int j = rowptr[i]; j < rowptr[i + 1]; ++j)
@@ -213,7 +239,7 @@ long long anneal(Problem &P, long long iters, uint64_t seed, long long *cost0_ou
         if (sb == sa) continue;
         const int a = P.cell_of[sa], b = P.cell_of[sb];
         const int wa = sa / per, wb = sb / per;
-        if (wa != wb && !(P.fits(a, wb) && P.fits(b, wa))) continue;
+        if (wa != wb && !(P.fits(a, wa, wb) && P.fits(b, wb, wa))) continue;
         touched.clear();
         for (int r : P.refs[a]) touched.push_back(P.slot_of[r] / 8);
         for (int r : P.refs[b]) touched.push_back(P.slot_of[r] / 8);
@@ -224,6 +250,7 @@ long long anneal(Problem &P, long long iters, uint64_t seed, long long *cost0_ou
         for (int g : touched) old_c += P.group_cost(g);
         std::swap(P.slot_of[a], P.slot_of[b]);
         P.cell_of[sa] = b; P.cell_of[sb] = a;
+        P.relayout(a, wb); P.relayout(b, wa);
         for (int g : touched) new_c += P.group_cost(g);
         const int delta = new_c - old_c;
         const double temp = t_start * std::pow(t_end / t_start, (double)it / (double)iters);
@@ -232,6 +259,7 @@ long long anneal(Problem &P, long long iters, uint64_t seed, long long *cost0_ou
         } else {
             std::swap(P.slot_of[a], P.slot_of[b]);
             P.cell_of[sa] = a; P.cell_of[sb] = b;
+            P.relayout(a, wa); P.relayout(b, wb);
         }
     }
     return cost;
@@ -269,45 +297,90 @@ int check_csr(int n, const int32_t *rowptr, const int32_t *colidx, const char *w
     return CAB200_OK;
 }
 
-// Start order: cells with the same (even-rounded) position range next to each other, so that a warp's
-// range is as tight as its cells allow.  Three sort keys are tried; the one with the fewest warp-wide
-// loads per step wins.
+// Start order.  Rows that do not fit the default diagonal point (more than ep entries before, or after, their
+// diagonal) come first: those of one kind fill the leading slots of one or more whole warps, topped up with
+// ordinary rows that fit the same diagonal point (preferring the ones that do not widen the warp's position
+// range).  The other cells follow with the same (even-rounded) position range next to each other, so that a
+// warp's range is as tight as its cells allow.  Three sort keys are tried; the one with the fewest warp-wide
+// loads per step wins.  Returns an empty vector when no feasible order was found (e.g. both kinds of special
+// rows in a geometry of a single warp): the caller reports it, the geometry then runs the general kernel.
 std::vector<int> shape_sorted_order(Problem &P)
 {
+    const int per = 32 * P.cpt, emax = 2 * P.ep;
+    std::vector<char> used(P.n, 0);
+    std::vector<int> head;
+    for (int kind = 0; kind < 2 && P.unit; ++kind) {
+        std::vector<int> spec;
+        int mnb = 0, mna = 0;
+        for (int c = 0; c < P.n; ++c)
+            if (P.special(c) && ((kind == 0) == (P.nb(c) > P.ep))) {
+                spec.push_back(c); mnb = std::max(mnb, P.nb(c)); mna = std::max(mna, P.na(c));
+            }
+        if (spec.empty()) continue;
+        const int D = k1_warp_diag(P.ep, mnb, mna);
+        if (D < 0) return {};
+        int mf = emax, ml = 0;
+        for (int c : spec) {
+            const K1Row r = k1_row(true, P.ep, P.rowlen(c), P.rdiag[c], D);
+            if (r.legacy) return {};
+            mf = std::min(mf, r.first & ~1); ml = std::max(ml, (r.last + 1) & ~1);
+            used[c] = 1;
+        }
+        const int need = (int)((spec.size() + per - 1) / per) * per - (int)spec.size();
+        std::vector<std::pair<int, int>> cand;                // (range growth in positions, cell)
+        for (int c = 0; c < P.n; ++c) {
+            if (used[c] || P.special(c) || P.nb(c) > D || P.na(c) > emax - D) continue;
+            const K1Row r = k1_row(true, P.ep, P.rowlen(c), P.rdiag[c], D);
+            if (r.legacy) continue;
+            const int grow = P.rowlen(c) ? std::max(0, mf - (r.first & ~1)) + std::max(0, ((r.last + 1) & ~1) - ml) : 0;
+            cand.push_back({grow, c});
+        }
+        std::stable_sort(cand.begin(), cand.end());
+        const int remaining = P.n - (int)head.size() - (int)spec.size();
+        if ((int)cand.size() < std::min(need, remaining)) return {};
+        head.insert(head.end(), spec.begin(), spec.end());
+        for (int i = 0; i < std::min(need, remaining); ++i) { head.push_back(cand[i].second); used[cand[i].second] = 1; }
+    }
     std::vector<int> best;
     long long best_rows = -1;
     for (int variant = 0; variant < 3; ++variant) {
-        std::vector<int> order(P.n);
-        std::iota(order.begin(), order.end(), 0);
-        auto fr = [&](int c) { return P.rowlen(c) ? (P.row[c].first & ~1) : 2 * P.ep; };
-        auto lr = [&](int c) { return P.rowlen(c) ? ((P.row[c].last + 1) & ~1) : 0; };
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            const bool ga = P.unit && P.row[a].legacy, gb = P.unit && P.row[b].legacy;
-            if (ga != gb) return ga;                               // legacy rows first, all in the leading warp(s)
+        std::vector<int> rest;
+        for (int c = 0; c < P.n; ++c) if (!used[c]) rest.push_back(c);
+        auto row0 = [&](int c) { return k1_row(P.unit, P.ep, P.rowlen(c), P.rdiag[c], P.ep); };
+        auto fr = [&](int c) { return P.rowlen(c) ? (row0(c).first & ~1) : 2 * P.ep; };
+        auto lr = [&](int c) { return P.rowlen(c) ? ((row0(c).last + 1) & ~1) : 0; };
+        std::stable_sort(rest.begin(), rest.end(), [&](int a, int b) {
             const int fa = fr(a), fb = fr(b), la = lr(a), lb = lr(b);
             if (variant == 0) return fa != fb ? fa < fb : la > lb;
             if (variant == 1) return la != lb ? la > lb : fa < fb;
             return (la - fa) != (lb - fb) ? (la - fa) > (lb - fb) : fa < fb;
         });
+        std::vector<int> order = head;
+        order.insert(order.end(), rest.begin(), rest.end());
         P.set_order(order);
+        if (!P.feasible) continue;
         const long long rows = P.gather_instructions();
         if (best_rows < 0 || rows < best_rows) { best_rows = rows; best = order; }
     }
     return best;
 }
 
-// number of rows that take the legacy layout
-int legacy_rows(int n, const int32_t *rowptr, const int32_t *colidx, bool unit, int ep)
+// number of rows that do not fit the default diagonal point (they pin their warp's); -1 - that number when some
+// row has several diagonal entries (no diagonal point fits: general kernel)
+int special_rows(int n, const int32_t *rowptr, const int32_t *colidx, int ep)
 {
     int cnt = 0;
+    bool several = false;
     for (int i = 0; i < n; ++i) {
         int nd = 0, di = -1;
         const int len = rowptr[i + 1] - rowptr[i];
         for (int j = 0; j < len; ++j)
             if (colidx[rowptr[i] + j] == i) { ++nd; di = j; }
-        if (unit && k1_row(true, ep, len, nd == 0 ? -1 : (nd == 1 ? di : -2)).legacy) ++cnt;
+        if (nd > 1) { several = true; continue; }
+        const int d = nd == 0 ? -1 : di;
+        if (k1_row_nb(len, d) > ep || k1_row_na(len, d) > ep) ++cnt;
     }
-    return cnt;
+    return several ? -1 - cnt : cnt;
 }
 
 int max_row_of(int n, const int32_t *rowptr)
@@ -340,6 +413,11 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
     P.ecol.assign(colidx, colidx + rowptr[n]);
     P.compute_rows();
     std::vector<int> order = shape_sorted_order(P);
+    if (order.empty()) {
+        set_error("cab200_plan_slots: no layout with one diagonal point per warp (rows with many entries on either side "
+                  "of the diagonal in too small a geometry, or several diagonal entries): run this geometry with unit = 0");
+        return CAB200_EINVAL;
+    }
     if (use_input) {
         std::vector<char> seen(n, 0);
         for (int i = 0; i < n; ++i) {
@@ -350,6 +428,7 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
         }
     }
     P.set_order(order);
+    if (!P.feasible) { set_error("cab200_plan_slots: the given plan puts rows into one warp that share no diagonal point"); return CAB200_EINVAL; }
     long long cost0 = 0;
     const long long cost = anneal(P, iters, seed, &cost0);
     std::vector<uint16_t> sel;
@@ -366,7 +445,7 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
 extern "C" int cab200_k1_legacy_rows(int n, const int32_t *rowptr, const int32_t *colidx)
 {
     if (n <= 0 || !rowptr || !colidx) { set_error("cab200_k1_legacy_rows: bad argument"); return CAB200_EINVAL; }
-    return legacy_rows(n, rowptr, colidx, true, k1_ep(max_row_of(n, rowptr)));
+    return special_rows(n, rowptr, colidx, k1_ep(max_row_of(n, rowptr)));
 }
 
 // See include/cab200.h.
@@ -435,7 +514,11 @@ extern "C" long long cab200_plan_cluster(int n, const int32_t *rowptr, const int
         }
         if (P.n == 0) { set_error("cab200_plan_cluster: empty part"); return CAB200_EINVAL; }
         P.compute_rows();
-        P.set_order(shape_sorted_order(P));
+        {
+            const std::vector<int> order0 = shape_sorted_order(P);
+            if (order0.empty()) { set_error("cab200_plan_cluster: part %d has no layout with one diagonal point per warp", q); return CAB200_EINVAL; }
+            P.set_order(order0);
+        }
         long long cost0 = 0;
         c1 += anneal(P, iters / n_cta, seed + 977 * (q + 1), &cost0);
         c0 += cost0;

@@ -101,6 +101,17 @@ class _DeviceGeometry:
         rows = np.repeat(np.arange(self.n), np.diff(rowptr))
         offdiag &= rows != col
         self.unit = bool(np.all(val[offdiag] == 1.0))
+        if self.unit and self.n:
+            # the unit-weight kernel adds the diagonal term from registers at one point per warp (csrc/k1_layout.cuh);
+            # a geometry whose rows cannot be grouped that way (several diagonal entries in a row; rows with many
+            # entries before and others with many after the diagonal in a geometry of one warp) runs the general kernel
+            lay = np.zeros(4, dtype=np.int64)
+            lib = _lib.load()
+            if lib.cab200_sim_layout(self.n, 1, _lib.FP64_STRICT, _lib.as_i64p(lay)) == 0:
+                probe = np.zeros(2 * self.n, dtype=np.uint16)
+                if lib.cab200_plan_slots(self.n, _lib.as_i32p(rowptr), _lib.as_i32p(col), int(lay[2]), 1, int(lay[1]), 0, 1, 0,
+                                         probe.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None) != 0:
+                    self.unit = False
         self.nnz = len(col)
         if self.nnz == 0:        # a graph without any entry still needs non-null device pointers
             col, val = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.float64)
@@ -183,8 +194,8 @@ def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool, n_cta: int = 
     rowptr, col, _ = geo.csr
     h = hashlib.sha1()
     h.update(rowptr.tobytes()); h.update(col.tobytes())
-    h.update(f"copies={copies}:cpt={cpt}:v4-diagreg".encode() if n_cta == 1          # v4: register-diagonal row layout
-             else f"copies={copies}:cpt={cpt}:ncta={n_cta}:v2-diagreg".encode())
+    h.update(f"copies={copies}:cpt={cpt}:v5-warpdiag".encode() if n_cta == 1         # v5: one diagonal point per warp
+             else f"copies={copies}:cpt={cpt}:ncta={n_cta}:v3-warpdiag".encode())
     name = f"plan_{h.hexdigest()[:16]}.npy"
     if tracked:
         return os.path.join(_PLANS_DIR, name)

@@ -73,6 +73,7 @@ class _Workspace:
             self.out = torch.empty((2, h, w), dtype=torch.int32, device=dev)
             self.scratch = torch.empty(max(int(lib.cab200_edt_scratch_bytes(2, h, w)), 16), dtype=torch.uint8, device=dev)
             self.luts = torch.empty((2, tables.n + 1), dtype=torch.int16, device=dev)
+            self.stream = torch.cuda.Stream(device=dev)      # pouch_prompts: one stream per worker thread
         self.host = torch.empty((2, h, w), dtype=torch.int32, pin_memory=True)
         self.host_luts = torch.empty((2, tables.n + 1), dtype=torch.int16, pin_memory=True)
 
@@ -396,6 +397,93 @@ def _frame_prompts_body(tables, lut, background_id, pos_lut, any_labelled, d2_bg
     if as_text:
         return _assemble(entries, negatives), len(entries)
     return prompts, negatives
+
+
+class _PromptTablesC(ctypes.Structure):
+    """``cab200_prompt_tables`` of include/cab200.h."""
+    _fields_ = [("n_cells", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("labels", ctypes.c_void_p), ("label_present", ctypes.c_void_p), ("area", ctypes.c_void_p),
+                ("cand_off", ctypes.c_void_p), ("cand_text", ctypes.c_void_p), ("cand_text_off", ctypes.c_void_p),
+                ("empty_flat", ctypes.c_void_p), ("empty_count", ctypes.c_int64), ("empty_d2", ctypes.c_void_p),
+                ("label_map_dev", ctypes.c_void_p)]
+
+
+def _native_tables(self, min_distance: int = 5) -> _PromptTablesC:
+    """The static tables in the form ``cab200_prompts_pouch`` reads (built once; the arrays stay referenced here)."""
+    key = int(min_distance)
+    got = getattr(self, "_native", {}).get(key)
+    if got is not None:
+        return got[0]
+    texts = [t.encode("ascii") for t in self.candidate_entries()]
+    blob = np.frombuffer(b"".join(texts) or b"\0", dtype=np.uint8).copy()
+    toff = np.concatenate([[0], np.cumsum([len(t) for t in texts])]).astype(np.int64)
+    present = np.zeros(self.n + 1, dtype=np.uint8)
+    present[self.present_labels[self.present_labels <= self.n]] = 1
+    flat, d2 = self.empty_frame_candidates(float(min_distance))
+    keep = {"blob": blob, "toff": toff, "present": present, "labels": np.ascontiguousarray(self.labels_u16),
+            "area": np.ascontiguousarray(self.area, dtype=np.int64), "cand_off": np.ascontiguousarray(self.cand_off, dtype=np.int64),
+            "flat": np.ascontiguousarray(flat, dtype=np.int64), "d2": np.ascontiguousarray(d2, dtype=np.int64)}
+    c = _PromptTablesC(self.n, self.H, self.W, keep["labels"].ctypes.data, present.ctypes.data, keep["area"].ctypes.data,
+                       keep["cand_off"].ctypes.data, blob.ctypes.data, toff.ctypes.data, keep["flat"].ctypes.data,
+                       int(keep["flat"].size), keep["d2"].ctypes.data, self.label_mask.data_ptr())
+    if not hasattr(self, "_native"):
+        self._native = {}
+    self._native[key] = (c, keep)
+    return c
+
+
+PromptTables.native_tables = _native_tables
+
+
+def pouch_prompts(tables: PromptTables, ca_frames: np.ndarray, rng, paths: Optional[List[Optional[str]]] = None,
+                  threshold: float = 0.1, quirk: bool = True, num_negative: int = 5, min_distance_from_cells: int = 5,
+                  min_cell_area: int = 10, return_text: bool = False):
+    """:func:`frame_prompts` for ALL sampled frames of one pouch (``ca_frames`` ``[F, n]``) in one native call outside the
+    interpreter lock (``cab200_prompts_pouch``): the frames' K4 passes, numpy's own draw / percentile algorithms on
+    ``rng``'s Mersenne-Twister state (advanced exactly as the per-frame calls would), and the prompt files written to
+    ``paths[f]`` (``None`` / missing: not written).  Returns ``(n_entries [F] -- -1 for a frame without any active
+    cell, for which the reference writes nothing --, texts or None)``."""
+    name, key, pos, has_gauss, cached = rng.get_state()
+    if name != "MT19937":
+        raise ValueError("legacy MT19937 generator expected")
+    ca = np.ascontiguousarray(ca_frames, dtype=np.float64)
+    F, n = ca.shape
+    if n != tables.n:
+        raise ValueError(f"ca_frames has {n} cells, the tables {tables.n}")
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    cpos = ctypes.c_int32(int(pos))
+    nent = np.zeros(max(F, 1), dtype=np.int32)
+    if paths is not None:
+        enc = [(p.encode() if p else b"") + b"\0" for p in paths]
+        pblob = b"".join(enc)
+        poff = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+    text_buf = text_off = None
+    if return_text:
+        text_buf = np.empty(F * (tables.n * 160 + 4096) + 16, dtype=np.uint8)
+        text_off = np.zeros(F + 1, dtype=np.int64)
+    ws = tables.acquire_workspace()
+    dev = tables.label_mask.device
+    lib = _lib.load()
+    try:
+        with torch.cuda.device(dev):
+            ws.stream.wait_stream(torch.cuda.current_stream(dev))
+            rc = lib.cab200_prompts_pouch(
+                ctypes.addressof(tables.native_tables(int(min_distance_from_cells))), F, ca.ctypes.data, float(threshold),
+                1 if quirk else 0, int(num_negative), int(min_distance_from_cells), int(min_cell_area), key.ctypes.data,
+                ctypes.addressof(cpos), pblob if paths is not None else None, poff.ctypes.data if paths is not None else None,
+                ws.out.data_ptr(), ws.scratch.data_ptr(), ws.scratch.numel(), ws.luts.data_ptr(), ws.host.data_ptr(),
+                ws.host_luts.data_ptr(), ws.stream.cuda_stream, nent.ctypes.data,
+                text_buf.ctypes.data if return_text else None, int(text_buf.size) if return_text else 0,
+                text_off.ctypes.data if return_text else None)
+            _lib.check(rc, "cab200_prompts_pouch")
+    finally:
+        tables.release_workspace(ws)
+    rng.set_state((name, key, int(cpos.value), has_gauss, cached))
+    texts = None
+    if return_text:
+        raw = text_buf.tobytes()
+        texts = [raw[text_off[f]:text_off[f + 1]].decode("ascii") if nent[f] >= 0 else None for f in range(F)]
+    return nent[:F], texts
 
 
 def _fmt_point(pt, ind: str) -> str:

@@ -324,3 +324,80 @@ def test_frame_prompts_host_logic_on_cpu(gold, monkeypatch, t, thr):
     assert rt.get_state()[2] == rs.get_state()[2] and np.array_equal(rt.get_state()[1], rs.get_state()[1])
     end = np.random.get_state()
     assert rs.get_state()[2] == end[2] and np.array_equal(rs.get_state()[1], end[1])
+
+
+def test_native_percentile_and_randint_are_numpys():
+    """The numpy restatements inside cab200_prompts_pouch (host code, no GPU): np.percentile(sqrt(d2), 80) -- method
+    "linear", two-sided lerp -- and RandomState.randint(0, high) element by element (masked rejection on 32-bit
+    outputs, no draw for a range of one): same values, same generator state."""
+    import ctypes
+    from calcium_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    R = np.random.RandomState(5)
+    for trial in range(300):
+        m = [1, 2, 3, 4, 5, 6, 7, 11, 100, 1001, 4096, 99999][trial % 12] + (trial // 12) * (trial % 5)
+        d2 = R.randint(1, [3, 50, 5000, 131072][trial % 4], m).astype(np.int32)
+        want = np.percentile(np.sqrt(d2.astype(np.float64)), 80)
+        got = ctypes.c_double(0)
+        assert lib.cab200_np_percentile80_sqrt(d2.ctypes.data, m, ctypes.byref(got)) == 0
+        assert got.value == want, (trial, m, got.value, want)
+    for trial in range(60):
+        a, b = np.random.RandomState(trial), np.random.RandomState(trial)
+        a.random_sample(trial * 11 % 640); b.random_sample(trial * 11 % 640)
+        k = [1, 5, 300, 1400][trial % 4]
+        high = R.randint(1, [2, 9, 70, 100000][trial % 4], k).astype(np.int64)
+        want = a.randint(0, high)
+        name, key, pos, hg, cg = b.get_state()
+        key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        cpos = ctypes.c_int32(int(pos))
+        out = np.zeros(k, dtype=np.int64)
+        assert lib.cab200_legacy_randint(key.ctypes.data, ctypes.addressof(cpos), high.ctypes.data, k, out.ctypes.data) == 0
+        assert np.array_equal(out, want), trial
+        sa = a.get_state()
+        assert sa[2] == cpos.value and np.array_equal(sa[1], key), trial
+        # ... and the scalar call the background instance's draw makes
+        h = int(high[0])
+        w1 = a.randint(h)
+        assert lib.cab200_legacy_randint(key.ctypes.data, ctypes.addressof(cpos), high[:1].ctypes.data, 1, out.ctypes.data) == 0
+        assert out[0] == w1 and a.get_state()[2] == cpos.value
+
+
+@pytest.mark.gpu
+def test_native_pouch_prompts_equal_the_frame_by_frame_path(cuda_device):
+    """cab200_prompts_pouch (all frames of a pouch in one native call) against frame_prompts frame by frame: the same
+    file text byte for byte, the same entry counts and the same generator state afterwards -- medium pouches of all
+    four sim types (frames with and without the background instance, quiet frames, frames without any labelled
+    pixel) and a small pouch at another output size."""
+    import torch
+    from calcium_b200 import build
+    build.build()
+    from calcium_b200 import prompts as P
+    from calcium_b200.ensemble import Ensemble, make_specs, build_label_maps
+    for size, osz, count in (("medium", (512, 512), 4), ("small", (200, 160), 4)):
+        specs = make_specs(count, size=size, first_seed=3)
+        steps = list(range(0, 18000, 1500))
+        ens = Ensemble(specs, device=cuda_device, frame_steps=steps, output_size=osz)
+        ens.simulate(); ens.synchronize()
+        tables = P.prompt_tables(build_label_maps(ens.geometries[0], osz, cuda_device)[1], ens.geometries[0].n_cells)
+        seen_bg = seen_quiet = 0
+        for i in range(count):
+            ca = ens.frames_of(i)[:, 0, :].cpu().numpy()
+            a, b = np.random.RandomState(100 + i), np.random.RandomState(100 + i)
+            want = []
+            for f in range(len(steps)):
+                if not (ca[f] > 0.1).any():
+                    want.append(None); seen_quiet += 1
+                    continue
+                seen_bg += bool(ca[f][0] > 0.1)
+                want.append(P.frame_prompts(tables, ca[f], rng=a, as_text=True))
+            nent, texts = P.pouch_prompts(tables, ca, b, return_text=True)
+            for f in range(len(steps)):
+                if want[f] is None:
+                    assert nent[f] == -1 and texts[f] is None
+                else:
+                    assert texts[f] == want[f][0], (size, i, f)
+                    assert nent[f] == want[f][1]
+            sa, sb = a.get_state(), b.get_state()
+            assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1]), (size, i)
+        assert seen_bg > 0

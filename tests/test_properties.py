@@ -42,8 +42,19 @@ def test_planner_returns_permutation_with_valid_copy_masks(n, seed, copies, cpt)
     cost = np.zeros(4, dtype=np.int64)
     rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 1, cpt, 3000, seed + 1, 0,
                                plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(cost))
-    assert rc == 0
+    nb = np.array([(col[rowptr[i]:rowptr[i + 1]] < i).sum() for i in range(n)])
+    na = np.array([(col[rowptr[i]:rowptr[i + 1]] > i).sum() for i in range(n)])
+    if rc != 0:
+        # the only refusal: rows with more than 5 entries before AND rows with more than 5 after their diagonal, too few
+        # ordinary rows to give each kind a warp of its own (k1_layout.cuh) -- such a geometry runs with unit = 0
+        assert rc == -1 and b"unit = 0" in lib.cab200_last_error()
+        assert (nb > 5).any() or (na > 5).any()
+        return
     assert sorted(plan[:n].tolist()) == list(range(n))
+    per = 32 * cpt
+    for w in range((n + per - 1) // per):                      # every warp has a diagonal point
+        mine = np.nonzero(plan[:n].astype(int) // per == w)[0]
+        assert any(nb[mine].max() <= d <= 10 - na[mine].max() for d in (1, 3, 5, 7, 9)), w
     lens = np.diff(rowptr)
     assert cost[1] == cost[2] <= cost[0]
     assert cost[3] * 32 >= int(lens.sum()) - n               # every off-diagonal entry is gathered somewhere
