@@ -321,6 +321,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         tables[g] = prompt_tables(build_label_maps(ens.geometries[g], output_size, ens.device)[1],
                                                   int(ens.g_ncell[g]))
                         tables[g].candidate_entries()                 # built before the threads start
+                        tables[g].native_tables(5)
                     if host_chain[li] and g not in cmask_host:         # pouch.get_cell_masks() (:292), a host int32 map
                         cmask_host[g] = build_label_maps(ens.geometries[g], output_size, ens.device)[1].cpu().numpy() \
                             .view(np.uint16).astype(np.int32)

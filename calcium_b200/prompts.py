@@ -116,6 +116,8 @@ class PromptTables:
         self._empty: Dict[float, Tuple[np.ndarray, np.ndarray]] = {}
         self._pool: List[_Workspace] = []                              # free K4 workspaces (pinned memory is
         self._pool_lock = threading.Lock()                             # expensive to allocate: 17 ms each)
+        self._native: Dict[int, Any] = {}                              # cab200_prompt_tables per min distance
+        self._native_lock = threading.Lock()
         d2 = edt_squared(label_mask)[0].cpu().numpy()
         flat = lab.ravel()
         order = np.argsort(flat, kind="stable")                       # groups pixels by label, row-major inside
@@ -411,7 +413,12 @@ class _PromptTablesC(ctypes.Structure):
 def _native_tables(self, min_distance: int = 5) -> _PromptTablesC:
     """The static tables in the form ``cab200_prompts_pouch`` reads (built once; the arrays stay referenced here)."""
     key = int(min_distance)
-    got = getattr(self, "_native", {}).get(key)
+    with self._native_lock:
+        return self._native_tables_locked(key, min_distance)
+
+
+def _native_tables_locked(self, key: int, min_distance: int) -> _PromptTablesC:
+    got = self._native.get(key)
     if got is not None:
         return got[0]
     texts = [t.encode("ascii") for t in self.candidate_entries()]
@@ -426,13 +433,12 @@ def _native_tables(self, min_distance: int = 5) -> _PromptTablesC:
     c = _PromptTablesC(self.n, self.H, self.W, keep["labels"].ctypes.data, present.ctypes.data, keep["area"].ctypes.data,
                        keep["cand_off"].ctypes.data, blob.ctypes.data, toff.ctypes.data, keep["flat"].ctypes.data,
                        int(keep["flat"].size), keep["d2"].ctypes.data, self.label_mask.data_ptr())
-    if not hasattr(self, "_native"):
-        self._native = {}
     self._native[key] = (c, keep)
     return c
 
 
 PromptTables.native_tables = _native_tables
+PromptTables._native_tables_locked = _native_tables_locked
 
 
 def pouch_prompts(tables: PromptTables, ca_frames: np.ndarray, rng, paths: Optional[List[Optional[str]]] = None,

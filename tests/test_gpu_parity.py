@@ -201,8 +201,9 @@ def test_false_unit_declaration_is_flagged(env):
     v = E.draw_vplc(prm, g.n_cells, 0)
     r0, _ = E.draw_initial_state(prm, g.n_cells, 0, v)
     ens = E.Ensemble([E.PouchSpec(params=prm, geometry=g, vplc=v.flatten(), r0=r0)], T=10, frame_steps=[9],
-                     device=env["dev"], use_plan=False)
-    ens.g_unit[:] = 1                      # lie: declare unit off-diagonals
+                     device=env["dev"])
+    ens.g_unit[:] = 1                      # lie: declare unit off-diagonals (with a plan: without one the general
+                                           # kernel runs whatever g_unit says)
     ens.simulate()
     with pytest.raises(env["L"].Cab200Error, match="rejected the geometry"):
         ens.check_status()
