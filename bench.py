@@ -525,7 +525,7 @@ def run_gpu(args) -> None:
                          "fp64_pipe_note": "an IEEE divide is ~9 FP64-pipe instructions, so 69.3 algorithmic flops are "
                                            "89.6 pipe instructions per cell-step (ncu instruction counts, profiles/); "
                                            "fp64_pipe_frac_est = pipe instructions/s over the measured DFMA issue rate; "
-                                           "ncu's own sm__pipe_fp64_cycles_active is in profiles/r1_k1_v3_immaddr_ncu.txt"}
+                                           "ncu's own sm__pipe_fp64_cycles_active (83.9 % of peak over the launch) is in profiles/r2_k1_v7_ncu.txt"}
         # the limiting roofline of K1: the shared-memory pipe (ncu: 88 % of peak wavefronts vs 75 % FP64 pipe).
         # Algorithmic bytes per cell-step: gather (c, p) of every row entry + publish own (c, p) = 16*nnz/n + 16
         # (no index or weight reads: entry addresses live in registers, unit weights are skipped) -- DESIGN.md K1.

@@ -1,0 +1,483 @@
+// encode_raw.cu -- K3r: PNG encoder for ARBITRARY two-channel frames on the device.
+//
+// K3 (encode.cu) owes its speed to flat shading: tokens can only start at static label boundaries and the
+// checksums collapse to per-label sums.  Frames that went through the edge blur (K2b, core/pouch.py:455-467) or
+// the deterministic defects (K5, utils/image_processing.py:130-175) are ordinary images; round 1 copied them to the
+// host as raw pixels (1.0 MiB per 512x512 frame over PCIe) and encoded them there with zlib.  This kernel produces
+// the same file the reference's save_image intends (utils/image_processing.py:252-269: 16-bit gray + alpha,
+// gray * 4, alpha * 257) from the uint8 (H, W, 2) frame in device memory:
+//   * PNG filter type 2 (Up) on every scanline: flat regions and vertical structure become zero bytes;
+//   * DEFLATE with the fixed Huffman code of RFC 1951 3.2.6 and one match distance (1: a run of equal bytes);
+//     a lane owns a contiguous span of a scanline's bytes and turns it into literals and run matches, a warp owns
+//     a scanline, the 16 warps of the CTA a pass of 16 scanlines;
+//   * every pass is its own DEFLATE block, closed by an empty stored block that byte-aligns the stream (the "sync
+//     flush" construction), so passes are encoded into a shared-memory bit buffer independently and appended to the
+//     frame's scratch slot as whole bytes;
+//   * Adler-32 of the filtered scanlines from per-lane sums (sum b, sum pos * b), CRC-32 of the IDAT chunk from 512
+//     pieces combined with x^(8k) powers in GF(2)[x] (CRC is linear);
+//   * the finished file goes to the arena at a cursor advanced by one atomicAdd, with a record (offset, size, flags),
+//     exactly like K3's files.
+// Any DEFLATE parse is a valid file, so the bytes are this repo's choice (restated in oracle/encode_oracle.py and
+// compared byte for byte); the decoded content is the reference's (checked with zlib and cv2 readers).
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cab200 {
+namespace rawenc {
+
+constexpr int NT = 512, NW = NT / 32;
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+constexpr int HEAD_BYTES = 43;      // signature 8 + IHDR chunk 25 + IDAT length 4 + "IDAT" 4 + zlib header 2
+
+struct Record {                     // == EncRecord of encode.cu
+    unsigned long long offset;
+    uint32_t size;
+    uint32_t flags;
+};
+
+struct Tables {
+    uint32_t lit[256];              // literal: bit-reversed fixed Huffman code | bits << 24
+    uint32_t len[260];              // run of 3..258 equal bytes: length code + extra bits + the 5-bit distance code 0 | bits << 24
+    uint32_t crc[256];              // reflected CRC-32 table
+    uint32_t pow8[32];              // x^(8 * 2^k) mod P
+};
+
+struct Args {
+    const uint8_t *img;             // [n_img][H][W][2] gray, alpha
+    int n_img, H, W;
+    int rows_per_pass, seg_words, row_stride_words, pass_words;
+    uint8_t *slots;                 // one scratch slot per CTA
+    unsigned long long slot_cap;
+    uint8_t *arena;
+    unsigned long long arena_bytes;
+    unsigned long long *cursor;
+    Record *records;
+    const Tables *tab;
+};
+
+__host__ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+#pragma unroll
+    for (int i = 31; i >= 0; --i) {
+        p ^= b & (0u - ((a >> i) & 1u));
+        b = (b >> 1) ^ (CRC_POLY & (0u - (b & 1u)));
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t gf2_xpow8(const uint32_t *pow8, uint32_t n)
+{
+    uint32_t r = 0x80000000u;
+    for (int k = 0; n; ++k, n >>= 1)
+        if (n & 1u) r = gf2_mulmod(r, pow8[k]);
+    return r;
+}
+__device__ __forceinline__ void put_bits(uint32_t *w, uint32_t pos, unsigned long long val, int nb)
+{
+    const uint32_t idx = pos >> 5, sh = pos & 31u;
+    const unsigned long long v0 = val << sh;
+    atomicOr(&w[idx], (uint32_t)v0);
+    if (sh + nb > 32) atomicOr(&w[idx + 1], (uint32_t)(v0 >> 32));
+}
+
+// The four stream bytes of a pixel (big-endian 16-bit gray * 4, alpha * 257) as one little-endian word.
+__device__ __forceinline__ uint32_t pixel_bytes(uint32_t gray, uint32_t alpha)
+{
+    return (gray >> 6) | (((gray << 2) & 0xffu) << 8) | (alpha << 16) | (alpha << 24);
+}
+__device__ __forceinline__ uint32_t sub_bytes(uint32_t a, uint32_t b)     // bytewise a - b mod 256
+{
+    return ((a | 0x80808080u) - (b & 0x7f7f7f7fu)) ^ ((a ^ ~b) & 0x80808080u);
+}
+
+// A lane's tokens for its span of one scanline: `emit == false` counts the bits, `emit == true` writes them at
+// bit position `pos` of the pass buffer.  prev: the stream byte in front of the span (a run may continue across
+// spans: distance-1 matches only look one byte back).  first_lit >= 0: a literal in front of the span (lane 0: the
+// filter byte).
+template <bool EMIT>
+__device__ __forceinline__ uint32_t lane_tokens(const uint32_t *seg, int nwords, uint32_t prev, int first_lit,
+                                               const uint32_t *lit_s, const uint32_t *len_s, uint32_t *bits, uint32_t pos)
+{
+    uint32_t total = 0;
+    auto out = [&](uint32_t entry) {
+        const int nb = (int)(entry >> 24);
+        if (EMIT) put_bits(bits, pos + total, entry & 0xffffffu, nb);
+        total += (uint32_t)nb;
+    };
+    auto flush = [&](uint32_t value, int run) {
+        while (run >= 3) {
+            const int m = run > 258 ? 258 : run;
+            out(len_s[m]);
+            run -= m;
+        }
+        for (; run > 0; --run) out(lit_s[value]);
+    };
+    if (first_lit >= 0) { out(lit_s[first_lit]); prev = (uint32_t)first_lit; }
+    int run = 0;
+    for (int j = 0; j < nwords; ++j) {
+        uint32_t w = seg[j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = w & 0xffu;
+            w >>= 8;
+            if (b == prev) {
+                ++run;
+            } else {
+                flush(prev, run);
+                run = 0;
+                out(lit_s[b]);
+                prev = b;
+            }
+        }
+    }
+    flush(prev, run);
+    return total;
+}
+
+__global__ void __launch_bounds__(NT, 2) encode_raw_kernel(const Args a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = a.H, W = a.W, RPP = a.rows_per_pass;
+    uint32_t *lit_s = reinterpret_cast<uint32_t *>(smem_raw);               // [256]
+    uint32_t *len_s = lit_s + 256;                                           // [260]
+    uint32_t *crc_s = len_s + 260;                                           // [256]
+    uint32_t *rows = crc_s + 256;                                            // [RPP][row_stride_words] filtered pixel bytes
+    uint32_t *bits = rows + (size_t)RPP * a.row_stride_words;                // [pass_words] bit buffer of one pass
+    __shared__ uint32_t rowbits[NW];
+    __shared__ unsigned long long s_sum, s_wsum, s_off;
+    __shared__ uint32_t pc[NT];
+    __shared__ uint32_t gpow[9];
+    for (int i = tid; i < 256; i += NT) { lit_s[i] = a.tab->lit[i]; crc_s[i] = a.tab->crc[i]; }
+    for (int i = tid; i < 260; i += NT) len_s[i] = a.tab->len[i];
+    uint8_t *slot = a.slots + (size_t)blockIdx.x * a.slot_cap;
+    const int ppl = (W + 31) / 32;                                           // pixels per lane span
+    const unsigned long long row_bytes = 4ull * W + 1ull;
+
+    for (int f = blockIdx.x; f < a.n_img; f += gridDim.x) {
+        const uint8_t *img = a.img + (size_t)f * H * W * 2;
+        if (tid == 0) { s_sum = 0ull; s_wsum = 0ull; }
+        unsigned long long sum_b = 0ull, sum_pb = 0ull;                      // this thread's share of sum b, sum pos * b
+        uint32_t off = 0;                                                    // bytes of the file written to the slot so far
+        bool overflow = false;
+        __syncthreads();
+        for (int r0 = 0; r0 < H; r0 += RPP) {
+            // ---- zero the pass buffer; the first pass starts with the file head ------------------------------------
+            for (int i = tid; i < a.pass_words; i += NT) bits[i] = 0u;
+            __syncthreads();
+            uint32_t head_bits = 0;
+            if (r0 == 0) {
+                head_bits = HEAD_BYTES * 8;
+                if (tid == 0) {
+                    uint8_t *hb = reinterpret_cast<uint8_t *>(bits);
+                    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+                    for (int i = 0; i < 8; ++i) hb[i] = sig[i];
+                    uint8_t ih[17] = {'I', 'H', 'D', 'R', (uint8_t)(W >> 24), (uint8_t)(W >> 16), (uint8_t)(W >> 8), (uint8_t)W,
+                                      (uint8_t)(H >> 24), (uint8_t)(H >> 16), (uint8_t)(H >> 8), (uint8_t)H, 16, 4, 0, 0, 0};
+                    hb[8] = 0; hb[9] = 0; hb[10] = 0; hb[11] = 13;
+                    uint32_t c = 0xffffffffu;
+                    for (int i = 0; i < 17; ++i) { hb[12 + i] = ih[i]; c = crc_s[(c ^ ih[i]) & 0xffu] ^ (c >> 8); }
+                    c ^= 0xffffffffu;
+                    hb[29] = (uint8_t)(c >> 24); hb[30] = (uint8_t)(c >> 16); hb[31] = (uint8_t)(c >> 8); hb[32] = (uint8_t)c;
+                    // hb[33..36]: IDAT length, filled at the end
+                    hb[37] = 'I'; hb[38] = 'D'; hb[39] = 'A'; hb[40] = 'T';
+                    hb[41] = 0x78; hb[42] = 0x01;                            // zlib header: deflate, 32K window, fastest
+                }
+            }
+            // ---- filtered scanline (filter type 2, Up) into the warp's padded row buffer --------------------------
+            const int r = r0 + warp;
+            const bool have_row = warp < RPP && r < H;
+            uint32_t *myrow = rows + (size_t)warp * a.row_stride_words;
+            if (have_row) {
+                const uint8_t *cur = img + (size_t)r * W * 2;
+                const uint8_t *up = cur - (size_t)W * 2;
+                const unsigned long long base = (unsigned long long)r * row_bytes;    // position of the filter byte
+                if (lane == 0) { sum_b += 2ull; sum_pb += 2ull * base; }
+                for (int x = lane; x < W; x += 32) {
+                    const uint32_t cw = pixel_bytes(cur[2 * x], cur[2 * x + 1]);
+                    const uint32_t uw = r > 0 ? pixel_bytes(up[2 * x], up[2 * x + 1]) : 0u;
+                    const uint32_t fw = sub_bytes(cw, uw);
+                    myrow[(x / ppl) * a.seg_words + (x % ppl)] = fw;
+                    const uint32_t b0 = fw & 0xffu, b1 = (fw >> 8) & 0xffu, b2 = (fw >> 16) & 0xffu, b3 = fw >> 24;
+                    const unsigned long long p0 = base + 1ull + 4ull * x;
+                    sum_b += b0 + b1 + b2 + b3;
+                    sum_pb += p0 * (b0 + b1 + b2 + b3) + b1 + 2ull * b2 + 3ull * b3;
+                }
+            }
+            __syncwarp();
+            // ---- tokens of this lane's span: count, scan, emit -----------------------------------------------------
+            const int x0 = lane * ppl, x1 = min(W, x0 + ppl);
+            const int nwords = have_row ? max(0, x1 - x0) : 0;
+            const uint32_t *seg = myrow + lane * a.seg_words;
+            uint32_t prev = 256u;                                            // no byte in front (never equals a byte)
+            int first_lit = -1;
+            if (have_row) {
+                if (lane == 0) first_lit = 2;
+                else if (nwords > 0) prev = myrow[(lane - 1) * a.seg_words + (ppl - 1)] >> 24;   // spans before a non-empty one are full
+            }
+            uint32_t nb = (nwords > 0 || first_lit >= 0) ? lane_tokens<false>(seg, nwords, prev, first_lit, lit_s, len_s, bits, 0u) : 0u;
+            uint32_t incl = nb;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) rowbits[warp] = incl;
+            __syncthreads();
+            uint32_t before = head_bits + 3u;                                // block header: BFINAL = 0, BTYPE = 01 (value 2, LSB first)
+            uint32_t pass_bits = head_bits + 3u;
+            for (int w2 = 0; w2 < NW; ++w2) { if (w2 < warp) before += rowbits[w2]; pass_bits += rowbits[w2]; }
+            if (nwords > 0 || first_lit >= 0)
+                lane_tokens<true>(seg, nwords, prev, first_lit, lit_s, len_s, bits, before + incl - nb);
+            // end of block (code 0000000), then empty stored blocks: 3 zero bits, pad to a byte, 00 00 FF FF -- one to
+            // byte-align, up to three more so that the bytes written so far stay a multiple of 4
+            uint32_t end_bits = pass_bits + 7u + 3u;
+            uint32_t nbytes = (end_bits + 7u) / 8u + 4u;
+            const uint32_t extra = (4u - ((off + nbytes) & 3u)) & 3u;        // each extra empty block adds 5 bytes = 1 mod 4
+            if (tid == 0) {
+                put_bits(bits, head_bits, 2u, 3);
+                uint8_t *hb = reinterpret_cast<uint8_t *>(bits);
+                uint32_t p = nbytes;
+                hb[p - 2] = 0xff; hb[p - 1] = 0xff;
+                for (uint32_t e = 0; e < extra; ++e) { hb[p + 3] = 0xff; hb[p + 4] = 0xff; p += 5; }
+            }
+            nbytes += 5u * extra;
+            __syncthreads();
+            // ---- append the pass to the slot (whole words) ---------------------------------------------------------
+            if ((unsigned long long)off + nbytes + 64ull > a.slot_cap) overflow = true;
+            if (!overflow) {
+                uint32_t *dst = reinterpret_cast<uint32_t *>(slot + off);
+                for (uint32_t i = tid; i < nbytes / 4u; i += NT) dst[i] = bits[i];
+            }
+            off += nbytes;
+            __syncthreads();
+        }
+        // ---- Adler-32 of the filtered scanlines ----------------------------------------------------------------------
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum_b += __shfl_xor_sync(0xffffffffu, sum_b, o);
+            sum_pb += __shfl_xor_sync(0xffffffffu, sum_pb, o);
+        }
+        if (lane == 0) { atomicAdd(&s_sum, sum_b); atomicAdd(&s_wsum, sum_pb); }
+        __syncthreads();
+        // ---- tail: final empty stored block, Adler-32, IDAT CRC, IEND ------------------------------------------------
+        const uint32_t data_end = off + 5u + 4u;                             // end of the IDAT data
+        if (!overflow && tid == 0) {
+            const unsigned long long N = (unsigned long long)H * row_bytes, M = 65521ull;
+            const unsigned long long A = s_sum % M;
+            const unsigned long long s1 = (1ull + A) % M;
+            const unsigned long long s2 = ((N % M) + (N % M) * A % M + M - (s_wsum % M)) % M;
+            uint8_t *t = slot + off;
+            t[0] = 0x01; t[1] = 0x00; t[2] = 0x00; t[3] = 0xff; t[4] = 0xff;
+            t[5] = (uint8_t)(s2 >> 8); t[6] = (uint8_t)s2; t[7] = (uint8_t)(s1 >> 8); t[8] = (uint8_t)s1;
+            const uint32_t idat_len = data_end - 41u;
+            slot[33] = (uint8_t)(idat_len >> 24); slot[34] = (uint8_t)(idat_len >> 16); slot[35] = (uint8_t)(idat_len >> 8); slot[36] = (uint8_t)idat_len;
+        }
+        __syncthreads();
+        // CRC-32 over "IDAT" + data = slot[37 .. data_end): pieces of C bytes per thread, the last piece ends at data_end
+        uint32_t total = 0;
+        if (!overflow) {
+            const uint32_t r_begin = 37u, Lr = data_end - r_begin;
+            const uint32_t C = (Lr + NT - 1) / NT;
+            {
+                const long long e = (long long)data_end - (long long)(NT - 1 - tid) * C;
+                long long b = e - C;
+                if (b < (long long)r_begin) b = r_begin;
+                uint32_t c = 0;
+                for (long long i = b; i < e; ++i) c = crc_s[(c ^ slot[i]) & 0xffu] ^ (c >> 8);
+                pc[tid] = c;
+            }
+            if (warp == 0) {
+                uint32_t g = gf2_xpow8(a.tab->pow8, C);
+                for (int k = 0; k < 9; ++k) {
+                    if (lane == 0) gpow[k] = g;
+                    g = gf2_mulmod(g, g);
+                }
+            }
+            __syncthreads();
+            uint32_t c = pc[tid];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int s = 1 << k;
+                const uint32_t left = __shfl_up_sync(0xffffffffu, c, s);
+                if ((lane & (2 * s - 1)) == 2 * s - 1) c ^= gf2_mulmod(left, gpow[k]);
+            }
+            __syncthreads();
+            if (lane == 31) pc[warp] = c;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t cw = (lane < NW) ? pc[lane] : 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int s = 1 << k;
+                    const uint32_t left = __shfl_up_sync(0xffffffffu, cw, s);
+                    if (lane < NW && (lane & (2 * s - 1)) == 2 * s - 1) cw ^= gf2_mulmod(left, gpow[5 + k]);
+                }
+                if (lane == NW - 1) pc[NT - 1] = cw;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t aff = gf2_mulmod(0xffffffffu, gf2_xpow8(a.tab->pow8, Lr)) ^ 0xffffffffu;
+                const uint32_t crc = pc[NT - 1] ^ aff;
+                uint8_t *t = slot + data_end;
+                t[0] = (uint8_t)(crc >> 24); t[1] = (uint8_t)(crc >> 16); t[2] = (uint8_t)(crc >> 8); t[3] = (uint8_t)crc;
+                const uint8_t iend[12] = {0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xae, 0x42, 0x60, 0x82};
+                for (int i = 0; i < 12; ++i) t[4 + i] = iend[i];
+            }
+            total = data_end + 16u;
+        }
+        // ---- slot -> arena ------------------------------------------------------------------------------------------
+        const uint32_t total16 = (total + 15u) & ~15u;
+        if (tid == 0) {
+            unsigned long long o = ~0ull;
+            uint32_t flags = CAB200_ENC_STAGE_FULL;
+            if (total) {
+                o = atomicAdd(a.cursor, (unsigned long long)total16);
+                flags = CAB200_ENC_OK;
+                if (o + total16 > a.arena_bytes) { o = ~0ull; flags = CAB200_ENC_ARENA_FULL; }
+            }
+            s_off = o;
+            a.records[f].offset = (o == ~0ull) ? 0ull : o;
+            a.records[f].size = (o == ~0ull) ? 0u : total;
+            a.records[f].flags = flags;
+        }
+        __syncthreads();                                                     // also orders thread 0's slot writes before the copy
+        const unsigned long long o = s_off;
+        if (o != ~0ull) {
+            uint4 *dst = reinterpret_cast<uint4 *>(a.arena + o);
+            const uint4 *src = reinterpret_cast<const uint4 *>(slot);
+            for (uint32_t i = tid; i < total16 / 16; i += NT) dst[i] = src[i];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+static uint32_t rev_bits(uint32_t v, int n)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+}
+
+static void build_tables(Tables *t)
+{
+    for (int s = 0; s < 256; ++s) {
+        if (s <= 143) t->lit[s] = rev_bits(0x30u + (uint32_t)s, 8) | (8u << 24);
+        else t->lit[s] = rev_bits(0x190u + (uint32_t)(s - 144), 9) | (9u << 24);
+    }
+    static const int base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const int extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    for (int L = 0; L < 260; ++L) t->len[L] = 0;
+    for (int L = 3; L <= 258; ++L) {
+        int i = 28;
+        while (L < base[i]) --i;
+        const int sym = 257 + i;
+        uint32_t code;
+        int nb;
+        if (sym <= 279) { code = rev_bits((uint32_t)(sym - 256), 7); nb = 7; }
+        else { code = rev_bits(0xC0u + (uint32_t)(sym - 280), 8); nb = 8; }
+        const uint32_t val = code | ((uint32_t)(L - base[i]) << nb);     // extra bits LSB first; the distance code (00000) follows
+        t->len[L] = val | ((uint32_t)(nb + extra[i] + 5) << 24);
+    }
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (CRC_POLY & (0u - (c & 1u)));
+        t->crc[i] = c;
+    }
+    uint32_t p = 0x00800000u;            // x^8 in the reflected representation (bit 31 = x^0)
+    for (int k = 0; k < 32; ++k) { t->pow8[k] = p; p = gf2_mulmod(p, p); }
+}
+
+struct Layout {
+    int rpp, seg_words, row_stride_words, pass_words;
+    size_t smem;
+    unsigned long long slot_cap;
+};
+
+static bool layout_for(int H, int W, Layout *L)
+{
+    const int ppl = (W + 31) / 32;
+    L->seg_words = ppl + 1 + (ppl & 1);                 // odd word stride between the lanes' spans: conflict-free word reads
+    if ((L->seg_words & 1) == 0) L->seg_words += 1;
+    L->row_stride_words = 32 * L->seg_words;
+    for (int rpp = NW; rpp >= 1; --rpp) {
+        // worst case of a pass: head + 3 + every byte a 9-bit literal + end of block + alignment blocks
+        const size_t bits = (size_t)HEAD_BYTES * 8 + 3 + (size_t)rpp * (4 * (size_t)W + 1) * 9 + 7 + 3;
+        const size_t words = (bits + 31) / 32 + 8;
+        const size_t smem = (256 + 260 + 256) * 4 + (size_t)rpp * L->row_stride_words * 4 + words * 4;
+        if (smem <= 100 * 1024) {
+            L->rpp = rpp; L->pass_words = (int)words; L->smem = smem;
+            const size_t passes = ((size_t)H + rpp - 1) / rpp;
+            L->slot_cap = ((unsigned long long)(passes * (words * 4) + 256) + 255ull) & ~255ull;
+            return true;
+        }
+    }
+    return false;
+}
+
+static std::mutex g_tab_mu;
+static Tables *g_tab_dev[64] = {};
+
+}  // namespace rawenc
+}  // namespace cab200
+
+using namespace cab200;
+
+extern "C" size_t cab200_encode_raw_scratch_bytes(int H, int W, int n_slots)
+{
+    rawenc::Layout L;
+    if (H < 1 || W < 1 || H > 2048 || W > 2048 || n_slots < 1 || !rawenc::layout_for(H, W, &L)) return 0;
+    return (size_t)L.slot_cap * (size_t)n_slots + 256;
+}
+
+extern "C" int cab200_encode_raw_batch(const uint8_t *images, int n_images, int H, int W, void *arena, size_t arena_bytes,
+                                       void *cursor, void *records, void *scratch, size_t scratch_bytes, int n_slots,
+                                       void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    rawenc::Layout L;
+    if (n_images < 0 || H < 1 || W < 1 || H > 2048 || W > 2048 || n_slots < 1 || !rawenc::layout_for(H, W, &L)) {
+        set_error("cab200_encode_raw_batch: bad size (H, W in [1, 2048])");
+        return CAB200_EINVAL;
+    }
+    if (n_images == 0) return CAB200_OK;
+    if (!images || !arena || !cursor || !records || !scratch || ((uintptr_t)arena & 15u)) {
+        set_error("cab200_encode_raw_batch: null or misaligned pointer argument");
+        return CAB200_EINVAL;
+    }
+    const uintptr_t slots = ((uintptr_t)scratch + 255u) & ~(uintptr_t)255u;
+    if (slots + (size_t)L.slot_cap * n_slots > (uintptr_t)scratch + scratch_bytes) {
+        set_error("cab200_encode_raw_batch: scratch too small (%zu < %zu)", scratch_bytes, cab200_encode_raw_scratch_bytes(H, W, n_slots));
+        return CAB200_ESIZE;
+    }
+    int dev = 0;
+    CAB_CUDA(cudaGetDevice(&dev));
+    rawenc::Tables *tab = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(rawenc::g_tab_mu);
+        if (dev < 0 || dev >= 64) { set_error("cab200_encode_raw_batch: device index %d", dev); return CAB200_EINVAL; }
+        if (!rawenc::g_tab_dev[dev]) {
+            rawenc::Tables host;
+            rawenc::build_tables(&host);
+            rawenc::Tables *d = nullptr;
+            CAB_CUDA(cudaMalloc(&d, sizeof(host)));
+            CAB_CUDA(cudaMemcpy(d, &host, sizeof(host), cudaMemcpyHostToDevice));
+            rawenc::g_tab_dev[dev] = d;
+        }
+        tab = rawenc::g_tab_dev[dev];
+    }
+    CAB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream));
+    rawenc::Args a;
+    a.img = images; a.n_img = n_images; a.H = H; a.W = W;
+    a.rows_per_pass = L.rpp; a.seg_words = L.seg_words; a.row_stride_words = L.row_stride_words; a.pass_words = L.pass_words;
+    a.slots = (uint8_t *)slots; a.slot_cap = L.slot_cap;
+    a.arena = (uint8_t *)arena; a.arena_bytes = arena_bytes; a.cursor = (unsigned long long *)cursor;
+    a.records = (rawenc::Record *)records; a.tab = tab;
+    CAB_CUDA(cudaFuncSetAttribute((const void *)rawenc::encode_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    const int grid = n_images < n_slots ? n_images : n_slots;
+    rawenc::encode_raw_kernel<<<grid, rawenc::NT, L.smem, stream>>>(a);
+    CAB_CUDA(cudaGetLastError());
+    return CAB200_OK;
+}
