@@ -34,7 +34,7 @@ EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
            "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
            "cab200_edge_maps", "cab200_raster_edges_batch", "cab200_legacy_choice", "cab200_sample_background", "cab200_prompts_pouch", "cab200_np_percentile80_sqrt", "cab200_legacy_randint", "cab200_defect_pass",
            "cab200_encode_tables_bytes", "cab200_encode_tables", "cab200_encode_scratch_bytes", "cab200_encode_batch",
-           "cab200_encode_geometry_bytes", "cab200_encode_geometry", "cab200_publish_to_host", "cab200_edt_scratch_bytes", "cab200_edt_classes",
+           "cab200_encode_geometry_bytes", "cab200_encode_geometry", "cab200_encode_raw_scratch_bytes", "cab200_encode_raw_batch", "cab200_publish_to_host", "cab200_edt_scratch_bytes", "cab200_edt_classes",
            "cab200_peak_fp64", "cab200_peak_hbm_write", "cab200_peak_smem", "cab200_selftest_division",
            "cab200_relay_alloc", "cab200_relay_free", "cab200_relay_open", "cab200_relay_close", "cab200_ipc_event_create",
            "cab200_ipc_event_open", "cab200_event_create", "cab200_event_record", "cab200_event_synchronize",
@@ -132,6 +132,11 @@ def load() -> ctypes.CDLL:
         c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cab200_defect_pass.restype = c_int
     lib.cab200_defect_pass.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.cab200_encode_raw_scratch_bytes.restype = c_size_t
+    lib.cab200_encode_raw_scratch_bytes.argtypes = [c_int, c_int, c_int]
+    lib.cab200_encode_raw_batch.restype = c_int
+    lib.cab200_encode_raw_batch.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
+                                            c_size_t, c_int, c_void_p]
     lib.cab200_prompts_pouch.restype = c_int
     lib.cab200_prompts_pouch.argtypes = [c_void_p, c_int, c_void_p, c_double, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,

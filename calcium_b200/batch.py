@@ -190,6 +190,24 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 fh.write(data)
         return len(items)
 
+    def _write_arena_files(arena: np.ndarray, items) -> int:
+        """Files that sit in a host arena (K3 / K3r output) -- ``items``: (path, offset, size) -- written by the native
+        writer pool (``cab200_write_files``) straight from the arena."""
+        from . import _lib as _clib
+        if not items:
+            return 0
+        paths = [p_.encode() for p_, _, _ in items]
+        blob = b"\0".join(paths) + b"\0"
+        poff = np.zeros(len(paths), dtype=np.int64)
+        np.cumsum([len(p_) + 1 for p_ in paths[:-1]], out=poff[1:])
+        o = np.asarray([x[1] for x in items], dtype=np.int64)
+        z = np.asarray([x[2] for x in items], dtype=np.int64)
+        written = np.zeros(1, dtype=np.int64)
+        a_ = np.ascontiguousarray(arena)
+        _clib.check(_clib.load().cab200_write_files(len(paths), blob, _clib.as_i64p(poff), a_.ctypes.data, _clib.as_i64p(o),
+                                                    _clib.as_i64p(z), int(n_wt), _clib.as_i64p(written)), "cab200_write_files")
+        return len(items)
+
     mappings_by_sim: Dict[int, List[tuple]] = {}
     warned_defects: List[bool] = []
     final_states: Dict[int, Any] = {}
@@ -229,7 +247,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
             names = {li: [d["name"] + x for x in tsfx] for li, d in enumerate(part)}
             image_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
             mask_files: Dict[int, List[str]] = {li: [] for li in range(len(part))}
-            img = ins = nact = masks_k3 = None
+            img = ins = nact = masks_k3 = png_k3r = None
             # configuration of (pouch, frame): the pouch's entry of defect_configs, else the per-frame random draw
             def frame_cfg(li: int, fi: int):
                 d_ = part[li]
@@ -297,7 +315,13 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         if gpu_defects[li]:
                             apply_defects(out["image"][li], pouch_cfgs[li], output_size)
                 ens.synchronize()
-                img = out["image"].cpu().numpy() if steps else None
+                if steps and write_files and not keep_arrays and not any(host_chain):
+                    # K3r: blurred / defect frames are no longer flat-shaded, but nothing on the host touches them
+                    # any more either: they are encoded on the device (cab200_encode_raw_batch) and arrive as
+                    # finished .png files, like K3's
+                    from .ensemble import encode_raw_frames
+                    png_k3r = encode_raw_frames(out["image"])
+                img = out["image"].cpu().numpy() if (steps and png_k3r is None) else None
                 ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and "instance" in out) else None
                 nact = out["n_active"].cpu().numpy() if steps else None
                 del out
@@ -368,23 +392,26 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         last_state = state
                 if last_state is not None:
                     final_states[part[-1]["sim_idx"]] = last_state
+            arena_pngs: List[tuple] = []
+            arena_masks: List[tuple] = []
             for li, d in enumerate(part):
-                if img is not None:
+                if img is not None or png_k3r is not None:
                     for fi, t in enumerate(steps):
                         if fi in skipped_frames[li]:                   # the reference's loop skips a failing frame entirely
                             continue
                         base = names[li][fi]
                         ipath = os.path.join(img_dir, base + ".png")
                         image_files[li].append(ipath)
-                        if pool is not None:
+                        if pool is not None and png_k3r is not None:
+                            arena_pngs.append((ipath, int(png_k3r[1][li, fi]), int(png_k3r[2][li, fi])))
+                        elif pool is not None:
                             pending.append(pool.submit(cio.save_gray_alpha_png, img[li, fi], ipath, 10))
                         if generate_masks and nact[li, fi] > 0:      # no active cell -> no mask (sam2_data_generator.py:318-319)
                             mpath = os.path.join(mask_dir, base + ".npz")
                             mask_files[li].append(mpath)
                             mappings_by_sim.setdefault(part[li]["sim_idx"], []).append((os.path.basename(ipath), os.path.basename(mpath)))
                             if pool is not None and masks_k3 is not None:
-                                o_, n_ = int(masks_k3[1][li, fi]), int(masks_k3[2][li, fi])
-                                pending.append(pool.submit(_write_many, [(mpath, masks_k3[0][o_:o_ + n_].tobytes())]))
+                                arena_masks.append((mpath, int(masks_k3[1][li, fi]), int(masks_k3[2][li, fi])))
                             elif pool is not None:
                                 pending.append(pool.submit(cio.save_instance_mask, ins[li, fi], mpath))
                 if keep_arrays:
@@ -405,6 +432,10 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     "simulation_type": d["type"], "pouch_size": d["size"], "parameters": d["params"],
                     "image_count": len(image_files[li]), "image_dir": img_dir, "mask_dir": mask_dir,
                     "mask_count": len(mask_files[li]), "prompt_count": len(prompt_files[li]), "pouch": pouch_obj})
+            if pool is not None and arena_pngs:
+                pending.append(pool.submit(_write_arena_files, png_k3r[0], arena_pngs))
+            if pool is not None and arena_masks:
+                pending.append(pool.submit(_write_arena_files, masks_k3[0], arena_masks))
             if not took_k3:
                 report_done(len(part))
             ens.release_files_ring()

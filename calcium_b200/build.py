@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcalcium_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
 SOURCES = ["integrate_f64.cu", "integrate_cl64.cu", "integrate_f32.cu", "integrate_cl32.cu", "integrate.cu",
-           "api.cu", "microbench.cu", "relay.cu", "filewriter.cu", "raster.cu", "edges.cu", "legacy_rng.cu", "prompts_host.cu", "defects.cu", "encode.cu", "edt.cu", "plan.cu"]
+           "api.cu", "microbench.cu", "relay.cu", "filewriter.cu", "raster.cu", "edges.cu", "legacy_rng.cu", "prompts_host.cu", "defects.cu", "encode.cu", "encode_raw.cu", "edt.cu", "plan.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 

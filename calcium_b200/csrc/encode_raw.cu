@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(NT, 2) encode_raw_kernel(const Args a)
             uint32_t end_bits = pass_bits + 7u + 3u;
             uint32_t nbytes = (end_bits + 7u) / 8u + 4u;
             const uint32_t extra = (4u - ((off + nbytes) & 3u)) & 3u;        // each extra empty block adds 5 bytes = 1 mod 4
+            __syncthreads();             // the token bits are in: the byte stores below may share a word with the last of them
             if (tid == 0) {
                 put_bits(bits, head_bits, 2u, 3);
                 uint8_t *hb = reinterpret_cast<uint8_t *>(bits);

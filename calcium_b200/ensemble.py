@@ -362,6 +362,49 @@ def build_edge_maps(geo: Geometry, output_size: Tuple[int, int], device: torch.d
     return dg.edge_maps[key]
 
 
+def encode_raw_frames(images: torch.Tensor, arena_bytes_per_pixel: float = 1.0
+                      ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """K3r (``cab200_encode_raw_batch``): the finished 16-bit gray + alpha ``.png`` of every frame of ``images``
+    (device uint8 ``[..., H, W, 2]`` -- frames that went through the edge blur or the deterministic defects and are
+    no longer flat-shaded) encoded on the device; what crosses PCIe is the files, not 1 MiB of raw pixels per frame.
+    Returns ``(arena, offset, size, flags)`` on the host, the last three of the leading shape of ``images``.  An arena
+    that turns out too small (``arena_bytes_per_pixel``; blurred 512 x 512 frames take 0.2-0.5 bytes per pixel) is
+    allocated again at the size the encoder asked for."""
+    lib = _lib.load()
+    dev = images.device
+    if images.dtype != torch.uint8 or images.dim() < 3 or images.shape[-1] != 2 or not images.is_contiguous():
+        raise ValueError("encode_raw_frames expects a contiguous uint8 tensor [..., H, W, 2]")
+    lead = tuple(images.shape[:-3])
+    h, w = int(images.shape[-3]), int(images.shape[-2])
+    n = int(np.prod(lead)) if lead else 1
+    with torch.cuda.device(dev):
+        n_slots = 2 * torch.cuda.get_device_properties(dev).multi_processor_count
+        nb = int(lib.cab200_encode_raw_scratch_bytes(h, w, n_slots))
+        if nb == 0:
+            raise _lib.Cab200Error(f"cab200_encode_raw_scratch_bytes: unsupported frame size {w}x{h}")
+        scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+        records = torch.empty((max(n, 1), 2), dtype=torch.int64, device=dev)
+        cursor = torch.zeros(2, dtype=torch.int64, device=dev)
+        cap = (int(n * h * w * arena_bytes_per_pixel) + (1 << 20) + 15) // 16 * 16
+        for _ in range(2):
+            arena = torch.empty(cap, dtype=torch.uint8, device=dev)
+            _lib.check(lib.cab200_encode_raw_batch(images.data_ptr(), n, h, w, arena.data_ptr(), cap, cursor.data_ptr(),
+                                                   records.data_ptr(), scratch.data_ptr(), nb, n_slots, _stream_ptr(dev)),
+                       "cab200_encode_raw_batch")
+            used = int(cursor[0].item())
+            if used <= cap:
+                break
+            cap = (used + (1 << 20) + 15) // 16 * 16
+        rec = records[:n].cpu().numpy()
+        host = arena[:used].cpu().numpy()
+    off = rec[:, 0].copy().reshape(lead)
+    size = (rec[:, 1] & 0xFFFFFFFF).reshape(lead)
+    flags = ((rec[:, 1] >> 32) & 0xFFFFFFFF).reshape(lead)
+    if np.any(flags != _lib.ENC_OK):
+        raise _lib.Cab200Error("cab200_encode_raw_batch: a frame did not fit its scratch slot or the arena")
+    return host, off, size, flags
+
+
 def _u16_numpy(t: torch.Tensor) -> np.ndarray:
     return t.cpu().numpy().view(np.uint16)
 

@@ -305,5 +305,134 @@ def decode_png(data: bytes) -> np.ndarray:
             idat += body
         pos += 12 + ln
     raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 4 * w)
-    assert not raw[:, 0].any()
-    return raw[:, 1:].copy().view(">u2").reshape(h, w, 2).astype(np.uint16)
+    ftype = raw[:, 0]
+    assert np.isin(ftype, (0, 2)).all()                      # K3 writes filter type 0, K3r type 2 (Up)
+    px = raw[:, 1:].copy()
+    for r in range(h):
+        if ftype[r] == 2 and r > 0:
+            px[r] += px[r - 1]                                # uint8 arithmetic wraps mod 256
+    return px.view(">u2").reshape(h, w, 2).astype(np.uint16)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K3r (calcium_b200/csrc/encode_raw.cu): PNG of an arbitrary (H, W, 2) uint8 gray + alpha frame.  The same parse,
+# restated with plain Python loops (small frames only): filter type 2 on every scanline, fixed-Huffman DEFLATE with
+# distance-1 run matches, a lane = a span of ceil(W / 32) pixels, one block per pass of scanlines closed by empty
+# stored blocks so that the file length stays a multiple of 4.  zlib is the checksum authority.
+# ---------------------------------------------------------------------------------------------------------------
+_RAW_LEN_BASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+_RAW_LEN_EXTRA = [0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0]
+
+
+def raw_rows_per_pass(H: int, W: int) -> int:
+    """Scanlines per pass = per DEFLATE block: what fits the kernel's 100 KB of shared memory (its layout_for)."""
+    ppl = (W + 31) // 32
+    seg = ppl + 1 + (ppl & 1)
+    for rpp in range(16, 0, -1):
+        bits = 43 * 8 + 3 + rpp * (4 * W + 1) * 9 + 7 + 3
+        words = (bits + 31) // 32 + 8
+        if (256 + 260 + 256) * 4 + rpp * 32 * seg * 4 + words * 4 <= 100 * 1024:
+            return rpp
+    raise ValueError("frame too wide")
+
+
+class _BitWriter:
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def put(self, value: int, nbits: int) -> None:          # LSB first
+        self.acc |= value << self.n
+        self.n += nbits
+        while self.n >= 8:
+            self.out.append(self.acc & 0xff)
+            self.acc >>= 8
+            self.n -= 8
+
+    def huff(self, code: int, nbits: int) -> None:           # Huffman codes go in MSB first
+        self.put(int(format(code, f"0{nbits}b")[::-1], 2), nbits)
+
+    def align(self) -> None:
+        if self.n:
+            self.put(0, 8 - self.n)
+
+
+def _raw_literal(bw: _BitWriter, b: int) -> None:
+    if b <= 143:
+        bw.huff(0x30 + b, 8)
+    else:
+        bw.huff(0x190 + b - 144, 9)
+
+
+def _raw_run(bw: _BitWriter, length: int) -> None:          # `length` more copies of the previous byte (distance 1)
+    i = max(k for k in range(29) if _RAW_LEN_BASE[k] <= length)
+    sym = 257 + i
+    if sym <= 279:
+        bw.huff(sym - 256, 7)
+    else:
+        bw.huff(0xC0 + sym - 280, 8)
+    bw.put(length - _RAW_LEN_BASE[i], _RAW_LEN_EXTRA[i])
+    bw.huff(0, 5)
+
+
+def _raw_flush(bw: _BitWriter, value: int, run: int) -> None:
+    while run >= 3:
+        m = min(run, 258)
+        _raw_run(bw, m)
+        run -= m
+    for _ in range(run):
+        _raw_literal(bw, value)
+
+
+def encode_raw_png(image: np.ndarray) -> bytes:
+    """The file ``cab200_encode_raw_batch`` writes for ``image`` ((H, W, 2) uint8), byte for byte."""
+    H, W = image.shape[:2]
+    g = image[..., 0].astype(np.uint16)
+    al = image[..., 1].astype(np.uint16)
+    px = np.stack([g >> 6, (g << 2) & 0xff, al, al], axis=-1).astype(np.uint8)            # (H, W, 4) stream bytes
+    up = np.concatenate([np.zeros((1, W, 4), np.uint8), px[:-1]])
+    filt = (px.astype(np.int16) - up.astype(np.int16)).astype(np.uint8).reshape(H, 4 * W)
+    raw = np.concatenate([np.full((H, 1), 2, np.uint8), filt], axis=1)                      # what zlib would be fed
+    rpp = raw_rows_per_pass(H, W)
+    ppl = (W + 31) // 32
+    ihdr = struct.pack(">IIBBBBB", W, H, 16, 4, 0, 0, 0)
+    head = (b"\x89PNG\r\n\x1a\n" + struct.pack(">I", 13) + b"IHDR" + ihdr + struct.pack(">I", zlib.crc32(b"IHDR" + ihdr))
+            + b"\0\0\0\0" + b"IDAT" + b"\x78\x01")
+    assert len(head) == 43
+    body = bytearray(head)
+    for r0 in range(0, H, rpp):
+        bw = _BitWriter()
+        bw.put(2, 3)                                          # BFINAL = 0, BTYPE = 01
+        for r in range(r0, min(H, r0 + rpp)):
+            row = filt[r]
+            for lane in range(32):
+                x0, x1 = lane * ppl, min(W, lane * ppl + ppl)
+                if lane == 0:
+                    _raw_literal(bw, 2)
+                    prev = 2
+                elif x1 > x0:
+                    prev = int(row[4 * x0 - 1])
+                else:
+                    continue
+                run = 0
+                for b in row[4 * x0:4 * x1].tolist():
+                    if b == prev:
+                        run += 1
+                    else:
+                        _raw_flush(bw, prev, run)
+                        run = 0
+                        _raw_literal(bw, b)
+                        prev = b
+                _raw_flush(bw, prev, run)
+        bw.put(0, 7)                                          # end of block
+        bw.put(0, 3)                                          # empty stored block: aligns to a byte
+        bw.align()
+        bw.out += b"\x00\x00\xff\xff"
+        while (len(body) + len(bw.out)) % 4:
+            bw.out += b"\x00\x00\x00\xff\xff"
+        body += bw.out
+    body += b"\x01\x00\x00\xff\xff" + struct.pack(">I", zlib.adler32(raw.tobytes()))
+    data_end = len(body)
+    body[33:37] = struct.pack(">I", data_end - 41)
+    body += struct.pack(">I", zlib.crc32(bytes(body[37:data_end])))
+    body += struct.pack(">I", 0) + b"IEND" + struct.pack(">I", zlib.crc32(b"IEND"))
+    return bytes(body)

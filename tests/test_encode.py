@@ -385,3 +385,66 @@ def test_batch_path_writes_the_encoded_frames(env, tmp_path):
         data = json.load(open(path))
         assert set(data) == {"positive_prompts", "negative_prompts", "num_cells", "version"}
         assert data["num_cells"] == len(data["positive_prompts"]) and len(data["negative_prompts"]) <= 5
+
+
+# ---- K3r: arbitrary frames (edge blur, defects) -----------------------------------------------------------------
+
+def test_raw_encoder_oracle_decodes_with_independent_readers():
+    """oracle/encode_oracle.encode_raw_png (the CPU restatement of K3r): the file decodes, with zlib (checksums
+    checked) and with cv2, to gray * 4 / alpha * 257 of the frame -- random frames, flat frames, odd sizes."""
+    import cv2
+    from oracle import encode_oracle as EO
+    R = np.random.RandomState(3)
+    for H, W in ((40, 70), (33, 50), (17, 31), (64, 64), (5, 200)):
+        for kind in range(3):
+            img = np.zeros((H, W, 2), np.uint8)
+            if kind == 0:
+                img[..., 0] = R.randint(0, 256, (H, W)); img[..., 1] = R.randint(0, 256, (H, W))
+            elif kind == 1:
+                img[H // 4: H // 2, W // 5: W // 2] = (90, 255); img[H // 2:, :, 1] = 255
+            png = EO.encode_raw_png(img)
+            dec = EO.decode_png(png)
+            assert np.array_equal(dec[..., 0], img[..., 0].astype(np.uint16) * 4)
+            assert np.array_equal(dec[..., 1], img[..., 1].astype(np.uint16) * 257)
+            cv = cv2.imdecode(np.frombuffer(png, np.uint8), cv2.IMREAD_UNCHANGED)
+            assert cv.dtype == np.uint16 and np.array_equal(cv[..., 0], dec[..., 0]) and np.array_equal(cv[..., 3], dec[..., 1])
+
+
+@pytest.mark.gpu
+def test_raw_encoder_matches_oracle_bytes_and_decodes(cuda_device):
+    """K3r on the device: byte for byte the oracle's restatement on small frames of several shapes (random pixels --
+    every byte a literal --, flat frames, real edge-blurred frames), and at 512 x 512 the decoded file is the frame."""
+    import torch
+    from calcium_b200 import build
+    build.build()
+    from calcium_b200.ensemble import Ensemble, encode_raw_frames, make_specs
+    from oracle import encode_oracle as EO
+    R = np.random.RandomState(11)
+    for H, W in ((40, 70), (33, 50), (17, 31), (64, 64), (5, 200), (96, 130)):
+        frames = np.zeros((7, H, W, 2), np.uint8)
+        frames[0, ..., 0] = R.randint(0, 256, (H, W)); frames[0, ..., 1] = R.randint(0, 256, (H, W))
+        frames[1] = 255
+        frames[3, H // 4: H // 2, W // 5: W // 2] = (90, 255); frames[3, H // 2:, :, 1] = 255
+        frames[4, ..., 0] = (np.arange(W)[None, :] * 3 + np.arange(H)[:, None]) % 256; frames[4, ..., 1] = 255
+        frames[5, ..., 0] = R.randint(0, 3, (H, W)) * 100; frames[5, ..., 1] = 255
+        frames[6, ::2] = 200
+        arena, off, size, flags = encode_raw_frames(torch.from_numpy(frames).to(cuda_device))
+        for i in range(len(frames)):
+            got = arena[off[i]: off[i] + size[i]].tobytes()
+            assert got == EO.encode_raw_png(frames[i]), (H, W, i)
+    # real frames: edge-blurred medium pouches at 512 x 512, content checked with the independent decoder
+    specs = make_specs(2, size="medium", first_seed=4)
+    ens = Ensemble(specs, device=cuda_device, frame_steps=[0, 6000, 12000, 17999])
+    ens.simulate()
+    out = ens.rasterize(image=True, instance=False, edge_blur=True, blur_kernel_size=3, blur_type="mean")
+    img = out["image"]
+    arena, off, size, flags = encode_raw_frames(img)
+    host = img.cpu().numpy()
+    assert off.shape == (2, 4)
+    for i in range(2):
+        for f in range(4):
+            dec = EO.decode_png(arena[off[i, f]: off[i, f] + size[i, f]].tobytes())
+            assert np.array_equal(dec[..., 0], host[i, f, ..., 0].astype(np.uint16) * 4)
+            assert np.array_equal(dec[..., 1], host[i, f, ..., 1].astype(np.uint16) * 257)
+    assert EO.encode_raw_png(host[1, 2]) == arena[off[1, 2]: off[1, 2] + size[1, 2]].tobytes()
+    assert size.mean() < 0.6 * 512 * 512           # blurred frames compress to a fraction of a byte per pixel
