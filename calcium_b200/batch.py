@@ -208,6 +208,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                                                     _clib.as_i64p(z), int(n_wt), _clib.as_i64p(written)), "cab200_write_files")
         return len(items)
 
+    k3r_writes: Dict[int, cf.Future] = {}       # per device: the write of the last K3r arena (a pinned buffer in reuse)
     mappings_by_sim: Dict[int, List[tuple]] = {}
     warned_defects: List[bool] = []
     final_states: Dict[int, Any] = {}
@@ -320,7 +321,10 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     # any more either: they are encoded on the device (cab200_encode_raw_batch) and arrive as
                     # finished .png files, like K3's
                     from .ensemble import encode_raw_frames
-                    png_k3r = encode_raw_frames(out["image"])
+                    prev = k3r_writes.pop(ens.device.index, None)
+                    if prev is not None:
+                        prev.result()                 # the writer threads still read the pinned landing buffer
+                    png_k3r = encode_raw_frames(out["image"], keep_pinned=True)
                 img = out["image"].cpu().numpy() if (steps and png_k3r is None) else None
                 ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and "instance" in out) else None
                 nact = out["n_active"].cpu().numpy() if steps else None
@@ -433,7 +437,10 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     "image_count": len(image_files[li]), "image_dir": img_dir, "mask_dir": mask_dir,
                     "mask_count": len(mask_files[li]), "prompt_count": len(prompt_files[li]), "pouch": pouch_obj})
             if pool is not None and arena_pngs:
-                pending.append(pool.submit(_write_arena_files, png_k3r[0], arena_pngs))
+                k3r_writes[ens.device.index] = pool.submit(_write_arena_files, png_k3r[0], arena_pngs)
+                pending.append(k3r_writes[ens.device.index])
+            elif png_k3r is not None:
+                png_k3r = None
             if pool is not None and arena_masks:
                 pending.append(pool.submit(_write_arena_files, masks_k3[0], arena_masks))
             if not took_k3:

@@ -298,25 +298,31 @@ int check_csr(int n, const int32_t *rowptr, const int32_t *colidx, const char *w
 }
 
 // Start order.  Rows that do not fit the default diagonal point (more than ep entries before, or after, their
-// diagonal) come first: those of one kind fill the leading slots of one or more whole warps, topped up with
-// ordinary rows that fit the same diagonal point (preferring the ones that do not widen the warp's position
-// range).  The other cells follow with the same (even-rounded) position range next to each other, so that a
-// warp's range is as tight as its cells allow.  Three sort keys are tried; the one with the fewest warp-wide
-// loads per step wins.  Returns an empty vector when no feasible order was found (e.g. both kinds of special
-// rows in a geometry of a single warp): the caller reports it, the geometry then runs the general kernel.
+// diagonal) go to the END of the slot space: those of one kind share whole warps -- the last kind the last,
+// usually partly empty, warp (cells only occupy slots 0 .. n-1) -- topped up with ordinary rows that fit the same
+// diagonal point (preferring the ones that do not widen the warp's position range).  The other cells come first,
+// with the same (even-rounded) position range next to each other, so that a warp's range is as tight as its cells
+// allow.  Three sort keys are tried; the one with the fewest warp-wide loads per step wins.  Returns an empty
+// vector when no feasible order was found (e.g. both kinds of special rows in a geometry of a single warp): the
+// caller reports it, the geometry then runs the general kernel.
 std::vector<int> shape_sorted_order(Problem &P)
 {
     const int per = 32 * P.cpt, emax = 2 * P.ep;
     std::vector<char> used(P.n, 0);
-    std::vector<int> head;
+    std::vector<std::vector<int>> kinds;                      // special rows: entries before > ep | entries after > ep
     for (int kind = 0; kind < 2 && P.unit; ++kind) {
         std::vector<int> spec;
-        int mnb = 0, mna = 0;
         for (int c = 0; c < P.n; ++c)
-            if (P.special(c) && ((kind == 0) == (P.nb(c) > P.ep))) {
-                spec.push_back(c); mnb = std::max(mnb, P.nb(c)); mna = std::max(mna, P.na(c));
-            }
-        if (spec.empty()) continue;
+            if (P.special(c) && ((kind == 0) == (P.nb(c) > P.ep))) spec.push_back(c);
+        if (!spec.empty()) kinds.push_back(spec);
+    }
+    const int last_cnt = P.n - ((P.n - 1) / per) * per;       // cells in the last warp that holds any
+    std::vector<int> tail;                                    // the sections, in slot order
+    int room = P.n;                                           // cells not yet given to a section
+    for (size_t ki = kinds.size(); ki-- > 0;) {               // the last kind first: it takes the partial warp
+        const std::vector<int> &spec = kinds[ki];
+        int mnb = 0, mna = 0;
+        for (int c : spec) { mnb = std::max(mnb, P.nb(c)); mna = std::max(mna, P.na(c)); }
         const int D = k1_warp_diag(P.ep, mnb, mna);
         if (D < 0) return {};
         int mf = emax, ml = 0;
@@ -326,7 +332,12 @@ std::vector<int> shape_sorted_order(Problem &P)
             mf = std::min(mf, r.first & ~1); ml = std::max(ml, (r.last + 1) & ~1);
             used[c] = 1;
         }
-        const int need = (int)((spec.size() + per - 1) / per) * per - (int)spec.size();
+        const bool is_last = ki + 1 == kinds.size();
+        int size = is_last ? last_cnt : 0;
+        while (size < (int)spec.size()) size += per;
+        size = std::min(size, room);
+        const int need = size - (int)spec.size();
+        if (need < 0) return {};
         std::vector<std::pair<int, int>> cand;                // (range growth in positions, cell)
         for (int c = 0; c < P.n; ++c) {
             if (used[c] || P.special(c) || P.nb(c) > D || P.na(c) > emax - D) continue;
@@ -336,10 +347,11 @@ std::vector<int> shape_sorted_order(Problem &P)
             cand.push_back({grow, c});
         }
         std::stable_sort(cand.begin(), cand.end());
-        const int remaining = P.n - (int)head.size() - (int)spec.size();
-        if ((int)cand.size() < std::min(need, remaining)) return {};
-        head.insert(head.end(), spec.begin(), spec.end());
-        for (int i = 0; i < std::min(need, remaining); ++i) { head.push_back(cand[i].second); used[cand[i].second] = 1; }
+        if ((int)cand.size() < need) return {};
+        std::vector<int> sec(spec);
+        for (int i = 0; i < need; ++i) { sec.push_back(cand[i].second); used[cand[i].second] = 1; }
+        tail.insert(tail.begin(), sec.begin(), sec.end());
+        room -= size;
     }
     std::vector<int> best;
     long long best_rows = -1;
@@ -355,8 +367,8 @@ std::vector<int> shape_sorted_order(Problem &P)
             if (variant == 1) return la != lb ? la > lb : fa < fb;
             return (la - fa) != (lb - fb) ? (la - fa) > (lb - fb) : fa < fb;
         });
-        std::vector<int> order = head;
-        order.insert(order.end(), rest.begin(), rest.end());
+        std::vector<int> order = rest;
+        order.insert(order.end(), tail.begin(), tail.end());
         P.set_order(order);
         if (!P.feasible) continue;
         const long long rows = P.gather_instructions();
