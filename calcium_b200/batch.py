@@ -209,6 +209,7 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
         return len(items)
 
     k3r_writes: Dict[int, cf.Future] = {}       # per device: the write of the last K3r arena (a pinned buffer in reuse)
+    k3r_locks: Dict[int, threading.Lock] = {}
     mappings_by_sim: Dict[int, List[tuple]] = {}
     warned_defects: List[bool] = []
     final_states: Dict[int, Any] = {}
@@ -321,10 +322,17 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     # any more either: they are encoded on the device (cab200_encode_raw_batch) and arrive as
                     # finished .png files, like K3's
                     from .ensemble import encode_raw_frames
-                    prev = k3r_writes.pop(ens.device.index, None)
-                    if prev is not None:
-                        prev.result()                 # the writer threads still read the pinned landing buffer
-                    png_k3r = encode_raw_frames(out["image"], keep_pinned=True)
+                    with k3r_locks.setdefault(ens.device.index, threading.Lock()):
+                        # one pinned landing buffer per device: the previous arena's files must be on disk before it
+                        # is reused, and this arena's write is queued before any other shard of this device encodes
+                        prev = k3r_writes.pop(ens.device.index, None)
+                        if prev is not None:
+                            prev.result()
+                        png_k3r = encode_raw_frames(out["image"], keep_pinned=True)
+                        items = [(os.path.join(img_dir, names[li][fi] + ".png"), int(png_k3r[1][li, fi]), int(png_k3r[2][li, fi]))
+                                 for li in range(len(part)) for fi in range(len(steps))]
+                        k3r_writes[ens.device.index] = pool.submit(_write_arena_files, png_k3r[0], items)
+                        pending.append(k3r_writes[ens.device.index])
                 img = out["image"].cpu().numpy() if (steps and png_k3r is None) else None
                 ins = out["instance"].cpu().numpy().view(np.uint16) if (steps and "instance" in out) else None
                 nact = out["n_active"].cpu().numpy() if steps else None
@@ -396,7 +404,6 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         last_state = state
                 if last_state is not None:
                     final_states[part[-1]["sim_idx"]] = last_state
-            arena_pngs: List[tuple] = []
             arena_masks: List[tuple] = []
             for li, d in enumerate(part):
                 if img is not None or png_k3r is not None:
@@ -406,8 +413,8 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         base = names[li][fi]
                         ipath = os.path.join(img_dir, base + ".png")
                         image_files[li].append(ipath)
-                        if pool is not None and png_k3r is not None:
-                            arena_pngs.append((ipath, int(png_k3r[1][li, fi]), int(png_k3r[2][li, fi])))
+                        if png_k3r is not None:
+                            pass                                       # already queued with the whole arena (K3r)
                         elif pool is not None:
                             pending.append(pool.submit(cio.save_gray_alpha_png, img[li, fi], ipath, 10))
                         if generate_masks and nact[li, fi] > 0:      # no active cell -> no mask (sam2_data_generator.py:318-319)
@@ -436,11 +443,6 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                     "simulation_type": d["type"], "pouch_size": d["size"], "parameters": d["params"],
                     "image_count": len(image_files[li]), "image_dir": img_dir, "mask_dir": mask_dir,
                     "mask_count": len(mask_files[li]), "prompt_count": len(prompt_files[li]), "pouch": pouch_obj})
-            if pool is not None and arena_pngs:
-                k3r_writes[ens.device.index] = pool.submit(_write_arena_files, png_k3r[0], arena_pngs)
-                pending.append(k3r_writes[ens.device.index])
-            elif png_k3r is not None:
-                png_k3r = None
             if pool is not None and arena_masks:
                 pending.append(pool.submit(_write_arena_files, masks_k3[0], arena_masks))
             if not took_k3:

@@ -648,10 +648,12 @@ def test_config3_head_against_reference_fixture(env, golden_dir):
     assert _max_rel(ens.frames_of(0).cpu().numpy(), z["large_frames"]) < RTOL
 
 
-def test_batch_sharded_over_two_shards_of_one_gpu_equals_unsharded(env, tmp_path):
+@pytest.mark.parametrize("edge_blur", [False, True])
+def test_batch_sharded_over_two_shards_of_one_gpu_equals_unsharded(env, tmp_path, edge_blur):
     """The ``devices=[...]`` drop-in sharding (LPT partition, one host thread per shard, results merged) on a
     one-GPU box: two shards on ``cuda:0`` run through exactly the code the multi-GPU call runs
-    (``run_on_device`` per entry of ``devices``) -- same files, result dict and generator state as unsharded."""
+    (``run_on_device`` per entry of ``devices``) -- same files, result dict and generator state as unsharded.  With
+    ``edge_blur`` the images come from K3r, whose pinned landing buffer the two shards of the device share."""
     import random
     from calcium_b200 import generate_simulation_batch
     outs = []
@@ -659,7 +661,7 @@ def test_batch_sharded_over_two_shards_of_one_gpu_equals_unsharded(env, tmp_path
         random.seed(13)
         d = tmp_path / f"run{k}"
         res = generate_simulation_batch(7, str(d), pouch_sizes=["xsmall", "small", "medium"], time_steps=[0, 6000, 12000],
-                                        image_size="128x128", devices=devs, defect_configs=[{}] * 7)
+                                        image_size="128x128", devices=devs, defect_configs=[{}] * 7, edge_blur=edge_blur)
         files = {}
         for sub in ("images", "masks", "prompts"):
             for name in sorted(os.listdir(d / sub / "train")):
