@@ -126,6 +126,12 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
     """
     if broken_defects not in ("skip", "off"):
         raise ValueError("broken_defects must be 'skip' or 'off'")
+    if generate_labels:
+        # deprecated in the reference ("use prompts instead", main.py:185) and broken there: the flag shadows the imported
+        # function, so `generate_labels(pouch, time_step)` (main.py:305) raises for every frame.  Said once, not ignored
+        # silently; memory_threshold (a gc.collect() trigger, main.py:205) and jpeg_quality (PNG output) change no output.
+        print("Note: generate_labels=True writes no label JSON here (outside this build's scope; the reference's own call "
+              "at main.py:305 fails because the flag shadows utils.labeling.generate_labels)")
     os.makedirs(output_dir, exist_ok=True)
     if pouch_sizes is None:
         pouch_sizes = list(DEFAULT_SIZES)

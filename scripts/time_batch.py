@@ -15,7 +15,8 @@ try:
             pr = cProfile.Profile() if (len(sys.argv) > 2 and rep == 1) else None
             t0 = time.perf_counter()
             if pr: pr.enable()
-            res = generate_simulation_batch(N, d, pouch_sizes=["medium"], defect_configs=[{}] * N, generate_prompts=prompts)
+            res = generate_simulation_batch(N, d, pouch_sizes=["medium"], defect_configs=[{}] * N, generate_prompts=prompts,
+                                            prompt_threads=int(os.environ["PROMPT_THREADS"]) if os.environ.get("PROMPT_THREADS") else None)
             if pr: pr.disable()
             dt = time.perf_counter() - t0
             print(f"N={N} prompts={prompts} rep={rep}: {dt:.3f} s  images {res['stats']['total_images']} masks {res['stats']['total_masks']}", file=out, flush=True)
