@@ -410,6 +410,20 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         last_state = state
                 if last_state is not None:
                     final_states[part[-1]["sim_idx"]] = last_state
+            if img is not None and png_k3r is None and pool is not None and any(host_chain):
+                # the frames the host chain finished (noise, defocus: numpy's generator and OpenCV) go back to the device
+                # for their PNG encoding: 0.5 MB up and ~0.2 MB down per frame instead of 8 ms of zlib on a host core
+                from .ensemble import encode_raw_frames
+                with k3r_locks.setdefault(ens.device.index, threading.Lock()):
+                    prev = k3r_writes.pop(ens.device.index, None)
+                    if prev is not None:
+                        prev.result()
+                    with torch.cuda.device(ens.device):
+                        png_k3r = encode_raw_frames(torch.from_numpy(img).to(ens.device), keep_pinned=True)
+                    items = [(os.path.join(img_dir, names[li][fi] + ".png"), int(png_k3r[1][li, fi]), int(png_k3r[2][li, fi]))
+                             for li in range(len(part)) for fi in range(len(steps)) if fi not in skipped_frames[li]]
+                    k3r_writes[ens.device.index] = pool.submit(_write_arena_files, png_k3r[0], items)
+                    pending.append(k3r_writes[ens.device.index])
             arena_masks: List[tuple] = []
             for li, d in enumerate(part):
                 if img is not None or png_k3r is not None:
