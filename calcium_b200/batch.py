@@ -380,8 +380,12 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                         # through one native call outside the interpreter lock (cab200_prompts_pouch) -- same draws,
                         # same files, same generator state as the frame loop below
                         ppaths = [os.path.join(prompt_dir, names[li][fi] + ".json") for fi in range(len(steps))]
-                        nent, _ = pouch_prompts(tables[g], ca_host[li], rs, paths=ppaths if write_files else None)
-                        return [ppaths[fi] for fi in range(len(steps)) if nent[fi] >= 0], rs.get_state()
+                        try:
+                            nent, _ = pouch_prompts(tables[g], ca_host[li], rs, paths=ppaths if write_files else None)
+                            return [ppaths[fi] for fi in range(len(steps)) if nent[fi] >= 0], rs.get_state()
+                        except Exception as e:  # noqa: BLE001 - one pouch must not abort the batch: redo it frame by frame
+                            print(f"Native prompt path failed for simulation {d['sim_idx']} ({e}); falling back to the frame loop")
+                            rs.set_state(d["rng_state"])
                     with torch.cuda.device(ens.device):
                         for fi in range(len(steps)):
                             try:
