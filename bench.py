@@ -669,6 +669,19 @@ def extra_legs(dev) -> dict:
         "bit_exact_vs_oracle_fp64": {sizes[i % 4]: exact(e64, i) for i in (4, 9, 14, 19)}}
     del e64, e32
     torch.cuda.empty_cache()
+    # ---- the headline ensemble (148 medium pouches) in the optional FP32 mode -----------------------------------
+    m64 = Ensemble(make_specs(POUCHES_PER_GPU, size=SIZE), T=T_STEPS, device=dev)
+    t64 = timed_k1(m64)
+    m32 = Ensemble(make_specs(POUCHES_PER_GPU, size=SIZE), T=T_STEPS, device=dev, precision=_lib.FP32)
+    t32 = timed_k1(m32)
+    a_ = m64.frames_of(0).cpu().numpy()[:, 0]
+    b_ = m32.frames_of(0).cpu().numpy()[:, 0].astype(np.float64)
+    out["configs"]["medium_148_fp32"] = {"fp64_k1_ms": t64, "fp32_k1_ms": t32, "fp32_speedup": t64 / t32,
+                                         "fp32_cell_timesteps_per_s": m32.cell_timesteps / t32 * 1e3,
+                                         "pouch0_max_abs_ca": float(np.abs(a_ - b_).max()),
+                                         "pouch0_active_set_flips": int(((a_ > 0.1) != (b_ > 0.1)).sum())}
+    del m64, m32
+    torch.cuda.empty_cache()
     # ---- the public batch call: 148 medium pouches -> .png / .npz (/ .json prompts) on tmpfs, wall clock --------
     import random
     n = POUCHES_PER_GPU
