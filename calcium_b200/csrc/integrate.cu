@@ -182,7 +182,7 @@ extern "C" int cab200_cluster_layout(int n, int n_cta, int precision, int64_t ou
     }
     int threads = 0, cpt = 0;
     cluster_shape((n + n_cta - 1) / n_cta, &threads, &cpt);
-    if (n_cta == 8 && threads && threads < 512) { threads = 512; cpt = 2; }      // clusters of 8: 512-thread shapes only
+    if (n_cta == 8 && threads && threads < 416) { threads = 416; cpt = 2; }      // clusters of 8: 416- / 512-thread shapes only
     if (n_cta == 3 && threads) { threads = 512; cpt = 3; }                       // clusters of 3: the 512 x 3 shape only
     if (!threads) { set_error("cab200_cluster_layout: %d cells exceed %d CTAs x 1536", n, n_cta); return CAB200_ESIZE; }
     const size_t elem2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;
@@ -350,7 +350,7 @@ extern "C" int cab200_sim_batch(
             if (max_row_c > 16 || max_row_c < 0) { set_error("cab200_sim_batch: geometry %d: longest CSR row %d outside [0,16]", g, max_row_c); return CAB200_ESIZE; }
             int cth = 0, ccpt = 0;
             cluster_shape((n + ncta - 1) / ncta, &cth, &ccpt);
-            if (ncta == 8 && cth && cth < 512) { cth = 512; ccpt = 2; }
+            if (ncta == 8 && cth && cth < 416) { cth = 416; ccpt = 2; }
             if (ncta == 3 && cth) { cth = 512; ccpt = 3; }
             if (!cth) { set_error("cab200_sim_batch: geometry %d: %d cells exceed %d CTAs x 1536", g, n, ncta); return CAB200_ESIZE; }
             const size_t el2 = (precision == CAB200_FP64_STRICT) ? 16 : 8;

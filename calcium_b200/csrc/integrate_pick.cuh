@@ -18,7 +18,7 @@ static KernelFn pick_cluster_variant(int ep, int copies)
     return integrate_kernel<R, THREADS, CPT, 8, true, 1, 1, NCTA>;
 }
 
-// Cluster kernels exist for three CTA shapes and cluster sizes 2 and 4, and for the two 512-thread shapes as
+// Cluster kernels exist for four CTA shapes and cluster sizes 2 and 4, and for the 416- / 512-thread shapes as
 // clusters of 8 (the portable maximum: pouches of up to 8 x 1536 = 12 288 cells, the reference's `xlarge`).
 template <typename R>
 static KernelFn pick_cluster_kernel(int threads, int cpt, int ncta, int ep, int copies)
@@ -29,9 +29,11 @@ static KernelFn pick_cluster_kernel(int threads, int cpt, int ncta, int ep, int 
         if (ncta == 4) return pick_cluster_variant<R, T_, C_, 4>(ep, copies); \
     }
     CAB_CSHAPE(256, 2)
+    CAB_CSHAPE(416, 2)
     CAB_CSHAPE(512, 2)
     CAB_CSHAPE(512, 3)
 #undef CAB_CSHAPE
+    if (ncta == 8 && threads == 416 && cpt == 2) return pick_cluster_variant<R, 416, 2, 8>(ep, copies);
     if (ncta == 3 && threads == 512 && cpt == 3) return pick_cluster_variant<R, 512, 3, 3>(ep, copies);   // see cab200_cluster_capacity
     if (ncta == 8 && threads == 512 && cpt == 2) return pick_cluster_variant<R, 512, 2, 8>(ep, copies);
     if (ncta == 8 && threads == 512 && cpt == 3) return pick_cluster_variant<R, 512, 3, 8>(ep, copies);
@@ -43,6 +45,7 @@ static inline void cluster_shape(int cells_per_cta, int *threads, int *cpt)
 {
     *threads = 0; *cpt = 0;
     if (cells_per_cta <= 512) { *threads = 256; *cpt = 2; }
+    else if (cells_per_cta <= 832) { *threads = 416; *cpt = 2; }      // 13 warps: a large pouch on 4 CTAs (814 cells each)
     else if (cells_per_cta <= 1024) { *threads = 512; *cpt = 2; }
     else if (cells_per_cta <= 1536) { *threads = 512; *cpt = 3; }
 }

@@ -64,7 +64,7 @@ def test_argument_validation_needs_no_gpu(lib):
     assert rc == -1 and b"null pointer" in lib.cab200_last_error()
     assert lib.cab200_publish_to_host(None, None, 16, None) == -1
     assert lib.cab200_sim_frames_tmp_bytes(1500, 1, 1, 64, 2, 10) == 2 * 10 * 4 * 1536 * 8
-    assert lib.cab200_sim_frames_tmp_bytes(3255, 4, 1, 64, 1, 10) == 10 * 4 * 4096 * 8
+    assert lib.cab200_sim_frames_tmp_bytes(3255, 4, 1, 64, 1, 10) == 10 * 4 * (4 * 832) * 8        # 4 CTAs of 416 x 2 slots
     assert lib.cab200_sim_set_plan(2000, 333, 2) == -1
     assert lib.cab200_sim_set_plan(0, 0, 0) == 0
 
@@ -192,7 +192,9 @@ def test_cluster_planner(lib):
         assert hcount.sum() < 0.25 * n                                         # thin boundaries
     assert lib.cab200_cluster_layout(1500, 5, 64, _lib.as_i64p(lay)) == -1        # sizes 2, 3, 4, 8
     assert lib.cab200_cluster_layout(3255, 3, 64, _lib.as_i64p(lay)) == 0 and lay[:2].tolist() == [512, 3]
-    assert lib.cab200_cluster_layout(6500, 8, 64, _lib.as_i64p(lay)) == 0 and lay[:2].tolist() == [512, 2]
+    assert lib.cab200_cluster_layout(6500, 8, 64, _lib.as_i64p(lay)) == 0 and lay[:2].tolist() == [416, 2]
+    assert lib.cab200_cluster_layout(3255, 4, 64, _lib.as_i64p(lay)) == 0 and lay[:2].tolist() == [416, 2]
+    assert lib.cab200_cluster_layout(8000, 8, 64, _lib.as_i64p(lay)) == 0 and lay[:2].tolist() == [512, 2]
     assert lib.cab200_cluster_layout(3255, 2, 64, _lib.as_i64p(lay)) == -3      # 1628 cells per CTA > 1536
     assert lib.cab200_cluster_layout(20000, 4, 64, _lib.as_i64p(lay)) == -3
 
