@@ -302,7 +302,7 @@ int check_csr(int n, const int32_t *rowptr, const int32_t *colidx, const char *w
 // usually partly empty, warp (cells only occupy slots 0 .. n-1) -- topped up with ordinary rows that fit the same
 // diagonal point (preferring the ones that do not widen the warp's position range).  The other cells come first,
 // with the same (even-rounded) position range next to each other, so that a warp's range is as tight as its cells
-// allow.  Three sort keys are tried; the one with the fewest warp-wide loads per step wins.  Returns an empty
+// allow.  Four sort keys are tried; the one with the fewest warp-wide loads per step wins.  Returns an empty
 // vector when no feasible order was found (e.g. both kinds of special rows in a geometry of a single warp): the
 // caller reports it, the geometry then runs the general kernel.
 std::vector<int> shape_sorted_order(Problem &P)
@@ -355,7 +355,7 @@ std::vector<int> shape_sorted_order(Problem &P)
     }
     std::vector<int> best;
     long long best_rows = -1;
-    for (int variant = 0; variant < 3; ++variant) {
+    for (int variant = 0; variant < 4; ++variant) {
         std::vector<int> rest;
         for (int c = 0; c < P.n; ++c) if (!used[c]) rest.push_back(c);
         auto row0 = [&](int c) { return k1_row(P.unit, P.ep, P.rowlen(c), P.rdiag[c], P.ep); };
@@ -365,6 +365,7 @@ std::vector<int> shape_sorted_order(Problem &P)
             const int fa = fr(a), fb = fr(b), la = lr(a), lb = lr(b);
             if (variant == 0) return fa != fb ? fa < fb : la > lb;
             if (variant == 1) return la != lb ? la > lb : fa < fb;
+            if (variant == 3) return fa != fb ? fa < fb : la < lb;
             return (la - fa) != (lb - fb) ? (la - fa) > (lb - fb) : fa < fb;
         });
         std::vector<int> order = rest;
