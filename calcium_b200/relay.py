@@ -232,38 +232,68 @@ def setup(rank: int, world: int, device: torch.device, cap_bytes: int, trial_byt
     ep.cap = (int(cap_bytes) + 255) // 256 * 256
     recv_of = {r: s for s, r in pairs.items()}
     mine: Dict[str, Any] = {}
+
+    def give_up(why: str) -> Endpoint:
+        """Every rank calls this together (the failure flags are gathered first): plain direct copies."""
+        try:
+            ep.close()
+        except Exception:  # noqa: BLE001
+            pass
+        ep.active = False
+        ep.info["mode"] = f"direct (relay set-up failed: {why})"
+        return ep
+
     with torch.cuda.device(device):
-        if rank in pairs:                                  # sender: events + mailbox
-            ep.role, ep.partner = "sender", pairs[rank]
-            ep._mb = _Mailbox(_mailbox_path(tag, rank), create=True)
-            hs = []
-            for _ in range(SLOTS):
-                ev, h = _vp(), (ctypes.c_ubyte * 64)()
-                _lib.check(lib.cab200_ipc_event_create(ctypes.byref(ev), h), "cab200_ipc_event_create")
-                ep._events.append(ev)
-                hs.append(bytes(h))
-            mine["events"] = hs
-        elif rank in recv_of:                              # receiver: staging ring
-            ep.role, ep.partner = "receiver", recv_of[rank]
-            ring, h = _vp(), (ctypes.c_ubyte * 64)()
-            _lib.check(lib.cab200_relay_alloc(SLOTS * ep.cap, ctypes.byref(ring), h), "cab200_relay_alloc")
-            ep._ring = ring
-            ep._h_ring = torch.empty(SLOTS * ep.cap, dtype=torch.uint8, pin_memory=True)
-            mine["ring"] = bytes(h)
+        # A rank that cannot create or open its IPC objects (a container without CUDA IPC, a GPU pair without peer
+        # access) must not leave the others waiting in a collective: every phase ends with the ranks agreeing on
+        # whether all of them got through, else all fall back to direct copies.
+        try:
+            if rank in pairs:                                  # sender: events + mailbox
+                ep.role, ep.partner = "sender", pairs[rank]
+                ep._mb = _Mailbox(_mailbox_path(tag, rank), create=True)
+                hs = []
+                for _ in range(SLOTS):
+                    ev, h = _vp(), (ctypes.c_ubyte * 64)()
+                    _lib.check(lib.cab200_ipc_event_create(ctypes.byref(ev), h), "cab200_ipc_event_create")
+                    ep._events.append(ev)
+                    hs.append(bytes(h))
+                mine["events"] = hs
+            elif rank in recv_of:                              # receiver: staging ring
+                ep.role, ep.partner = "receiver", recv_of[rank]
+                ring, h = _vp(), (ctypes.c_ubyte * 64)()
+                _lib.check(lib.cab200_relay_alloc(SLOTS * ep.cap, ctypes.byref(ring), h), "cab200_relay_alloc")
+                ep._ring = ring
+                ep._h_ring = torch.empty(SLOTS * ep.cap, dtype=torch.uint8, pin_memory=True)
+                mine["ring"] = bytes(h)
+        except Exception as e:  # noqa: BLE001
+            mine = {"error": f"rank {rank}: {e}"}
         everyone: List[Any] = [None] * world
         dist.all_gather_object(everyone, mine)
-        if ep.role == "sender":
-            ring = _vp()
-            hb = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[ep.partner]["ring"])
-            _lib.check(lib.cab200_relay_open(hb, ctypes.byref(ring)), "cab200_relay_open")
-            ep._ring = ring
-        elif ep.role == "receiver":
-            for hbytes in everyone[ep.partner]["events"]:
-                ev = _vp()
-                hb = (ctypes.c_ubyte * 64).from_buffer_copy(hbytes)
-                _lib.check(lib.cab200_ipc_event_open(hb, ctypes.byref(ev)), "cab200_ipc_event_open")
-                ep._events.append(ev)
-            ep._mb = _Mailbox(_mailbox_path(tag, ep.partner), create=False)
+        errors = [m["error"] for m in everyone if isinstance(m, dict) and "error" in m]
+        if errors:
+            return give_up(errors[0])
+        err = ""
+        try:
+            if ep.role == "sender":
+                ring = _vp()
+                hb = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[ep.partner]["ring"])
+                _lib.check(lib.cab200_relay_open(hb, ctypes.byref(ring)), "cab200_relay_open")
+                ep._ring = ring
+            elif ep.role == "receiver":
+                for hbytes in everyone[ep.partner]["events"]:
+                    ev = _vp()
+                    hb = (ctypes.c_ubyte * 64).from_buffer_copy(hbytes)
+                    _lib.check(lib.cab200_ipc_event_open(hb, ctypes.byref(ev)), "cab200_ipc_event_open")
+                    ep._events.append(ev)
+                ep._mb = _Mailbox(_mailbox_path(tag, ep.partner), create=False)
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {rank}: {e}"
+        opened: List[Any] = [None] * world
+        dist.all_gather_object(opened, err)
+        errors = [m for m in opened if m]
+        if errors:
+            return give_up(errors[0])
+        if ep.role == "receiver":
             ep._thread = threading.Thread(target=ep._forward_loop, daemon=True, name="cab200-relay")
             ep._thread.start()
         barrier()
