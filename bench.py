@@ -699,7 +699,7 @@ def extra_legs(dev) -> dict:
             random.seed(1)
             d = os.path.join(root, name)
             best = None
-            for rep in range(2 if extra else 1):       # the first edge_blur call sizes the pinned landing buffer of K3r
+            for rep in range(2):                       # best of two: the first call of a kind sizes pinned buffers
                 shutil.rmtree(d, ignore_errors=True)
                 t0 = time.perf_counter()
                 res = generate_simulation_batch(n, d, generate_prompts=prompts, **dict(kw, **extra))
