@@ -566,13 +566,17 @@ def run_gpu(args) -> None:
             if tr.get("k1_ncu"):                 # the hardware counters of the same launch (not measured in this run)
                 roofline["ncu"] = tr["k1_ncu"]
         cores = os.cpu_count() or 1
-        cpu = cpu_port = None
+        cpu = cpu_port = cpu_ref_1core = None
         if not args.no_cpu_baseline and world == 1:          # the contract: on rank 0 at N = 1 only
             cpu_port = cpu_port_throughput(max(cores, 8), cores, min_seconds=5.0)
             cpu = cpu_port
             if not args.port_only:
                 try:                                       # the unmodified reference, if oracle/_ref travelled with the tree
                     cpu = cpu_reference_throughput(cores, cores)
+                    # ... and the way the reference actually runs: one process, one pouch after the other (main.py:202;
+                    # max_cores at main.py:149 is never used) -- BASELINE.md section 3, step 4
+                    one = cpu_reference_throughput(1, 1)
+                    cpu_ref_1core = {k: one[k] for k in ("value", "unit", "cores", "kind", "sample")}
                 except Exception as e:  # noqa: BLE001
                     cpu_port["sample"] += f"; reference unavailable here: {type(e).__name__}: {e}"
         line = {
@@ -587,6 +591,7 @@ def run_gpu(args) -> None:
             "cpu_baseline_port": ({k: cpu_port[k] for k in ("value", "unit", "cores", "kind", "sample")}
                                   if (cpu_port and cpu is not cpu_port) else None),
             "cpu_baseline_reference_style": (cpu_reference_style_throughput() if cpu else None),
+            "cpu_baseline_reference_1core": cpu_ref_1core,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": moved["h2d_bytes"],
                     "d2h_bytes_per_step": moved["d2h_bytes"], "ms_per_step": e2e_ms_v, "steps": e2e_files_steps,
                     "path": "Ensemble.run_files_to_host (what generate_simulation_batch runs): pinned host inputs -> K1 -> "
