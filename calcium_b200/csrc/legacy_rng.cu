@@ -11,6 +11,10 @@
 // interpreter lock: same indices out, same generator state afterwards (tests/test_prompts.py compares both with
 // numpy itself).
 #include <stdint.h>
+#include <stdlib.h>
+#if defined(__GNUC__) && defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <vector>
@@ -118,6 +122,50 @@ struct MtBlock {
     }
 };
 
+// 64 masked outputs against the window [sure, top] (see choice_first_k): -1 when one of them falls into the band
+// (sure, top], else the accepted ones (<= sure) are written to dst in order and their number is returned.
+static int block64_generic(const uint32_t *o, uint32_t mask, uint32_t top, uint32_t sure, uint32_t *dst)
+{
+    uint32_t v[64];
+    uint32_t band = 0;
+    for (int j = 0; j < 64; ++j) {
+        v[j] = o[j] & mask;
+        band |= (uint32_t)(v[j] > sure) & (uint32_t)(v[j] <= top);
+    }
+    if (band) return -1;
+    int cnt = 0;
+    for (int j = 0; j < 64; ++j) { dst[cnt] = v[j]; cnt += (v[j] <= sure) ? 1 : 0; }      // a rejected one is overwritten
+    return cnt;
+}
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target("avx512f"))) static int block64_avx512(const uint32_t *o, uint32_t mask, uint32_t top, uint32_t sure, uint32_t *dst)
+{
+    const __m512i m = _mm512_set1_epi32((int)mask), t = _mm512_set1_epi32((int)top), s = _mm512_set1_epi32((int)sure);
+    __m512i v[4];
+    __mmask16 band = 0;
+    for (int q = 0; q < 4; ++q) {
+        v[q] = _mm512_and_si512(_mm512_loadu_si512((const void *)(o + 16 * q)), m);
+        band |= _mm512_cmpgt_epu32_mask(v[q], s) & _mm512_cmple_epu32_mask(v[q], t);
+    }
+    if (band) return -1;
+    int cnt = 0;
+    for (int q = 0; q < 4; ++q) {
+        const __mmask16 acc = _mm512_cmple_epu32_mask(v[q], s);
+        _mm512_mask_compressstoreu_epi32((void *)(dst + cnt), acc, v[q]);
+        cnt += __builtin_popcount((unsigned)acc);
+    }
+    return cnt;
+}
+static bool block64_use_avx512()
+{
+    static const bool yes = __builtin_cpu_supports("avx512f") && !getenv("CAB200_NO_AVX512");     // the variable: tests of the generic path
+    return yes;
+}
+#else
+static int block64_avx512(const uint32_t *o, uint32_t mask, uint32_t top, uint32_t sure, uint32_t *dst) { return block64_generic(o, mask, top, sure, dst); }
+static bool block64_use_avx512() { return false; }
+#endif
+
 // permutation(n)[:k] on the generator mt: numpy's _shuffle_raw + random_interval (see the file header).
 // The shuffle runs i = n-1 .. 1, swap(a[i], a[j_i]); only a[0..k) is wanted.  Instead of swapping inside a
 // megabyte-sized array (random accesses), the draws j_i are stored in generator order and the k wanted positions
@@ -127,20 +175,21 @@ struct MtBlock {
 void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
 {
     // one scratch array per host thread, kept between calls: a fresh 1 MB vector per frame means an mmap / munmap
-    // pair per call, and with 32 prompt threads those serialise on the process's address-space lock
-    thread_local std::vector<uint32_t> J;
-    J.resize((size_t)n);
+    // pair per call, and with 32 prompt threads those serialise on the process's address-space lock.  The draws are
+    // kept in GENERATOR order: Jr[t] is the draw for i = n - 1 - t.
+    thread_local std::vector<uint32_t> Jr;
+    Jr.resize((size_t)n + 64);
     MtBlock blk(mt);
     // random_interval(i): smallest bit mask >= i, rejection on masked 32-bit outputs (i <= 0x7fffffff here).  The
     // accept / reject outcome is close to a coin flip for i just above a power of two, so nothing here branches on
     // it.  Outputs are taken 64 at a time: output j of a block is compared with i minus the number of outputs
     // accepted before it, which lies in [i - 63, i] -- so an output <= i - 63 is accepted and one > i rejected
     // whatever came before, and unless some output falls into the narrow band between (probability 64 / mask each)
-    // the block reduces to a branch-free compaction whose only serial dependency is the running count.  Every output
-    // is stored at J[i - count]; a rejected one is overwritten by the next.
+    // the block reduces to a compaction of the accepted outputs (AVX-512: four compress-stores).
     {
         int64_t i = n - 1;
-        uint32_t *Jp = J.data();
+        uint32_t *Jp = Jr.data();
+        const bool wide = block64_use_avx512();
         while (i >= 1) {
             uint32_t mask = (uint32_t)i;
             mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
@@ -149,17 +198,11 @@ void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
                 if (mt.pos == blk.end) blk.fill();
                 constexpr int B = 64;
                 if (blk.end - mt.pos >= B && i - lo + 1 >= B) {
-                    const uint32_t *o = blk.out + mt.pos;
                     const uint32_t top = (uint32_t)i, sure = (uint32_t)(i - (B - 1));
-                    uint32_t v[B];
-                    uint32_t band = 0;
-                    for (int j = 0; j < B; ++j) {
-                        v[j] = o[j] & mask;
-                        band |= (uint32_t)(v[j] > sure) & (uint32_t)(v[j] <= top);
-                    }
-                    if (!band) {
-                        int64_t cnt = 0;
-                        for (int j = 0; j < B; ++j) { Jp[i - cnt] = v[j]; cnt += (v[j] <= sure) ? 1 : 0; }
+                    uint32_t *dst = Jp + (n - 1 - i);
+                    const int cnt = wide ? block64_avx512(blk.out + mt.pos, mask, top, sure, dst)
+                                         : block64_generic(blk.out + mt.pos, mask, top, sure, dst);
+                    if (cnt >= 0) {
                         mt.pos += B;
                         i -= cnt;
                         continue;
@@ -169,20 +212,23 @@ void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
                 const int e = std::min(blk.end, p + B);
                 while (p < e && i >= lo) {
                     const uint32_t w = blk.out[p++] & mask;
-                    Jp[i] = w;
+                    Jp[n - 1 - i] = w;
                     i -= (w <= (uint32_t)i) ? 1 : 0;
                 }
                 mt.pos = p;
             }
         }
     }
+    const uint32_t *J = Jr.data() + (n - 1);                 // J[-i] ... use the accessor below
+    auto draw = [&](int64_t i) -> uint32_t { return Jr[(size_t)(n - 1 - i)]; };
+    (void)J;
     constexpr int KMAX = 32;
     if (k <= KMAX) {
         uint32_t pos[KMAX];
         for (int32_t q = 0; q < k; ++q) pos[q] = (uint32_t)q;
         const int64_t head = std::min<int64_t>(n, (int64_t)k);
         for (int64_t i = 1; i < head; ++i) {                 // i < k: a tracked position can also BE i
-            const uint32_t j = J[(size_t)i];
+            const uint32_t j = draw(i);
             for (int32_t q = 0; q < k; ++q) {
                 if (pos[q] == (uint32_t)i) pos[q] = j;
                 else if (pos[q] == j) pos[q] = (uint32_t)i;
@@ -192,31 +238,32 @@ void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
             uint32_t p0 = pos[0], p1 = pos[1], p2 = pos[2], p3 = pos[3], p4 = pos[4];
             // a hit is rare (k / i per draw): test 16 draws at a time (a reduction the compiler vectorises) and
             // walk a chunk one by one only when it holds a hit
-            const uint32_t *Jp = J.data();
+            const uint32_t *Jp = Jr.data();
             int64_t i = head;
             for (; i + 16 <= n; i += 16) {
+                const uint32_t *c = Jp + (n - 1 - (i + 15));       // draws of i + 15 .. i (generator order)
                 uint32_t hit = 0;
                 for (int e = 0; e < 16; ++e) {
-                    const uint32_t j = Jp[i + e];
+                    const uint32_t j = c[e];
                     hit |= (uint32_t)(j == p0) | (uint32_t)(j == p1) | (uint32_t)(j == p2) | (uint32_t)(j == p3) | (uint32_t)(j == p4);
                 }
                 if (hit) {
                     for (int e = 0; e < 16; ++e) {
-                        const uint32_t j = Jp[i + e], ii = (uint32_t)(i + e);
+                        const uint32_t j = c[15 - e], ii = (uint32_t)(i + e);
                         p0 = (j == p0) ? ii : p0; p1 = (j == p1) ? ii : p1; p2 = (j == p2) ? ii : p2;
                         p3 = (j == p3) ? ii : p3; p4 = (j == p4) ? ii : p4;
                     }
                 }
             }
             for (; i < n; ++i) {
-                const uint32_t j = Jp[i], ii = (uint32_t)i;
+                const uint32_t j = draw(i), ii = (uint32_t)i;
                 p0 = (j == p0) ? ii : p0; p1 = (j == p1) ? ii : p1; p2 = (j == p2) ? ii : p2;
                 p3 = (j == p3) ? ii : p3; p4 = (j == p4) ? ii : p4;
             }
             pos[0] = p0; pos[1] = p1; pos[2] = p2; pos[3] = p3; pos[4] = p4;
         } else {
             for (int64_t i = head; i < n; ++i) {
-                const uint32_t j = J[(size_t)i];
+                const uint32_t j = draw(i);
                 for (int32_t q = 0; q < k; ++q) pos[q] = (j == pos[q]) ? (uint32_t)i : pos[q];
             }
         }
@@ -227,7 +274,7 @@ void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
     thread_local std::vector<int32_t> a;
     a.resize((size_t)n);
     for (int64_t i = 0; i < n; ++i) a[(size_t)i] = (int32_t)i;
-    for (int64_t i = n - 1; i >= 1; --i) std::swap(a[(size_t)i], a[J[(size_t)i]]);
+    for (int64_t i = n - 1; i >= 1; --i) std::swap(a[(size_t)i], a[draw(i)]);
     for (int32_t q = 0; q < k; ++q) out[q] = a[(size_t)q];
 }
 

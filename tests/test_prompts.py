@@ -401,3 +401,14 @@ def test_native_pouch_prompts_equal_the_frame_by_frame_path(cuda_device):
             sa, sb = a.get_state(), b.get_state()
             assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1]), (size, i)
         assert seen_bg > 0
+
+
+def test_legacy_choice_generic_path_without_avx512():
+    """The block compaction of cab200_legacy_choice has an AVX-512 and a generic implementation, chosen at run time;
+    the numpy-equality tests above run once more in a process where the wide one is switched off."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_prompts.py"), "-q", "-x", "-k",
+                          "test_legacy_choice_is_numpys_choice or test_sample_background_is_the_numpy"],
+                         capture_output=True, text=True, env=dict(os.environ, CAB200_NO_AVX512="1"), cwd=root, timeout=600)
+    assert res.returncode == 0 and "2 passed" in res.stdout, res.stdout[-1500:] + res.stderr[-500:]
