@@ -309,12 +309,17 @@ std::vector<int> shape_sorted_order(Problem &P)
 {
     const int per = 32 * P.cpt, emax = 2 * P.ep;
     std::vector<char> used(P.n, 0);
-    std::vector<std::vector<int>> kinds;                      // special rows: entries before > ep | entries after > ep
-    for (int kind = 0; kind < 2 && P.unit; ++kind) {
-        std::vector<int> spec;
-        for (int c = 0; c < P.n; ++c)
-            if (P.special(c) && ((kind == 0) == (P.nb(c) > P.ep))) spec.push_back(c);
-        if (!spec.empty()) kinds.push_back(spec);
+    // special rows grouped by the diagonal point they need: the one closest to ep that fits the row itself
+    std::vector<std::vector<int>> kinds;
+    std::vector<int> kind_d;
+    for (int c = 0; c < P.n && P.unit; ++c) {
+        if (!P.special(c)) continue;
+        const int d = k1_warp_diag(P.ep, P.nb(c), P.na(c));
+        if (d < 0) return {};
+        size_t ki = 0;
+        for (; ki < kind_d.size() && kind_d[ki] != d; ++ki) {}
+        if (ki == kind_d.size()) { kind_d.push_back(d); kinds.emplace_back(); }
+        kinds[ki].push_back(c);
     }
     const int last_cnt = P.n - ((P.n - 1) / per) * per;       // cells in the last warp that holds any
     std::vector<int> tail;                                    // the sections, in slot order
