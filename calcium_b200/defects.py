@@ -256,14 +256,22 @@ def _lut(image: np.ndarray, table: np.ndarray, by_max: bool) -> np.ndarray:
     return table[row][image]
 
 
+_GRADIENT07: Dict[Tuple[int, int], np.ndarray] = {}
+
+
 def _nonuniform_background(image, intensity, rs):                       # artifacts/background.py:21-45, 58
     import cv2
     max_val = np.max(image)
     rows, cols = image.shape[:2]
-    yy, xx = np.mgrid[0:rows, 0:cols]
-    gradient = np.sin(xx / cols * 3 * np.pi) * np.sin(yy / rows * 2 * np.pi) * 0.5 + 0.5
+    g07 = _GRADIENT07.get((rows, cols))
+    if g07 is None:                      # static per frame size: the same numpy expression, evaluated once
+        yy, xx = np.mgrid[0:rows, 0:cols]
+        gradient = np.sin(xx / cols * 3 * np.pi) * np.sin(yy / rows * 2 * np.pi) * 0.5 + 0.5
+        g07 = gradient * 0.7
+        g07.setflags(write=False)
+        _GRADIENT07[(rows, cols)] = g07
     noise = cv2.GaussianBlur(rs.rand(rows, cols), (99, 99), 30)
-    background = (gradient * 0.7 + noise * 0.3) * intensity * max_val
+    background = (g07 + noise * 0.3) * intensity * max_val
     out = image.copy()
     for ch in range(image.shape[2]):
         out[:, :, ch] = np.clip(out[:, :, ch] + background, 0, max_val)
