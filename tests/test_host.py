@@ -354,3 +354,67 @@ def test_batch_device_list_resolution():
         _resolve_devices(None, [])
     with pytest.raises(ValueError):
         _resolve_devices(None, "both")
+
+
+def test_k1_gather_order_emulation_on_random_graphs(lib, tmp_path):
+    """CPU emulation of K1's gather order (tests/csrc/k1_layout_check.cpp, built on the layout header the kernel and the
+    planner share): for the plans of every synthetic geometry and of random graphs with long rows on either side of the
+    diagonal, every stored entry of every row is added exactly once, in CSR order, with the register diagonal at its
+    place and inside the warp's position range -- before and after annealing."""
+    import subprocess
+    from calcium_b200 import _lib
+    from calcium_b200.ensemble import plan_layout
+    from calcium_b200.geometry import Geometry, get_geometry
+    so = str(tmp_path / "k1_layout_check.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", os.path.join(ROOT, "tests", "csrc", "k1_layout_check.cpp"), "-o", so],
+                   check=True)
+    chk = ctypes.CDLL(so)
+    chk.k1_layout_check.restype = ctypes.c_longlong
+
+    def fuzz_graph(trial, n):
+        rng = np.random.RandomState(100 + trial)
+        deg = np.zeros(n, dtype=int)
+        edges = set()
+
+        def link(a, b):
+            if a != b and (min(a, b), max(a, b)) not in edges and deg[a] < 9 and deg[b] < 9:
+                edges.add((min(a, b), max(a, b))); deg[a] += 1; deg[b] += 1
+        n_hub = max(1, n // (40 if trial % 3 == 2 else 150))
+        for hub in rng.choice(max(2, n // 6), size=n_hub, replace=False):
+            for j in rng.choice(np.arange(hub + 1, n), size=min(7, n - hub - 1), replace=False):
+                link(int(hub), int(j))
+        for hub in n - 1 - rng.choice(max(2, n // 6), size=n_hub, replace=False):
+            for j in rng.choice(np.arange(0, hub), size=min(7, hub), replace=False):
+                link(int(hub), int(j))
+        for _ in range(2 * n):
+            a, b = rng.randint(0, n, 2)
+            link(int(a), int(b))
+        verts = np.empty(n, dtype=object)
+        for i in range(n):
+            verts[i] = np.array([[i, 0.0], [i + 1, 0.0], [i + 1, 1.0], [i, 1.0]])
+        return Geometry(size=f"fuzz{n}", vertices=verts, edges=np.array(sorted(edges), dtype=np.int32).reshape(-1, 2))
+
+    geos = [get_geometry(s_) for s_ in ("xsmall", "small", "medium", "large")]
+    geos += [fuzz_graph(t, n) for t, n in enumerate((24, 40, 90, 150, 333, 700, 1300))]
+    checked = special_points = 0
+    for g in geos:
+        rowptr, col, _ = g.csr
+        n = g.n_cells
+        copies, cpt = plan_layout(n, True, 64)
+        lay = np.zeros(4, dtype=np.int64)
+        assert lib.cab200_sim_layout(n, 1, 64, _lib.as_i64p(lay)) == 0
+        n_slots = int(lay[0] * lay[1])
+        for iters in (0, 40000):
+            plan = np.zeros(2 * n, dtype=np.uint16)
+            rc = lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 1, cpt, iters, 5, 0,
+                                       plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None)
+            if rc != 0:                                   # refused: this geometry runs the general kernel
+                assert b"unit = 0" in lib.cab200_last_error()
+                break
+            wd = np.zeros(64, dtype=np.int32)
+            bad = chk.k1_layout_check(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)),
+                                      cpt, n_slots, _lib.as_i32p(wd))
+            assert bad == 0, (g.size, iters, int(bad))
+            checked += 1
+            special_points += int(np.isin(wd, (1, 3, 7, 9)).sum())
+    assert checked >= 12 and special_points >= 10         # warps with diagonal points 1, 3, 7, 9 were among them
