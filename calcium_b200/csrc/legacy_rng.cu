@@ -219,9 +219,7 @@ void choice_first_k(Mt &mt, int64_t n, int32_t k, int64_t *out)
             }
         }
     }
-    const uint32_t *J = Jr.data() + (n - 1);                 // J[-i] ... use the accessor below
-    auto draw = [&](int64_t i) -> uint32_t { return Jr[(size_t)(n - 1 - i)]; };
-    (void)J;
+    auto draw = [&](int64_t i) -> uint32_t { return Jr[(size_t)(n - 1 - i)]; };      // the draw j_i of swap(a[i], a[j_i])
     constexpr int KMAX = 32;
     if (k <= KMAX) {
         uint32_t pos[KMAX];
