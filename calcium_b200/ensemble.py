@@ -500,7 +500,18 @@ class Ensemble:
         for gi, d in enumerate(self.dgeo):
             nc = int(self.g_cluster[gi])
             if use_plan or nc > 1:          # a cluster cannot run without its partition plan
-                t = d.plan(precision, nc)
+                try:
+                    t = d.plan(precision, nc)
+                except _lib.Cab200Error:
+                    # some part of the cluster partition has rows that share no diagonal point (k1_layout.cuh): the
+                    # pouch stays on one CTA when the library chose the cluster itself and one CTA can hold it
+                    if nc == 1 or cluster != "auto" or d.n > 4096:
+                        raise
+                    nc = 1
+                    self.g_cluster[gi] = 1
+                    if not use_plan:
+                        continue
+                    t = d.plan(precision, 1)
                 self.g_plan_off[gi] = off
                 plans.append(t)
                 off += int(t.numel())
