@@ -308,6 +308,26 @@ __device__ __forceinline__ bool place_rows(uint32_t lanebits, uint32_t *rowbits,
     return (bitpos + total + 7u + 7u) / 8u + tail_room <= cap;
 }
 
+// The same for the event parse, whose tokens are interleaved over the lanes: only the row's total is needed
+// (warp-uniform), and what comes back is the absolute bit position of the row's first token.
+__device__ __forceinline__ bool place_row_totals(uint32_t rowtotal, uint32_t *rowbits, uint32_t bitpos, uint32_t tail_room,
+                                                 uint32_t cap, uint32_t &rowpos, uint32_t &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) rowbits[warp] = rowtotal;
+    __syncthreads();
+    const uint32_t mine = (lane < ENC_NW) ? rowbits[lane] : 0u;
+    uint32_t sc = mine;
+#pragma unroll
+    for (int o = 1; o < ENC_NW; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o);
+        if (lane >= o) sc += t;
+    }
+    rowpos = bitpos + __shfl_sync(0xffffffffu, sc - mine, warp);
+    total = __shfl_sync(0xffffffffu, sc, ENC_NW - 1);
+    return (bitpos + total + 7u + 7u) / 8u + tail_room <= cap;
+}
+
 // One token -> (bits, count).  A match of `len` pixels in mode up/left, or the literal pixel `key`
 // (also for a one-pixel match of a 2-byte pixel, which is too short for DEFLATE).
 template <bool IMG>
@@ -603,38 +623,74 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                 const uint32_t m = (dsc >> 12) & 3u;
                 make_token<IMG>(sm, m != 0u, m == 2u, (int)(dsc & 0xfffu), dsc >> 16, dist_up, dist_left, val, nb);
             };
-            // bit counts, one token per lane and round
-            uint32_t lanebits = 0;
-            for (int b0 = 0; b0 < ntok; b0 += ENC_TCAP) {
-                if (b0) __syncwarp();
-                fill(b0);
-                const int nt = min(ntok - b0, ENC_TCAP);
-                for (int t = lane; t < nt; t += 32) {
-                    unsigned long long val; int nb;
-                    token_at(t, val, nb);
-                    lanebits += (uint32_t)nb;
-                }
-            }
-            uint32_t pos;
-            if (!place_rows(lanebits, rowbits[par], bitpos, tail_room, (uint32_t)a.stage_cap, pos, pass_bits)) { overflow = true; break; }
-            // tokens are interleaved over the lanes by round, not contiguous per lane: take the row's start
-            // (lane 0's position) and scan round by round
-            uint32_t rowpos = __shfl_sync(0xffffffffu, pos, 0);
-            for (int b0 = 0; b0 < ntok; b0 += ENC_TCAP) {
-                if (ntok > ENC_TCAP) { __syncwarp(); fill(b0); }       // a single batch is still in the list
-                const int nt = min(ntok - b0, ENC_TCAP);
-                for (int r0 = 0; r0 < nt; r0 += 32) {
-                    const int t = r0 + lane;
-                    unsigned long long val = 0; int nb = 0;
-                    if (t < nt) token_at(t, val, nb);
-                    uint32_t inc = (uint32_t)nb;
+            // A row with at most ENC_TCAP tokens (all but pathological ones) builds every token ONCE: bits, bit
+            // count and the position relative to the row start (a warp scan per round of 32 tokens) stay in
+            // registers across the pass-wide prefix sum, and the write phase is one put_bits per token.
+            const bool onebatch = ntok <= ENC_TCAP;                            // warp-uniform
+            unsigned long long cval[ENC_TCAP / 32];
+            uint32_t cmeta[ENC_TCAP / 32];                                     // relative bit position | bit count << 24
+            uint32_t rowtotal = 0;
+            if (onebatch) {
+                fill(0);
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += u;
+                for (int r = 0; r < ENC_TCAP / 32; ++r) {
+                    cval[r] = 0; cmeta[r] = 0;
+                    if (r * 32 < ntok) {                                       // warp-uniform
+                        const int t = r * 32 + lane;
+                        unsigned long long val = 0; int nb = 0;
+                        if (t < ntok) token_at(t, val, nb);
+                        uint32_t inc = (uint32_t)nb;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += u;
+                        }
+                        cval[r] = val;
+                        cmeta[r] = (rowtotal + inc - (uint32_t)nb) | ((uint32_t)nb << 24);
+                        rowtotal += __shfl_sync(0xffffffffu, inc, 31);
                     }
-                    if (t < nt && valid) put_bits(stage32, rowpos + inc - (uint32_t)nb, val, nb);
-                    rowpos += __shfl_sync(0xffffffffu, inc, 31);
+                }
+            } else {
+                // bit counts, one token per lane and round
+                uint32_t lanebits = 0;
+                for (int b0 = 0; b0 < ntok; b0 += ENC_TCAP) {
+                    if (b0) __syncwarp();
+                    fill(b0);
+                    const int nt = min(ntok - b0, ENC_TCAP);
+                    for (int t = lane; t < nt; t += 32) {
+                        unsigned long long val; int nb;
+                        token_at(t, val, nb);
+                        lanebits += (uint32_t)nb;
+                    }
+                }
+                rowtotal = __reduce_add_sync(0xffffffffu, lanebits);
+            }
+            uint32_t rowpos;
+            if (!place_row_totals(rowtotal, rowbits[par], bitpos, tail_room, (uint32_t)a.stage_cap, rowpos, pass_bits)) { overflow = true; break; }
+            if (onebatch) {
+#pragma unroll
+                for (int r = 0; r < ENC_TCAP / 32; ++r) {
+                    const int nb = (int)(cmeta[r] >> 24);
+                    if (nb && valid) put_bits(stage32, rowpos + (cmeta[r] & 0xffffffu), cval[r], nb);
+                }
+            } else {
+                // tokens are interleaved over the lanes by round, not contiguous per lane: scan round by round
+                for (int b0 = 0; b0 < ntok; b0 += ENC_TCAP) {
+                    __syncwarp(); fill(b0);
+                    const int nt = min(ntok - b0, ENC_TCAP);
+                    for (int r0 = 0; r0 < nt; r0 += 32) {
+                        const int t = r0 + lane;
+                        unsigned long long val = 0; int nb = 0;
+                        if (t < nt) token_at(t, val, nb);
+                        uint32_t inc = (uint32_t)nb;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += u;
+                        }
+                        if (t < nt && valid) put_bits(stage32, rowpos + inc - (uint32_t)nb, val, nb);
+                        rowpos += __shfl_sync(0xffffffffu, inc, 31);
+                    }
                 }
             }
         }
