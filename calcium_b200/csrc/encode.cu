@@ -131,8 +131,8 @@ __device__ __forceinline__ void put_bits(uint32_t *w, uint32_t pos, unsigned lon
 // shared window base (S2R + LEA + ...) in front of every predicated load -- 6 instructions per look-up.
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    uint32_t v;                                  // a wider destination is zero-extended: no PRMT afterwards
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
@@ -180,12 +180,13 @@ __device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n,
 
 // Static event list of one label map: per 512-pixel row segment the pixels whose label differs from the
 // left or the upper neighbour, plus the forced cut positions (every `maxpix` pixels), ENC_ECAP slots:
-// x = {x | label << 16}, y = {label_left | label_up << 16} (0xffff = no such neighbour); padding slots
-// have x = segment end.  Every other pixel has the label of both neighbours, hence -- whatever a frame's
-// values -- the mode "up" (or "left" where no row above is usable).  One warp per segment; max_count
-// receives the largest number of events in a segment (a list is truncated at ENC_ECAP: the caller
-// then must not use it).
-__global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, int H, int W, int maxpix, int use_up,
+// x = {x | o << 16}, y = {o_left | o_up << 16}, o = BYTE OFFSET of the label's entry in the frame's 16-bit key
+// LUT (2 * label); a missing neighbour and the padding slots (x = segment end) point at entry n + 1, which
+// encode_kernel fills with a key no pixel has -- the look-ups and comparisons of the parse need no special
+// cases.  Every other pixel has the label of both neighbours, hence -- whatever a frame's values -- the mode
+// "up" (or "left" where no row above is usable).  One warp per segment; max_count receives the largest number
+// of events in a segment (a list is truncated at ENC_ECAP: the caller then must not use it).
+__global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, int H, int W, int n, int maxpix, int use_up,
                                                          uint2 *events, int *max_count)
 {
     const int lane = threadIdx.x & 31;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, 
     if (item >= H * nseg) return;
     const int y = item / nseg, x0 = (item % nseg) * 512, xend = min(W, x0 + 512);
     uint2 *out = events + (size_t)item * ENC_ECAP;
+    const uint32_t none = 2u * (uint32_t)(n + 1);
     int count = 0;
     for (int c = x0; c < xend; c += 32) {
         const int x = c + lane;
@@ -204,10 +206,12 @@ __global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, 
         const bool isev = inb && ((x % maxpix) == 0 || labL == 0xffffu || lab != labL || (labU != 0xffffu && lab != labU));
         const unsigned b = __ballot_sync(0xffffffffu, isev);
         const int idx = count + __popc(b & ((1u << lane) - 1u));
-        if (isev && idx < ENC_ECAP) out[idx] = make_uint2((uint32_t)x | (lab << 16), labL | (labU << 16));
+        if (isev && idx < ENC_ECAP)
+            out[idx] = make_uint2((uint32_t)x | ((2u * lab) << 16),
+                                  (labL == 0xffffu ? none : 2u * labL) | ((labU == 0xffffu ? none : 2u * labU) << 16));
         count += __popc(b);
     }
-    for (int j = min(count, ENC_ECAP) + lane; j < ENC_ECAP; j += 32) out[j] = make_uint2((uint32_t)xend | 0xffff0000u, 0xffffffffu);
+    for (int j = min(count, ENC_ECAP) + lane; j < ENC_ECAP; j += 32) out[j] = make_uint2((uint32_t)xend | (none << 16), none | (none << 16));
     if (lane == 0) atomicMax(max_count, count);
 }
 
@@ -527,18 +531,19 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                 const uint32_t kl_a = smem_addr(IMG ? lut.rank1 : lut.inst_lut);
     #pragma unroll
                 for (int e = 0; e < K; e += 2) {
-                    uint4 r = make_uint4((uint32_t)xend | 0xffff0000u, 0xffffffffu, (uint32_t)xend | 0xffff0000u, 0xffffffffu);
+                    const uint32_t none = 2u * (uint32_t)(n + 1);
+                    uint4 r = make_uint4((uint32_t)xend | (none << 16), none | (none << 16), (uint32_t)xend | (none << 16), none | (none << 16));
                     if (valid) r = __ldg(reinterpret_cast<const uint4 *>(ev + e));
                     const uint32_t rx[2] = {r.x, r.z}, ry[2] = {r.y, r.w};
     #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t x = rx[h] & 0xffffu, lab = rx[h] >> 16, labL = ry[h] & 0xffffu, labU = ry[h] >> 16;
-                        // padding slots and missing neighbours carry label 0xffff: read entry 0 instead and
-                        // discard, so the three look-ups are unconditional
-                        const uint32_t k = lds_u16(kl_a + 2u * (lab == 0xffffu ? 0u : lab));
-                        const uint32_t kL = lds_u16(kl_a + 2u * (labL == 0xffffu ? 0u : labL));
-                        const uint32_t kU = lds_u16(kl_a + 2u * (labU == 0xffffu ? 0u : labU));
-                        const uint32_t m = (labU != 0xffffu && k == kU) ? 2u : ((labL != 0xffffu && k == kL) ? 1u : 0u);
+                        // a missing neighbour (and a padding slot) reads the LUT's extra entry n + 1, a key no
+                        // pixel has: three unconditional look-ups, two plain comparisons
+                        const uint32_t x = rx[h] & 0xffffu;
+                        const uint32_t k = lds_u16(kl_a + (rx[h] >> 16));
+                        const uint32_t kL = lds_u16(kl_a + (ry[h] & 0xffffu));
+                        const uint32_t kU = lds_u16(kl_a + (ry[h] >> 16));
+                        const uint32_t m = (k == kU) ? 2u : ((k == kL) ? 1u : 0u);
                         ex[e + h] = x;
                         info[e + h] = x | (m << 12) | (k << 16);
                     }
@@ -880,6 +885,9 @@ __global__ void __launch_bounds__(ENC_NT, 2) encode_kernel(const EncodeArgs a)
     // image pixel key per label value: gray | 0x100 (alpha set), 0 for the background; the rank
     // scratch of the LUT build is free now
     for (int v = tid; v <= n; v += ENC_NT) lut.rank1[v] = v ? (uint16_t)(lut.gray_lut[v] | 0x100u) : (uint16_t)0;
+    // entry n + 1 of both key LUTs: "no such neighbour" in the static event lists (image keys are < 0x200,
+    // instance ids <= n <= 32766)
+    if (tid == 0) { lut.rank1[n + 1] = 0xffffu; lut.inst_lut[n + 1] = 0xffffu; }
     __syncthreads();
     EncRecord *rec = a.records + (size_t)pf * 2;
     const size_t gbase = (size_t)pe.geom * a.H * a.W;
@@ -1203,13 +1211,14 @@ extern "C" int cab200_encode_geometry(int n_cells, const uint16_t *label_img, co
     const bool up_img = 1 + 4 * W <= 32768, up_msk = 2 * W <= 32768;     // the distances DEFLATE can express
     uint2 *ev_img = (uint2 *)(out + geom_tab_sums_bytes(n_cells));
     uint2 *ev_msk = (uint2 *)(out + geom_tab_sums_bytes(n_cells) + geom_tab_events_bytes(H, W));
-    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_img, H, W, 64, up_img ? 1 : 0, ev_img, d_max);
-    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_mask, H, W, 128, up_msk ? 1 : 0, ev_msk, d_max + 1);
+    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_img, H, W, n_cells, 64, up_img ? 1 : 0, ev_img, d_max);
+    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_mask, H, W, n_cells, 128, up_msk ? 1 : 0, ev_msk, d_max + 1);
     CAB_CUDA(cudaGetLastError());
     int h_max[2] = {0, 0};
     CAB_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
     CAB_CUDA(cudaStreamSynchronize(stream));
-    *max_events_out = std::max(h_max[0], h_max[1]);
+    // the event lists address the key LUT with 16-bit byte offsets: larger label ranges take the per-pixel parse
+    *max_events_out = (n_cells > 32766) ? (1 << 30) : std::max(h_max[0], h_max[1]);
     return CAB200_OK;
 }
 
