@@ -539,7 +539,7 @@ class Ensemble:
         self._scratch = torch.empty(
             int(self.lib.cab200_sim_scratch_bytes(self.P, self.F)
                 + self.lib.cab200_raster_scratch_bytes(self.P)
-                + self.lib.cab200_encode_scratch_bytes(self.P, len(self.dgeo))) + 96,
+                + 2 * self.lib.cab200_encode_scratch_bytes(self.P, len(self.dgeo))) + 128,   # two halves: K3 chunks on two streams
             dtype=torch.uint8, device=self.device)
         self._label_img: Optional[torch.Tensor] = None
         self._edge_maps: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -591,6 +591,14 @@ class Ensemble:
             self.upload()
         real = torch.float64 if self.precision == _lib.FP64_STRICT else torch.float32
         with torch.cuda.device(self.device):
+            # kernels on side streams that still read the frames this launch overwrites (K3 chunks of
+            # run_files_to_host): waited for here, after the upload, so that the upload overlaps them
+            readers = getattr(self, "_frames_readers", None)
+            if readers:
+                cur_ = torch.cuda.current_stream(self.device)
+                for ev_ in readers:
+                    cur_.wait_event(ev_)
+                self._frames_readers = []
             if self.frames is None or self.frames.dtype != real:
                 self.frames = torch.empty(max(self.frame_elems, 1), dtype=real, device=self.device)
                 self.status = torch.zeros(self.P, dtype=torch.int32, device=self.device)
@@ -777,15 +785,17 @@ class Ensemble:
 
     def encode(self, image: bool = True, mask: bool = True, pouches: Optional[Tuple[int, int]] = None,
                threshold: float = 0.1, quirk: bool = True, out: Optional[Dict[str, torch.Tensor]] = None,
-               arena_bytes: Optional[int] = None, stage_bytes: int = 0, parse: str = "events"
-               ) -> Dict[str, torch.Tensor]:
+               arena_bytes: Optional[int] = None, stage_bytes: int = 0, parse: str = "events",
+               scratch_half: int = 0) -> Dict[str, torch.Tensor]:
         """K3 over pouches ``[a, b)``: every frame rasterised and encoded on the device into the files
         the reference's batch path stores -- a 16-bit gray+alpha ``.png`` (``save_image``,
         utils/image_processing.py:252-269) and a ``.npz`` holding ``mask`` (the instance mask,
         utils/sam2_data_generator.py:203).  Returns device tensors ``arena`` (uint8), ``cursor``
         (int64[1], bytes used), ``records`` (int64 ``[p, F, 2, 2]``: for image / mask the arena offset
         and ``size | flags << 32``) and ``n_active [p, F]``.  See :func:`records_to_host`.
-        ``parse="pixels"`` forces the per-pixel parse (same files; the event parse is the fast path)."""
+        ``parse="pixels"`` forces the per-pixel parse (same files; the event parse is the fast path).
+        ``scratch_half`` (0 / 1): which half of the launch scratch (pouch table) the call uses -- calls that may
+        run concurrently on two streams (:meth:`run_files_to_host`) must not share one."""
         if self.frames is None:
             raise RuntimeError("simulate() first")
         if self.precision != _lib.FP64_STRICT:
@@ -827,6 +837,8 @@ class Ensemble:
             scr_off = int(self.lib.cab200_sim_scratch_bytes(self.P, self.F)) + int(
                 self.lib.cab200_raster_scratch_bytes(self.P))
             scr_off = (scr_off + 15) // 16 * 16
+            if scratch_half:
+                scr_off += (int(self.lib.cab200_encode_scratch_bytes(self.P, len(self.dgeo))) + 15) // 16 * 16
             rc = self.lib.cab200_encode_batch(
                 cnt, _lib.as_i32p(gid), len(self.dgeo), _lib.as_i32p(self.g_ncell), _lib.as_i64p(coff),
                 limg.data_ptr(), lmsk.data_ptr(), h, w, self.F, self.frames.data_ptr(),
@@ -910,6 +922,12 @@ class Ensemble:
                         "h_nact": torch.empty((cp * self.F + 3) // 4 * 4, dtype=torch.int32, pin_memory=True),
                         "meta": torch.cuda.Event(), "data": torch.cuda.Event(), "busy": None})
             st = {"key": key, "pool_key": pool_key, "cs": torch.cuda.Stream(device=dev), "fs": torch.cuda.Stream(device=dev),
+                  # K3 chunks alternate between two streams: the next chunk's CTAs fill the SMs the previous
+                  # chunk's last wave leaves idle (one stream: 4 x 3.33 ms per 148 pouches, one launch: 12.9 ms)
+                  "ks": [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)], "k3_done": [None, None],
+                  # the few bytes the host waits for (sizes, records) are published from a high-priority stream:
+                  # behind the other K3 stream's thousands of pending CTAs they would arrive milliseconds late
+                  "ps": torch.cuda.Stream(device=dev, priority=-1),
                   "slots": slots, "launched": [], "copying": [],
                   "frames_done": torch.cuda.Event(),
                   "h_frames": (torch.empty(max(self.frame_elems, 1), dtype=torch.float64, pin_memory=True)
@@ -934,6 +952,8 @@ class Ensemble:
                 # the chunk outgrew its arena slot: encode it again into an arena of the size it asked for
                 # (synchronous and rare; the files of a flat-shaded frame take ~0.16 bytes per pixel)
                 consumer_, threshold_, quirk_ = e["consumer"]
+                for ks_ in st["ks"]:
+                    ks_.synchronize()            # the launch scratch is shared with the chunks in flight
                 big = self.encode(image=image, mask=mask, pouches=(e["lo"], e["hi"]), threshold=threshold_, quirk=quirk_,
                                   out={}, arena_bytes=used + (1 << 20), stage_bytes=stage_bytes)
                 torch.cuda.current_stream(dev).synchronize()
@@ -999,34 +1019,49 @@ class Ensemble:
             if st["h_frames"] is not None:
                 d2h += st["h_frames"].numel() * 8
             k = st.get("k", 0)
+            for ks in st["ks"]:
+                ks.wait_event(ev)                    # K1 (and whatever the caller queued before it)
             for lo in range(0, self.P, cp):
                 hi = min(lo + cp, self.P)
                 slot = st["slots"][k % 4]
+                ks = st["ks"][k % 2]                  # slot k % 4 always meets stream k % 2
                 if slot["busy"] is not None:             # its previous chunk must be out of the way
                     e = slot["busy"]
                     if e in launched:
                         launched.remove(e); queue_copy(e)
                     if e in copying:
                         copying.remove(e); finish(e)
-                cur.wait_event(slot["data"])
-                enc = self.encode(image=image, mask=mask, pouches=(lo, hi), threshold=threshold, quirk=quirk,
-                                  out=slot["dev"], arena_bytes=cap, stage_bytes=stage_bytes)
-                n = hi - lo
-                # the sizes reach the host by zero-copy stores, not through the copy engine (it is busy
-                # with megabytes of earlier chunks, and the host needs these bytes to queue the next copy)
-                for dst, src in ((slot["h_rec"], enc["records"]), (slot["h_nact"], enc["n_active16"]),
-                                 (slot["h_cur"], enc["cursor16"])):
-                    nbytes = src.numel() * src.element_size()
-                    _lib.check(self.lib.cab200_publish_to_host(dst.data_ptr(), src.data_ptr(), nbytes // 16 * 16,
-                                                               _stream_ptr(dev)), "cab200_publish_to_host")
-                slot["meta"].record(cur)
+                ks.wait_event(slot["data"])
+                with torch.cuda.stream(ks):
+                    enc = self.encode(image=image, mask=mask, pouches=(lo, hi), threshold=threshold, quirk=quirk,
+                                      out=slot["dev"], arena_bytes=cap, stage_bytes=stage_bytes, scratch_half=k % 2)
+                    n = hi - lo
+                    k3_ev = torch.cuda.Event()
+                    k3_ev.record(ks)
+                st["k3_done"][k % 2] = k3_ev
+                ps = st["ps"]
+                ps.wait_event(k3_ev)
+                with torch.cuda.stream(ps):
+                    # the sizes reach the host by zero-copy stores, not through the copy engine (it is busy
+                    # with megabytes of earlier chunks, and the host needs these bytes to queue the next copy)
+                    for dst, src in ((slot["h_rec"], enc["records"]), (slot["h_nact"], enc["n_active16"]),
+                                     (slot["h_cur"], enc["cursor16"])):
+                        nbytes = src.numel() * src.element_size()
+                        _lib.check(self.lib.cab200_publish_to_host(dst.data_ptr(), src.data_ptr(), nbytes // 16 * 16,
+                                                                   _stream_ptr(dev)), "cab200_publish_to_host")
+                    slot["meta"].record(ps)
                 d2h += 8 + enc["records"].numel() * 8 + enc["n_active"].numel() * 4
                 e = {"lo": lo, "hi": hi, "slot": slot, "consumer": (consumer, threshold, quirk)}
                 slot["busy"] = e
                 launched.append(e)
-                if len(launched) >= 2:
+                # copy-outs are queued as soon as a chunk's size is known; the launch loop itself only blocks
+                # when every ring slot is in flight (blocking earlier would hold back the chunk that is to
+                # follow the pair running concurrently on the two K3 streams)
+                while launched and (len(launched) >= 4 or launched[0]["slot"]["meta"].query()):
                     queue_copy(launched.pop(0))
                 k += 1
+            # the next integration overwrites the frames these chunks read: simulate() waits for them
+            self._frames_readers = [done for done in st["k3_done"] if done is not None]
             st["k"] = k
             if wait:
                 self.flush_files()
