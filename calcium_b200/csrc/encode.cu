@@ -162,11 +162,13 @@ struct GeomTab {
     const uint32_t *Q, *cnt;
     const unsigned long long *M;
     const uint2 *ev_img, *ev_msk;      // static event lists (enc_events_kernel), [H * nseg][ENC_ECAP] each
+    const uint32_t *span;              // [n+1][2] rows a mask label touches: {max (H-1-y), max y}; both 0 = absent or row 0 only
 };
 constexpr int ENC_ECAP = 256;
 __host__ __device__ inline size_t geom_tab_sums_bytes(int n) { return ((((size_t)(n + 1) * 8 + 7) & ~(size_t)7) + (size_t)(n + 1) * 8 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t geom_tab_events_bytes(int H, int W) { return (size_t)H * ((W + 511) / 512) * ENC_ECAP * sizeof(uint2); }
-__host__ __device__ inline size_t geom_tab_bytes(int n, int H, int W) { return geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16; }   // + two event counters
+__host__ __device__ inline size_t geom_tab_span_bytes(int n) { return ((size_t)(n + 1) * 8 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t geom_tab_bytes(int n, int H, int W) { return geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16 + geom_tab_span_bytes(n); }   // + two event counters + the row spans
 __device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n, int H, int W)
 {
     GeomTab t;
@@ -175,6 +177,7 @@ __device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n,
     t.M = reinterpret_cast<const unsigned long long *>(p + (((size_t)(n + 1) * 8 + 7) & ~(size_t)7));
     t.ev_img = reinterpret_cast<const uint2 *>(p + geom_tab_sums_bytes(n));
     t.ev_msk = reinterpret_cast<const uint2 *>(p + geom_tab_sums_bytes(n) + geom_tab_events_bytes(H, W));
+    t.span = reinterpret_cast<const uint32_t *>(p + geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16);
     return t;
 }
 
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(256) enc_geometry_kernel(const uint16_t *label
     const unsigned long long N = tab->img.raw_len;
     const unsigned long long row_bytes = 1ull + 4ull * (unsigned long long)W;
     const int npix = H * W;
+    uint32_t *span = reinterpret_cast<uint32_t *>(out + geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         const int y = i / W, x = i - y * W;
         const int li = label_img[i], lm = label_mask[i];
@@ -236,7 +240,12 @@ __global__ void __launch_bounds__(256) enc_geometry_kernel(const uint16_t *label
             atomicAdd(&cnt[li], 1u);
             atomicAdd(&M[li], N - ((unsigned long long)y * row_bytes + 1ull + 4ull * (unsigned long long)x));
         }
-        if (lm <= n) atomicXor(&Q[lm], gf2_mulmod(tab->rowshift[y], colpx[x]));
+        if (lm <= n) {
+            atomicXor(&Q[lm], gf2_mulmod(tab->rowshift[y], colpx[x]));
+            // first / last row of the label (a new extreme is rare: test before the atomic)
+            if (span[2 * lm] < (uint32_t)(H - 1 - y)) atomicMax(&span[2 * lm], (uint32_t)(H - 1 - y));
+            if (span[2 * lm + 1] < (uint32_t)y) atomicMax(&span[2 * lm + 1], (uint32_t)y);
+        }
     }
 }
 
@@ -372,6 +381,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
     __shared__ unsigned long long red64[2][ENC_NW];
     __shared__ uint32_t pc[ENC_NT];
     __shared__ uint32_t s_crc;
+    __shared__ uint32_t rowact[ENC_MAXDIM / 32];     // mask stream: bit y = some label of row y has an instance id
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W;
     uint32_t *stage32 = reinterpret_cast<uint32_t *>(sm.stage);
@@ -381,7 +391,21 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
     for (int i = tid; i < a.stage_cap / 16; i += ENC_NT)
         reinterpret_cast<uint4 *>(sm.stage)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_crc = 0;
+    if constexpr (!IMG && K > 0) {
+        // label 0 with an id (the reference's "background instance", D5) makes every row active
+        for (int i = tid; i < ENC_MAXDIM / 32; i += ENC_NT) rowact[i] = lut.inst_lut[0] ? 0xffffffffu : 0u;
+    }
     __syncthreads();
+    if constexpr (!IMG && K > 0) {
+        for (int v = 1 + tid; v <= n; v += ENC_NT) {
+            if (!lut.inst_lut[v]) continue;
+            const int y0 = H - 1 - (int)gt.span[2 * v], y1 = (int)gt.span[2 * v + 1];      // rows the label touches
+            for (int w = y0 >> 5; w <= (y1 >> 5); ++w) {
+                const int lo = max(y0 - 32 * w, 0), hi = min(y1 - 32 * w, 31);
+                atomicOr(&rowact[w], (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
+            }
+        }
+    }
     for (int i = tid; i < d.prefix_len; i += ENC_NT) sm.stage[i] = d.prefix[i];
     // this stream's Huffman tables
     for (int i = tid; i < 260; i += ENC_NT) sm.len_s[i] = d.len[i];
@@ -524,92 +548,108 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
         } else {
             // ---- phase A (events): K static events per lane; values only decide each event's own mode ------
             const uint32_t gm = (y > 0 && use_up) ? 2u : 1u;            // mode of every non-event pixel: up, else left
-            uint32_t info[K];                                           // x | mode << 12 | key << 16
-            uint32_t ex[K];
-            {
-                const uint2 *ev = events + (size_t)item * ENC_ECAP + lane * K;
-                const uint32_t kl_a = smem_addr(IMG ? lut.rank1 : lut.inst_lut);
-    #pragma unroll
-                for (int e = 0; e < K; e += 2) {
-                    const uint32_t none = 2u * (uint32_t)(n + 1);
-                    uint4 r = make_uint4((uint32_t)xend | (none << 16), none | (none << 16), (uint32_t)xend | (none << 16), none | (none << 16));
-                    if (valid) r = __ldg(reinterpret_cast<const uint4 *>(ev + e));
-                    const uint32_t rx[2] = {r.x, r.z}, ry[2] = {r.y, r.w};
-    #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        // a missing neighbour (and a padding slot) reads the LUT's extra entry n + 1, a key no
-                        // pixel has: three unconditional look-ups, two plain comparisons
-                        const uint32_t x = rx[h] & 0xffffu;
-                        const uint32_t k = lds_u16(kl_a + (rx[h] >> 16));
-                        const uint32_t kL = lds_u16(kl_a + (ry[h] & 0xffffu));
-                        const uint32_t kU = lds_u16(kl_a + (ry[h] >> 16));
-                        const uint32_t m = (k == kU) ? 2u : ((k == kL) ? 1u : 0u);
-                        ex[e + h] = x;
-                        info[e + h] = x | (m << 12) | (k << 16);
-                    }
-                }
-            }
-            // token starts: slot 2e = at the event pixel (forced cut, literal, or mode differs from the pixel
-            // before), slot 2e+1 = at the pixel after it (the gap's static mode differs from the event's)
-            uint32_t S = 0;
-            {
-                const uint32_t pinfo = __shfl_up_sync(0xffffffffu, info[K - 1], 1);
-                uint32_t nx0 = __shfl_down_sync(0xffffffffu, ex[0], 1);
-                if (lane == 31) nx0 = (uint32_t)xend;
-                uint32_t px = pinfo & 0xfffu, pm = (pinfo >> 12) & 3u;
-    #pragma unroll
-                for (int e = 0; e < K; ++e) {
-                    const uint32_t x = ex[e], m = (info[e] >> 12) & 3u;
-                    const bool isev = (int)x < xend;
-                    const uint32_t before = (x - px > 1u) ? gm : pm;     // mode of pixel x-1
-                    const bool forced = ((x & (uint32_t)(MAXPIX - 1)) == 0u);
-                    const uint32_t nx = (e + 1 < K) ? ex[(e + 1 < K) ? e + 1 : e] : nx0;
-                    if (isev && (forced || m == 0u || m != before)) S |= 1u << (2 * e);
-                    if (isev && nx - x > 1u && m != gm) S |= 2u << (2 * e);
-                    px = x; pm = m;
-                }
-            }
-            // ---- tokens, compacted.  A lane's events start 0..2K tokens (most: none), so walking them
-            // per lane would cost every lane the longest walk of the warp.  Instead each lane drops its
-            // token descriptors (pixels | mode << 12 | key << 16) at their rank into a per-warp list and
-            // the warp then handles them 32 at a time, one token per lane.
-            uint32_t desc[2 * K];
-            {
-                // first token start at or after the next lane's first event: the end of this lane's last token
-                int fs = 0x7fffffff;
-#pragma unroll
-                for (int sidx = 2 * K - 1; sidx >= 0; --sidx)
-                    if ((S >> sidx) & 1u) fs = (int)ex[sidx >> 1] + (sidx & 1);
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_down_sync(0xffffffffu, fs, o);
-                    if (lane + o < 32) fs = min(fs, t);
-                }
-                int nextpos = __shfl_down_sync(0xffffffffu, fs, 1);
-                if (lane == 31) nextpos = 0x7fffffff;
-                nextpos = min(nextpos, xend);
-#pragma unroll
-                for (int sidx = 2 * K - 1; sidx >= 0; --sidx) {
-                    const int pos = (int)ex[sidx >> 1] + (sidx & 1);
-                    const uint32_t m = (sidx & 1) ? gm : ((info[sidx >> 1] >> 12) & 3u);
-                    desc[sidx] = ((uint32_t)(nextpos - pos) & 0xfffu) | (m << 12) | (info[sidx >> 1] & 0xffff0000u);
-                    if ((S >> sidx) & 1u) nextpos = pos;
-                }
-            }
-            const bool lead = IMG && lane == 0 && x0 == 0 && valid;           // the PNG filter byte of the row
-            int ntok, rank0;
-            {
-                const int mine = __popc(S) + (lead ? 1 : 0);
-                int incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                ntok = __shfl_sync(0xffffffffu, incl, 31);
-                rank0 = incl - mine;
+            // Mask stream: a row none of whose labels has an instance id in this frame, under a row of the same
+            // kind, is all zeros over zeros -- every pixel in mode "up", tokens only at the forced cuts.  Its
+            // descriptors are known without looking at a single event (most rows of most frames: the active set
+            // of a pouch is small).
+            bool fast = false;
+            if constexpr (!IMG) {
+                if (valid && nseg == 1 && use_up && y > 0)
+                    fast = (((rowact[y >> 5] >> (y & 31)) | (rowact[(y - 1) >> 5] >> ((y - 1) & 31))) & 1u) == 0u;
             }
             const uint32_t list_a = sm.tok_a + (uint32_t)(warp * ENC_TCAP) * 4u;
+            const bool lead = IMG && lane == 0 && x0 == 0 && valid;           // the PNG filter byte of the row
+            uint32_t S = 0;
+            uint32_t desc[2 * K];
+            int ntok, rank0 = 0;
+            if (fast) {
+                const int ncut = (xend + MAXPIX - 1) / MAXPIX;                  // <= 512 / 128
+                if (lane < ncut) sts_u32(list_a + 4u * (uint32_t)lane, (uint32_t)min(MAXPIX, xend - lane * MAXPIX) | (2u << 12));
+                __syncwarp();
+                ntok = ncut;
+            } else {
+                uint32_t info[K];                                           // x | mode << 12 | key << 16
+                uint32_t ex[K];
+                {
+                    const uint2 *ev = events + (size_t)item * ENC_ECAP + lane * K;
+                    const uint32_t kl_a = smem_addr(IMG ? lut.rank1 : lut.inst_lut);
+        #pragma unroll
+                    for (int e = 0; e < K; e += 2) {
+                        const uint32_t none = 2u * (uint32_t)(n + 1);
+                        uint4 r = make_uint4((uint32_t)xend | (none << 16), none | (none << 16), (uint32_t)xend | (none << 16), none | (none << 16));
+                        if (valid) r = __ldg(reinterpret_cast<const uint4 *>(ev + e));
+                        const uint32_t rx[2] = {r.x, r.z}, ry[2] = {r.y, r.w};
+        #pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            // a missing neighbour (and a padding slot) reads the LUT's extra entry n + 1, a key no
+                            // pixel has: three unconditional look-ups, two plain comparisons
+                            const uint32_t x = rx[h] & 0xffffu;
+                            const uint32_t k = lds_u16(kl_a + (rx[h] >> 16));
+                            const uint32_t kL = lds_u16(kl_a + (ry[h] & 0xffffu));
+                            const uint32_t kU = lds_u16(kl_a + (ry[h] >> 16));
+                            const uint32_t m = (k == kU) ? 2u : ((k == kL) ? 1u : 0u);
+                            ex[e + h] = x;
+                            info[e + h] = x | (m << 12) | (k << 16);
+                        }
+                    }
+                }
+                // token starts: slot 2e = at the event pixel (forced cut, literal, or mode differs from the pixel
+                // before), slot 2e+1 = at the pixel after it (the gap's static mode differs from the event's)
+                {
+                    const uint32_t pinfo = __shfl_up_sync(0xffffffffu, info[K - 1], 1);
+                    uint32_t nx0 = __shfl_down_sync(0xffffffffu, ex[0], 1);
+                    if (lane == 31) nx0 = (uint32_t)xend;
+                    uint32_t px = pinfo & 0xfffu, pm = (pinfo >> 12) & 3u;
+        #pragma unroll
+                    for (int e = 0; e < K; ++e) {
+                        const uint32_t x = ex[e], m = (info[e] >> 12) & 3u;
+                        const bool isev = (int)x < xend;
+                        const uint32_t before = (x - px > 1u) ? gm : pm;     // mode of pixel x-1
+                        const bool forced = ((x & (uint32_t)(MAXPIX - 1)) == 0u);
+                        const uint32_t nx = (e + 1 < K) ? ex[(e + 1 < K) ? e + 1 : e] : nx0;
+                        if (isev && (forced || m == 0u || m != before)) S |= 1u << (2 * e);
+                        if (isev && nx - x > 1u && m != gm) S |= 2u << (2 * e);
+                        px = x; pm = m;
+                    }
+                }
+                // ---- tokens, compacted.  A lane's events start 0..2K tokens (most: none), so walking them
+                // per lane would cost every lane the longest walk of the warp.  Instead each lane drops its
+                // token descriptors (pixels | mode << 12 | key << 16) at their rank into a per-warp list and
+                // the warp then handles them 32 at a time, one token per lane.
+                {
+                    // first token start at or after the next lane's first event: the end of this lane's last token
+                    int fs = 0x7fffffff;
+    #pragma unroll
+                    for (int sidx = 2 * K - 1; sidx >= 0; --sidx)
+                        if ((S >> sidx) & 1u) fs = (int)ex[sidx >> 1] + (sidx & 1);
+    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_down_sync(0xffffffffu, fs, o);
+                        if (lane + o < 32) fs = min(fs, t);
+                    }
+                    int nextpos = __shfl_down_sync(0xffffffffu, fs, 1);
+                    if (lane == 31) nextpos = 0x7fffffff;
+                    nextpos = min(nextpos, xend);
+    #pragma unroll
+                    for (int sidx = 2 * K - 1; sidx >= 0; --sidx) {
+                        const int pos = (int)ex[sidx >> 1] + (sidx & 1);
+                        const uint32_t m = (sidx & 1) ? gm : ((info[sidx >> 1] >> 12) & 3u);
+                        desc[sidx] = ((uint32_t)(nextpos - pos) & 0xfffu) | (m << 12) | (info[sidx >> 1] & 0xffff0000u);
+                        if ((S >> sidx) & 1u) nextpos = pos;
+                    }
+                }
+                {
+                    const int mine = __popc(S) + (lead ? 1 : 0);
+                    int incl = mine;
+    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    ntok = __shfl_sync(0xffffffffu, incl, 31);
+                    rank0 = incl - mine;
+                }
+            }
             // descriptors with rank in [b0, b0 + ENC_TCAP) -> list (rows with more tokens go batch by batch);
             // the rank of slot s is rank0 + (lead) + the number of starts below it
             auto fill = [&](int b0) {
@@ -636,7 +676,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
             uint32_t cmeta[ENC_TCAP / 32];                                     // relative bit position | bit count << 24
             uint32_t rowtotal = 0;
             if (onebatch) {
-                fill(0);
+                if (!fast) fill(0);
 #pragma unroll
                 for (int r = 0; r < ENC_TCAP / 32; ++r) {
                     cval[r] = 0; cmeta[r] = 0;
@@ -1201,6 +1241,8 @@ extern "C" int cab200_encode_geometry(int n_cells, const uint16_t *label_img, co
     }
     unsigned char *out = (unsigned char *)geom_out;
     CAB_CUDA(cudaMemsetAsync(out, 0, geom_tab_sums_bytes(n_cells), stream));
+    CAB_CUDA(cudaMemsetAsync(out + geom_tab_sums_bytes(n_cells) + 2 * geom_tab_events_bytes(H, W) + 16, 0,
+                             geom_tab_span_bytes(n_cells), stream));
     enc_geometry_kernel<<<148 * 4, 256, sizeof(uint32_t) * (size_t)W, stream>>>(
         label_img, label_mask, H, W, n_cells, (const EncTables *)tables, out);
     CAB_CUDA(cudaGetLastError());
