@@ -39,6 +39,7 @@ namespace cab200 {
 constexpr int ENC_NT = 512;
 constexpr int ENC_NW = ENC_NT / 32;
 constexpr int ENC_MAXDIM = 2048;
+constexpr int ENC_NPIECE = 4096;         // 64-byte pieces of a staged file: 256 KB, more than an SM's shared memory
 constexpr uint32_t CRC_POLY = 0xEDB88320u;
 
 struct EncStream {
@@ -69,6 +70,8 @@ struct EncTables {
     uint32_t pow8[32];       // x^(8 * 2^k) mod P
     uint32_t rowshift[ENC_MAXDIM];        // mask: x^(8 * bytes after row y)
     uint32_t colshift[ENC_MAXDIM / 16];   // mask: x^(8 * bytes after 16-pixel chunk c inside its row)
+    uint32_t pow64[ENC_NPIECE];           // x^(8 * 64 * j): the IDAT CRC is combined from 64-byte pieces counted from the end
+    uint32_t pow1[64];                    // x^(8 * k), k < 64
     EncStream img, msk;
     int H, W;
 };
@@ -379,7 +382,6 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
 {
     __shared__ uint32_t rowbits[2][ENC_NW];
     __shared__ unsigned long long red64[2][ENC_NW];
-    __shared__ uint32_t pc[ENC_NT];
     __shared__ uint32_t s_crc;
     __shared__ uint32_t rowact[ENC_MAXDIM / 32];     // mask stream: bit y = some label of row y has an instance id
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -782,56 +784,32 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
             put_be32(sm.stage + d.p_len_prefix, L + 6u);          // zlib header 2 + deflate + Adler 4
         }
         __syncthreads();
-        // CRC-32 of the IDAT chunk (type + data): equal pieces aligned to the END of the range (leading
-        // zeros do not change a CRC started from 0), combined pairwise with x^(8*piece) powers
+        // CRC-32 of the IDAT chunk (type + data).  crc0 (CRC from a zero register, no final xor) is linear and
+        // crc0(A | B) = crc0(A) * x^(8|B|) ^ crc0(B), so the range is cut into 64-byte pieces counted from its
+        // END (the first one may be shorter), piece j contributes crc0(piece) * x^(8 * 64 * j) with a power
+        // from a static table, and the contributions are XOR-ed: one polynomial product per piece, none of
+        // them dependent on another.
         const uint32_t r0 = (uint32_t)d.p_len_prefix + 4u, r1 = plen + L + 4u;
         const uint32_t Lr = r1 - r0;
-        const uint32_t C = (Lr + ENC_NT - 1) / ENC_NT;
         {
-            const long long e = (long long)r1 - (long long)(ENC_NT - 1 - tid) * C;
-            long long b = e - C;
-            if (b < (long long)r0) b = r0;
-            uint32_t c = 0;
-            for (long long i = b; i < e; ++i) c = crc_s[(c ^ sm.stage[i]) & 0xffu] ^ (c >> 8);
-            pc[tid] = c;
-        }
-        // g_k = x^(8*C*2^k), k = 0..8, computed once (sequential squarings) by warp 0
-        __shared__ uint32_t gpow[9];
-        if (warp == 0) {
-            uint32_t g = gf2_xpow8(a.tab->pow8, C);
-            for (int k = 0; k < 9; ++k) {
-                if (lane == 0) gpow[k] = g;
-                g = gf2_mulmod(g, g);
+            uint32_t acc = 0;
+            for (uint32_t j = (uint32_t)tid; j * 64u < Lr; j += ENC_NT) {
+                const uint32_t e = r1 - 64u * j;
+                const uint32_t b = (e - r0 >= 64u) ? e - 64u : r0;
+                uint32_t c = 0;
+                for (uint32_t i = b; i < e; ++i) c = crc_s[(c ^ sm.stage[i]) & 0xffu] ^ (c >> 8);
+                acc ^= gf2_mulmod(c, a.tab->pow64[j]);
             }
-        }
-        __syncthreads();
-        // crc0(A | B) = crc0(A) * x^(8|B|) ^ crc0(B): up-sweep inside each warp with shuffles ...
-        uint32_t c = pc[tid];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const int s = 1 << k;
-            const uint32_t left = __shfl_up_sync(0xffffffffu, c, s);
-            if ((lane & (2 * s - 1)) == 2 * s - 1) c ^= gf2_mulmod(left, gpow[k]);
-        }
-        __syncthreads();
-        if (lane == 31) pc[warp] = c;
-        __syncthreads();
-        // ... then over the 16 warp results
-        if (warp == 0) {
-            uint32_t cw = (lane < ENC_NW) ? pc[lane] : 0u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int s = 1 << k;
-                const uint32_t left = __shfl_up_sync(0xffffffffu, cw, s);
-                if (lane < ENC_NW && (lane & (2 * s - 1)) == 2 * s - 1) cw ^= gf2_mulmod(left, gpow[5 + k]);
-            }
-            if (lane == ENC_NW - 1) pc[ENC_NT - 1] = cw;
+            for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0 && acc) atomicXor(&s_crc, acc);
         }
         __syncthreads();
         if (tid == 0) {
             // CRC(M) = crc0(M) ^ CRC(zeros(|M|));  CRC(zeros(n)) = (0xFFFFFFFF * x^(8n)) ^ 0xFFFFFFFF
-            const uint32_t aff = gf2_mulmod(0xffffffffu, gf2_xpow8(a.tab->pow8, Lr)) ^ 0xffffffffu;
-            put_be32(sm.stage + r1, pc[ENC_NT - 1] ^ aff);
+            const uint32_t xl = gf2_mulmod(a.tab->pow64[Lr >> 6], a.tab->pow1[Lr & 63u]);
+            const uint32_t aff = gf2_mulmod(0xffffffffu, xl) ^ 0xffffffffu;
+            put_be32(sm.stage + r1, s_crc ^ aff);
             for (int i = 0; i < d.suffix_len; ++i) sm.stage[r1 + 4 + i] = d.suffix[i];
         }
         total_bytes = r1 + 4u + (uint32_t)d.suffix_len;
@@ -1136,6 +1114,10 @@ static void build_tables(int H, int W, bool tuned, EncTables *t)
     for (int k = 1; k < 32; ++k) t->pow8[k] = gf2_mulmod(t->pow8[k - 1], t->pow8[k - 1]);
     for (int y = 0; y < H; ++y) t->rowshift[y] = host_xpow8(t->pow8, 2ull * W * (unsigned long long)(H - 1 - y));
     for (int c = 0; c * 16 < W; ++c) t->colshift[c] = host_xpow8(t->pow8, 2ull * (unsigned long long)(W - std::min(W, 16 * (c + 1))));
+    t->pow1[0] = 0x80000000u;                     // x^0
+    for (int k = 1; k < 64; ++k) t->pow1[k] = gf2_mulmod(t->pow1[k - 1], t->pow8[0]);
+    t->pow64[0] = 0x80000000u;
+    for (int j = 1; j < ENC_NPIECE; ++j) t->pow64[j] = gf2_mulmod(t->pow64[j - 1], t->pow8[6]);      // x^(8 * 64)
 
     // ---- PNG, colour type 4 (gray + alpha), 16 bit: signature | IHDR | IDAT(zlib) | IEND ---------------
     EncStream &g = t->img;
