@@ -192,7 +192,7 @@ __device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n,
 // cases.  Every other pixel has the label of both neighbours, hence -- whatever a frame's values -- the mode
 // "up" (or "left" where no row above is usable).  One warp per segment; max_count receives the largest number
 // of events in a segment (a list is truncated at ENC_ECAP: the caller then must not use it).
-__global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, int H, int W, int n, int maxpix, int use_up,
+__global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, int H, int W, int n, int maxpix, int use_up, int one_px_literal,
                                                          uint2 *events, int *max_count)
 {
     const int lane = threadIdx.x & 31;
@@ -209,7 +209,19 @@ __global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, 
         const uint32_t lab = inb ? label[(size_t)y * W + x] : 0u;
         const uint32_t labL = (inb && x > 0) ? label[(size_t)y * W + x - 1] : 0xffffu;
         const uint32_t labU = (inb && y > 0 && use_up) ? label[(size_t)(y - 1) * W + x] : 0xffffu;
-        const bool isev = inb && ((x % maxpix) == 0 || labL == 0xffffu || lab != labL || (labU != 0xffffu && lab != labU));
+        // With a usable row above, a pixel that has the label of its upper neighbour has its value too, whatever
+        // the frame: mode "up", like every non-event pixel -- also where its LEFT neighbour differs.  Such
+        // pixels are no events (44 instead of 77 per row of a medium 512 x 512 map, at most 88 instead of 127).
+        // A token that starts at such a pixel takes its key from the event in front of it; the key only matters
+        // for a match too short for DEFLATE (one 2-byte pixel), so where a pixel is 2 bytes (`one_px_literal`)
+        // the pixel is dropped only if its right neighbour continues the run (same label, same label above, no
+        // forced cut): then no token that starts there is a single pixel.
+        bool staticup = labU != 0xffffu && lab == labU;
+        if (staticup && one_px_literal) {
+            const int xn = x + 1;
+            staticup = xn < xend && (xn % maxpix) != 0 && label[(size_t)y * W + xn] == lab && label[(size_t)(y - 1) * W + xn] == lab;
+        }
+        const bool isev = inb && ((x % maxpix) == 0 || labL == 0xffffu || (staticup ? false : (lab != labL || (labU != 0xffffu && lab != labU))));
         const unsigned b = __ballot_sync(0xffffffffu, isev);
         const int idx = count + __popc(b & ((1u << lane) - 1u));
         if (isev && idx < ENC_ECAP)
@@ -575,24 +587,36 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                 {
                     const uint2 *ev = events + (size_t)item * ENC_ECAP + lane * K;
                     const uint32_t kl_a = smem_addr(IMG ? lut.rank1 : lut.inst_lut);
-        #pragma unroll
-                    for (int e = 0; e < K; e += 2) {
-                        const uint32_t none = 2u * (uint32_t)(n + 1);
-                        uint4 r = make_uint4((uint32_t)xend | (none << 16), none | (none << 16), (uint32_t)xend | (none << 16), none | (none << 16));
-                        if (valid) r = __ldg(reinterpret_cast<const uint4 *>(ev + e));
-                        const uint32_t rx[2] = {r.x, r.z}, ry[2] = {r.y, r.w};
-        #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            // a missing neighbour (and a padding slot) reads the LUT's extra entry n + 1, a key no
-                            // pixel has: three unconditional look-ups, two plain comparisons
-                            const uint32_t x = rx[h] & 0xffffu;
-                            const uint32_t k = lds_u16(kl_a + (rx[h] >> 16));
-                            const uint32_t kL = lds_u16(kl_a + (ry[h] & 0xffffu));
-                            const uint32_t kU = lds_u16(kl_a + (ry[h] >> 16));
-                            const uint32_t m = (k == kU) ? 2u : ((k == kL) ? 1u : 0u);
-                            ex[e + h] = x;
-                            info[e + h] = x | (m << 12) | (k << 16);
+                    const uint32_t none = 2u * (uint32_t)(n + 1);
+                    uint32_t rx[K], ry[K];
+#pragma unroll
+                    for (int e = 0; e < K; ++e) { rx[e] = (uint32_t)xend | (none << 16); ry[e] = none | (none << 16); }
+                    if (valid) {
+                        if constexpr (K % 2 == 0) {
+#pragma unroll
+                            for (int e = 0; e < K; e += 2) {
+                                const uint4 r = __ldg(reinterpret_cast<const uint4 *>(ev + e));
+                                rx[e] = r.x; ry[e] = r.y; rx[e + 1] = r.z; ry[e + 1] = r.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < K; ++e) {
+                                const uint2 r = __ldg(ev + e);
+                                rx[e] = r.x; ry[e] = r.y;
+                            }
                         }
+                    }
+#pragma unroll
+                    for (int e = 0; e < K; ++e) {
+                        // a missing neighbour (and a padding slot) reads the LUT's extra entry n + 1, a key no
+                        // pixel has: three unconditional look-ups, two plain comparisons
+                        const uint32_t x = rx[e] & 0xffffu;
+                        const uint32_t k = lds_u16(kl_a + (rx[e] >> 16));
+                        const uint32_t kL = lds_u16(kl_a + (ry[e] & 0xffffu));
+                        const uint32_t kU = lds_u16(kl_a + (ry[e] >> 16));
+                        const uint32_t m = (k == kU) ? 2u : ((k == kL) ? 1u : 0u);
+                        ex[e] = x;
+                        info[e] = x | (m << 12) | (k << 16);
                     }
                 }
                 // token starts: slot 2e = at the event pixel (forced cut, literal, or mode differs from the pixel
@@ -1235,8 +1259,8 @@ extern "C" int cab200_encode_geometry(int n_cells, const uint16_t *label_img, co
     const bool up_img = 1 + 4 * W <= 32768, up_msk = 2 * W <= 32768;     // the distances DEFLATE can express
     uint2 *ev_img = (uint2 *)(out + geom_tab_sums_bytes(n_cells));
     uint2 *ev_msk = (uint2 *)(out + geom_tab_sums_bytes(n_cells) + geom_tab_events_bytes(H, W));
-    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_img, H, W, n_cells, 64, up_img ? 1 : 0, ev_img, d_max);
-    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_mask, H, W, n_cells, 128, up_msk ? 1 : 0, ev_msk, d_max + 1);
+    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_img, H, W, n_cells, 64, up_img ? 1 : 0, 0, ev_img, d_max);
+    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_mask, H, W, n_cells, 128, up_msk ? 1 : 0, 1, ev_msk, d_max + 1);
     CAB_CUDA(cudaGetLastError());
     int h_max[2] = {0, 0};
     CAB_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
@@ -1314,7 +1338,8 @@ extern "C" int cab200_encode_batch(
     a.records = (EncRecord *)records_out;
     a.n_active_out = n_active_out;
     const size_t smem = fixed + cap;
-    void (*kern)(const EncodeArgs) = (max_ev <= 128) ? encode_kernel<4> : (max_ev <= 256) ? encode_kernel<8> : encode_kernel<0>;
+    void (*kern)(const EncodeArgs) = (max_ev <= 64) ? encode_kernel<2> : (max_ev <= 96) ? encode_kernel<3> : (max_ev <= 128) ? encode_kernel<4>
+                                     : (max_ev <= 256) ? encode_kernel<8> : encode_kernel<0>;      // events per lane
     CAB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)pf, ENC_NT, smem, stream>>>(a);
     CAB_CUDA(cudaGetLastError());
