@@ -166,12 +166,17 @@ struct GeomTab {
     const unsigned long long *M;
     const uint2 *ev_img, *ev_msk;      // static event lists (enc_events_kernel), [H * nseg][ENC_ECAP] each
     const uint32_t *span;              // [n+1][2] rows a mask label touches: {max (H-1-y), max y}; both 0 = absent or row 0 only
+    const uint16_t *cnt_img, *cnt_msk; // [H * nseg] events of each row segment (capped at ENC_ECAP)
 };
 constexpr int ENC_ECAP = 256;
 __host__ __device__ inline size_t geom_tab_sums_bytes(int n) { return ((((size_t)(n + 1) * 8 + 7) & ~(size_t)7) + (size_t)(n + 1) * 8 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t geom_tab_events_bytes(int H, int W) { return (size_t)H * ((W + 511) / 512) * ENC_ECAP * sizeof(uint2); }
 __host__ __device__ inline size_t geom_tab_span_bytes(int n) { return ((size_t)(n + 1) * 8 + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t geom_tab_bytes(int n, int H, int W) { return geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16 + geom_tab_span_bytes(n); }   // + two event counters + the row spans
+__host__ __device__ inline size_t geom_tab_rowcnt_bytes(int H, int W) { return ((size_t)H * ((W + 511) / 512) * 2 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t geom_tab_bytes(int n, int H, int W)
+{   // sums | two event lists | two event counters | row spans | two per-row event counts
+    return geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16 + geom_tab_span_bytes(n) + 2 * geom_tab_rowcnt_bytes(H, W);
+}
 __device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n, int H, int W)
 {
     GeomTab t;
@@ -181,6 +186,8 @@ __device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n,
     t.ev_img = reinterpret_cast<const uint2 *>(p + geom_tab_sums_bytes(n));
     t.ev_msk = reinterpret_cast<const uint2 *>(p + geom_tab_sums_bytes(n) + geom_tab_events_bytes(H, W));
     t.span = reinterpret_cast<const uint32_t *>(p + geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16);
+    t.cnt_img = reinterpret_cast<const uint16_t *>(p + geom_tab_sums_bytes(n) + 2 * geom_tab_events_bytes(H, W) + 16 + geom_tab_span_bytes(n));
+    t.cnt_msk = t.cnt_img + geom_tab_rowcnt_bytes(H, W) / 2;
     return t;
 }
 
@@ -193,7 +200,7 @@ __device__ __forceinline__ GeomTab geom_tab_carve(const unsigned char *p, int n,
 // "up" (or "left" where no row above is usable).  One warp per segment; max_count receives the largest number
 // of events in a segment (a list is truncated at ENC_ECAP: the caller then must not use it).
 __global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, int H, int W, int n, int maxpix, int use_up, int one_px_literal,
-                                                         uint2 *events, int *max_count)
+                                                         uint2 *events, uint16_t *row_count, int *max_count)
 {
     const int lane = threadIdx.x & 31;
     const int nseg = (W + 511) / 512;
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(256) enc_events_kernel(const uint16_t *label, 
         count += __popc(b);
     }
     for (int j = min(count, ENC_ECAP) + lane; j < ENC_ECAP; j += 32) out[j] = make_uint2((uint32_t)xend | (none << 16), none | (none << 16));
-    if (lane == 0) atomicMax(max_count, count);
+    if (lane == 0) { atomicMax(max_count, count); row_count[item] = (uint16_t)min(count, ENC_ECAP); }
 }
 
 // Fills one geometry's block (zeroed by the caller).  One thread per pixel, atomics on ~n addresses;
@@ -582,60 +589,63 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                 __syncwarp();
                 ntok = ncut;
             } else {
+                // events per lane in THIS row: its static event count spread over the 32 lanes (a medium row has
+                // 44 events on average, 88 at most: mostly 2 per lane, K only where the map is busiest); every
+                // per-event block below is skipped, warp-uniformly, beyond kr
+                const int kr = valid ? min(K, max(1, ((int)__ldg((IMG ? gt.cnt_img : gt.cnt_msk) + item) + 31) >> 5)) : 1;
                 uint32_t info[K];                                           // x | mode << 12 | key << 16
                 uint32_t ex[K];
                 {
-                    const uint2 *ev = events + (size_t)item * ENC_ECAP + lane * K;
+                    const uint2 *ev = events + (size_t)item * ENC_ECAP + lane * kr;
                     const uint32_t kl_a = smem_addr(IMG ? lut.rank1 : lut.inst_lut);
                     const uint32_t none = 2u * (uint32_t)(n + 1);
                     uint32_t rx[K], ry[K];
 #pragma unroll
-                    for (int e = 0; e < K; ++e) { rx[e] = (uint32_t)xend | (none << 16); ry[e] = none | (none << 16); }
-                    if (valid) {
-                        if constexpr (K % 2 == 0) {
-#pragma unroll
-                            for (int e = 0; e < K; e += 2) {
-                                const uint4 r = __ldg(reinterpret_cast<const uint4 *>(ev + e));
-                                rx[e] = r.x; ry[e] = r.y; rx[e + 1] = r.z; ry[e + 1] = r.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < K; ++e) {
-                                const uint2 r = __ldg(ev + e);
-                                rx[e] = r.x; ry[e] = r.y;
-                            }
+                    for (int e = 0; e < K; ++e) {
+                        rx[e] = (uint32_t)xend | (none << 16); ry[e] = none | (none << 16);
+                        if (valid && e < kr) {
+                            const uint2 r = __ldg(ev + e);
+                            rx[e] = r.x; ry[e] = r.y;
                         }
                     }
 #pragma unroll
                     for (int e = 0; e < K; ++e) {
-                        // a missing neighbour (and a padding slot) reads the LUT's extra entry n + 1, a key no
-                        // pixel has: three unconditional look-ups, two plain comparisons
-                        const uint32_t x = rx[e] & 0xffffu;
-                        const uint32_t k = lds_u16(kl_a + (rx[e] >> 16));
-                        const uint32_t kL = lds_u16(kl_a + (ry[e] & 0xffffu));
-                        const uint32_t kU = lds_u16(kl_a + (ry[e] >> 16));
-                        const uint32_t m = (k == kU) ? 2u : ((k == kL) ? 1u : 0u);
-                        ex[e] = x;
-                        info[e] = x | (m << 12) | (k << 16);
+                        ex[e] = (uint32_t)xend; info[e] = (uint32_t)xend;
+                        if (e < kr) {
+                            // a missing neighbour (and a padding slot) reads the LUT's extra entry n + 1, a key no
+                            // pixel has: three unconditional look-ups, two plain comparisons
+                            const uint32_t x = rx[e] & 0xffffu;
+                            const uint32_t k = lds_u16(kl_a + (rx[e] >> 16));
+                            const uint32_t kL = lds_u16(kl_a + (ry[e] & 0xffffu));
+                            const uint32_t kU = lds_u16(kl_a + (ry[e] >> 16));
+                            const uint32_t m = (k == kU) ? 2u : ((k == kL) ? 1u : 0u);
+                            ex[e] = x;
+                            info[e] = x | (m << 12) | (k << 16);
+                        }
                     }
                 }
                 // token starts: slot 2e = at the event pixel (forced cut, literal, or mode differs from the pixel
                 // before), slot 2e+1 = at the pixel after it (the gap's static mode differs from the event's)
                 {
-                    const uint32_t pinfo = __shfl_up_sync(0xffffffffu, info[K - 1], 1);
+                    uint32_t last = info[0];                               // the lane's last event: info[kr - 1]
+#pragma unroll
+                    for (int e = 1; e < K; ++e) last = (e < kr) ? info[e] : last;
+                    const uint32_t pinfo = __shfl_up_sync(0xffffffffu, last, 1);
                     uint32_t nx0 = __shfl_down_sync(0xffffffffu, ex[0], 1);
                     if (lane == 31) nx0 = (uint32_t)xend;
                     uint32_t px = pinfo & 0xfffu, pm = (pinfo >> 12) & 3u;
-        #pragma unroll
+#pragma unroll
                     for (int e = 0; e < K; ++e) {
-                        const uint32_t x = ex[e], m = (info[e] >> 12) & 3u;
-                        const bool isev = (int)x < xend;
-                        const uint32_t before = (x - px > 1u) ? gm : pm;     // mode of pixel x-1
-                        const bool forced = ((x & (uint32_t)(MAXPIX - 1)) == 0u);
-                        const uint32_t nx = (e + 1 < K) ? ex[(e + 1 < K) ? e + 1 : e] : nx0;
-                        if (isev && (forced || m == 0u || m != before)) S |= 1u << (2 * e);
-                        if (isev && nx - x > 1u && m != gm) S |= 2u << (2 * e);
-                        px = x; pm = m;
+                        if (e < kr) {
+                            const uint32_t x = ex[e], m = (info[e] >> 12) & 3u;
+                            const bool isev = (int)x < xend;
+                            const uint32_t before = (x - px > 1u) ? gm : pm;     // mode of pixel x-1
+                            const bool forced = ((x & (uint32_t)(MAXPIX - 1)) == 0u);
+                            const uint32_t nx = (e + 1 < K && e + 1 < kr) ? ex[(e + 1 < K) ? e + 1 : e] : nx0;
+                            if (isev && (forced || m == 0u || m != before)) S |= 1u << (2 * e);
+                            if (isev && nx - x > 1u && m != gm) S |= 2u << (2 * e);
+                            px = x; pm = m;
+                        }
                     }
                 }
                 // ---- tokens, compacted.  A lane's events start 0..2K tokens (most: none), so walking them
@@ -658,10 +668,12 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                     nextpos = min(nextpos, xend);
     #pragma unroll
                     for (int sidx = 2 * K - 1; sidx >= 0; --sidx) {
-                        const int pos = (int)ex[sidx >> 1] + (sidx & 1);
-                        const uint32_t m = (sidx & 1) ? gm : ((info[sidx >> 1] >> 12) & 3u);
-                        desc[sidx] = ((uint32_t)(nextpos - pos) & 0xfffu) | (m << 12) | (info[sidx >> 1] & 0xffff0000u);
-                        if ((S >> sidx) & 1u) nextpos = pos;
+                        if ((sidx >> 1) < kr) {
+                            const int pos = (int)ex[sidx >> 1] + (sidx & 1);
+                            const uint32_t m = (sidx & 1) ? gm : ((info[sidx >> 1] >> 12) & 3u);
+                            desc[sidx] = ((uint32_t)(nextpos - pos) & 0xfffu) | (m << 12) | (info[sidx >> 1] & 0xffff0000u);
+                            if ((S >> sidx) & 1u) nextpos = pos;
+                        }
                     }
                 }
                 {
@@ -683,6 +695,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                 if (lead && (unsigned)(rank0 - b0) < (unsigned)ENC_TCAP) sts_u32(list_a + 4u * (uint32_t)(rank0 - b0), 0xffffffffu);
 #pragma unroll
                 for (int sidx = 0; sidx < 2 * K; ++sidx) {
+                    if ((S >> sidx) == 0u) break;                  // warp-divergent at worst: nothing above this slot
                     const int at = base + __popc(S & ((1u << sidx) - 1u));
                     if (((S >> sidx) & 1u) && (unsigned)at < (unsigned)ENC_TCAP) sts_u32(list_a + 4u * (uint32_t)at, desc[sidx]);
                 }
@@ -1259,8 +1272,10 @@ extern "C" int cab200_encode_geometry(int n_cells, const uint16_t *label_img, co
     const bool up_img = 1 + 4 * W <= 32768, up_msk = 2 * W <= 32768;     // the distances DEFLATE can express
     uint2 *ev_img = (uint2 *)(out + geom_tab_sums_bytes(n_cells));
     uint2 *ev_msk = (uint2 *)(out + geom_tab_sums_bytes(n_cells) + geom_tab_events_bytes(H, W));
-    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_img, H, W, n_cells, 64, up_img ? 1 : 0, 0, ev_img, d_max);
-    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_mask, H, W, n_cells, 128, up_msk ? 1 : 0, 1, ev_msk, d_max + 1);
+    uint16_t *rc_img = (uint16_t *)(out + geom_tab_sums_bytes(n_cells) + 2 * geom_tab_events_bytes(H, W) + 16 + geom_tab_span_bytes(n_cells));
+    uint16_t *rc_msk = rc_img + geom_tab_rowcnt_bytes(H, W) / 2;
+    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_img, H, W, n_cells, 64, up_img ? 1 : 0, 0, ev_img, rc_img, d_max);
+    enc_events_kernel<<<(items + 7) / 8, 256, 0, stream>>>(label_mask, H, W, n_cells, 128, up_msk ? 1 : 0, 1, ev_msk, rc_msk, d_max + 1);
     CAB_CUDA(cudaGetLastError());
     int h_max[2] = {0, 0};
     CAB_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
