@@ -459,7 +459,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
     bool overflow = false;
     int par = 0;
 
-    for (int item0 = 0; item0 < nitems; item0 += ENC_NW, par ^= 1) {
+    for (int item0 = 0; item0 < nitems; item0 += ENC_NW) {           // par flips with every pass that has a barrier
         const int item = item0 + warp;
         const bool valid = item < nitems;
         const int y = valid ? (nseg == 1 ? item : item / nseg) : 0;
@@ -575,6 +575,29 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
             // of a pouch is small).
             bool fast = false;
             if constexpr (!IMG) {
+                // a whole pass of such rows (CTA-uniform: rows item0 - 1 .. item0 + 15 without an id) needs neither
+                // the per-row bit counts nor the barrier that exchanges them: every row is the same R bits
+                if (nseg == 1 && use_up && item0 >= 1 && item0 + ENC_NW <= nitems) {
+                    const int yb = item0 - 1;
+                    const unsigned long long two = (unsigned long long)rowact[yb >> 5] |
+                                                   ((unsigned long long)rowact[min((yb >> 5) + 1, ENC_MAXDIM / 32 - 1)] << 32);
+                    if (((two >> (yb & 31)) & 0x1ffffull) == 0ull) {
+                        const int ncut = (xend + MAXPIX - 1) / MAXPIX;          // <= 4 tokens per row (W <= 512)
+                        unsigned long long val = 0; int nb = 0;
+                        if (lane < ncut) make_token<false>(sm, true, true, min(MAXPIX, xend - lane * MAXPIX), 0u, dist_up, dist_left, val, nb);
+                        uint32_t inc = (uint32_t)nb;
+#pragma unroll
+                        for (int o = 1; o < 4; o <<= 1) {
+                            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += u;
+                        }
+                        const uint32_t R = __shfl_sync(0xffffffffu, inc, 3);
+                        if ((bitpos + (uint32_t)ENC_NW * R + 7u + 7u) / 8u + tail_room > (uint32_t)a.stage_cap) { overflow = true; break; }
+                        if (lane < ncut) put_bits(stage32, bitpos + (uint32_t)warp * R + inc - (uint32_t)nb, val, nb);
+                        bitpos += (uint32_t)ENC_NW * R;
+                        continue;
+                    }
+                }
                 if (valid && nseg == 1 && use_up && y > 0)
                     fast = (((rowact[y >> 5] >> (y & 31)) | (rowact[(y - 1) >> 5] >> ((y - 1) & 31))) & 1u) == 0u;
             }
@@ -779,6 +802,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
             }
         }
         bitpos += pass_bits;
+        par ^= 1;
     }
     __syncthreads();
     if (overflow) return 0u;

@@ -1,10 +1,11 @@
 """Dynamic instruction counts per source line of K3 (encode_kernel<4>): joins the line table of the built object
 (nvdisasm -g) with the per-instruction 'Instructions Executed' of an ncu report taken from the same build.
-usage: python scripts/k3_line_profile.py gpurun_out/x.ncu-rep [frames]"""
+usage: python scripts/k3_line_profile.py gpurun_out/x.ncu-rep [frames] [K]"""
 import collections, csv, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3330
+kinst = sys.argv[3] if len(sys.argv) > 3 else "3"      # encode_kernel<K>: events per lane of the profiled launch
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "calcium_b200", "_obj", "encode.o")], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -12,7 +13,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=tmp, capture_output=Tr
 line_of, cur, infun = {}, None, False
 for l in dis:
     if l.startswith(".text."):
-        infun = "encode_kernelILi4E" in l
+        infun = f"encode_kernelILi{kinst}E" in l
         continue
     if not infun: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
