@@ -734,7 +734,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pouches-per-gpu", type=int, default=POUCHES_PER_GPU)
     ap.add_argument("--raster-chunk", type=int, default=37)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-chunk", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e_api / config 2 / config 5 legs (N = 1)")
