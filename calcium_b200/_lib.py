@@ -29,7 +29,7 @@ DEFECT_MAX_ONLY, DEFECT_LUT_MAX, DEFECT_LUT_FLAG, DEFECT_MUL = 0, 1, 2, 3
 
 #: every symbol include/cab200.h declares (tests check the library exports all of them)
 EXPORTS = ["cab200_version", "cab200_last_error", "cab200_device_info",
-           "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_frames_tmp_bytes", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_k1_legacy_rows", "cab200_sim_layout",
+           "cab200_sim_scratch_bytes", "cab200_sim_batch", "cab200_sim_frames_tmp_bytes", "cab200_sim_set_plan", "cab200_plan_slots", "cab200_plan_slots_entry", "cab200_k1_legacy_rows", "cab200_sim_layout",
            "cab200_cluster_layout", "cab200_cluster_capacity", "cab200_plan_cluster",
            "cab200_raster_scratch_bytes", "cab200_raster_batch", "cab200_cells_mask", "cab200_paint_label_map",
            "cab200_edge_maps", "cab200_raster_edges_batch", "cab200_legacy_choice", "cab200_sample_background", "cab200_prompts_pouch", "cab200_np_percentile80_sqrt", "cab200_legacy_randint", "cab200_defect_pass",
@@ -79,6 +79,9 @@ def load() -> ctypes.CDLL:
     lib.cab200_k1_legacy_rows.argtypes = [c_int, i32p, i32p]
     lib.cab200_plan_slots.argtypes = [c_int, i32p, i32p, c_int, c_int, c_int, ctypes.c_longlong,
                                       ctypes.c_ulonglong, c_int, POINTER(ctypes.c_uint16), i64p]
+    lib.cab200_plan_slots_entry.restype = c_int
+    lib.cab200_plan_slots_entry.argtypes = [c_int, i32p, i32p, c_int, c_int, c_int, c_int, ctypes.c_longlong,
+                                            ctypes.c_ulonglong, c_int, POINTER(ctypes.c_uint16), i64p]
     lib.cab200_cluster_capacity.restype = c_int
     lib.cab200_cluster_capacity.argtypes = [c_int, c_int, c_int, c_int]
     lib.cab200_cluster_layout.restype = c_int

@@ -42,6 +42,8 @@ namespace {
 // positions by k1_row (k1_layout.cuh) -- the same rule the kernel applies.
 struct Problem {
     int n, np, copies, cpt, ep;
+    int pl = 8;                               // lanes served together by one shared-memory phase = number of bank groups an
+                                              // entry can fall into: 8 for 16-byte entries (FP64, LDS.128), 16 for 8-byte ones (FP32, LDS.64)
     bool unit;
     std::vector<int> rowptr, ecol;
     std::vector<K1Row> row;                   // laid out for the diagonal point of the warp the cell sits in
@@ -77,9 +79,9 @@ struct Problem {
     inline int phase_cost(int g, int pos, unsigned *sel_out) const
     {
         const int zero_idx = copies * np;
-        int a_idx[8], b_idx[8];     // candidate entry indices (b = -1: no choice)
-        for (int l = 0; l < 8; ++l) {
-            const int c = cell_of[g * 8 + l];
+        int a_idx[16], b_idx[16];     // candidate entry indices (b = -1: no choice)
+        for (int l = 0; l < pl; ++l) {
+            const int c = cell_of[g * pl + l];
             a_idx[l] = zero_idx;
             b_idx[l] = -1;
             if (c < 0) continue;
@@ -90,40 +92,41 @@ struct Problem {
             a_idx[l] = slot_of[cc];
             if (copies == 2) b_idx[l] = np + (slot_of[cc] ^ 4);
         }
-        int chosen[8];
-        int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int chosen[16];
+        int load[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const int bm = pl - 1;
         auto present = [&](int idx, int skip) {
-            for (int j = 0; j < 8; ++j) if (j != skip && chosen[j] == idx) return true;
+            for (int j = 0; j < pl; ++j) if (j != skip && chosen[j] == idx) return true;
             return false;
         };
-        for (int l = 0; l < 8; ++l) chosen[l] = -2;
-        for (int l = 0; l < 8; ++l)      // lanes without a choice first
-            if (b_idx[l] < 0) { if (!present(a_idx[l], l)) ++load[a_idx[l] & 7]; chosen[l] = a_idx[l]; }
-        for (int l = 0; l < 8; ++l) {    // greedy: the lighter bank group (or an address already read)
+        for (int l = 0; l < pl; ++l) chosen[l] = -2;
+        for (int l = 0; l < pl; ++l)      // lanes without a choice first
+            if (b_idx[l] < 0) { if (!present(a_idx[l], l)) ++load[a_idx[l] & bm]; chosen[l] = a_idx[l]; }
+        for (int l = 0; l < pl; ++l) {    // greedy: the lighter bank group (or an address already read)
             if (b_idx[l] < 0) continue;
             int pick;
             if (present(a_idx[l], l)) pick = a_idx[l];
             else if (present(b_idx[l], l)) pick = b_idx[l];
-            else pick = (load[a_idx[l] & 7] <= load[b_idx[l] & 7]) ? a_idx[l] : b_idx[l];
-            if (!present(pick, l)) ++load[pick & 7];
+            else pick = (load[a_idx[l] & bm] <= load[b_idx[l] & bm]) ? a_idx[l] : b_idx[l];
+            if (!present(pick, l)) ++load[pick & bm];
             chosen[l] = pick;
         }
-        for (int l = 0; l < 8; ++l) {    // one refinement pass
+        for (int l = 0; l < pl; ++l) {    // one refinement pass
             if (b_idx[l] < 0) continue;
             const int cur = chosen[l], alt = (cur == a_idx[l]) ? b_idx[l] : a_idx[l];
             if (present(cur, l)) continue;
-            const int lc = load[cur & 7], la = load[alt & 7] + (present(alt, l) ? 0 : 1);
+            const int lc = load[cur & bm], la = load[alt & bm] + (present(alt, l) ? 0 : 1);
             if (la < lc) {
-                --load[cur & 7];
-                if (!present(alt, l)) ++load[alt & 7];
+                --load[cur & bm];
+                if (!present(alt, l)) ++load[alt & bm];
                 chosen[l] = alt;
             }
         }
         int mx = 1;
-        for (int b = 0; b < 8; ++b) mx = std::max(mx, load[b]);
+        for (int b = 0; b < pl; ++b) mx = std::max(mx, load[b]);
         if (sel_out) {
             unsigned m = 0;
-            for (int l = 0; l < 8; ++l) if (b_idx[l] >= 0 && chosen[l] == b_idx[l]) m |= 1u << l;
+            for (int l = 0; l < pl; ++l) if (b_idx[l] >= 0 && chosen[l] == b_idx[l]) m |= 1u << l;
             *sel_out = m;
         }
         return mx;
@@ -131,7 +134,7 @@ struct Problem {
 
     int group_cost(int g) const
     {
-        const int w = (g * 8) / (32 * cpt);
+        const int w = (g * pl) / (32 * cpt);
         int cost = 0;
         for (int pos = wstart[w]; pos < wend[w]; ++pos) cost += phase_cost(g, pos, nullptr);
         return cost;
@@ -189,7 +192,7 @@ struct Problem {
     void set_order(const std::vector<int> &order)
     {
         np = (n + 31) & ~31;
-        n_groups = np / 8;
+        n_groups = np / pl;
         slot_of.assign(n, 0);
         cell_of.assign(np, -1);
         for (int s = 0; s < n; ++s) { slot_of[order[s]] = s; cell_of[s] = order[s]; }
@@ -203,7 +206,7 @@ struct Problem {
     long long gather_instructions() const      // warp-wide loads per step
     {
         long long rows = 0;
-        for (int g = 0; g < n_groups; g += 4) { const int w = (g * 8) / (32 * cpt); rows += wend[w] - wstart[w]; }
+        for (int g = 0; g < n_groups; g += 32 / pl) { const int w = (g * pl) / (32 * cpt); rows += wend[w] - wstart[w]; }
         return rows;
     }
 };
@@ -241,9 +244,9 @@ long long anneal(Problem &P, long long iters, uint64_t seed, long long *cost0_ou
         const int wa = sa / per, wb = sb / per;
         if (wa != wb && !(P.fits(a, wa, wb) && P.fits(b, wb, wa))) continue;
         touched.clear();
-        for (int r : P.refs[a]) touched.push_back(P.slot_of[r] / 8);
-        for (int r : P.refs[b]) touched.push_back(P.slot_of[r] / 8);
-        touched.push_back(sa / 8); touched.push_back(sb / 8);
+        for (int r : P.refs[a]) touched.push_back(P.slot_of[r] / P.pl);
+        for (int r : P.refs[b]) touched.push_back(P.slot_of[r] / P.pl);
+        touched.push_back(sa / P.pl); touched.push_back(sb / P.pl);
         std::sort(touched.begin(), touched.end());
         touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
         int old_c = 0, new_c = 0;
@@ -271,13 +274,13 @@ void emit_sel(const Problem &P, std::vector<uint16_t> &sel)
     sel.assign(P.n, 0);
     if (P.copies != 2) return;
     for (int g = 0; g < P.n_groups; ++g) {
-        const int w = (g * 8) / (32 * P.cpt);
+        const int w = (g * P.pl) / (32 * P.cpt);
         for (int pos = P.wstart[w]; pos < P.wend[w]; ++pos) {
             unsigned m = 0;
             P.phase_cost(g, pos, &m);
-            for (int l = 0; l < 8; ++l)
+            for (int l = 0; l < P.pl; ++l)
                 if ((m >> l) & 1u) {
-                    const int c = P.cell_of[g * 8 + l];
+                    const int c = P.cell_of[g * P.pl + l];
                     sel[c] |= (uint16_t)(1u << k1_entry_at(P.row[c], P.ep, pos));     // bit e: row entry e reads copy B
                 }
         }
@@ -418,14 +421,23 @@ extern "C" int cab200_plan_slots(int n, const int32_t *rowptr, const int32_t *co
                                  int cells_per_thread, long long iters, unsigned long long seed,
                                  int use_input, uint16_t *plan_out, int64_t *cost_out)
 {
+    return cab200_plan_slots_entry(n, rowptr, colidx, copies, unit, cells_per_thread, 16, iters, seed, use_input, plan_out, cost_out);
+}
+
+// See include/cab200.h.
+extern "C" int cab200_plan_slots_entry(int n, const int32_t *rowptr, const int32_t *colidx, int copies, int unit,
+                                       int cells_per_thread, int entry_bytes, long long iters, unsigned long long seed,
+                                       int use_input, uint16_t *plan_out, int64_t *cost_out)
+{
     if (n <= 0 || n > 32767 || !rowptr || !colidx || !plan_out || (copies != 1 && copies != 2) ||
-        cells_per_thread < 1 || cells_per_thread > 8) {
+        cells_per_thread < 1 || cells_per_thread > 8 || (entry_bytes != 16 && entry_bytes != 8)) {
         set_error("cab200_plan_slots: bad argument");
         return CAB200_EINVAL;
     }
     if (int rc = check_csr(n, rowptr, colidx, "cab200_plan_slots")) return rc;
     Problem P;
     P.n = n; P.copies = copies; P.cpt = cells_per_thread;
+    P.pl = 128 / entry_bytes;                 // lanes (and bank groups) of one shared-memory phase
     P.unit = unit != 0; P.ep = k1_ep(max_row_of(n, rowptr));
     P.rowptr.assign(rowptr, rowptr + n + 1);
     P.ecol.assign(colidx, colidx + rowptr[n]);

@@ -187,7 +187,7 @@ def plan_layout(n: int, unit: bool, precision: int) -> Tuple[int, int]:
     return int(lay[2]), int(lay[1])
 
 
-def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool, n_cta: int = 1) -> str:
+def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool, n_cta: int = 1, entry_bytes: int = 16) -> str:
     """Plans are keyed by the CSR structure and the layout they were made for.  ``tracked`` plans
     (long offline annealing, scripts/make_plans.py) ship with the package under ``plans/``; others
     are computed on first use and cached next to the synthetic geometry cache."""
@@ -196,6 +196,8 @@ def plan_path(geo: Geometry, copies: int, cpt: int, tracked: bool, n_cta: int = 
     h.update(rowptr.tobytes()); h.update(col.tobytes())
     h.update(f"copies={copies}:cpt={cpt}:v5-warpdiag".encode() if n_cta == 1         # v5: one diagonal point per warp
              else f"copies={copies}:cpt={cpt}:ncta={n_cta}:v3-warpdiag".encode())
+    if entry_bytes != 16:
+        h.update(f":entry={entry_bytes}".encode())      # FP32 mode: 8-byte entries, another bank-conflict model
     name = f"plan_{h.hexdigest()[:16]}.npy"
     if tracked:
         return os.path.join(_PLANS_DIR, name)
@@ -218,7 +220,10 @@ def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = 
     rowptr, col, _ = geo.csr
     n = geo.n_cells
     copies, cpt = plan_layout(n, unit, precision) if n_cta == 1 else cluster_layout(n, n_cta, precision)
-    paths = [plan_path(geo, copies, cpt, True, n_cta), plan_path(geo, copies, cpt, False, n_cta)]
+    # one CTA per pouch: the plan is annealed against the bank-conflict model of the entry size the kernel loads
+    # (16-byte (c, p) pairs in FP64, 8-byte ones in the FP32 mode); cluster plans use the FP64 model for both
+    entry_bytes = 8 if (precision == _lib.FP32 and n_cta == 1) else 16
+    paths = [plan_path(geo, copies, cpt, True, n_cta, entry_bytes), plan_path(geo, copies, cpt, False, n_cta, entry_bytes)]
     if iters is None:
         for path in paths:
             if os.path.exists(path):
@@ -231,9 +236,10 @@ def slot_plan(geo: Geometry, unit: bool, precision: int, iters: Optional[int] = 
     n_it = PLAN_ITERS if iters is None else iters
     if n_cta == 1:
         plan = np.zeros(2 * n, dtype=np.uint16)
-        _lib.check(lib.cab200_plan_slots(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 1 if unit else 0, cpt, n_it, 1, 0,
-                                         plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None),
-                   "cab200_plan_slots")
+        _lib.check(lib.cab200_plan_slots_entry(n, _lib.as_i32p(rowptr), _lib.as_i32p(col), copies, 1 if unit else 0, cpt,
+                                               entry_bytes, n_it, 1, 0,
+                                               plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None),
+                   "cab200_plan_slots_entry")
     else:
         cap = 3 * n + n_cta + n_cta * n
         plan = np.zeros(cap, dtype=np.uint16)

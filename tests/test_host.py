@@ -100,6 +100,39 @@ def test_layout_and_planner(lib):
     assert lib.cab200_k1_legacy_rows(n, _lib.as_i32p(rowptr), _lib.as_i32p(col)) <= 8
 
 
+def test_planner_models_the_entry_size(lib):
+    """cab200_plan_slots_entry: the FP32 mode loads 8-byte entries (LDS.64: 16 lanes and 16 bank groups per
+    phase), FP64 16-byte ones (8 and 8).  Same output format, cab200_plan_slots == entry size 16, annealing lowers the
+    cost under the model it was given, and a conflict-free phase costs 2 wavefronts per warp-wide load with 8-byte
+    entries (4 with 16-byte ones)."""
+    from calcium_b200 import _lib
+    from calcium_b200.geometry import get_geometry
+    g = get_geometry("small")
+    rowptr, col, _ = g.csr
+    n = g.n_cells
+    args = (n, _lib.as_i32p(rowptr), _lib.as_i32p(col), 2, 1, 2)
+
+    def run(entry, iters, use_input=0, start=None):
+        plan = np.zeros(2 * n, dtype=np.uint16) if start is None else start.copy()
+        cost = np.zeros(4, dtype=np.int64)
+        assert lib.cab200_plan_slots_entry(*args, entry, iters, 7, use_input, plan.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)),
+                                           _lib.as_i64p(cost)) == 0
+        assert sorted(plan[:n].tolist()) == list(range(n))
+        return plan, cost
+
+    p16, c16 = run(16, 20000)
+    ref = np.zeros(2 * n, dtype=np.uint16)
+    cref = np.zeros(4, dtype=np.int64)
+    assert lib.cab200_plan_slots(*args, 20000, 7, 0, ref.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), _lib.as_i64p(cref)) == 0
+    assert np.array_equal(ref, p16) and np.array_equal(cref, c16)
+    p8, c8 = run(8, 20000)
+    assert c8[1] == c8[2] < c8[0] and c8[3] == c16[3]          # same warp ranges, another conflict model
+    assert 2 * c8[3] <= c8[1] and 4 * c16[3] <= c16[1]         # never below the conflict-free count
+    _, c8_of_16 = run(8, 0, use_input=1, start=p16)            # the FP64 plan judged by the FP32 model: worse than its own
+    assert c8_of_16[1] > c8[1]
+    assert lib.cab200_plan_slots_entry(*args, 12, 0, 7, 0, p8.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), None) != 0
+
+
 def test_planner_gives_every_warp_one_diagonal_point(lib):
     """K1 adds a row's diagonal term from registers after D gather positions, D one value per warp (k1_layout.cuh):
     the planner must put the rows with more than EP = 5 entries on one side of their diagonal into warps whose other
