@@ -32,6 +32,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
+from . import _lib as _lib_status
 from . import io as cio
 from .defects import (BROKEN_IN_REFERENCE, apply_all_defects_host, apply_defects, host_defects, plan as defect_plan,
                       random_defect_config)
@@ -66,6 +67,16 @@ def _parse_image_size(image_size) -> tuple:
 
 _RUN_ID_LOCK = threading.Lock()
 _LAST_RUN_ID: List[datetime.datetime] = []
+
+
+def _warn_nonfinite(status, part) -> None:
+    """A diverged trajectory: the reference's generate_image raises on the first NaN frame and its loop skips that time
+    step (main.py:342-351); here the frames are rendered from the clipped values -- said, not silent (not reachable with
+    the parameter ranges of SimulationParameters)."""
+    for li, d_ in enumerate(part):
+        if int(status[li]) & _lib_status.ST_NONFINITE:
+            print(f"Warning: simulation {d_['sim_idx']} ({d_['name']}) produced non-finite values; "
+                  f"the reference would skip its frames from the first such time step on")
 
 
 def _unique_run_id(img_dir: str) -> str:
@@ -302,9 +313,11 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
                 ens.run_files_to_host(chunk_pouches=min(len(part), 37), image=True, mask=bool(generate_masks),
                                       consumer=consumer)
                 status = ens.check_status()
+                _warn_nonfinite(status, part)
             else:
                 ens.simulate()
                 status = ens.check_status()
+                _warn_nonfinite(status, part)
                 # edge_blur (main.py:281-287): K2b blends the blurred frame in along the cell outlines; these
                 # frames are not flat-shaded any more, so they take the raw-array path and the host PNG writer
                 # the instance masks are not touched by blur or defects: unless the caller wants the arrays, they
