@@ -32,7 +32,8 @@ class _EncStream(ctypes.Structure):        # mirror of csrc/encode.cu: struct En
 
 class _EncTables(ctypes.Structure):        # struct EncTables
     _fields_ = [("crc", ctypes.c_uint32 * 256), ("pow8", ctypes.c_uint32 * 32), ("rowshift", ctypes.c_uint32 * 2048),
-                ("colshift", ctypes.c_uint32 * 128), ("img", _EncStream), ("msk", _EncStream),
+                ("colshift", ctypes.c_uint32 * 128), ("pow64", ctypes.c_uint32 * 4096), ("pow1", ctypes.c_uint32 * 64),
+                ("img", _EncStream), ("msk", _EncStream),
                 ("H", ctypes.c_int), ("W", ctypes.c_int)]
 
 
@@ -40,7 +41,8 @@ def _tables(lib, L, H, W, huffman=1):
     assert int(lib.cab200_encode_tables_bytes()) == ctypes.sizeof(_EncTables)
     raw = _EncTables()
     L.check(lib.cab200_encode_tables(H, W, huffman, ctypes.addressof(raw)), "cab200_encode_tables")
-    t = dict(crc=np.array(raw.crc), pow8=np.array(raw.pow8), rowshift=np.array(raw.rowshift), colshift=np.array(raw.colshift))
+    t = dict(crc=np.array(raw.crc), pow8=np.array(raw.pow8), rowshift=np.array(raw.rowshift), colshift=np.array(raw.colshift),
+             pow64=np.array(raw.pow64), pow1=np.array(raw.pow1))
     for name in ("img", "msk"):
         st = getattr(raw, name)
         d = {k: getattr(st, k) for k, _ in _EncStream._fields_ if not hasattr(getattr(st, k), "__len__")}
@@ -141,6 +143,24 @@ def test_host_tables_match_the_oracle_and_zlib():
         n = 1 << k
         assert (_mulmod(0xFFFFFFFF, x) ^ 0xFFFFFFFF) == (zlib.crc32(bytes(n)) & 0xFFFFFFFF)
         x = _mulmod(x, x)
+    # x^(8k) and x^(8*64*j); the IDAT CRC exactly as the kernel assembles it: 64-byte pieces counted from the END of
+    # the range (the first may be shorter), piece j's crc0 times x^(8*64*j), all XOR-ed, then the zeros term
+    x = 0x80000000
+    for k in range(64):
+        assert int(t["pow1"][k]) == x
+        x = _mulmod(x, 0x00800000)
+    assert int(t["pow64"][1]) == x and int(t["pow64"][2]) == _mulmod(x, x) and int(t["pow64"][0]) == 0x80000000
+    assert int(t["pow64"][4095]) == _mulmod(int(t["pow64"][4094]), x)
+    rngb = np.random.default_rng(11)
+    for Lr in (1, 63, 64, 65, 1000, 33333):
+        msg = rngb.integers(0, 256, Lr, dtype=np.uint8).tobytes()
+        acc, j = 0, 0
+        while 64 * j < Lr:
+            e = Lr - 64 * j
+            acc ^= _mulmod(_crc0_slow(msg[max(0, e - 64):e], 0), int(t["pow64"][j]))
+            j += 1
+        xl = _mulmod(int(t["pow64"][Lr >> 6]), int(t["pow1"][Lr & 63]))
+        assert (acc ^ _mulmod(0xFFFFFFFF, xl) ^ 0xFFFFFFFF) == (zlib.crc32(msg) & 0xFFFFFFFF)
     # the mask CRC exactly as the kernel assembles it: per 16-pixel chunk crc0, shifted into place
     rng = np.random.default_rng(5)
     inst = np.where(rng.random((H, W)) < 0.3, rng.integers(0, 65536, (H, W)), 0).astype("<u2")
