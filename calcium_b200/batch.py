@@ -534,7 +534,8 @@ def generate_simulation_batch(num_simulations, output_dir, pouch_sizes=None, sim
         print(f"Error saving results: {str(e)}")
     if keep_arrays:
         results["arrays"] = arrays
-    gc.collect()
+    # (the reference ends with gc.collect() because it holds (n, 4, T) histories per pouch; nothing of that size lives
+    # on the host here, and a full collection over the call's ~10^5 small objects cost 36 ms of a 0.17 s call)
     return results
 
 
