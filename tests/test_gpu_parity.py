@@ -306,6 +306,23 @@ def test_fp32_mode_tracks_fp64_and_reports_error(env):
         assert np.isfinite(got).all() and got[:, 0].min() >= 0 and got[:, 0].max() < 5.0
         # the ER store follows from c by the same identity as in FP64 (core/pouch.py:95), to float precision
         assert np.allclose(got[:, 2], (s.params["c_tot"] - got[:, 0]) / s.params["beta"], rtol=1e-5, atol=1e-6)
+    # the FP32 mode has its own slot plans (8-byte entries: cab200_plan_slots_entry): which cell sits in which slot and
+    # which copy an entry reads is not arithmetic -- the plan made for 16-byte entries gives the same float32 bits.
+    # (Without any plan the rows take the legacy layout, whose diagonal term is a rounded product read from shared
+    # memory instead of an FFMA from registers: last-bit differences in this non-strict mode, 6e-6 here.)
+    from calcium_b200.ensemble import slot_plan
+    import torch
+    msp = E.make_specs(2, size="medium", first_seed=7)
+    runs = []
+    for variant in ("own", "fp64-plan", "none"):
+        ens = E.Ensemble(msp, T=2500, frame_steps=[0, 1200, 2499], device=env["dev"], precision=L.FP32,
+                         use_plan=variant != "none", cluster=1)
+        if variant == "fp64-plan":
+            ens.d_plan = torch.from_numpy(slot_plan(msp[0].geometry, True, L.FP64_STRICT).view(np.int16)).to(env["dev"])
+        runs.append(ens.simulate().cpu().numpy().copy())
+        assert not ens.check_status().any()
+    assert np.array_equal(runs[0], runs[1])
+    assert np.allclose(runs[0], runs[2], rtol=1e-3, atol=1e-4)
 
 
 # ---- K0 / K2 ----------------------------------------------------------------------------------------
