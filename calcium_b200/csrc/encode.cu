@@ -13,13 +13,17 @@
 //
 // One CTA per (pouch, frame).  It builds the per-frame look-up tables (frame_lut.cuh), then encodes
 // the two streams one after the other into a shared-memory staging buffer:
-//   * the pixel rows are never materialised: a warp handles one 512-pixel row segment, a lane 16
-//     consecutive pixels, read from the static label map (L2 resident) through the LUT;
+//   * the pixel rows are never materialised: a warp handles one 512-pixel row segment.  The fast path parses
+//     only the segment's static EVENTS (the pixels whose label differs from the one above, plus the forced cuts;
+//     1 to K per lane, chosen per row) -- every other pixel is in mode "up" whatever the frame's values; rows of
+//     the mask without any instance id are written without reading even those.  The general path (K = 0) reads
+//     16 consecutive pixels per lane from the static label map (L2 resident) through the LUT;
 //   * LZ77 parse restricted to two match distances: the previous pixel (runs inside a cell) and the
 //     pixel above (rows of flat-shaded polygons mostly repeat the row above).  Per pixel the mode is
 //     "up" if it equals the pixel above, else "left" if it equals the previous pixel, else literal;
 //     a token is a maximal run of one mode, cut at multiples of 256 bytes and at segment ends;
-//   * DEFLATE with the fixed Huffman code (one final block): token bit lengths are known from small
+//   * DEFLATE with a static Huffman code per stream kind (tuned, sent as a dynamic-block header; or the fixed
+//     code), one final block: token bit lengths are known from small
 //     tables, a warp scan + a CTA scan over the 16 rows of a pass give every token its bit
 //     position, and the bits are OR-ed into the zeroed staging buffer with shared-memory atomics;
 //   * checksums on the fly: Adler-32 of the PNG scanlines (plain sums), CRC-32 of the .npy bytes
