@@ -585,7 +585,7 @@ __device__ uint32_t encode_stream(const EncodeArgs &a, const EncStream &d, const
                     const int yb = item0 - 1;
                     const unsigned long long two = (unsigned long long)rowact[yb >> 5] |
                                                    ((unsigned long long)rowact[min((yb >> 5) + 1, ENC_MAXDIM / 32 - 1)] << 32);
-                    if (((two >> (yb & 31)) & 0x1ffffull) == 0ull) {
+                    if (((two >> (yb & 31)) & ((1ull << (ENC_NW + 1)) - 1ull)) == 0ull) {
                         const int ncut = (xend + MAXPIX - 1) / MAXPIX;          // <= 4 tokens per row (W <= 512)
                         unsigned long long val = 0; int nb = 0;
                         if (lane < ncut) make_token<false>(sm, true, true, min(MAXPIX, xend - lane * MAXPIX), 0u, dist_up, dist_left, val, nb);
